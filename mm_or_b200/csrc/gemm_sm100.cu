@@ -1,0 +1,383 @@
+// tcgen05 GEMM for sm_100a:  C[M,N] = epilogue(A[M,K] . B[N,K]^T), bf16 operands, fp32 accumulation in TMEM.
+//
+// This one kernel carries ~95 % of the MM2SG hot path's FLOPs: every nn.Linear of the CLIP ViT-L tower
+// (reference call site clip_encoder.py:48), the BERT image pooler (multimodal_projector/builder.py:173),
+// the mlp2x_gelu projector (llava_arch.py:182) and the Llama-7B decoder + lm_head (llava_llama.py:93).
+// In the reference each of them is a cuBLAS call followed by separate bias / activation / residual kernels.
+//
+// Design (one CTA per SM, persistent over output tiles, warp-specialised):
+//   warp 0      TMA producer: cp.async.bulk.tensor 2-D loads of a 128 x 64 A tile and a BN x 64 B tile per
+//               pipeline stage into 128B-swizzled shared memory, completion on an mbarrier (expect_tx).
+//   warp 1      MMA issuer (+ TMEM allocator): one elected thread issues tcgen05.mma.cta_group::1.kind::f16
+//               (M = 128, N = BN, K = 16) four times per stage; tcgen05.commit releases the stage back to the
+//               producer and, after the last K block, hands the accumulator to the epilogue.
+//   warps 2..5  epilogue: tcgen05.ld the 128 x BN fp32 accumulator (one output row per thread), apply
+//               bias / activation / SwiGLU pairing / residual / row scatter, convert to bf16 and store 16 B
+//               vectors. TMEM holds two accumulators so the epilogue of tile i overlaps the main loop of i+1.
+#include <cstdarg>
+#include <mutex>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace b200 {
+
+static constexpr int kBM = 128;
+static constexpr int kBK = 64;  // 64 bf16 = 128 B = one swizzle row
+static constexpr int kGemmThreads = 192;
+static constexpr int kRasterGroupM = 16;
+
+struct GemmArgs {
+  void* C;
+  int ldc;
+  int M, N, K;
+  int m_tiles, n_tiles;
+  GemmEpilogue epi;
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kStageBytesA = kBM * kBK * 2;
+  static constexpr int kStageBytesB = BN * kBK * 2;
+  static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
+  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128) ? 6 : 8;
+  static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;  // power of two for BN in {32,64,128,256}
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ void tile_coords(int tile, int m_tiles, int n_tiles, int& mt, int& nt) {
+  // grouped rasterisation: kRasterGroupM consecutive M tiles share every B tile while it is L2-hot
+  const int per_group = kRasterGroupM * n_tiles;
+  const int group = tile / per_group;
+  const int first_m = group * kRasterGroupM;
+  const int gsize = min(kRasterGroupM, m_tiles - first_m);
+  const int r = tile - group * per_group;
+  mt = first_m + r % gsize;
+  nt = r / gsize;
+}
+
+__device__ __forceinline__ float act_apply(float x, int act) {
+  if (act == kActQuickGelu) return x / (1.0f + __expf(-1.702f * x));
+  if (act == kActGeluErf) return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+  return x;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+    gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                        const GemmArgs g) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int kStages = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);  // 1024 B aligned for SWIZZLE_128B
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kStages * Cfg::kStageBytesA;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full = empty_bar + kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = g.m_tiles * g.n_tiles;
+  const int k_blocks = (g.K + kBK - 1) / kBK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full[b], 1);
+      mbar_init(&tmem_empty[b], 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        int mt, nt;
+        tile_coords(tile, g.m_tiles, g.n_tiles, mt, nt);
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          tma_load_2d(smem_a + stage * Cfg::kStageBytesA, &tmA, &full_bar[stage], kb * kBK, mt * kBM);
+          tma_load_2d(smem_b + stage * Cfg::kStageBytesB, &tmB, &full_bar[stage], kb * kBK, nt * BN);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        mbar_wait(&tmem_empty[buf], ((it >> 1) & 1u) ^ 1u);
+        tc_fence_after_sync();
+        const uint32_t d_addr = tmem_base + static_cast<uint32_t>(buf * BN);
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after_sync();
+          const uint64_t da = umma_desc_kmajor_sw128(smem_u32(smem_a + stage * Cfg::kStageBytesA));
+          const uint64_t db = umma_desc_kmajor_sw128(smem_u32(smem_b + stage * Cfg::kStageBytesB));
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in the (addr >> 4) field
+            umma_bf16_ss(d_addr, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // stage reusable once these MMAs have read it
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit(&tmem_full[buf]);  // accumulator complete
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    const GemmEpilogue& e = g.epi;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      int mt, nt;
+      tile_coords(tile, g.m_tiles, g.n_tiles, mt, nt);
+      const int buf = it & 1;
+      mbar_wait(&tmem_full[buf], (it >> 1) & 1u);
+      tc_fence_after_sync();
+      const int row = mt * kBM + q * 32 + lane;
+      int out_row = row;
+      bool ok = row < g.M;
+      if (ok && e.row_map != nullptr) {
+        out_row = e.row_map[row];
+        ok = out_row >= 0;
+      }
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * BN);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(t_row + c * 32, v);
+        tmem_ld_wait();
+        const int n0 = nt * BN + c * 32;
+        if (!ok || n0 >= g.N) continue;
+        float x[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
+        if (e.bias != nullptr) {
+#pragma unroll
+          for (int j8 = 0; j8 < 4; ++j8) {
+            if (n0 + j8 * 8 < g.N) {
+              const uint4 b = __ldg(reinterpret_cast<const uint4*>(e.bias + n0 + j8 * 8));
+              x[j8 * 8 + 0] += bf16lo(b.x);
+              x[j8 * 8 + 1] += bf16hi(b.x);
+              x[j8 * 8 + 2] += bf16lo(b.y);
+              x[j8 * 8 + 3] += bf16hi(b.y);
+              x[j8 * 8 + 4] += bf16lo(b.z);
+              x[j8 * 8 + 5] += bf16hi(b.z);
+              x[j8 * 8 + 6] += bf16lo(b.w);
+              x[j8 * 8 + 7] += bf16hi(b.w);
+            }
+          }
+        }
+        if (e.act == kActSwiGLU) {
+          // 32 accumulator columns -> 16 outputs
+          const int o0 = n0 >> 1;
+          bf16* crow = reinterpret_cast<bf16*>(g.C) + static_cast<size_t>(out_row) * g.ldc + o0;
+#pragma unroll
+          for (int j8 = 0; j8 < 2; ++j8) {
+            if (n0 + j8 * 16 < g.N) {
+              float y[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float gt = x[j8 * 16 + 2 * j], up = x[j8 * 16 + 2 * j + 1];
+                y[j] = gt / (1.0f + __expf(-gt)) * up;
+              }
+              uint4 o;
+              o.x = pack_bf16x2(y[0], y[1]);
+              o.y = pack_bf16x2(y[2], y[3]);
+              o.z = pack_bf16x2(y[4], y[5]);
+              o.w = pack_bf16x2(y[6], y[7]);
+              *reinterpret_cast<uint4*>(crow + j8 * 8) = o;
+            }
+          }
+          continue;
+        }
+        if (e.act != kActNone) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] = act_apply(x[j], e.act);
+        }
+        if (e.residual != nullptr) {
+          const bf16* rrow = e.residual + static_cast<size_t>(row) * e.ldr + n0;
+#pragma unroll
+          for (int j8 = 0; j8 < 4; ++j8) {
+            if (n0 + j8 * 8 < g.N) {
+              const uint4 r = *reinterpret_cast<const uint4*>(rrow + j8 * 8);
+              x[j8 * 8 + 0] += bf16lo(r.x);
+              x[j8 * 8 + 1] += bf16hi(r.x);
+              x[j8 * 8 + 2] += bf16lo(r.y);
+              x[j8 * 8 + 3] += bf16hi(r.y);
+              x[j8 * 8 + 4] += bf16lo(r.z);
+              x[j8 * 8 + 5] += bf16hi(r.z);
+              x[j8 * 8 + 6] += bf16lo(r.w);
+              x[j8 * 8 + 7] += bf16hi(r.w);
+            }
+          }
+        }
+        if (e.out_fp32) {
+          float* crow = reinterpret_cast<float*>(g.C) + static_cast<size_t>(out_row) * g.ldc + n0;
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            if (n0 + j4 * 4 < g.N)
+              *reinterpret_cast<float4*>(crow + j4 * 4) =
+                  make_float4(x[j4 * 4], x[j4 * 4 + 1], x[j4 * 4 + 2], x[j4 * 4 + 3]);
+          }
+        } else {
+          bf16* crow = reinterpret_cast<bf16*>(g.C) + static_cast<size_t>(out_row) * g.ldc + n0;
+#pragma unroll
+          for (int j8 = 0; j8 < 4; ++j8) {
+            if (n0 + j8 * 8 < g.N) {
+              uint4 o;
+              o.x = pack_bf16x2(x[j8 * 8 + 0], x[j8 * 8 + 1]);
+              o.y = pack_bf16x2(x[j8 * 8 + 2], x[j8 * 8 + 3]);
+              o.z = pack_bf16x2(x[j8 * 8 + 4], x[j8 * 8 + 5]);
+              o.w = pack_bf16x2(x[j8 * 8 + 6], x[j8 * 8 + 7]);
+              *reinterpret_cast<uint4*>(crow + j8 * 8) = o;
+            }
+          }
+        }
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// 2-D bf16 tensor map over a row-major [rows, cols] matrix with leading dimension ld (elements); box = box_rows x 64
+// elements, 128-byte swizzle, out-of-bounds elements read as zero.
+int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (fn == nullptr) return fail(-6, "cuTensorMapEncodeTiled entry point not available");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld * 2) % 16 != 0)
+    return fail(-2, "TMA operand must be 16-byte aligned (ptr %p, ld %llu)", base, (unsigned long long)ld);
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(-6, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return 0;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n;
+}
+
+template <int BN>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    B200_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      Cfg::kSmemBytes));
+    configured = true;
+  }
+  const int tiles = g.m_tiles * g.n_tiles;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  gemm_bf16_tn_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, g);
+  B200_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int gemm_bf16_tn(const bf16* A, int lda, const bf16* B, int ldb, void* C, int ldc, int M, int N, int K,
+                 const GemmEpilogue& epi, int bn_hint, cudaStream_t stream) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  if (K % 8 != 0 || N % 8 != 0) return fail(-2, "gemm: K (%d) and N (%d) must be multiples of 8", K, N);
+  if (epi.act == kActSwiGLU && (N % 16 != 0 || epi.out_fp32 || epi.residual))
+    return fail(-2, "gemm: SwiGLU epilogue needs N %% 16 == 0, bf16 output and no residual");
+  const int m_tiles = (M + kBM - 1) / kBM;
+  int bn = bn_hint;
+  if (bn == 0) {
+    // largest tile that still gives every SM work; small-M (decode) problems get narrow tiles so that all
+    // 148 SMs stream weights
+    bn = 256;
+    const int sms = num_sms();
+    while (bn > 32 && m_tiles * ((N + bn - 1) / bn) < sms) bn >>= 1;
+  }
+  if (bn != 32 && bn != 64 && bn != 128 && bn != 256) return fail(-2, "gemm: unsupported BN %d", bn);
+  GemmArgs g;
+  g.C = C;
+  g.ldc = ldc;
+  g.M = M;
+  g.N = N;
+  g.K = K;
+  g.m_tiles = m_tiles;
+  g.n_tiles = (N + bn - 1) / bn;
+  g.epi = epi;
+  CUtensorMap tmA, tmB;
+  B200_TRY(make_tmap_2d(&tmA, A, M, K, lda, kBM));
+  B200_TRY(make_tmap_2d(&tmB, B, N, K, ldb, bn));
+  switch (bn) {
+    case 256: return launch_gemm<256>(tmA, tmB, g, stream);
+    case 128: return launch_gemm<128>(tmA, tmB, g, stream);
+    case 64: return launch_gemm<64>(tmA, tmB, g, stream);
+    default: return launch_gemm<32>(tmA, tmB, g, stream);
+  }
+}
+
+}  // namespace b200
