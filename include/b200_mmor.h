@@ -1,19 +1,19 @@
 /*
  * b200_mmor.h -- C ABI of libb200mmor.so, the B200 (sm_100a) implementation of MM2SG's multimodal hot path
- * (reference: egeozsoy/MM-OR, scene_graph_generation/LLaVA/llava).
+ * (reference: egeozsoy/MM-OR, scene_graph_generation/LLaVA/llava; paths below are relative to that directory).
  *
  * The reference has no FFI: the path sits behind Python objects that call HF transformers / torch ops
  * (SURVEY.md 8b). These entry points are what the Python mirror of that interface (mm_or_b200/model/*.py) binds
  * with ctypes. Each entry point cites the reference call site whose arithmetic it replaces.
  *
  * Conventions
- *   - all pointers are DEVICE pointers unless the name ends in _host; bf16 tensors are row-major and dense
- *     unless a leading dimension is given; sizes are in elements.
+ *   - all pointers are DEVICE pointers unless documented as host; bf16 tensors are row-major and dense unless a
+ *     leading dimension is given; sizes are in elements; weight structs are plain host structs of device pointers.
  *   - every function returns 0 on success, a negative code on failure (-2 bad argument, -5 CUDA error,
  *     -6 driver entry point missing); b200_last_error() returns the message for the calling thread.
  *   - functions enqueue work on `stream` (a cudaStream_t passed as void*) and never synchronise or allocate;
  *     scratch memory is passed in as (workspace, workspace_bytes) and sized by the matching *_workspace_bytes.
- *   - re-entrant per stream; no global mutable state besides lazily initialised function attributes.
+ *   - re-entrant per stream; the only global state is lazily initialised kernel attributes.
  */
 #ifndef B200_MMOR_H_
 #define B200_MMOR_H_
@@ -29,19 +29,196 @@ typedef void* b200_stream_t; /* cudaStream_t */
 
 const char* b200_last_error(void);
 int b200_abi_version(void);
+/* sizeof() of the weight structs below, in declaration order (0 = b200_vit_layer ... 8 = b200_kv_cache); lets a
+ * binding verify its struct mirrors. Returns 0 for an unknown index. */
+size_t b200_sizeof_struct(int which);
 
-/* ------------------------------------------------------------------------------------------------------------
- * Dense linear:  C[M,N] = epilogue(A[M,K] . W[N,K]^T)      bf16 in, fp32 accumulate (tcgen05 / TMEM)
- * Replaces every nn.Linear on the path: CLIP q/k/v/out_proj, fc1, fc2 (clip_encoder.py:48 -> HF CLIPEncoderLayer),
- * BERT pooler dense layers (multimodal_projector/builder.py:173), mm_projector (llava_arch.py:182),
- * Llama q/k/v/o/gate/up/down_proj and lm_head (llava_llama.py:93).
+/* ============================================================================================================
+ * Operator level (used by the stage entry points below and by the parity tests)
+ * ========================================================================================================== */
+
+/* Dense linear:  C[M,N] = epilogue(A[M,K] . W[N,K]^T)      bf16 in, fp32 accumulate (tcgen05 / TMEM)
+ * Replaces every nn.Linear on the path: CLIP q/k/v/out_proj, fc1, fc2 (model/multimodal_encoder/clip_encoder.py:48 ->
+ * HF CLIPEncoderLayer), BERT pooler dense layers (model/multimodal_projector/builder.py:173), mm_projector
+ * (model/llava_arch.py:182), Llama q/k/v/o/gate/up/down_proj and lm_head (model/language_model/llava_llama.py:93).
  *   act: 0 none, 1 quick_gelu, 2 gelu(erf), 3 SwiGLU over interleaved (gate, up) column pairs (C has N/2 columns)
  *   bias [N] / residual [M, ldr] / row_map [M] (output row per logical row, <0 drops the row) may be NULL
- *   out_fp32: C is float instead of bf16.  bn_hint: 0 = auto tile width, or 32/64/128/256.
- * ---------------------------------------------------------------------------------------------------------- */
+ *   out_fp32: C is float instead of bf16.  bn_hint: 0 = auto tile width, or 32/64/128/256. */
 int b200_gemm_bf16(const void* A, int lda, const void* W, int ldw, void* C, int ldc, int M, int N, int K,
                    const void* bias, const void* residual, int ldr, const int32_t* row_map, int act, int out_fp32,
                    int bn_hint, b200_stream_t stream);
+
+/* y = LayerNorm(gather(x)[row] + add[row % period]) * gamma + beta  (HF CLIP LayerNorm eps 1e-5, BERT eps 1e-12).
+ * row_map (source row per output row, <0 = zero row), add may be NULL. */
+int b200_layernorm(const void* x, int64_t ldx, const int32_t* row_map, const void* add, int period, const void* gamma,
+                   const void* beta, float eps, void* out, int64_t ldo, int M, int D, b200_stream_t stream);
+
+/* y = w * x * rsqrt(mean(x^2) + eps)   (HF LlamaRMSNorm) */
+int b200_rmsnorm(const void* x, int64_t ldx, const void* w, float eps, void* out, int64_t ldo, int M, int D,
+                 b200_stream_t stream);
+
+/* Fused attention softmax(Q K^T * scale + mask) V with online softmax (scores never reach HBM).
+ * Strides are in elements: *_bs batch, *_rs row/token, *_hs head. head_dim 64 or 128.
+ * kv_start[B] (first visible key: left padding), kv_len[B] (keys >= kv_len masked: key padding) may be NULL;
+ * causal != 0: key j visible to query i iff j <= i + (Lk - Lq).
+ * Replaces HF CLIPAttention / BertSelfAttention / LlamaAttention eager bmm-softmax-bmm and the training-time
+ * flash_attn_varlen_qkvpacked_func (train/llama_flash_attn_monkey_patch.py:78-89). */
+int b200_flash_attention(const void* q, int64_t q_bs, int64_t q_rs, int64_t q_hs, const void* k, int64_t k_bs,
+                         int64_t k_rs, int64_t k_hs, const void* v, int64_t v_bs, int64_t v_rs, int64_t v_hs, void* o,
+                         int64_t o_bs, int64_t o_rs, int64_t o_hs, int B, int H, int Lq, int Lk, int head_dim,
+                         const int32_t* kv_start, const int32_t* kv_len, int causal, float scale,
+                         b200_stream_t stream);
+
+/* Single-token attention against the KV cache [B][H][cap][128] (decode step, model/llava_arch.py:192-201 + HF
+ * LlamaAttention with past_key_values). ctx = slots in use; kv_start as above. splits: 0 = auto. */
+size_t b200_decode_attention_workspace_bytes(int B, int H, int ctx);
+int b200_decode_attention(const void* q, int64_t q_rs, const void* k_cache, const void* v_cache, void* o, int64_t o_rs,
+                          int B, int H, int cap, int ctx, const int32_t* kv_start, float scale, int splits,
+                          void* workspace, size_t workspace_bytes, b200_stream_t stream);
+
+/* RoPE (theta via the fp32 cos/sin tables [max_pos, 64]) on q (in place) and k, plus KV-cache append of k and v.
+ * qkv: [B*Lq, 3*H*128]. Token (b, l) goes to slot slot0 + l, rotary position slot - kv_start[b]. */
+int b200_rope_kv_write(void* qkv, const int32_t* kv_start, const float* cos_table, const float* sin_table, int max_pos,
+                       void* k_cache, void* v_cache, int B, int H, int Lq, int slot0, int cap, b200_stream_t stream);
+
+/* out[r] = table[ids[r]] (ids >= 0), zeros (ids == -1), untouched (ids <= -2): embed_tokens gather + zero pad rows
+ * of the multimodal pack (model/llava_arch.py:262, :317-338). */
+int b200_embed_rows(const int32_t* ids, const void* table, void* out, int64_t ldo, int rows, int D, int vocab,
+                    b200_stream_t stream);
+
+/* Greedy argmax per row, lowest index wins ties. finished/history may be NULL. */
+int b200_argmax(const void* logits, int is_fp32, int64_t ld, int rows, int V, int32_t* out_tok, int32_t* finished,
+                int eos_id, int pad_id, b200_stream_t stream);
+
+/* im2col for the CLIP patch embedding conv (k = s = P): pixels [N,C,S,S] -> cols [N*(S/P)^2, Kpad]. */
+int b200_patchify(const void* pixels, void* cols, int N, int C, int S, int P, int Kpad, b200_stream_t stream);
+
+/* ============================================================================================================
+ * Stage level
+ * ========================================================================================================== */
+
+/* ---- CLIP ViT tower: CLIPVisionTower.forward + feature_select (model/multimodal_encoder/clip_encoder.py:29-51) ---- */
+typedef struct {
+  const void *ln1_w, *ln1_b;
+  const void *qkv_w, *qkv_b; /* [3*hidden, hidden] = cat(q*head_dim^-0.5, k, v), bias likewise */
+  const void *out_w, *out_b;
+  const void *ln2_w, *ln2_b;
+  const void *fc1_w, *fc1_b;
+  const void *fc2_w, *fc2_b;
+} b200_vit_layer;
+
+typedef struct {
+  int hidden, heads, ffn, image_size, patch, kpad;
+  int n_layers;            /* layers to execute: hidden_states[select_layer] (select_layer=-2 of 24 -> 23) */
+  float ln_eps;
+  const void* patch_w;     /* [hidden, kpad] patch_embedding.weight flattened (c, ky, kx), zero padded */
+  const void* pos_cls;     /* [1 + (image/patch)^2, hidden] position_embedding, row 0 += class_embedding */
+  const void *pre_ln_w, *pre_ln_b;
+  const b200_vit_layer* layers; /* host array [n_layers] */
+} b200_vit_weights;
+
+size_t b200_vit_workspace_bytes(const b200_vit_weights* w, int n_img);
+/* pixels [n_img, 3, S, S] bf16 -> hidden [n_img, 1 + P, hidden] bf16 (CLS row kept; callers drop it by row maps). */
+int b200_vit_forward(const b200_vit_weights* w, const void* pixels, void* hidden_out, int n_img, void* workspace,
+                     size_t workspace_bytes, b200_stream_t stream);
+
+/* ---- image pooler: ImageEmbeddingPooler.forward BERT part (model/multimodal_projector/builder.py:169-175) ---- */
+typedef struct {
+  const void *qkv_w, *qkv_b; /* [3*hidden, hidden] = cat(query, key, value) */
+  const void *ao_w, *ao_b, *ao_ln_w, *ao_ln_b;     /* attention.output.dense + LayerNorm */
+  const void *fc1_w, *fc1_b;                       /* intermediate.dense */
+  const void *fc2_w, *fc2_b, *out_ln_w, *out_ln_b; /* output.dense + LayerNorm */
+} b200_bert_layer;
+
+typedef struct {
+  int hidden, heads, ffn, n_layers, max_pos;
+  float ln_eps;
+  const void* pos_type;  /* [max_pos, hidden] position_embeddings + token_type_embeddings[0] */
+  const void *emb_ln_w, *emb_ln_b;
+  const b200_bert_layer* layers; /* host array */
+} b200_pooler_weights;
+
+size_t b200_pooler_workspace_bytes(const b200_pooler_weights* w, int B, int S);
+/* src [*, hidden] rows addressed through gather_map [B*S] (<0 = zero padding row, model/llava_arch.py:143-170);
+ * kv_len[B] = valid tokens per sample; keeps the first `keep` (576) tokens of every sample and writes them to
+ * out[b * out_tokens + t] (out is [B, out_tokens, hidden], extra-modality tokens follow at t >= keep). */
+int b200_pooler_forward(const b200_pooler_weights* w, const void* src, int64_t src_ld, const int32_t* gather_map,
+                        const int32_t* kv_len, int B, int S, int keep, void* out, int out_tokens, void* workspace,
+                        size_t workspace_bytes, b200_stream_t stream);
+
+/* ---- seg-mask tokens: SegmentationMapFeatureExtractor.forward
+ *      (model/multimodal_projector/segmentation_map_feature_extractor.py:53-75) ---- */
+typedef struct {
+  const void* emb;       /* [30, 8] */
+  const void* conv_w[5]; /* [Cout, Cin, 3, 3], channels 8-64-128-256-512-1024 */
+  const void* conv_b[5];
+} b200_segmask_weights;
+size_t b200_segmask_workspace_bytes(int n_maps);
+/* cls [n_maps, 32, 32] uint8 -> out[out_row_map[n]][0..1024) (row stride out_ld) */
+int b200_segmask_forward(const b200_segmask_weights* w, const uint8_t* cls, int n_maps, void* out, int64_t out_ld,
+                         const int32_t* out_row_map, void* workspace, size_t workspace_bytes, b200_stream_t stream);
+
+/* ---- mm_projector + multimodal token pack (model/llava_arch.py:182 and :235-338) ---- */
+typedef struct {
+  int in_dim, hidden;
+  const void *w0, *b0; /* Linear(in_dim, hidden) */
+  const void *w2, *b2; /* Linear(hidden, hidden) */
+} b200_projector_weights;
+size_t b200_projector_workspace_bytes(const b200_projector_weights* w, int n_tokens);
+/* tokens [n_tokens, in_dim] -> GELU MLP -> rows scattered into embeds[row_map[i]] (row stride = hidden);
+ * then text rows gathered from embed_tokens by text_ids [n_rows] (see b200_embed_rows). text_ids may be NULL. */
+int b200_projector_pack(const b200_projector_weights* w, const void* tokens, int n_tokens, const int32_t* row_map,
+                        const int32_t* text_ids, const void* embed_table, int vocab, void* embeds, int n_rows,
+                        void* workspace, size_t workspace_bytes, b200_stream_t stream);
+
+/* ---- Llama decoder (HF LlamaForCausalLM.forward reached from model/language_model/llava_llama.py:93) ---- */
+typedef struct {
+  const void* attn_norm;
+  const void* qkv_w;     /* [3*hidden, hidden] = cat(q_proj, k_proj, v_proj) */
+  const void* o_w;
+  const void* mlp_norm;
+  const void* gate_up_w; /* [2*ffn, hidden], rows interleaved: 2j = gate_proj[j], 2j+1 = up_proj[j] */
+  const void* down_w;    /* [hidden, ffn] */
+} b200_llama_layer;
+
+typedef struct {
+  int hidden, heads, ffn, n_layers, vocab, max_pos;
+  float rms_eps;
+  const b200_llama_layer* layers; /* host array */
+  const void* final_norm;
+  const void* lm_head;      /* [vocab, hidden] */
+  const void* embed_tokens; /* [vocab, hidden] */
+  const float* rope_cos;    /* [max_pos, 64] fp32 */
+  const float* rope_sin;
+} b200_llama_weights;
+
+typedef struct {
+  void* k;              /* [n_layers][batch][heads][cap][128] bf16 */
+  void* v;
+  int64_t layer_stride; /* elements between layers (= batch_total * heads * cap * 128) */
+  int cap;
+} b200_kv_cache;
+
+size_t b200_llama_prefill_workspace_bytes(const b200_llama_weights* w, int B, int L, int all_logits);
+/* x [B*L, hidden]: packed inputs_embeds, overwritten with the final hidden states. Tokens of sample b occupy cache
+ * slots [0, L); kv_start[b] = number of left-pad rows (NULL = none); kv_len[b] = valid rows for right padding
+ * (NULL = L). cache.k/v must already point at this batch slice. logits: [B, vocab] for the last position
+ * (all_logits = 0) or [B*L, vocab] (all_logits = 1); logits_fp32 selects float output. */
+int b200_llama_prefill(const b200_llama_weights* w, void* x, const int32_t* kv_start, const int32_t* kv_len,
+                       const b200_kv_cache* cache, int B, int L, void* logits, int all_logits, int logits_fp32,
+                       void* workspace, size_t workspace_bytes, b200_stream_t stream);
+
+size_t b200_llama_decode_workspace_bytes(const b200_llama_weights* w, int B, int cap);
+/* One greedy decode step for B sequences (model/llava_arch.py:192-201 + HF greedy_search):
+ * tokens [B] int32 (in: token to feed, out: argmax token), state[2] int32 device = {slots in use, step index} --
+ * read on the device and incremented at the end, so the identical launch sequence can be replayed from a CUDA graph.
+ * finished [B] int32 (HF unfinished_sequences semantics: finished rows emit pad_id; rows finish on eos_id), may be
+ * NULL; history [B, hist_ld] int32 receives the produced token at column state[1]; logits_out (bf16 [B, vocab]) may
+ * be NULL to use workspace. ctx_bound = upper bound of slots in use for this call (launch sizing). */
+int b200_llama_decode_step(const b200_llama_weights* w, int32_t* tokens, int32_t* state, const int32_t* kv_start,
+                           const b200_kv_cache* cache, int B, int ctx_bound, int32_t* finished, int eos_id, int pad_id,
+                           int32_t* history, int hist_ld, void* logits_out, void* workspace, size_t workspace_bytes,
+                           b200_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -13,9 +13,90 @@ LIB_PATH = os.path.join(_HERE, "libb200mmor.so")
 
 _lib = None
 
+vp, ci, cf, i64, sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_int64, ctypes.c_size_t
+
 
 class B200Error(RuntimeError):
     pass
+
+
+# ---- struct mirrors of include/b200_mmor.h -------------------------------------------------------------------
+class VitLayer(ctypes.Structure):
+    _fields_ = [(n, vp) for n in ("ln1_w", "ln1_b", "qkv_w", "qkv_b", "out_w", "out_b", "ln2_w", "ln2_b",
+                                  "fc1_w", "fc1_b", "fc2_w", "fc2_b")]
+
+
+class VitWeights(ctypes.Structure):
+    _fields_ = [("hidden", ci), ("heads", ci), ("ffn", ci), ("image_size", ci), ("patch", ci), ("kpad", ci),
+                ("n_layers", ci), ("ln_eps", cf), ("patch_w", vp), ("pos_cls", vp), ("pre_ln_w", vp),
+                ("pre_ln_b", vp), ("layers", ctypes.POINTER(VitLayer))]
+
+
+class BertLayer(ctypes.Structure):
+    _fields_ = [(n, vp) for n in ("qkv_w", "qkv_b", "ao_w", "ao_b", "ao_ln_w", "ao_ln_b", "fc1_w", "fc1_b",
+                                  "fc2_w", "fc2_b", "out_ln_w", "out_ln_b")]
+
+
+class PoolerWeights(ctypes.Structure):
+    _fields_ = [("hidden", ci), ("heads", ci), ("ffn", ci), ("n_layers", ci), ("max_pos", ci), ("ln_eps", cf),
+                ("pos_type", vp), ("emb_ln_w", vp), ("emb_ln_b", vp), ("layers", ctypes.POINTER(BertLayer))]
+
+
+class SegmaskWeights(ctypes.Structure):
+    _fields_ = [("emb", vp), ("conv_w", vp * 5), ("conv_b", vp * 5)]
+
+
+class ProjectorWeights(ctypes.Structure):
+    _fields_ = [("in_dim", ci), ("hidden", ci), ("w0", vp), ("b0", vp), ("w2", vp), ("b2", vp)]
+
+
+class LlamaLayer(ctypes.Structure):
+    _fields_ = [(n, vp) for n in ("attn_norm", "qkv_w", "o_w", "mlp_norm", "gate_up_w", "down_w")]
+
+
+class LlamaWeights(ctypes.Structure):
+    _fields_ = [("hidden", ci), ("heads", ci), ("ffn", ci), ("n_layers", ci), ("vocab", ci), ("max_pos", ci),
+                ("rms_eps", cf), ("layers", ctypes.POINTER(LlamaLayer)), ("final_norm", vp), ("lm_head", vp),
+                ("embed_tokens", vp), ("rope_cos", vp), ("rope_sin", vp)]
+
+
+class KvCache(ctypes.Structure):
+    _fields_ = [("k", vp), ("v", vp), ("layer_stride", i64), ("cap", ci)]
+
+
+_P = ctypes.POINTER
+
+_SIGS = {
+    # name: (restype, argtypes)
+    "b200_abi_version": (ci, []),
+    "b200_sizeof_struct": (sz, [ci]),
+    "b200_gemm_bf16": (ci, [vp, ci, vp, ci, vp, ci, ci, ci, ci, vp, vp, ci, vp, ci, ci, ci, vp]),
+    "b200_layernorm": (ci, [vp, i64, vp, vp, ci, vp, vp, cf, vp, i64, ci, ci, vp]),
+    "b200_rmsnorm": (ci, [vp, i64, vp, cf, vp, i64, ci, ci, vp]),
+    "b200_flash_attention": (ci, [vp, i64, i64, i64, vp, i64, i64, i64, vp, i64, i64, i64, vp, i64, i64, i64,
+                                  ci, ci, ci, ci, ci, vp, vp, ci, cf, vp]),
+    "b200_decode_attention_workspace_bytes": (sz, [ci, ci, ci]),
+    "b200_decode_attention": (ci, [vp, i64, vp, vp, vp, i64, ci, ci, ci, ci, vp, cf, ci, vp, sz, vp]),
+    "b200_rope_kv_write": (ci, [vp, vp, vp, vp, ci, vp, vp, ci, ci, ci, ci, ci, vp]),
+    "b200_embed_rows": (ci, [vp, vp, vp, i64, ci, ci, ci, vp]),
+    "b200_argmax": (ci, [vp, ci, i64, ci, ci, vp, vp, ci, ci, vp]),
+    "b200_patchify": (ci, [vp, vp, ci, ci, ci, ci, ci, vp]),
+    "b200_vit_workspace_bytes": (sz, [_P(VitWeights), ci]),
+    "b200_vit_forward": (ci, [_P(VitWeights), vp, vp, ci, vp, sz, vp]),
+    "b200_pooler_workspace_bytes": (sz, [_P(PoolerWeights), ci, ci]),
+    "b200_pooler_forward": (ci, [_P(PoolerWeights), vp, i64, vp, vp, ci, ci, ci, vp, ci, vp, sz, vp]),
+    "b200_segmask_workspace_bytes": (sz, [ci]),
+    "b200_segmask_forward": (ci, [_P(SegmaskWeights), vp, ci, vp, i64, vp, vp, sz, vp]),
+    "b200_projector_workspace_bytes": (sz, [_P(ProjectorWeights), ci]),
+    "b200_projector_pack": (ci, [_P(ProjectorWeights), vp, ci, vp, vp, vp, ci, vp, ci, vp, sz, vp]),
+    "b200_llama_prefill_workspace_bytes": (sz, [_P(LlamaWeights), ci, ci, ci]),
+    "b200_llama_prefill": (ci, [_P(LlamaWeights), vp, vp, vp, _P(KvCache), ci, ci, vp, ci, ci, vp, sz, vp]),
+    "b200_llama_decode_workspace_bytes": (sz, [_P(LlamaWeights), ci, ci]),
+    "b200_llama_decode_step": (ci, [_P(LlamaWeights), vp, vp, vp, _P(KvCache), ci, ci, vp, ci, ci, vp, ci, vp, vp,
+                                    sz, vp]),
+}
+
+EXPORTED_SYMBOLS = ["b200_last_error"] + sorted(_SIGS)
 
 
 def lib():
@@ -25,23 +106,15 @@ def lib():
         if not os.path.exists(LIB_PATH):
             raise B200Error(
                 f"{LIB_PATH} not found: build it with `python -m mm_or_b200.build` (no CPU fallback exists)")
-        _lib = ctypes.CDLL(LIB_PATH)
-        _lib.b200_last_error.restype = ctypes.c_char_p
-        _declare(_lib)
+        L = ctypes.CDLL(LIB_PATH)
+        L.b200_last_error.restype = ctypes.c_char_p
+        L.b200_last_error.argtypes = []
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
     return _lib
-
-
-def _declare(L):
-    vp, ci, cf, cl = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_longlong
-    L.b200_abi_version.restype = ci
-    sigs = {
-        "b200_gemm_bf16": [vp, ci, vp, ci, vp, ci, ci, ci, ci, vp, vp, ci, vp, ci, ci, ci, vp],
-    }
-    for name, argtypes in sigs.items():
-        fn = getattr(L, name)
-        fn.argtypes = argtypes
-        fn.restype = ci
-    return cf, cl
 
 
 def check(rc, what=""):
@@ -54,7 +127,8 @@ def ptr(t):
     """Device pointer of a tensor (None -> NULL)."""
     if t is None:
         return None
-    assert t.is_cuda, "libb200mmor operates on CUDA tensors only"
+    if not t.is_cuda:
+        raise B200Error("libb200mmor operates on CUDA tensors only (no CPU fallback)")
     return ctypes.c_void_p(t.data_ptr())
 
 
@@ -62,9 +136,23 @@ def stream_ptr():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+class Workspace:
+    """Grow-only device scratch buffer handed to the stage entry points."""
+
+    def __init__(self):
+        self.buf = None
+
+    def get(self, nbytes, device):
+        if self.buf is None or self.buf.numel() < nbytes or self.buf.device != device:
+            self.buf = None
+            self.buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+        return self.buf
+
+
 ACT_NONE, ACT_QUICK_GELU, ACT_GELU, ACT_SWIGLU = 0, 1, 2, 3
 
 
+# ---- thin operator wrappers (used by the parity tests and by host code outside the stage entry points) ---------
 def gemm(a, w, out=None, bias=None, residual=None, row_map=None, act=ACT_NONE, out_fp32=False, bn=0,
          out_rows=None):
     """out = epilogue(a @ w.T). a: (M,K) bf16 (row stride allowed), w: (N,K) bf16."""
@@ -80,3 +168,48 @@ def gemm(a, w, out=None, bias=None, residual=None, row_map=None, act=ACT_NONE, o
                               ptr(bias), ptr(residual), ldr, ptr(row_map), act, int(out_fp32), bn, stream_ptr())
     check(rc, "b200_gemm_bf16")
     return out
+
+
+def layernorm(x, gamma, beta, eps, row_map=None, add=None, out=None):
+    M = x.shape[0] if row_map is None else row_map.numel()
+    D = x.shape[1]
+    if out is None:
+        out = torch.empty((M, D), device=x.device, dtype=torch.bfloat16)
+    period = add.shape[0] if add is not None else 1
+    check(lib().b200_layernorm(ptr(x), x.stride(0), ptr(row_map), ptr(add), period, ptr(gamma), ptr(beta), eps,
+                               ptr(out), out.stride(0), M, D, stream_ptr()), "b200_layernorm")
+    return out
+
+
+def rmsnorm(x, w, eps, out=None):
+    M, D = x.shape
+    if out is None:
+        out = torch.empty((M, D), device=x.device, dtype=torch.bfloat16)
+    check(lib().b200_rmsnorm(ptr(x), x.stride(0), ptr(w), eps, ptr(out), out.stride(0), M, D, stream_ptr()),
+          "b200_rmsnorm")
+    return out
+
+
+def flash_attention(q, k, v, causal=False, kv_start=None, kv_len=None, scale=None):
+    """q (B, Lq, H, d), k/v (B, Lk, H, d) views with unit stride on d -> (B, Lq, H, d) bf16."""
+    B, Lq, H, d = q.shape
+    Lk = k.shape[1]
+    o = torch.empty((B, Lq, H, d), device=q.device, dtype=torch.bfloat16)
+    scale = d ** -0.5 if scale is None else scale
+    check(lib().b200_flash_attention(ptr(q), q.stride(0), q.stride(1), q.stride(2), ptr(k), k.stride(0), k.stride(1),
+                                     k.stride(2), ptr(v), v.stride(0), v.stride(1), v.stride(2), ptr(o), o.stride(0),
+                                     o.stride(1), o.stride(2), B, H, Lq, Lk, d, ptr(kv_start), ptr(kv_len),
+                                     int(causal), scale, stream_ptr()), "b200_flash_attention")
+    return o
+
+
+def decode_attention(q, k_cache, v_cache, ctx, kv_start=None, splits=0):
+    """q (B, H*128); caches (B, H, cap, 128) -> (B, H*128)."""
+    B, H, cap, d = k_cache.shape
+    o = torch.empty((B, H * d), device=q.device, dtype=torch.bfloat16)
+    nb = lib().b200_decode_attention_workspace_bytes(B, H, ctx)
+    ws = torch.empty(max(nb, 256), dtype=torch.uint8, device=q.device)
+    check(lib().b200_decode_attention(ptr(q), q.stride(0), ptr(k_cache), ptr(v_cache), ptr(o), o.stride(0), B, H, cap,
+                                      ctx, ptr(kv_start), d ** -0.5, splits, ptr(ws), ws.numel(), stream_ptr()),
+          "b200_decode_attention")
+    return o

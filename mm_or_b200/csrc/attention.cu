@@ -19,23 +19,6 @@
 
 namespace b200 {
 
-struct AttnArgs {
-  const bf16* q;
-  const bf16* k;
-  const bf16* v;
-  bf16* o;
-  // element strides
-  long long q_bs, q_rs, q_hs;
-  long long k_bs, k_rs, k_hs;
-  long long v_bs, v_rs, v_hs;
-  long long o_bs, o_rs, o_hs;
-  int B, H, Lq, Lk;
-  const int* kv_start;  // [B] first valid key (left padding) or null
-  const int* kv_len;    // [B] number of valid keys counted from 0 (key padding) or null
-  int causal;           // key j visible to query i iff j <= i + (Lk - Lq)
-  float scale_log2;     // softmax scale * log2(e)
-};
-
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool pred) {
   const uint32_t s = smem_u32(smem);
   const int sz = pred ? 16 : 0;  // src-size 0 => zero fill
@@ -282,23 +265,6 @@ int flash_attn(const AttnArgs& a, int head_dim, cudaStream_t stream) {
 // ---------------------------------------------------------------------------------------------------
 // decode attention: one query token per (sequence, head), head_dim 128, KV cache [B][H][ctx_cap][128]
 // ---------------------------------------------------------------------------------------------------
-struct DecodeArgs {
-  const bf16* q;  // [B, q_rs] with head h at h*128
-  long long q_rs;
-  const bf16* kc;  // [B][H][cap][128]
-  const bf16* vc;
-  bf16* o;  // [B, o_rs]
-  long long o_rs;
-  int B, H, cap;
-  int ctx;               // number of cache slots in use (keys 0..ctx-1)
-  const int* kv_start;   // [B] first valid slot (left padding), or null
-  float scale_log2;
-  // split-KV workspace (only when splits > 1): partial o [B*H*splits][128] fp32, m/l [B*H*splits][2]
-  int splits;
-  float* part_o;
-  float* part_ml;
-};
-
 static constexpr int kDecThreads = 256;
 static constexpr int kDecWarps = kDecThreads / 32;
 static constexpr int kDecMaxCtx = 8192;  // per split chunk, scores staged in smem
@@ -316,10 +282,11 @@ __global__ void __launch_bounds__(kDecThreads) decode_attn_kernel(const DecodeAr
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   const int start = a.kv_start ? a.kv_start[b] : 0;
-  const int total = a.ctx - start;
+  const int ctx = a.ctx_dev ? min(*a.ctx_dev + a.ctx_add, a.cap) : a.ctx;
+  const int total = max(0, ctx - start);
   const int per = (total + a.splits - 1) / a.splits;
   const int k0 = start + split * per;
-  const int k1 = min(a.ctx, k0 + per);
+  const int k1 = min(ctx, k0 + per);
   const int n = max(0, k1 - k0);
 
   if (threadIdx.x < 128) q_s[threadIdx.x] = __bfloat162float(a.q[b * a.q_rs + h * 128 + threadIdx.x]);

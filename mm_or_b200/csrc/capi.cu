@@ -15,6 +15,21 @@ const char* b200_last_error(void) { return last_error_cstr(); }
 
 int b200_abi_version(void) { return 1; }
 
+size_t b200_sizeof_struct(int which) {
+  switch (which) {
+    case 0: return sizeof(b200_vit_layer);
+    case 1: return sizeof(b200_vit_weights);
+    case 2: return sizeof(b200_bert_layer);
+    case 3: return sizeof(b200_pooler_weights);
+    case 4: return sizeof(b200_segmask_weights);
+    case 5: return sizeof(b200_projector_weights);
+    case 6: return sizeof(b200_llama_layer);
+    case 7: return sizeof(b200_llama_weights);
+    case 8: return sizeof(b200_kv_cache);
+    default: return 0;
+  }
+}
+
 int b200_gemm_bf16(const void* A, int lda, const void* W, int ldw, void* C, int ldc, int M, int N, int K,
                    const void* bias, const void* residual, int ldr, const int32_t* row_map, int act, int out_fp32,
                    int bn_hint, b200_stream_t stream) {
@@ -27,6 +42,87 @@ int b200_gemm_bf16(const void* A, int lda, const void* W, int ldw, void* C, int 
   e.out_fp32 = out_fp32;
   return gemm_bf16_tn(static_cast<const bf16*>(A), lda, static_cast<const bf16*>(W), ldw, C, ldc, M, N, K, e,
                       bn_hint, static_cast<cudaStream_t>(stream));
+}
+
+
+int b200_layernorm(const void* x, int64_t ldx, const int32_t* row_map, const void* add, int period, const void* gamma,
+                   const void* beta, float eps, void* out, int64_t ldo, int M, int D, b200_stream_t stream) {
+  return layernorm(static_cast<const bf16*>(x), ldx, row_map, static_cast<const bf16*>(add), period,
+                   static_cast<const bf16*>(gamma), static_cast<const bf16*>(beta), eps, static_cast<bf16*>(out), ldo, M,
+                   D, 0, 0, static_cast<cudaStream_t>(stream));
+}
+
+int b200_rmsnorm(const void* x, int64_t ldx, const void* w, float eps, void* out, int64_t ldo, int M, int D,
+                 b200_stream_t stream) {
+  return rmsnorm(static_cast<const bf16*>(x), ldx, static_cast<const bf16*>(w), eps, static_cast<bf16*>(out), ldo, M, D,
+                 static_cast<cudaStream_t>(stream));
+}
+
+int b200_flash_attention(const void* q, int64_t q_bs, int64_t q_rs, int64_t q_hs, const void* k, int64_t k_bs,
+                         int64_t k_rs, int64_t k_hs, const void* v, int64_t v_bs, int64_t v_rs, int64_t v_hs, void* o,
+                         int64_t o_bs, int64_t o_rs, int64_t o_hs, int B, int H, int Lq, int Lk, int head_dim,
+                         const int32_t* kv_start, const int32_t* kv_len, int causal, float scale,
+                         b200_stream_t stream) {
+  AttnArgs a{};
+  a.q = static_cast<const bf16*>(q);
+  a.k = static_cast<const bf16*>(k);
+  a.v = static_cast<const bf16*>(v);
+  a.o = static_cast<bf16*>(o);
+  a.q_bs = q_bs; a.q_rs = q_rs; a.q_hs = q_hs;
+  a.k_bs = k_bs; a.k_rs = k_rs; a.k_hs = k_hs;
+  a.v_bs = v_bs; a.v_rs = v_rs; a.v_hs = v_hs;
+  a.o_bs = o_bs; a.o_rs = o_rs; a.o_hs = o_hs;
+  a.B = B; a.H = H; a.Lq = Lq; a.Lk = Lk;
+  a.kv_start = kv_start;
+  a.kv_len = kv_len;
+  a.causal = causal;
+  a.scale_log2 = scale * 1.4426950408889634f;
+  return flash_attn(a, head_dim, static_cast<cudaStream_t>(stream));
+}
+
+size_t b200_decode_attention_workspace_bytes(int B, int H, int ctx) {
+  (void)ctx;
+  return decode_attn_workspace_bytes(B, H, 16);
+}
+
+int b200_decode_attention(const void* q, int64_t q_rs, const void* k_cache, const void* v_cache, void* o, int64_t o_rs,
+                          int B, int H, int cap, int ctx, const int32_t* kv_start, float scale, int splits,
+                          void* workspace, size_t workspace_bytes, b200_stream_t stream) {
+  DecodeArgs a{};
+  a.q = static_cast<const bf16*>(q);
+  a.q_rs = q_rs;
+  a.kc = static_cast<const bf16*>(k_cache);
+  a.vc = static_cast<const bf16*>(v_cache);
+  a.o = static_cast<bf16*>(o);
+  a.o_rs = o_rs;
+  a.B = B; a.H = H; a.cap = cap; a.ctx = ctx;
+  a.kv_start = kv_start;
+  a.scale_log2 = scale * 1.4426950408889634f;
+  a.splits = splits;
+  return decode_attn(a, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int b200_rope_kv_write(void* qkv, const int32_t* kv_start, const float* cos_table, const float* sin_table, int max_pos,
+                       void* k_cache, void* v_cache, int B, int H, int Lq, int slot0, int cap, b200_stream_t stream) {
+  return rope_kv_write(static_cast<bf16*>(qkv), kv_start, cos_table, sin_table, max_pos, static_cast<bf16*>(k_cache),
+                       static_cast<bf16*>(v_cache), B, H, Lq, slot0, nullptr, cap, static_cast<cudaStream_t>(stream));
+}
+
+int b200_embed_rows(const int32_t* ids, const void* table, void* out, int64_t ldo, int rows, int D, int vocab,
+                    b200_stream_t stream) {
+  return embed_rows(ids, static_cast<const bf16*>(table), static_cast<bf16*>(out), ldo, rows, D, vocab,
+                    static_cast<cudaStream_t>(stream));
+}
+
+int b200_argmax(const void* logits, int is_fp32, int64_t ld, int rows, int V, int32_t* out_tok, int32_t* finished,
+                int eos_id, int pad_id, b200_stream_t stream) {
+  return argmax_rows(logits, is_fp32, ld, rows, V, out_tok, finished, eos_id, pad_id, nullptr, 0, 0, nullptr,
+                     static_cast<cudaStream_t>(stream));
+}
+
+int b200_patchify(const void* pixels, void* cols, int N, int C, int S, int P, int Kpad, b200_stream_t stream) {
+  return patchify_im2col(static_cast<const bf16*>(pixels), static_cast<bf16*>(cols), N, C, S, P, Kpad,
+                         static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -47,6 +47,8 @@ struct GemmEpilogue {
   const bf16* residual = nullptr;  // [M, ldr], added after the activation, optional (may alias C)
   const int* row_map = nullptr;    // [M] logical row -> output row, negative = drop, optional
   int ldr = 0;
+  int res_group = 0;         // 0: residual row = row; else (row / res_group) * res_group_stride + row % res_group
+  int res_group_stride = 0;  // (lets a compact (B*576)-row GEMM read its residual from a (B, S, D) tensor)
   int act = kActNone;
   int out_fp32 = 0;  // 0: C is bf16, 1: C is fp32
 };
@@ -54,5 +56,72 @@ struct GemmEpilogue {
 // bn_hint: 0 = choose automatically, else one of 32/64/128/256
 int gemm_bf16_tn(const bf16* A, int lda, const bf16* B, int ldb, void* C, int ldc, int M, int N, int K,
                  const GemmEpilogue& epi, int bn_hint, cudaStream_t stream);
+
+// ---------------------------------------------------------------------------------------------
+// norms (norm.cu)
+// ---------------------------------------------------------------------------------------------
+int layernorm(const bf16* x, long long ldx, const int* row_map, const bf16* add, int period, const bf16* gamma,
+              const bf16* beta, float eps, bf16* out, long long ldo, int M, int D, int out_group,
+              int out_group_stride, cudaStream_t stream);
+int rmsnorm(const bf16* x, long long ldx, const bf16* w, float eps, bf16* out, long long ldo, int M, int D,
+            cudaStream_t stream);
+
+// ---------------------------------------------------------------------------------------------
+// attention (attention.cu)
+// ---------------------------------------------------------------------------------------------
+struct AttnArgs {
+  const bf16* q;
+  const bf16* k;
+  const bf16* v;
+  bf16* o;
+  // element strides: batch, row (token), head
+  long long q_bs, q_rs, q_hs;
+  long long k_bs, k_rs, k_hs;
+  long long v_bs, v_rs, v_hs;
+  long long o_bs, o_rs, o_hs;
+  int B, H, Lq, Lk;
+  const int* kv_start;  // [B] first valid key (left padding) or null
+  const int* kv_len;    // [B] number of valid keys counted from 0 (key padding) or null
+  int causal;           // key j visible to query i iff j <= i + (Lk - Lq)
+  float scale_log2;     // softmax scale * log2(e)
+};
+int flash_attn(const AttnArgs& a, int head_dim, cudaStream_t stream);
+
+struct DecodeArgs {
+  const bf16* q;  // [B, q_rs] with head h at h*128
+  long long q_rs;
+  const bf16* kc;  // [B][H][cap][128]
+  const bf16* vc;
+  bf16* o;  // [B, o_rs]
+  long long o_rs;
+  int B, H, cap;
+  int ctx;              // number of cache slots in use (keys 0..ctx-1) ...
+  const int* ctx_dev;   // ... or, when non-null, *ctx_dev + ctx_add (decode under a CUDA graph); ctx is then the
+  int ctx_add;          //     upper bound used for launch sizing
+  const int* kv_start;  // [B] first valid slot (left padding), or null
+  float scale_log2;
+  int splits;  // 0 = choose
+  float* part_o;
+  float* part_ml;
+};
+size_t decode_attn_workspace_bytes(int B, int H, int splits);
+int decode_attn_pick_splits(int B, int H, int ctx);
+int decode_attn(DecodeArgs a, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
+// ---------------------------------------------------------------------------------------------
+// misc.cu
+// ---------------------------------------------------------------------------------------------
+int patchify_im2col(const bf16* pixels, bf16* cols, int N, int C, int S, int P, int Kpad, cudaStream_t stream);
+int rope_kv_write(bf16* qkv, const int* kv_start, const float* cos_t, const float* sin_t, int max_pos, bf16* kc,
+                  bf16* vc, int B, int H, int Lq, int slot0, const int* slot0_dev, int cap, cudaStream_t stream);
+int bump_counters(int* state, cudaStream_t stream);
+int embed_rows(const int* ids, const bf16* table, bf16* out, long long ldo, int rows, int D, int vocab,
+               cudaStream_t stream);
+int argmax_rows(const void* logits, int is_fp32, long long ld, int rows, int V, int* out_tok, int* finished, int eos_id,
+                int pad_id, int* history, int hist_ld, int step, const int* step_dev, cudaStream_t stream);
+size_t segmask_workspace_bytes(int n_maps);
+int segmask_forward(const uint8_t* cls, int n_maps, const bf16* emb, const bf16* const* conv_w,
+                    const bf16* const* conv_b, bf16* out, long long out_ld, const int* out_row_map, void* workspace,
+                    size_t workspace_bytes, cudaStream_t stream);
 
 }  // namespace b200

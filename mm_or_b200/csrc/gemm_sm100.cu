@@ -227,7 +227,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
           for (int j = 0; j < 32; ++j) x[j] = act_apply(x[j], e.act);
         }
         if (e.residual != nullptr) {
-          const bf16* rrow = e.residual + static_cast<size_t>(row) * e.ldr + n0;
+          const size_t rr = e.res_group > 0
+                                ? static_cast<size_t>(row / e.res_group) * e.res_group_stride + row % e.res_group
+                                : static_cast<size_t>(row);
+          const bf16* rrow = e.residual + rr * e.ldr + n0;
 #pragma unroll
           for (int j8 = 0; j8 < 4; ++j8) {
             if (n0 + j8 * 8 < g.N) {

@@ -1,0 +1,89 @@
+"""Host-side index arithmetic of the multimodal token pack.
+
+Mirror of the control flow in LlavaMetaForCausalLM.prepare_inputs_labels_for_multimodal
+(reference: LLaVA/llava/model/llava_arch.py:235-338): strip padding by the attention mask, split every row at the
+<image> placeholder (-200), splice T_vis visual tokens in, IGNORE_INDEX labels over them, truncate to
+tokenizer_model_max_length, pad left or right to the batch maximum, rebuild mask / position_ids. The reference does
+this with ~40 tiny torch ops and .tolist() syncs per sample; here it is pure numpy on the host and produces the
+index tables the device kernels consume (b200_projector_pack / b200_embed_rows), so no embedding row is ever
+copied twice.
+"""
+import numpy as np
+
+from ..constants import IGNORE_INDEX, IMAGE_TOKEN_INDEX, VIS_DESCRIPTOR_TOKEN_INDEX
+
+PAD_ROW = -1        # zero embedding row
+VISUAL_BASE = -2    # src == VISUAL_BASE - j  <=>  j-th visual token of the sample
+
+
+class PackPlan:
+    __slots__ = ("src", "labels", "mask", "pos", "lengths", "kv_start", "row_map", "L", "t_vis")
+
+
+def plan_pack(input_ids, attention_mask, labels, t_vis, padding_side="right", max_len=None):
+    """input_ids (B, Lt) int array with IMAGE_TOKEN_INDEX placeholders; attention_mask / labels optional.
+    Returns a PackPlan:
+      src      (B, L) int32   >= 0 token id | PAD_ROW | VISUAL_BASE - j
+      labels   (B, L) int64   IGNORE_INDEX on visual and pad rows
+      mask     (B, L) bool
+      pos      (B, L) int64   arange over real rows, 0 on pads
+      lengths  (B,)   int32   real rows per sample
+      kv_start (B,)   int32   first real row (left padding) else 0
+      row_map  (B * t_vis,) int32  flat row (b * L + l) of visual token (b, j), or -1 if truncated / absent
+    """
+    ids = np.asarray(input_ids)
+    B = ids.shape[0]
+    am = np.ones_like(ids, dtype=bool) if attention_mask is None else np.asarray(attention_mask).astype(bool)
+    lab = np.full_like(ids, IGNORE_INDEX) if labels is None else np.asarray(labels)
+    rows, rlabels = [], []
+    for b in range(B):
+        r_ids = ids[b][am[b]]                      # compaction: interior pads are dropped too (llava_arch.py:235)
+        r_lab = lab[b][am[b]]
+        n_img = int((r_ids == IMAGE_TOKEN_INDEX).sum())
+        if n_img == 0:                              # text-only row (llava_arch.py:244-251)
+            rows.append(r_ids.astype(np.int64))
+            rlabels.append(r_lab)
+            continue
+        cuts = np.where((r_ids == IMAGE_TOKEN_INDEX) | (r_ids == VIS_DESCRIPTOR_TOKEN_INDEX))[0]
+        bounds = [-1] + cuts.tolist() + [len(r_ids)]
+        vis = VISUAL_BASE - np.arange(t_vis, dtype=np.int64)
+        vlab = np.full(t_vis, IGNORE_INDEX, dtype=r_lab.dtype)
+        parts, lparts = [], []
+        # only the chunks up to the image count are emitted when vis_descriptor_embs is None (llava_arch.py:268-294)
+        for i in range(n_img + 1):
+            parts.append(r_ids[bounds[i] + 1:bounds[i + 1]].astype(np.int64))
+            lparts.append(r_lab[bounds[i] + 1:bounds[i + 1]])
+            if i < n_img:
+                if n_img > 1:
+                    raise NotImplementedError("one <image> placeholder per sample (MM2SG prompts have exactly one)")
+                parts.append(vis)
+                lparts.append(vlab)
+        rows.append(np.concatenate(parts))
+        rlabels.append(np.concatenate(lparts))
+    if max_len is not None:
+        rows = [r[:max_len] for r in rows]
+        rlabels = [r[:max_len] for r in rlabels]
+    L = max(len(r) for r in rows)
+    p = PackPlan()
+    p.L, p.t_vis = L, t_vis
+    p.src = np.full((B, L), PAD_ROW, dtype=np.int32)
+    p.labels = np.full((B, L), IGNORE_INDEX, dtype=np.int64)
+    p.mask = np.zeros((B, L), dtype=bool)
+    p.pos = np.zeros((B, L), dtype=np.int64)
+    p.lengths = np.zeros(B, dtype=np.int32)
+    p.kv_start = np.zeros(B, dtype=np.int32)
+    p.row_map = np.full(B * t_vis, -1, dtype=np.int32)
+    for b, (r, rl) in enumerate(zip(rows, rlabels)):
+        n = len(r)
+        p.lengths[b] = n
+        if n == 0:
+            continue
+        off = L - n if padding_side == "left" else 0
+        p.kv_start[b] = off
+        p.src[b, off:off + n] = r
+        p.labels[b, off:off + n] = rl
+        p.mask[b, off:off + n] = True
+        p.pos[b, off:off + n] = np.arange(n)
+        vis_at = np.where(r <= VISUAL_BASE)[0]
+        p.row_map[b * t_vis + (VISUAL_BASE - r[vis_at])] = b * L + off + vis_at
+    return p

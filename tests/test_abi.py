@@ -1,0 +1,47 @@
+"""CPU: the C-ABI library builds/loads and exports every symbol include/b200_mmor.h declares (no compute calls)."""
+import ctypes
+import os
+import re
+
+from mm_or_b200 import _lib as L
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "b200_mmor.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(b200_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    if not os.path.exists(L.LIB_PATH):
+        from mm_or_b200.build import build
+        build()
+    lib = ctypes.CDLL(L.LIB_PATH)
+    names = header_symbols()
+    assert len(names) >= 24
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/b200_mmor.h but not exported"
+
+
+def test_binding_covers_header():
+    assert sorted(L.EXPORTED_SYMBOLS) == header_symbols()
+    lib = L.lib()
+    assert lib.b200_abi_version() == 1
+
+
+def test_struct_sizes_match_header_layout():
+    lib = L.lib()
+    mirrors = [L.VitLayer, L.VitWeights, L.BertLayer, L.PoolerWeights, L.SegmaskWeights, L.ProjectorWeights,
+               L.LlamaLayer, L.LlamaWeights, L.KvCache]
+    for i, m in enumerate(mirrors):
+        assert lib.b200_sizeof_struct(i) == ctypes.sizeof(m), m.__name__
+    assert lib.b200_sizeof_struct(99) == 0
+
+
+def test_no_cpu_fallback():
+    import pytest
+    import torch
+    with pytest.raises(L.B200Error):
+        L.ptr(torch.zeros(4))

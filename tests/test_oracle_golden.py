@@ -1,0 +1,57 @@
+"""CPU: the oracle restatement reproduces the golden outputs recorded from the reference's own model code
+(tests/golden/make_golden.py). This is what pins the oracle."""
+import os
+
+import pytest
+import torch
+
+import golden_cases as gc
+from helpers import oracle_cfg, rel_err
+from oracle import mm2sg_oracle as O
+
+
+@pytest.fixture(scope="module")
+def setup():
+    torch.set_grad_enabled(False)
+    cfg = gc.small_config()
+    return cfg, oracle_cfg(cfg), gc.bf16_round(gc.small_weights(cfg))
+
+
+@pytest.mark.parametrize("name", list(gc.CASES))
+def test_oracle_matches_reference_golden(setup, name):
+    cfg, ocfg, sd = setup
+    g = torch.load(os.path.join(gc.GOLDEN_DIR, name + ".pt"))
+    case = gc.make_case(cfg, name)
+    out = O.multimodal_prefill(sd, ocfg, case["input_ids"], case["attention_mask"], case["images"], case.get("labels"),
+                               case.get("audio"), case.get("segmasks"), padding_side=case["side"])
+    assert list(out["logits"].shape) == g["logits_shape"].tolist()
+    feats = O.clip_tower_forward(sd, torch.cat(case["images"], 0), ocfg.vit)
+    assert rel_err(feats[:, ::48, ::8], g["vit_slice"]) < 2e-3            # golden slices are stored in fp16
+    assert rel_err(out["visual"][:, ::24, ::4], g["visual_slice"]) < 2e-3
+    assert rel_err(out["visual"][:, 570:], g["visual_tail"]) < 2e-3
+    mask = out["mask"]
+    if case["side"] == "left":
+        assert rel_err(out["logits"][:, -1], g["logits_last"]) < 1e-5
+    rows = out["logits"][:, ::37]
+    m = mask[:, ::37]
+    assert rel_err(rows[m], g["logits_rows"].float()[m]) < 2e-3
+    if "modified_labels" in g:
+        assert torch.equal(out["modified_labels"], g["modified_labels"])
+        vw = torch.linspace(0.2, 1.0, cfg.vocab_size)
+        assert abs(O.weighted_ce(out["logits"], out["modified_labels"], vw).item() - g["weighted_loss"].item()) < 1e-4
+        sl = out["logits"][..., :-1, :].reshape(-1, cfg.vocab_size)
+        tl = out["modified_labels"][..., 1:].reshape(-1)
+        assert abs(torch.nn.functional.cross_entropy(sl, tl).item() - g["hf_loss"].item()) < 1e-4
+    if "greedy_ids" in g:
+        steps = g["greedy_ids"].shape[1]
+        toks, lg = O.greedy_decode(sd, ocfg, out["logits"][:, -1], out["kv"], out["mask"], steps, stop_on_eos=False)
+        assert rel_err(lg, g["greedy_logits"]) < 2e-3
+        assert torch.equal(toks, g["greedy_ids"])
+
+
+def test_token_weights_formula():
+    # train/train.py:1316-1322
+    import math
+    w = O.token_weights({5: 100.0, 7: 10.0}, 16)
+    assert abs(w[5].item() - 1 / (math.log(100.0) + 1)) < 1e-7
+    assert abs(w[0].item() - w[5].item() / 100) < 1e-9

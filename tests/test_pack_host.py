@@ -1,0 +1,79 @@
+"""CPU: the host-side pack planner (mm_or_b200/model/pack.py) against the oracle's restatement of
+prepare_inputs_labels_for_multimodal (llava_arch.py:235-338), including the edge cases the reference handles:
+ragged lengths, interior pads, left / right padding, truncation, text-only rows."""
+import numpy as np
+import pytest
+import torch
+
+from mm_or_b200.constants import IGNORE_INDEX, IMAGE_TOKEN_INDEX
+from mm_or_b200.model.pack import PAD_ROW, VISUAL_BASE, plan_pack
+from oracle import mm2sg_oracle as O
+
+
+def random_batch(rng, B, Lt, with_labels, interior_pad=False, text_only_row=False):
+    ids = torch.zeros(B, Lt, dtype=torch.long)
+    for b in range(B):
+        n = int(rng.integers(3, Lt + 1))
+        row = torch.from_numpy(rng.integers(3, 500, n))
+        if not (text_only_row and b == 0):
+            row[int(rng.integers(0, n))] = IMAGE_TOKEN_INDEX
+        if interior_pad and n > 4:
+            row[2] = 0
+        ids[b, Lt - n:] = row
+    labels = None
+    if with_labels:
+        labels = ids.clone()
+        labels[ids <= 0] = IGNORE_INDEX
+    return ids, ids.ne(0), labels
+
+
+@pytest.mark.parametrize("side", ["left", "right"])
+@pytest.mark.parametrize("with_labels", [False, True])
+@pytest.mark.parametrize("max_len", [None, 40])
+def test_plan_matches_oracle(side, with_labels, max_len):
+    rng = np.random.default_rng(0)
+    for trial in range(8):
+        ids, mask, labels = random_batch(rng, B=4, Lt=20, with_labels=with_labels, interior_pad=trial % 2 == 1,
+                                         text_only_row=trial == 3)
+        t_vis = int(rng.integers(1, 33))
+        src, lab, m, pos = O.pack_plan(ids, mask, labels, t_vis, side, max_len)
+        p = plan_pack(ids.numpy(), mask.numpy(), None if labels is None else labels.numpy(), t_vis, side, max_len)
+        assert np.array_equal(p.src, src.numpy())
+        assert np.array_equal(p.labels, lab.numpy())
+        assert np.array_equal(p.mask, m.numpy())
+        assert np.array_equal(p.pos, pos.numpy())
+        # derived tables
+        assert np.array_equal(p.lengths, m.sum(1).numpy())
+        for b in range(ids.shape[0]):
+            if side == "left" and p.lengths[b]:
+                assert p.kv_start[b] == p.L - p.lengths[b]
+            for j in range(t_vis):
+                r = p.row_map[b * t_vis + j]
+                where = np.where(p.src[b] == VISUAL_BASE - j)[0]
+                if len(where):
+                    assert r == b * p.L + where[0]
+                else:
+                    assert r == -1
+
+
+def test_no_mask_no_labels():
+    ids = torch.tensor([[5, IMAGE_TOKEN_INDEX, 6, 7]])
+    p = plan_pack(ids.numpy(), None, None, 3)
+    assert p.src.tolist() == [[5, -2, -3, -4, 6, 7]]
+    assert p.labels.tolist() == [[IGNORE_INDEX] * 6]
+    assert p.row_map.tolist() == [1, 2, 3]
+
+
+def test_empty_row_and_truncation():
+    ids = torch.tensor([[0, 0, 0, 0], [9, IMAGE_TOKEN_INDEX, 8, 7]])
+    p = plan_pack(ids.numpy(), ids.ne(0).numpy(), None, 5, "left", max_len=4)
+    assert p.L == 4 and p.lengths.tolist() == [0, 4]
+    assert (p.src[0] == PAD_ROW).all()
+    assert p.src[1].tolist() == [9, -2, -3, -4]              # visual tokens 3, 4 and the trailing text are truncated
+    assert p.row_map.tolist()[5:] == [5, 6, 7, -1, -1]
+
+
+def test_two_images_rejected():
+    ids = torch.tensor([[IMAGE_TOKEN_INDEX, 4, IMAGE_TOKEN_INDEX]])
+    with pytest.raises(NotImplementedError):
+        plan_pack(ids.numpy(), None, None, 2)
