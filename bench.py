@@ -1,0 +1,389 @@
+#!/usr/bin/env python
+"""bench.py -- MM2SG scene-graph inference throughput on B200 (BASELINE.json metric, config 2).
+
+One "step" = one batch of B samples per GPU through the whole hot path: 6 x 336^2 RGB views per sample -> CLIP ViT-L
+(23 layers) -> BERT image pooler -> mlp2x_gelu projector -> multimodal token pack -> Llama-7B prefill (L ~ 831)
+-> 256 greedy decode steps. Synthetic pixels / token ids, random-init weights of the real architecture.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl b200|reference]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N ...
+
+Prints ONE JSON line (rank 0). Keys: see the bench contract in DESIGN.md ("Measurement").
+  value     inferences/s, whole job, inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e       same metric through the public API (model.generate) with pinned HOST inputs: H2D of pixels and D2H of
+            the generated ids inside the timed region
+  roofline  dominant kernel family of one extra, event-instrumented step (per-launch CUDA events on the launching
+            stream, grouped by family inside libb200mmor.so): algorithmic bytes or FLOPs / summed device time
+  cpu_baseline  the CPU oracle (oracle/mm2sg_oracle.py, a port of the reference's PyTorch path) timed on this box's
+            host cores on a bounded sample of the same workload (rank 0, N = 1 only)
+--impl reference: the oracle port alone, on the host cores (the Python reference cannot travel to the GPU box).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch
+
+METRIC = "scene-graph inferences/sec (6-view, 7B)"
+UNIT = "inferences/s"
+
+
+def parse_args():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=3)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    p.add_argument("--batch", type=int, default=64, help="samples per GPU per step")
+    p.add_argument("--views", type=int, default=6)
+    p.add_argument("--text-len", type=int, default=256)
+    p.add_argument("--new-tokens", type=int, default=256)
+    p.add_argument("--jitter", type=int, default=16, help="prompt-length jitter (exercises left padding)")
+    p.add_argument("--layers", type=int, default=32, help="debug only: fewer decoder layers => NOT the benchmark")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-roofline", action="store_true")
+    p.add_argument("--cpu-decode-steps", type=int, default=4)
+    return p.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d["bf16_tflops_sustained"],
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 8:
+                continue
+            try:
+                sm.append(float(c[1]))
+                smax.append(float(c[2]))
+                power.append(float(c[3]))
+            except ValueError:
+                continue
+            for n, v in zip(names, c[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        os.unlink(self.f.name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "power_w_max": max(power),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# workload
+# ---------------------------------------------------------------------------------------------------------------------
+def full_config(layers=32):
+    from mm_or_b200.config import LlavaConfig
+    return LlavaConfig(num_hidden_layers=layers, tokenizer_padding_side="left", mv_type="learned")
+
+
+def make_inputs(cfg, args, seed):
+    """Host inputs in the shape ModelWrapper.forward hands to generate() (scene_graph_prediction_model.py:117-231)."""
+    from mm_or_b200.synth import synth_batch
+    b = synth_batch(cfg, args.batch, args.views, args.text_len, seed=seed, jitter=args.jitter, image_pos=40,
+                    dtype=torch.bfloat16)
+    images = torch.stack(b["images"]).contiguous()           # (B, V, 3, S, S) bf16
+    return images, b["input_ids"]
+
+
+def algorithmic_flops_per_inference(V, L, n_new):
+    """SURVEY.md 8(d) formulae."""
+    vit = 23 * 577 * ((4 * 1024 ** 2 + 2 * 1024 * 4096) * 2 + 4 * 577 * 1024) + 576 * 1024 * 588 * 2
+    S = V * 576
+    pooler = 2 * S * ((4 * 1024 ** 2 + 2 * 1024 * 4096) * 2 + 4 * S * 1024)
+    proj = 576 * (1024 * 4096 + 4096 ** 2) * 2
+    prefill = 2 * 6.476e9 * L + 32 * 4 * L * L * 4096 / 2 + 2 * 4096 * 32000
+    decode = sum(2 * (6.476e9 + 0.131e9) + 32 * 4 * (L + t) * 4096 for t in range(n_new))
+    return V * vit + pooler + proj + prefill + decode
+
+
+def run_b200(args):
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the B200 arm has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    import torch.distributed as dist
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    torch.set_grad_enabled(False)
+
+    from mm_or_b200 import _lib as L
+    from mm_or_b200.model.llava_llama import LlavaLlamaForCausalLM
+    from mm_or_b200.synth import make_state_dict
+
+    cfg = full_config(args.layers)
+    t0 = time.time()
+    sd = make_state_dict(cfg, seed=0, device=dev, dtype=torch.bfloat16)
+    model = LlavaLlamaForCausalLM(cfg).load_state_dict(sd, device=dev)
+    del sd
+    torch.cuda.empty_cache()
+    if world > 1:
+        model.set_process_group(dist.group.WORLD)
+    t_init = time.time() - t0
+
+    images_host, ids = make_inputs(cfg, args, seed=100 + rank)
+    images_host = images_host.pin_memory()
+    images_dev = images_host.to(dev)
+    B = args.batch
+    gen_kw = dict(do_sample=False, use_cache=True, max_new_tokens=args.new_tokens, stop_on_eos=False)
+
+    def step_resident():
+        return model.generate(ids, images=images_dev, **gen_kw)
+
+    def step_e2e():
+        out = model.generate(ids, images=images_host, **gen_kw)
+        return out.to("cpu", non_blocking=False)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = L.launch_count()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        launches = L.launch_count() - n0
+        barrier()
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), launches
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_total, launches = timed(step_resident, args.steps, args.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e, _ = timed(step_e2e, args.steps, 1)
+    n_inf = B * world * args.steps
+    value = n_inf / (ms_total / 1e3)
+    e2e_value = n_inf / (ms_e2e / 1e3)
+
+    # ---- event-instrumented step: per-family device time (eager decode loop; launches inside a replayed CUDA graph
+    #      cannot carry events)
+    roof = None
+    L_packed = args.text_len - 1 + 576
+    if not args.no_roofline and rank == 0:
+        L.prof_enable(True)
+        model.generate(ids, images=images_dev, use_cuda_graph=False, **gen_kw)
+        fam = L.prof_collect()
+        L.prof_enable(False)
+        pk = peaks()
+        lens = (ids != 0).sum(1) - 1 + 576                                   # packed length per sample
+        kv_bytes = sum(float((lens + t + 1).sum()) for t in range(args.new_tokens - 1)) * 2 * 32 * 128 * 2 * args.layers
+        fam["decode_attn"]["bytes"] = kv_bytes
+        total_ms = sum(f["ms"] for f in fam.values())
+        name, top = max(fam.items(), key=lambda kv: kv[1]["ms"])
+        tensor_bound = name in ("gemm", "flash_attn")
+        n_launch = max(1, top["launches"])
+        if tensor_bound:
+            ach = top["flops"] / (top["ms"] / 1e3) / 1e12
+            peak = pk["tf_sustained"]
+            roof = {"bound": "tensor", "achieved": round(ach, 1), "peak": peak, "unit": "TFLOP/s",
+                    "frac": round(ach / peak, 4)}
+        else:
+            ach = top["bytes"] / (top["ms"] / 1e3) / 1e9
+            peak = pk["hbm"]
+            roof = {"bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
+                    "frac": round(ach / peak, 4)}
+        roof.update({"kernel": name, "traffic": measured_traffic(name), "peak_source": pk["source"],
+                     "launches": top["launches"], "avg_launch_us": round(top["ms"] * 1e3 / n_launch, 2),
+                     "share_of_step": round(top["ms"] / total_ms, 4),
+                     "families": {k: {"ms": round(v["ms"], 2), "launches": v["launches"],
+                                      "tflops": round(v["flops"] / max(v["ms"], 1e-9) / 1e9, 1) if v["flops"] else None,
+                                      "gbs": round(v["bytes"] / max(v["ms"], 1e-9) / 1e6, 1) if v["bytes"] else None}
+                                  for k, v in fam.items() if v["launches"]}})
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_reference_sample(args, layers=args.layers)
+
+    if rank == 0:
+        flops = algorithmic_flops_per_inference(args.views, L_packed, args.new_tokens)
+        line = {
+            "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(ms_total / args.steps, 2), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "configs[1]: 6-view 336x336 RGB -> CLIP ViT-L/14 (23 layers) + BERT pooler + "
+                                   "mlp2x_gelu projector + Llama-7B prefill + %d-token greedy decode" % args.new_tokens,
+                       "samples_per_gpu_per_step": B, "views": args.views, "text_tokens": args.text_len,
+                       "packed_len": L_packed, "new_tokens": args.new_tokens, "decoder_layers": args.layers,
+                       "weights": "random-init, seed 0, bf16", "l2": "inputs larger than L2 (13.5 GB of weights + "
+                       "KV cache streamed every decode step)", "parallelism": "dp%d" % world,
+                       "model_tflop_per_inference": round(flops / 1e12, 2)},
+            "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": int(images_host.numel() * 2
+                    + ids.numel() * 8), "d2h_bytes_per_step": int(B * (ids.shape[1] + args.new_tokens) * 8),
+                    "ms_per_step": round(ms_e2e / args.steps, 2)},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "tensor_frac_whole_step": round(flops * n_inf / (ms_total / 1e3) / 1e12 / world / peaks()["tf_sustained"], 4),
+            "init_s": round(t_init, 1),
+        }
+        if roof is not None:
+            line["roofline"] = roof
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def measured_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/traffic.json), or None."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f).get(kernel)
+    return None
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference's PyTorch path, on the host cores
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_weights(cfg):
+    """bf16 weights for TIMING the CPU path: every tensor is a window of one N(0, 0.02^2) pool (gains = 1 + pool), so
+    the 7B parameter set is materialised at memcpy speed; values do not influence the instruction stream."""
+    from mm_or_b200.synth import weight_specs
+    g = torch.Generator().manual_seed(0)
+    pool = (torch.randn(1 << 26, generator=g) * 0.02).to(torch.bfloat16)
+    sd, off = {}, 0
+    for name, shape, kind in weight_specs(cfg):
+        n = 1
+        for s in shape:
+            n *= s
+        reps = -(-n // pool.numel())
+        src = pool if reps == 1 else pool.repeat(reps)
+        start = off % max(1, src.numel() - n)
+        t = src[start:start + n].clone().view(shape)
+        if kind == "g":
+            t = t + 1
+        sd[name] = t
+        off += 7919 * 64
+    return sd
+
+
+def cpu_reference_sample(args, layers=32):
+    """Times ONE inference of the config-2 workload on the CPU oracle: encode (6 views) + pack + prefill measured in
+    full, decode measured on `cpu_decode_steps` steps and extrapolated linearly to new_tokens (each step streams the
+    same 13.2 GB of weights; KV growth changes a CPU step by < 1 %)."""
+    from oracle import mm2sg_oracle as O
+    torch.set_grad_enabled(False)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = full_config(layers)
+    ocfg = O.cfg_from_llava(cfg)
+    sd = cpu_weights(cfg)
+    sub = argparse.Namespace(**vars(args))
+    sub.batch = 1
+    images, ids = make_inputs(cfg, sub, seed=100)
+    images = [images[0]]
+    t0 = time.perf_counter()
+    visual = O.encode_images_pooled(sd, images, ocfg)
+    t_enc = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    src, _, mask, pos = O.pack_plan(ids, ids.ne(0), None, visual.shape[1], "left", None)
+    emb = O.pack_embeds(sd, src, visual)
+    logits, kv = O.llama_forward(sd, emb, mask, pos, ocfg.llm, last_only=True)
+    t_pre = time.perf_counter() - t0
+    n = max(1, args.cpu_decode_steps)
+    t0 = time.perf_counter()
+    O.greedy_decode(sd, ocfg, logits[:, -1], kv, mask, n + 1, stop_on_eos=False, logits_dtype=torch.bfloat16)
+    t_dec = (time.perf_counter() - t0) / n
+    total = t_enc + t_pre + t_dec * (args.new_tokens - 1)
+    return {"value": round(1.0 / total, 5), "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "1 inference (6 views, L=%d): encode %.1fs + prefill %.1fs measured in full; %d decode steps "
+                      "measured (%.3fs/step), extrapolated to %d tokens; torch %s CPU bf16, %d threads"
+                      % (emb.shape[1], t_enc, t_pre, n, t_dec, args.new_tokens, torch.__version__, cores),
+            "seconds_per_inference": round(total, 1)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    # one sample per step would take minutes of CPU time; weights are built once, each "step" is one bounded sample
+    vals, last = [], None
+    reps = max(1, min(args.steps, 3))
+    for i in range(reps):
+        last = cpu_reference_sample(args, layers=args.layers)
+        vals.append(last["value"])
+    v = max(vals)
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": reps,
+            "warmup": 0, "ms_per_step": round(1e3 / v, 1), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "configs[1] on host cores through the CPU oracle (port of the reference's PyTorch "
+                                   "path): bounded sample per step, see cpu_baseline.sample",
+                       "views": args.views, "text_tokens": args.text_len, "new_tokens": args.new_tokens,
+                       "decoder_layers": args.layers},
+            "cpu_baseline": dict(last, value=v),
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

@@ -33,6 +33,19 @@ int b200_abi_version(void);
  * binding verify its struct mirrors. Returns 0 for an unknown index. */
 size_t b200_sizeof_struct(int which);
 
+/* Launch accounting (no reference counterpart: the reference launches its kernels from Python, op by op).
+ * b200_launch_count: kernels this library has launched (or captured into a CUDA graph) in this process.
+ * b200_prof_enable(1) starts bracketing every launch with CUDA events on the launching stream, grouped by kernel
+ * family (b200_prof_family_name); b200_prof_collect waits for the recorded events (the one call here that blocks
+ * the host) and returns, per family, the summed device milliseconds, the algorithmic bytes / FLOPs the launchers
+ * were asked for, and the launch count. Arrays must hold b200_prof_family_count() entries. Launches made while the
+ * stream is capturing a CUDA graph are counted but not timed. */
+long long b200_launch_count(void);
+int b200_prof_enable(int on);
+int b200_prof_family_count(void);
+const char* b200_prof_family_name(int family);
+int b200_prof_collect(double* ms, double* alg_bytes, double* alg_flops, long long* launches);
+
 /* ============================================================================================================
  * Operator level (used by the stage entry points below and by the parity tests)
  * ========================================================================================================== */

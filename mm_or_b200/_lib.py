@@ -70,6 +70,11 @@ _SIGS = {
     # name: (restype, argtypes)
     "b200_abi_version": (ci, []),
     "b200_sizeof_struct": (sz, [ci]),
+    "b200_launch_count": (ctypes.c_longlong, []),
+    "b200_prof_enable": (ci, [ci]),
+    "b200_prof_family_count": (ci, []),
+    "b200_prof_family_name": (ctypes.c_char_p, [ci]),
+    "b200_prof_collect": (ci, [vp, vp, vp, vp]),
     "b200_gemm_bf16": (ci, [vp, ci, vp, ci, vp, ci, ci, ci, ci, vp, vp, ci, vp, ci, ci, ci, vp]),
     "b200_layernorm": (ci, [vp, i64, vp, vp, ci, vp, vp, cf, vp, i64, ci, ci, vp]),
     "b200_rmsnorm": (ci, [vp, i64, vp, cf, vp, i64, ci, ci, vp]),
@@ -213,3 +218,31 @@ def decode_attention(q, k_cache, v_cache, ctx, kv_start=None, splits=0):
                                       ctx, ptr(kv_start), d ** -0.5, splits, ptr(ws), ws.numel(), stream_ptr()),
           "b200_decode_attention")
     return o
+
+
+# ---- launch accounting ------------------------------------------------------------------------------------------
+_graph_launches = 0   # kernels executed through CUDA-graph replays (the library only sees the capture)
+
+
+def note_graph_replay(kernels):
+    global _graph_launches
+    _graph_launches += int(kernels)
+
+
+def launch_count():
+    """Kernels of this library executed so far in this process (direct launches + graph replays)."""
+    return int(lib().b200_launch_count()) + _graph_launches
+
+
+def prof_enable(on=True):
+    check(lib().b200_prof_enable(int(on)), "b200_prof_enable")
+
+
+def prof_collect():
+    """{family: dict(ms, bytes, flops, launches)} for the launches since prof_enable(True). Blocks on the events."""
+    n = lib().b200_prof_family_count()
+    ms, by, fl = (ctypes.c_double * n)(), (ctypes.c_double * n)(), (ctypes.c_double * n)()
+    la = (ctypes.c_longlong * n)()
+    check(lib().b200_prof_collect(ms, by, fl, la), "b200_prof_collect")
+    return {lib().b200_prof_family_name(i).decode(): dict(ms=ms[i], bytes=by[i], flops=fl[i], launches=la[i])
+            for i in range(n)}

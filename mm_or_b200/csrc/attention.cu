@@ -239,6 +239,9 @@ __global__ void __launch_bounds__(kFaThreads) flash_attn_kernel(const AttnArgs a
 int flash_attn(const AttnArgs& a, int head_dim, cudaStream_t stream) {
   if (a.B <= 0 || a.H <= 0 || a.Lq <= 0) return 0;
   dim3 grid((a.Lq + kFaBM - 1) / kFaBM, a.H, a.B);
+  const double qk = static_cast<double>(a.B) * a.H * a.Lq * a.Lk * (a.causal ? 0.5 : 1.0);
+  LaunchScope scope(kFamFlashAttn, stream,
+                    2.0 * a.B * a.H * head_dim * (2.0 * a.Lq + 2.0 * a.Lk), 4.0 * qk * head_dim);
   if (head_dim == 64) {
     constexpr int smem = (4 * kFaBN + kFaBM) * 64 * 2;
     static bool cfg = false;
@@ -301,7 +304,8 @@ __global__ void __launch_bounds__(kDecThreads) decode_attn_kernel(const DecodeAr
 #pragma unroll
   for (int j = 0; j < 16; ++j) qreg[j] = q_s[sub * 16 + j];
   float lmax = -INFINITY;
-  for (int i = warp * 4 + kq; i < n + 3; i += kDecWarps * 4) {
+  for (int base = warp * 4; base < n; base += kDecWarps * 4) {  // warp-uniform trip count (shuffles inside)
+    const int i = base + kq;
     const bool ok = i < n;
     float acc = 0.f;
     if (ok) {
@@ -436,6 +440,7 @@ int decode_attn(DecodeArgs a, void* workspace, size_t workspace_bytes, cudaStrea
                                       kDecMaxCtx * (int)sizeof(float)));
     cfg = true;
   }
+  LaunchScope scope(kFamDecodeAttn, stream, 0.0, 0.0, a.splits > 1 ? 2 : 1);  // bytes depend on the device-side ctx
   decode_attn_kernel<<<dim3(a.B * a.H, a.splits), kDecThreads, smem, stream>>>(a);
   B200_CUDA_OK(cudaGetLastError());
   if (a.splits > 1) {

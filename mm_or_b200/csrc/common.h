@@ -33,6 +33,37 @@ int fail(int code, const char* fmt, ...);
 int num_sms();
 
 // ---------------------------------------------------------------------------------------------
+// launch accounting + optional per-family CUDA-event timing (errors.cu). Every host launcher opens a
+// LaunchScope around its <<<>>>; the counter feeds bench.py's "gpu_launches", the event timing its
+// "roofline" object (events are recorded on the launching stream; skipped while the stream is capturing).
+// ---------------------------------------------------------------------------------------------
+enum KernelFamily : int {
+  kFamGemm = 0,     // tcgen05 GEMM, M > 128 (tensor bound)
+  kFamGemmSkinny,   // tcgen05 GEMM, M <= 128 (decode: weight streaming, HBM bound)
+  kFamFlashAttn,    // prefill / ViT / pooler attention
+  kFamDecodeAttn,   // single-token attention over the KV cache (HBM bound)
+  kFamNorm,         // LayerNorm / RMSNorm
+  kFamRope,         // RoPE + KV-cache append
+  kFamEmbed,        // embedding gather / pack rows
+  kFamArgmax,
+  kFamPatchify,
+  kFamSegmask,
+  kFamMisc,
+  kFamTrain,        // backward / loss / optimizer kernels
+  kFamCount
+};
+struct LaunchScope {
+  LaunchScope(int family, cudaStream_t stream, double alg_bytes = 0.0, double alg_flops = 0.0, int kernels = 1);
+  ~LaunchScope();
+  LaunchScope(const LaunchScope&) = delete;
+  LaunchScope& operator=(const LaunchScope&) = delete;
+
+ private:
+  cudaStream_t stream_;
+  int slot_;
+};
+
+// ---------------------------------------------------------------------------------------------
 // GEMM  C[M,N] = epilogue(A[M,K] . B[N,K]^T)   (both operands K-major, bf16, fp32 accumulate)
 // ---------------------------------------------------------------------------------------------
 enum GemmAct : int {

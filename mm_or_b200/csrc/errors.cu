@@ -1,7 +1,11 @@
-// Error plumbing shared by every entry point of libb200mmor.so.
+// Error plumbing and launch accounting shared by every entry point of libb200mmor.so.
+#include <atomic>
 #include <cstdarg>
+#include <mutex>
 #include <string>
+#include <vector>
 
+#include "../../include/b200_mmor.h"
 #include "common.h"
 
 namespace b200 {
@@ -22,4 +26,94 @@ int fail(int code, const char* fmt, ...) {
 
 const char* last_error_cstr() { return g_last_error.c_str(); }
 
+// ---------------------------------------------------------------------------------------------
+// launch counter + per-family event timing
+// ---------------------------------------------------------------------------------------------
+static std::atomic<long long> g_launches{0};
+static std::atomic<int> g_prof_on{0};
+
+struct ProfSlot {
+  cudaEvent_t e0, e1;
+  int family;
+  bool used;
+};
+static std::mutex g_prof_mu;
+static std::vector<ProfSlot> g_slots;      // event pool; [0, g_slots_used) hold the current measurement
+static size_t g_slots_used = 0;
+static double g_fam_bytes[kFamCount], g_fam_flops[kFamCount];
+static long long g_fam_launches[kFamCount];
+
+LaunchScope::LaunchScope(int family, cudaStream_t stream, double alg_bytes, double alg_flops, int kernels)
+    : stream_(stream), slot_(-1) {
+  g_launches.fetch_add(kernels, std::memory_order_relaxed);
+  if (!g_prof_on.load(std::memory_order_relaxed)) return;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(stream, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (g_slots_used == g_slots.size()) {
+    ProfSlot s{};
+    if (cudaEventCreate(&s.e0) != cudaSuccess || cudaEventCreate(&s.e1) != cudaSuccess) return;
+    g_slots.push_back(s);
+  }
+  ProfSlot& s = g_slots[g_slots_used];
+  s.family = family;
+  s.used = true;
+  slot_ = static_cast<int>(g_slots_used++);
+  g_fam_bytes[family] += alg_bytes;
+  g_fam_flops[family] += alg_flops;
+  g_fam_launches[family] += kernels;
+  cudaEventRecord(s.e0, stream);
+}
+
+LaunchScope::~LaunchScope() {
+  if (slot_ < 0) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  cudaEventRecord(g_slots[slot_].e1, stream_);
+}
+
 }  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+long long b200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int b200_prof_enable(int on) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_slots_used = 0;
+  for (int f = 0; f < kFamCount; ++f) {
+    g_fam_bytes[f] = g_fam_flops[f] = 0.0;
+    g_fam_launches[f] = 0;
+  }
+  g_prof_on.store(on ? 1 : 0);
+  return 0;
+}
+
+int b200_prof_family_count(void) { return kFamCount; }
+
+const char* b200_prof_family_name(int family) {
+  static const char* names[kFamCount] = {"gemm",  "gemm_skinny", "flash_attn", "decode_attn", "norm",  "rope_kv",
+                                         "embed", "argmax",      "patchify",   "segmask",     "misc",  "train"};
+  return family >= 0 && family < kFamCount ? names[family] : "";
+}
+
+int b200_prof_collect(double* ms, double* alg_bytes, double* alg_flops, long long* launches) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (int f = 0; f < kFamCount; ++f) {
+    ms[f] = 0.0;
+    alg_bytes[f] = g_fam_bytes[f];
+    alg_flops[f] = g_fam_flops[f];
+    launches[f] = g_fam_launches[f];
+  }
+  for (size_t i = 0; i < g_slots_used; ++i) {
+    ProfSlot& s = g_slots[i];
+    B200_CUDA_OK(cudaEventSynchronize(s.e1));
+    float t = 0.f;
+    B200_CUDA_OK(cudaEventElapsedTime(&t, s.e0, s.e1));
+    ms[s.family] += t;
+  }
+  return 0;
+}
+
+}  // extern "C"

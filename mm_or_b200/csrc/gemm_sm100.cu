@@ -342,6 +342,12 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   }
   const int tiles = g.m_tiles * g.n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
+  const double mnk = static_cast<double>(g.M) * g.N * g.K;
+  const int n_out = g.epi.act == kActSwiGLU ? g.N / 2 : g.N;
+  const double bytes = 2.0 * (static_cast<double>(g.M) * g.K + static_cast<double>(g.N) * g.K) +
+                       static_cast<double>(g.M) * n_out * (g.epi.out_fp32 ? 4 : 2) +
+                       (g.epi.residual ? 2.0 * g.M * g.N : 0.0);
+  LaunchScope scope(g.M <= 128 ? kFamGemmSkinny : kFamGemm, stream, bytes, 2.0 * mnk);
   gemm_bf16_tn_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, g);
   B200_CUDA_OK(cudaGetLastError());
   return 0;

@@ -44,6 +44,7 @@ int patchify_im2col(const bf16* pixels, bf16* cols, int N, int C, int S, int P, 
   if (S % P != 0 || Kpad < C * P * P) return fail(-2, "patchify: bad geometry S=%d P=%d Kpad=%d", S, P, Kpad);
   const int G = S / P;
   const long long total = static_cast<long long>(N) * G * G * C * P;
+  LaunchScope scope(kFamPatchify, stream, 2.0 * N * G * G * (C * P * P + Kpad), 0.0);
   patchify_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(pixels, cols, N, C, S, P, G, Kpad);
   B200_CUDA_OK(cudaGetLastError());
   return 0;
@@ -98,6 +99,7 @@ int rope_kv_write(bf16* qkv, const int* kv_start, const float* cos_t, const floa
   if (warps <= 0) return 0;
   if (slot0_dev == nullptr && slot0 + Lq > cap)
     return fail(-2, "rope_kv_write: slot %d + %d exceeds cache capacity %d", slot0, Lq, cap);
+  LaunchScope scope(kFamRope, stream, static_cast<double>(warps) * 128 * 2 * 5, 0.0);
   rope_kv_kernel<<<static_cast<unsigned>((warps + 3) / 4), 128, 0, stream>>>(qkv, kv_start, cos_t, sin_t, kc, vc, B * Lq,
                                                                              H, Lq, slot0, slot0_dev, cap, max_pos);
   B200_CUDA_OK(cudaGetLastError());
@@ -129,6 +131,7 @@ int embed_rows(const int* ids, const bf16* table, bf16* out, long long ldo, int 
                cudaStream_t stream) {
   if (rows <= 0) return 0;
   if (D % 8) return fail(-2, "embed_rows: D must be a multiple of 8");
+  LaunchScope scope(kFamEmbed, stream, 4.0 * rows * D, 0.0);
   embed_rows_kernel<<<(rows + 3) / 4, 128, 0, stream>>>(ids, table, out, ldo, rows, D, vocab);
   B200_CUDA_OK(cudaGetLastError());
   return 0;
@@ -193,6 +196,7 @@ __global__ void __launch_bounds__(256) argmax_kernel(const T* __restrict__ logit
 int argmax_rows(const void* logits, int is_fp32, long long ld, int rows, int V, int* out_tok, int* finished, int eos_id,
                 int pad_id, int* history, int hist_ld, int step, const int* step_dev, cudaStream_t stream) {
   if (rows <= 0) return 0;
+  LaunchScope scope(kFamArgmax, stream, static_cast<double>(rows) * V * (is_fp32 ? 4 : 2), 0.0);
   if (is_fp32)
     argmax_kernel<float><<<rows, 256, 0, stream>>>(static_cast<const float*>(logits), ld, V, out_tok, finished, eos_id,
                                                    pad_id, history, hist_ld, step, step_dev);
@@ -209,6 +213,7 @@ __global__ void bump_counters_kernel(int* state) {
   state[1] += 1;
 }
 int bump_counters(int* state, cudaStream_t stream) {
+  LaunchScope scope(kFamMisc, stream);
   bump_counters_kernel<<<1, 1, 0, stream>>>(state);
   B200_CUDA_OK(cudaGetLastError());
   return 0;
@@ -284,6 +289,7 @@ int segmask_forward(const uint8_t* cls, int n_maps, const bf16* emb, const bf16*
   float* x1 = x0 + static_cast<size_t>(n_maps) * 8 * 1024;
   float* x2 = x1 + static_cast<size_t>(n_maps) * 64 * 256;
   const long long tot = static_cast<long long>(n_maps) * 8 * 1024;
+  LaunchScope scope(kFamSegmask, stream, 0.0, 0.0, 6);
   segmask_embed_kernel<<<static_cast<unsigned>((tot + 255) / 256), 256, 0, stream>>>(cls, emb, x0, n_maps, 8, 1024, 30);
   B200_CUDA_OK(cudaGetLastError());
   const int chans[6] = {8, 64, 128, 256, 512, 1024};

@@ -125,6 +125,7 @@ static int launch_norm(const LnArgs& a, cudaStream_t stream) {
   if (a.D % 256 != 0) return fail(-2, "norm: hidden size %d must be a multiple of 256", a.D);
   if ((a.ldx % 8) || (a.ldo % 8)) return fail(-2, "norm: row strides must be multiples of 8 elements");
   const int grid = (a.M + 3) / 4;
+  LaunchScope scope(kFamNorm, stream, 4.0 * a.M * a.D, 0.0);
   switch (a.D / 256) {
     case 1: norm_kernel<1, kRms><<<grid, 128, 0, stream>>>(a); break;
     case 2: norm_kernel<2, kRms><<<grid, 128, 0, stream>>>(a); break;

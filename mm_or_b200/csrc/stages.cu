@@ -72,7 +72,10 @@ static int vit_forward(const b200_vit_weights* w, const bf16* pixels, bf16* x, i
   GemmEpilogue e0;
   B200_TRY(gemm_bf16_tn(big, w->kpad, B(w->patch_w), w->kpad, patches, D, n * P, D, w->kpad, e0, 0, st));
   // x = pre_layrnorm([CLS ; patches] + position_embedding)
-  vit_row_map_kernel<<<(rows + 255) / 256, 256, 0, st>>>(map, n, T);
+  {
+    LaunchScope scope(kFamMisc, st);
+    vit_row_map_kernel<<<(rows + 255) / 256, 256, 0, st>>>(map, n, T);
+  }
   B200_CUDA_OK(cudaGetLastError());
   B200_TRY(layernorm(patches, D, map, B(w->pos_cls), T, B(w->pre_ln_w), B(w->pre_ln_b), w->ln_eps, x, D, rows, D, 0, 0,
                      st));

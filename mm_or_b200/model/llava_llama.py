@@ -387,6 +387,7 @@ class LlavaLlamaForCausalLM:
         self.vit_chunk = 96
         self.pooler_chunk = 16
         self.training = False
+        self._pg = None
 
     # ---- reference accessors --------------------------------------------------------------------------------
     def get_model(self):
@@ -404,6 +405,11 @@ class LlavaLlamaForCausalLM:
 
     def to(self, *a, **k):
         return self
+
+    def set_process_group(self, group):
+        """Multi-GPU inference: every rank encodes its own samples; the projected visual tokens are
+        all-gathered over NCCL/NVLink before LLM fusion and each rank decodes its slice of the gathered batch."""
+        self._pg = group
 
     def resize_token_embeddings(self, n):
         if n != self.config.vocab_size:
@@ -481,7 +487,10 @@ class LlavaLlamaForCausalLM:
     def _images_to_batch(self, images):
         if type(images) is list or images.ndim == 5:
             if getattr(self.config, "mv_type") == "learned":
-                concat = torch.cat([im.to(self.device, BF) for im in images], dim=0)
+                if torch.is_tensor(images):          # (B, V, 3, S, S): one copy instead of B
+                    concat = images.to(self.device, BF, non_blocking=True).flatten(0, 1)
+                    return concat, [int(images.shape[1])] * int(images.shape[0])
+                concat = torch.cat([im.to(self.device, BF, non_blocking=True) for im in images], dim=0)
                 return concat, [int(im.shape[0]) for im in images]
             raise NotImplementedError("only mv_type == 'learned' is used by MM2SG")
         raise Exception("SHOULD NOT BE HERE")                                     # llava_arch.py:209
@@ -663,12 +672,16 @@ class LlavaLlamaForCausalLM:
                 graph = torch.cuda.CUDAGraph()
                 side = torch.cuda.Stream()
                 side.wait_stream(torch.cuda.current_stream())
+                n0 = lib.b200_launch_count()
                 with torch.cuda.stream(side):
                     with torch.cuda.graph(graph, stream=side):
                         step()
+                graph_kernels = lib.b200_launch_count() - n0
+                L.note_graph_replay(-graph_kernels)       # the capture itself executed nothing
                 torch.cuda.current_stream().wait_stream(side)
             if graph is not None:
                 graph.replay()
+                L.note_graph_replay(graph_kernels)
             else:
                 step()
             if return_logits:

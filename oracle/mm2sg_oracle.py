@@ -76,6 +76,19 @@ class Mm2sgCfg:
     llm: LlmCfg = field(default_factory=LlmCfg)
 
 
+def cfg_from_llava(cfg) -> Mm2sgCfg:
+    """Oracle geometry from a LlavaConfig-like attribute bag (mm_or_b200.config.LlavaConfig)."""
+    vc = cfg.vision_config()
+    return Mm2sgCfg(
+        vit=VitCfg(hidden=vc["hidden_size"], heads=vc["num_attention_heads"], layers=vc["num_hidden_layers"],
+                   ffn=vc["intermediate_size"], image=vc["image_size"], patch=vc["patch_size"],
+                   select_layer=cfg.mm_vision_select_layer),
+        pooler=PoolerCfg(),
+        llm=LlmCfg(hidden=cfg.hidden_size, heads=cfg.num_attention_heads, layers=cfg.num_hidden_layers,
+                   ffn=cfg.intermediate_size, vocab=cfg.vocab_size, eps=cfg.rms_norm_eps,
+                   rope_theta=cfg.rope_theta, max_pos=cfg.max_position_embeddings))
+
+
 def _lin(x, sd, name, bias=True):
     return F.linear(x, sd[name + ".weight"], sd[name + ".bias"] if bias else None)
 

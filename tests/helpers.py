@@ -5,15 +5,7 @@ from oracle import mm2sg_oracle as O
 
 
 def oracle_cfg(cfg):
-    vc = cfg.vision_config()
-    return O.Mm2sgCfg(
-        vit=O.VitCfg(hidden=vc["hidden_size"], heads=vc["num_attention_heads"], layers=vc["num_hidden_layers"],
-                     ffn=vc["intermediate_size"], image=vc["image_size"], patch=vc["patch_size"],
-                     select_layer=cfg.mm_vision_select_layer),
-        pooler=O.PoolerCfg(),
-        llm=O.LlmCfg(hidden=cfg.hidden_size, heads=cfg.num_attention_heads, layers=cfg.num_hidden_layers,
-                     ffn=cfg.intermediate_size, vocab=cfg.vocab_size, eps=cfg.rms_norm_eps,
-                     rope_theta=cfg.rope_theta, max_pos=cfg.max_position_embeddings))
+    return O.cfg_from_llava(cfg)
 
 
 def rel_err(a, b):
