@@ -51,6 +51,9 @@ def parse_args():
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-roofline", action="store_true")
     p.add_argument("--cpu-decode-steps", type=int, default=4)
+    p.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer arm")
+    p.add_argument("--no-graph", action="store_true", help="profiling runs only: eager decode loop (every launch "
+                   "visible to ncu)")
     return p.parse_args()
 
 
@@ -169,15 +172,32 @@ def run_b200(args):
     model = LlavaLlamaForCausalLM(cfg).load_state_dict(sd, device=dev)
     del sd
     torch.cuda.empty_cache()
-    if world > 1:
-        model.set_process_group(dist.group.WORLD)
     t_init = time.time() - t0
 
     images_host, ids = make_inputs(cfg, args, seed=100 + rank)
     images_host = images_host.pin_memory()
     images_dev = images_host.to(dev)
     B = args.batch
-    gen_kw = dict(do_sample=False, use_cache=True, max_new_tokens=args.new_tokens, stop_on_eos=False)
+    gen_kw = dict(do_sample=False, use_cache=True, max_new_tokens=args.new_tokens, stop_on_eos=False,
+                  use_cuda_graph=not args.no_graph)
+
+    exchange = None
+    if world > 1:
+        # samples sharded over ranks, one exchange step (visual tokens, all-gather over NVLink). Preferred:
+        # the projector GEMM's epilogue stores into every rank's symmetric buffer; if symmetric memory cannot be set
+        # up on this box, the same exchange runs as ncclAllGather (said so in config.exchange).
+        exchange = "peer"
+        try:
+            model.set_process_group(dist.group.WORLD, exchange="peer")
+            model.generate(ids[:, :], images=images_dev, do_sample=False, max_new_tokens=2, stop_on_eos=False)
+            ok = torch.ones(1, device=dev)
+        except Exception as e:  # noqa: BLE001 - any failure of the peer path selects the NCCL path on ALL ranks
+            print(f"[bench] rank {rank}: peer-store exchange unavailable ({e!r}); using ncclAllGather", file=sys.stderr)
+            ok = torch.zeros(1, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if ok.item() == 0:
+            exchange = "nccl"
+            model.set_process_group(dist.group.WORLD, exchange="nccl")
 
     def step_resident():
         return model.generate(ids, images=images_dev, **gen_kw)
@@ -214,7 +234,7 @@ def run_b200(args):
         sampler.start()
     ms_total, launches = timed(step_resident, args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
-    ms_e2e, _ = timed(step_e2e, args.steps, 1)
+    ms_e2e = float("nan") if args.no_e2e else timed(step_e2e, args.steps, 1)[0]
     n_inf = B * world * args.steps
     value = n_inf / (ms_total / 1e3)
     e2e_value = n_inf / (ms_e2e / 1e3)
@@ -225,7 +245,7 @@ def run_b200(args):
     L_packed = args.text_len - 1 + 576
     if not args.no_roofline and rank == 0:
         L.prof_enable(True)
-        model.generate(ids, images=images_dev, use_cuda_graph=False, **gen_kw)
+        model.generate(ids, images=images_dev, **dict(gen_kw, use_cuda_graph=False))
         fam = L.prof_collect()
         L.prof_enable(False)
         pk = peaks()
@@ -270,6 +290,8 @@ def run_b200(args):
                        "packed_len": L_packed, "new_tokens": args.new_tokens, "decoder_layers": args.layers,
                        "weights": "random-init, seed 0, bf16", "l2": "inputs larger than L2 (13.5 GB of weights + "
                        "KV cache streamed every decode step)", "parallelism": "dp%d" % world,
+                       "exchange": {None: "none (1 GPU)", "peer": "visual tokens all-gathered by the projector GEMM "
+                                    "epilogue (peer stores over NVLink)", "nccl": "ncclAllGather of visual tokens"}[exchange],
                        "model_tflop_per_inference": round(flops / 1e12, 2)},
             "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": int(images_host.numel() * 2
                     + ids.numel() * 8), "d2h_bytes_per_step": int(B * (ids.shape[1] + args.new_tokens) * 8),

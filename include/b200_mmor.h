@@ -61,6 +61,15 @@ int b200_gemm_bf16(const void* A, int lda, const void* W, int ldw, void* C, int 
                    const void* bias, const void* residual, int ldr, const int32_t* row_map, int act, int out_fp32,
                    int bn_hint, b200_stream_t stream);
 
+/* Same contract for M <= 256 rows (the single-token decode step, model/llava_arch.py:192-201 -> HF LlamaDecoderLayer /
+ * lm_head): weights are the tensor-core M operand and are streamed exactly once, K is split across CTAs and reduced in
+ * split order inside the kernel (deterministic). No row_map. splits: 0 = auto. The first 4096 bytes of `workspace`
+ * are tile counters and must be ZERO on entry (the kernel leaves them zero); size by the *_workspace_bytes call. */
+size_t b200_gemm_skinny_workspace_bytes(int M, int N, int K);
+int b200_gemm_bf16_skinny(const void* A, int lda, const void* W, int ldw, void* C, int ldc, int M, int N, int K,
+                          const void* bias, const void* residual, int ldr, int act, int out_fp32, int splits,
+                          void* workspace, size_t workspace_bytes, b200_stream_t stream);
+
 /* y = LayerNorm(gather(x)[row] + add[row % period]) * gamma + beta  (HF CLIP LayerNorm eps 1e-5, BERT eps 1e-12).
  * row_map (source row per output row, <0 = zero row), add may be NULL. */
 int b200_layernorm(const void* x, int64_t ldx, const int32_t* row_map, const void* add, int period, const void* gamma,
@@ -183,6 +192,16 @@ size_t b200_projector_workspace_bytes(const b200_projector_weights* w, int n_tok
 int b200_projector_pack(const b200_projector_weights* w, const void* tokens, int n_tokens, const int32_t* row_map,
                         const int32_t* text_ids, const void* embed_table, int vocab, void* embeds, int n_rows,
                         void* workspace, size_t workspace_bytes, b200_stream_t stream);
+
+/* Multi-GPU variant (BASELINE.json north_star / SURVEY.md 8e: "NCCL all-gather of visual tokens over NVLink before LLM
+ * fusion"; the reference itself has no multi-GPU inference path). The second projector GEMM stores every output
+ * tile to the same slot of all `n_peers` (<= 8) peer-mapped buffers -- peers[p] + slot_offset_bytes + row * hidden * 2 --
+ * so the all-gather rides on the GEMM epilogue over NVLink instead of running as a separate collective. peers is a
+ * HOST array of device pointers valid on this GPU (peer mappings, own buffer included). The caller orders readers
+ * behind the writers (a barrier over the symmetric-memory signal pads after this call). */
+int b200_projector_gather(const b200_projector_weights* w, const void* tokens, int n_tokens, void* const* peers,
+                          int n_peers, size_t slot_offset_bytes, void* workspace, size_t workspace_bytes,
+                          b200_stream_t stream);
 
 /* ---- Llama decoder (HF LlamaForCausalLM.forward reached from model/language_model/llava_llama.py:93) ---- */
 typedef struct {

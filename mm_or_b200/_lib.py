@@ -76,6 +76,8 @@ _SIGS = {
     "b200_prof_family_name": (ctypes.c_char_p, [ci]),
     "b200_prof_collect": (ci, [vp, vp, vp, vp]),
     "b200_gemm_bf16": (ci, [vp, ci, vp, ci, vp, ci, ci, ci, ci, vp, vp, ci, vp, ci, ci, ci, vp]),
+    "b200_gemm_skinny_workspace_bytes": (sz, [ci, ci, ci]),
+    "b200_gemm_bf16_skinny": (ci, [vp, ci, vp, ci, vp, ci, ci, ci, ci, vp, vp, ci, ci, ci, ci, vp, sz, vp]),
     "b200_layernorm": (ci, [vp, i64, vp, vp, ci, vp, vp, cf, vp, i64, ci, ci, vp]),
     "b200_rmsnorm": (ci, [vp, i64, vp, cf, vp, i64, ci, ci, vp]),
     "b200_flash_attention": (ci, [vp, i64, i64, i64, vp, i64, i64, i64, vp, i64, i64, i64, vp, i64, i64, i64,
@@ -94,6 +96,7 @@ _SIGS = {
     "b200_segmask_forward": (ci, [_P(SegmaskWeights), vp, ci, vp, i64, vp, vp, sz, vp]),
     "b200_projector_workspace_bytes": (sz, [_P(ProjectorWeights), ci]),
     "b200_projector_pack": (ci, [_P(ProjectorWeights), vp, ci, vp, vp, vp, ci, vp, ci, vp, sz, vp]),
+    "b200_projector_gather": (ci, [_P(ProjectorWeights), vp, ci, vp, ci, sz, vp, sz, vp]),
     "b200_llama_prefill_workspace_bytes": (sz, [_P(LlamaWeights), ci, ci, ci]),
     "b200_llama_prefill": (ci, [_P(LlamaWeights), vp, vp, vp, _P(KvCache), ci, ci, vp, ci, ci, vp, sz, vp]),
     "b200_llama_decode_workspace_bytes": (sz, [_P(LlamaWeights), ci, ci]),
@@ -172,6 +175,27 @@ def gemm(a, w, out=None, bias=None, residual=None, row_map=None, act=ACT_NONE, o
     rc = lib().b200_gemm_bf16(ptr(a), a.stride(0), ptr(w), w.stride(0), ptr(out), out.stride(0), M, N, K,
                               ptr(bias), ptr(residual), ldr, ptr(row_map), act, int(out_fp32), bn, stream_ptr())
     check(rc, "b200_gemm_bf16")
+    return out
+
+
+def gemm_skinny(a, w, out=None, bias=None, residual=None, act=ACT_NONE, out_fp32=False, splits=0, ws=None):
+    """Decode-step GEMM (M <= 256): out = epilogue(a @ w.T), weights streamed once, split-K reduced in the kernel.
+    ws: uint8 scratch whose first 4096 bytes are zero (allocated and cleared here when None)."""
+    M, K = a.shape
+    N = w.shape[0]
+    assert w.shape[1] == K and a.stride(1) == 1 and w.stride(1) == 1
+    n_out = N // 2 if act == ACT_SWIGLU else N
+    if out is None:
+        out = torch.empty((M, n_out), device=a.device, dtype=torch.float32 if out_fp32 else torch.bfloat16)
+    if ws is None:
+        nb = lib().b200_gemm_skinny_workspace_bytes(M, N, K) * (4 if splits > 8 else 1)
+        ws = torch.empty(max(int(nb), 4096), dtype=torch.uint8, device=a.device)
+        ws[:4096].zero_()
+    ldr = residual.stride(0) if residual is not None else 0
+    rc = lib().b200_gemm_bf16_skinny(ptr(a), a.stride(0), ptr(w), w.stride(0), ptr(out), out.stride(0), M, N, K,
+                                     ptr(bias), ptr(residual), ldr, act, int(out_fp32), splits, ptr(ws), ws.numel(),
+                                     stream_ptr())
+    check(rc, "b200_gemm_bf16_skinny")
     return out
 
 

@@ -43,7 +43,20 @@ int b200_gemm_bf16(const void* A, int lda, const void* W, int ldw, void* C, int 
   return gemm_bf16_tn(static_cast<const bf16*>(A), lda, static_cast<const bf16*>(W), ldw, C, ldc, M, N, K, e,
                       bn_hint, static_cast<cudaStream_t>(stream));
 }
+size_t b200_gemm_skinny_workspace_bytes(int M, int N, int K) { return gemm_skinny_workspace_bytes(M, N, K); }
 
+int b200_gemm_bf16_skinny(const void* A, int lda, const void* W, int ldw, void* C, int ldc, int M, int N, int K,
+                          const void* bias, const void* residual, int ldr, int act, int out_fp32, int splits,
+                          void* workspace, size_t workspace_bytes, b200_stream_t stream) {
+  GemmEpilogue e;
+  e.bias = static_cast<const bf16*>(bias);
+  e.residual = static_cast<const bf16*>(residual);
+  e.ldr = ldr;
+  e.act = act;
+  e.out_fp32 = out_fp32;
+  return gemm_skinny(static_cast<const bf16*>(A), lda, static_cast<const bf16*>(W), ldw, C, ldc, M, N, K, e, splits,
+                     workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
 
 int b200_layernorm(const void* x, int64_t ldx, const int32_t* row_map, const void* add, int period, const void* gamma,
                    const void* beta, float eps, void* out, int64_t ldo, int M, int D, b200_stream_t stream) {

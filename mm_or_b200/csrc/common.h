@@ -82,11 +82,22 @@ struct GemmEpilogue {
   int res_group_stride = 0;  // (lets a compact (B*576)-row GEMM read its residual from a (B, S, D) tensor)
   int act = kActNone;
   int out_fp32 = 0;  // 0: C is bf16, 1: C is fp32
+  // fused GEMM -> all-gather: when n_peers > 0 every bf16 output vector is stored to the same offset of each
+  // peer_c[p] (peer-mapped device pointers over NVLink, this rank's own buffer included) instead of C.
+  int n_peers = 0;
+  void* peer_c[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 // bn_hint: 0 = choose automatically, else one of 32/64/128/256
 int gemm_bf16_tn(const bf16* A, int lda, const bf16* B, int ldb, void* C, int ldc, int M, int N, int K,
                  const GemmEpilogue& epi, int bn_hint, cudaStream_t stream);
+
+// Decode-step GEMM (gemm_skinny.cu): M <= 256, weights streamed once, split-K with an in-kernel ordered reduction.
+// The first gemm_skinny_counter_bytes() of the workspace are per-tile arrival counters: zero on entry, zero on exit.
+size_t gemm_skinny_workspace_bytes(int M, int N, int K);
+static inline size_t gemm_skinny_counter_bytes() { return 4096; }
+int gemm_skinny(const bf16* A, int lda, const bf16* W, int ldw, void* C, int ldc, int M, int N, int K,
+                const GemmEpilogue& epi, int splits_hint, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 
 // ---------------------------------------------------------------------------------------------
 // norms (norm.cu)

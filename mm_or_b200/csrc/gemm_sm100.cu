@@ -255,7 +255,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
                   make_float4(x[j4 * 4], x[j4 * 4 + 1], x[j4 * 4 + 2], x[j4 * 4 + 3]);
           }
         } else {
-          bf16* crow = reinterpret_cast<bf16*>(g.C) + static_cast<size_t>(out_row) * g.ldc + n0;
+          const size_t coff = static_cast<size_t>(out_row) * g.ldc + n0;
+          bf16* crow = reinterpret_cast<bf16*>(g.C) + coff;
 #pragma unroll
           for (int j8 = 0; j8 < 4; ++j8) {
             if (n0 + j8 * 8 < g.N) {
@@ -264,7 +265,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
               o.y = pack_bf16x2(x[j8 * 8 + 2], x[j8 * 8 + 3]);
               o.z = pack_bf16x2(x[j8 * 8 + 4], x[j8 * 8 + 5]);
               o.w = pack_bf16x2(x[j8 * 8 + 6], x[j8 * 8 + 7]);
-              *reinterpret_cast<uint4*>(crow + j8 * 8) = o;
+              if (e.n_peers == 0) {
+                *reinterpret_cast<uint4*>(crow + j8 * 8) = o;
+              } else {
+                // all-gather fused into the epilogue: the tile goes straight into every rank's copy over NVLink
+                for (int p = 0; p < e.n_peers; ++p)
+                  *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(e.peer_c[p]) + coff + j8 * 8) = o;
+              }
             }
           }
         }
@@ -359,6 +366,8 @@ int gemm_bf16_tn(const bf16* A, int lda, const bf16* B, int ldb, void* C, int ld
   if (K % 8 != 0 || N % 8 != 0) return fail(-2, "gemm: K (%d) and N (%d) must be multiples of 8", K, N);
   if (epi.act == kActSwiGLU && (N % 16 != 0 || epi.out_fp32 || epi.residual))
     return fail(-2, "gemm: SwiGLU epilogue needs N %% 16 == 0, bf16 output and no residual");
+  if (epi.n_peers < 0 || epi.n_peers > 8 || (epi.n_peers > 0 && (epi.out_fp32 || epi.act == kActSwiGLU)))
+    return fail(-2, "gemm: peer stores need 1..8 peers, bf16 output and no SwiGLU pairing");
   const int m_tiles = (M + kBM - 1) / kBM;
   int bn = bn_hint;
   if (bn == 0) {

@@ -221,14 +221,27 @@ static size_t llama_prefill_ws(const b200_llama_weights* w, int Bn, int L, int a
   return s;
 }
 
+// scratch of the decode-step GEMMs (split-K partials + tile counters); p == nullptr selects the prefill kernel
+struct SkinnyWs {
+  void* p = nullptr;
+  size_t bytes = 0;
+};
+
+// nn.Linear dispatch: the weight-streaming kernel for the decode step (T <= 256 rows), the tiled one otherwise
+static int linear(const bf16* A, int lda, const bf16* W, int ldw, void* C, int ldc, int T, int N, int K,
+                  const GemmEpilogue& e, const SkinnyWs& sk, cudaStream_t st) {
+  if (sk.p != nullptr && T <= 256) return gemm_skinny(A, lda, W, ldw, C, ldc, T, N, K, e, 0, sk.p, sk.bytes, st);
+  return gemm_bf16_tn(A, lda, W, ldw, C, ldc, T, N, K, e, 0, st);
+}
+
 static int llama_layer(const b200_llama_weights* w, const b200_llama_layer& Ly, bf16* x, bf16* nbuf, bf16* qkv,
                        bf16* act, const int* kv_start, const int* kv_len, bf16* kc, bf16* vc, int cap, int Bn, int L,
                        int decode, const int* state, int ctx_bound, void* dec_ws, size_t dec_ws_bytes,
-                       cudaStream_t st) {
+                       const SkinnyWs& sk, cudaStream_t st) {
   const int D = w->hidden, H = w->heads, T = Bn * L;
   B200_TRY(rmsnorm(x, D, B(Ly.attn_norm), w->rms_eps, nbuf, D, T, D, st));
   GemmEpilogue e;
-  B200_TRY(gemm_bf16_tn(nbuf, D, B(Ly.qkv_w), D, qkv, 3 * D, T, 3 * D, D, e, 0, st));
+  B200_TRY(linear(nbuf, D, B(Ly.qkv_w), D, qkv, 3 * D, T, 3 * D, D, e, sk, st));
   B200_TRY(rope_kv_write(qkv, kv_start, w->rope_cos, w->rope_sin, w->max_pos, kc, vc, Bn, H, L, 0,
                          decode ? state : nullptr, cap, st));
   if (!decode) {
@@ -276,15 +289,15 @@ static int llama_layer(const b200_llama_weights* w, const b200_llama_layer& Ly, 
   GemmEpilogue eo;
   eo.residual = x;
   eo.ldr = D;
-  B200_TRY(gemm_bf16_tn(nbuf, D, B(Ly.o_w), D, x, D, T, D, D, eo, 0, st));
+  B200_TRY(linear(nbuf, D, B(Ly.o_w), D, x, D, T, D, D, eo, sk, st));
   B200_TRY(rmsnorm(x, D, B(Ly.mlp_norm), w->rms_eps, nbuf, D, T, D, st));
   GemmEpilogue eg;
   eg.act = kActSwiGLU;
-  B200_TRY(gemm_bf16_tn(nbuf, D, B(Ly.gate_up_w), D, act, w->ffn, T, 2 * w->ffn, D, eg, 0, st));
+  B200_TRY(linear(nbuf, D, B(Ly.gate_up_w), D, act, w->ffn, T, 2 * w->ffn, D, eg, sk, st));
   GemmEpilogue ed;
   ed.residual = x;
   ed.ldr = D;
-  B200_TRY(gemm_bf16_tn(act, w->ffn, B(Ly.down_w), w->ffn, x, D, T, D, w->ffn, ed, 0, st));
+  B200_TRY(linear(act, w->ffn, B(Ly.down_w), w->ffn, x, D, T, D, w->ffn, ed, sk, st));
   return 0;
 }
 
@@ -306,7 +319,7 @@ static int llama_prefill(const b200_llama_weights* w, bf16* x, const int* kv_sta
     bf16* kc = static_cast<bf16*>(c->k) + l * c->layer_stride;
     bf16* vc = static_cast<bf16*>(c->v) + l * c->layer_stride;
     B200_TRY(llama_layer(w, w->layers[l], x, nbuf, qkv, act, kv_start, kv_len, kc, vc, c->cap, Bn, L, 0, nullptr, 0,
-                         nullptr, 0, st));
+                         nullptr, 0, SkinnyWs{}, st));
   }
   if (logits != nullptr) {
     GemmEpilogue e;
@@ -324,6 +337,16 @@ static int llama_prefill(const b200_llama_weights* w, bf16* x, const int* kv_sta
   return 0;
 }
 
+static size_t llama_skinny_ws(const b200_llama_weights* w, int Bn) {
+  if (Bn > 256) return 0;
+  const int D = w->hidden, F = w->ffn;
+  size_t m = gemm_skinny_workspace_bytes(Bn, 3 * D, D);
+  const size_t c[4] = {gemm_skinny_workspace_bytes(Bn, D, D), gemm_skinny_workspace_bytes(Bn, 2 * F, D),
+                       gemm_skinny_workspace_bytes(Bn, D, F), gemm_skinny_workspace_bytes(Bn, w->vocab, D)};
+  for (size_t v : c) m = v > m ? v : m;
+  return m;
+}
+
 static size_t llama_decode_ws(const b200_llama_weights* w, int Bn, int cap) {
   size_t s = 0;
   s += al(static_cast<size_t>(Bn) * w->hidden * 2) * 2;  // x, norm/context
@@ -331,6 +354,7 @@ static size_t llama_decode_ws(const b200_llama_weights* w, int Bn, int cap) {
   s += al(static_cast<size_t>(Bn) * w->ffn * 2);         // swiglu
   s += al(static_cast<size_t>(Bn) * w->vocab * 2);       // logits
   s += al(decode_attn_workspace_bytes(Bn, w->heads, 16));
+  s += al(llama_skinny_ws(w, Bn));
   (void)cap;
   return s;
 }
@@ -350,17 +374,23 @@ static int llama_decode_step(const b200_llama_weights* w, int* tokens, int* stat
   bf16* logits = a.take<bf16>(static_cast<size_t>(Bn) * w->vocab);
   const size_t dws_bytes = decode_attn_workspace_bytes(Bn, w->heads, 16);
   void* dws = a.take<uint8_t>(dws_bytes);
+  SkinnyWs sk;
+  sk.bytes = llama_skinny_ws(w, Bn);
+  if (sk.bytes > 0) {
+    sk.p = a.take<uint8_t>(sk.bytes);
+    B200_CUDA_OK(cudaMemsetAsync(sk.p, 0, gemm_skinny_counter_bytes(), st));  // split-K tile counters
+  }
   if (logits_out != nullptr) logits = static_cast<bf16*>(logits_out);
   B200_TRY(embed_rows(tokens, B(w->embed_tokens), x, D, Bn, D, w->vocab, st));
   for (int l = 0; l < w->n_layers; ++l) {
     bf16* kc = static_cast<bf16*>(c->k) + l * c->layer_stride;
     bf16* vc = static_cast<bf16*>(c->v) + l * c->layer_stride;
     B200_TRY(llama_layer(w, w->layers[l], x, nbuf, qkv, act, kv_start, nullptr, kc, vc, c->cap, Bn, 1, 1, state,
-                         ctx_bound, dws, dws_bytes, st));
+                         ctx_bound, dws, dws_bytes, sk, st));
   }
   B200_TRY(rmsnorm(x, D, B(w->final_norm), w->rms_eps, nbuf, D, Bn, D, st));
   GemmEpilogue e;
-  B200_TRY(gemm_bf16_tn(nbuf, D, B(w->lm_head), D, logits, w->vocab, Bn, w->vocab, D, e, 0, st));
+  B200_TRY(linear(nbuf, D, B(w->lm_head), D, logits, w->vocab, Bn, w->vocab, D, e, sk, st));
   B200_TRY(argmax_rows(logits, 0, w->vocab, Bn, w->vocab, tokens, finished, eos_id, pad_id, history, hist_ld, 0,
                        state + 1, st));
   B200_TRY(bump_counters(state, st));
@@ -427,6 +457,32 @@ int b200_projector_pack(const b200_projector_weights* w, const void* tokens, int
   if (text_ids != nullptr)
     B200_TRY(embed_rows(text_ids, B(embed_table), static_cast<bf16*>(embeds), w->hidden, n_rows, w->hidden, vocab, st));
   return 0;
+}
+
+int b200_projector_gather(const b200_projector_weights* w, const void* tokens, int n_tokens, void* const* peers,
+                          int n_peers, size_t slot_offset_bytes, void* workspace, size_t workspace_bytes,
+                          b200_stream_t stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (n_tokens <= 0) return 0;
+  if (n_peers < 1 || n_peers > 8 || peers == nullptr) return fail(-2, "projector_gather: 1..8 peer buffers expected");
+  if (slot_offset_bytes % 16 != 0) return fail(-2, "projector_gather: slot offset must be 16-byte aligned");
+  if (workspace_bytes < b200_projector_workspace_bytes(w, n_tokens))
+    return fail(-2, "projector_gather: workspace too small");
+  bf16* h = static_cast<bf16*>(workspace);
+  GemmEpilogue e0;
+  e0.bias = B(w->b0);
+  e0.act = kActGeluErf;
+  B200_TRY(gemm_bf16_tn(B(tokens), w->in_dim, B(w->w0), w->in_dim, h, w->hidden, n_tokens, w->hidden, w->in_dim, e0, 0,
+                        st));
+  GemmEpilogue e2;
+  e2.bias = B(w->b2);
+  e2.n_peers = n_peers;
+  for (int p = 0; p < n_peers; ++p) {
+    if (peers[p] == nullptr) return fail(-2, "projector_gather: peer %d is NULL", p);
+    e2.peer_c[p] = static_cast<uint8_t*>(peers[p]) + slot_offset_bytes;
+  }
+  return gemm_bf16_tn(h, w->hidden, B(w->w2), w->hidden, e2.peer_c[0], w->hidden, n_tokens, w->hidden, w->hidden, e2, 0,
+                      st);
 }
 
 size_t b200_llama_prefill_workspace_bytes(const b200_llama_weights* w, int Bn, int L, int all_logits) {

@@ -1,0 +1,89 @@
+"""Multi-GPU plumbing of the MM2SG inference path: one process per GPU, weights replicated, samples
+sharded across ranks, one exchange step -- the all-gather of projected visual tokens before LLM fusion.
+
+The reference has no multi-GPU inference path (its eval runs one process on one GPU, scene_graph_prediction/main.py:
+57-60; only training is data parallel through HF Trainer / DeepSpeed). BASELINE.json's north_star defines the
+partitioning: every rank encodes the views of its own samples (CLIP ViT + pooler + projector), the projected tokens
+(B_local, T_vis, 4096) are all-gathered over NVLink, and every rank then decodes a slice of the gathered batch.
+
+Two exchange implementations:
+  * `all_gather_tokens`  -- torch.distributed all_gather_into_tensor (NCCL on GPUs; gloo in the CPU tests)
+  * `PeerGather`         -- symmetric-memory buffer whose peer pointers are handed to the projector GEMM so that its
+                            epilogue stores every output tile straight into all ranks' copies (b200_projector_pack
+                            with `peers`): the transfer overlaps the GEMM tile by tile and no separate collective runs.
+Host logic here is device agnostic so that world_size-2 gloo tests on CPU cover it.
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n, rank, world):
+    """Contiguous block partition of n units over `world` ranks (first n % world ranks get one extra)."""
+    if world <= 0 or not 0 <= rank < world:
+        raise ValueError(f"bad rank/world {rank}/{world}")
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def decode_owner(rank, world, shift=0):
+    """Which rank's encoded samples `rank` decodes. shift = 0: its own (the gathered copy is then only read locally);
+    shift != 0 rotates the assignment, which is how the tests prove that the gathered tokens are the peers' tokens."""
+    return (rank + shift) % world
+
+
+def all_gather_tokens(local, group=None):
+    """local (B_local, T, D), same shape on every rank -> (world, B_local, T, D) ordered by rank."""
+    world = dist.get_world_size(group)
+    out = torch.empty((world,) + tuple(local.shape), dtype=local.dtype, device=local.device)
+    if local.is_cuda:
+        dist.all_gather_into_tensor(out.view(-1), local.contiguous().view(-1), group=group)
+    else:  # gloo has no all_gather_into_tensor for every dtype (bf16): go through a list of views
+        src = local.contiguous()
+        if src.dtype == torch.bfloat16:
+            raw = src.view(torch.uint8)
+            parts = [torch.empty_like(raw) for _ in range(world)]
+            dist.all_gather(parts, raw, group=group)
+            for r, p in enumerate(parts):
+                out[r] = p.view(torch.bfloat16)
+        else:
+            parts = [torch.empty_like(src) for _ in range(world)]
+            dist.all_gather(parts, src, group=group)
+            for r, p in enumerate(parts):
+                out[r] = p
+    return out
+
+
+def all_gather_objects_equal(value, group=None):
+    """True iff `value` (small python object) is identical on every rank; used to validate batch geometry."""
+    world = dist.get_world_size(group)
+    got = [None] * world
+    dist.all_gather_object(got, value, group=group)
+    return all(g == got[0] for g in got), got
+
+
+class PeerGather:
+    """Symmetric (world, B_local, T, D) bf16 buffer on every rank with every peer's base pointer, for the fused
+    projector-GEMM + all-gather epilogue. Needs CUDA, NVLink peer access and torch symmetric memory."""
+
+    def __init__(self, b_local, t_vis, hidden, group=None):
+        import torch.distributed._symmetric_memory as symm
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self.shape = (self.world, b_local, t_vis, hidden)
+        self.buf = symm.empty(self.shape, dtype=torch.bfloat16, device=torch.device("cuda", torch.cuda.current_device()))
+        self.hdl = symm.rendezvous(self.buf, self.group)
+        self.peer_ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        if len(self.peer_ptrs) != self.world:
+            raise RuntimeError("symmetric memory rendezvous returned %d peers for world %d"
+                               % (len(self.peer_ptrs), self.world))
+
+    def slot_offset_bytes(self):
+        """Byte offset of this rank's (B_local, T, D) slot inside every peer's buffer."""
+        _, b, t, d = self.shape
+        return self.rank * b * t * d * 2
+
+    def barrier(self):
+        """All peers' stores into this rank's buffer have landed (device-side signal pads) -- call after the GEMM."""
+        self.hdl.barrier()

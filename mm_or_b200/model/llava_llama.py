@@ -388,6 +388,9 @@ class LlavaLlamaForCausalLM:
         self.pooler_chunk = 16
         self.training = False
         self._pg = None
+        self._exchange = "peer"
+        self._decode_shift = 0
+        self._peer = None
 
     # ---- reference accessors --------------------------------------------------------------------------------
     def get_model(self):
@@ -406,10 +409,49 @@ class LlavaLlamaForCausalLM:
     def to(self, *a, **k):
         return self
 
-    def set_process_group(self, group):
-        """Multi-GPU inference: every rank encodes its own samples; the projected visual tokens are
-        all-gathered over NCCL/NVLink before LLM fusion and each rank decodes its slice of the gathered batch."""
+    def set_process_group(self, group, exchange="peer", decode_shift=0):
+        """Multi-GPU inference: every rank encodes the views of its own samples; the projected visual
+        tokens are all-gathered over NVLink before LLM fusion and each rank decodes the slice of the gathered batch
+        that rank (rank + decode_shift) % world encoded (`input_ids` passed to generate()/forward() are that slice's).
+        exchange = "peer": the second projector GEMM stores its output tiles into every rank's symmetric buffer
+        (fused GEMM + all-gather, b200_projector_gather); "nccl": projector, then ncclAllGather."""
+        import torch.distributed as dist
+        if exchange not in ("peer", "nccl"):
+            raise ValueError(f"unknown exchange {exchange!r}")
         self._pg = group
+        self._exchange = exchange
+        self._decode_shift = int(decode_shift)
+        self._peer = None
+        if group is not None and dist.get_world_size(group) > 8:
+            raise ValueError("one NVSwitch box: at most 8 ranks")
+
+    def _project_and_gather(self, pooled):
+        """pooled (B, T_vis, 1024) of this rank's samples -> projected tokens (B, T_vis, D) of the samples this rank
+        decodes, after the all-gather over ranks."""
+        import torch.distributed as dist
+        from .. import dist as D_
+        world, rank = dist.get_world_size(self._pg), dist.get_rank(self._pg)
+        owner = D_.decode_owner(rank, world, self._decode_shift)
+        B, t_vis, _ = pooled.shape
+        Dh = self.config.hidden_size
+        proj = self.model.mm_projector
+        if self._exchange == "peer":
+            if self._peer is None or self._peer.shape != (world, B, t_vis, Dh):
+                self._peer = D_.PeerGather(B, t_vis, Dh, self._pg)
+            pg = self._peer
+            pg.barrier()                              # every reader of the previous step's tokens is done
+            lib = L.lib()
+            n = B * t_vis
+            nb = lib.b200_projector_workspace_bytes(ctypes.byref(proj._w), n)
+            ws = proj._ws.get(nb, self.device)
+            peers = (ctypes.c_void_p * world)(*pg.peer_ptrs)
+            L.check(lib.b200_projector_gather(ctypes.byref(proj._w), L.ptr(pooled.view(n, -1)), n, peers, world,
+                                              pg.slot_offset_bytes(), L.ptr(ws), ws.numel(), L.stream_ptr()),
+                    "b200_projector_gather")
+            pg.barrier()                              # all peers' tiles have landed in this rank's copy
+            return pg.buf[owner]
+        local = proj(pooled)                                                      # (B, T_vis, D)
+        return D_.all_gather_tokens(local, self._pg)[owner]
 
     def resize_token_embeddings(self, n):
         if n != self.config.vocab_size:
@@ -512,9 +554,22 @@ class LlavaLlamaForCausalLM:
                          getattr(self.config, "tokenizer_model_max_length", None))
         D = self.config.hidden_size
         embeds = torch.empty((B, plan.L, D), device=self.device, dtype=BF)
-        self.model.mm_projector.project_pack(pooled.view(B * t_vis, -1), _i32(plan.row_map, self.device),
-                                             _i32(plan.src.reshape(-1), self.device), self.model.embed_tokens,
-                                             self.config.vocab_size, embeds, B * plan.L)
+        if self._pg is None:
+            self.model.mm_projector.project_pack(pooled.view(B * t_vis, -1), _i32(plan.row_map, self.device),
+                                                 _i32(plan.src.reshape(-1), self.device), self.model.embed_tokens,
+                                                 self.config.vocab_size, embeds, B * plan.L)
+        else:
+            vis = self._project_and_gather(pooled)                                # (B, T_vis, D), gathered copy
+            src = plan.src.reshape(B, plan.L).astype(np.int64)
+            # two row gathers into the packed buffer: text / pad rows from embed_tokens, visual rows from `vis`
+            text_ids = np.where(src >= -1, src, -2).astype(np.int32)
+            vis_ids = np.where(src <= -2, np.arange(B)[:, None] * t_vis + (-2 - src), -2).astype(np.int32)
+            lib = L.lib()
+            L.check(lib.b200_embed_rows(L.ptr(_i32(text_ids.reshape(-1), self.device)), L.ptr(self.model.embed_tokens),
+                                        L.ptr(embeds), D, B * plan.L, D, self.config.vocab_size, L.stream_ptr()),
+                    "b200_embed_rows")
+            L.check(lib.b200_embed_rows(L.ptr(_i32(vis_ids.reshape(-1), self.device)), L.ptr(vis), L.ptr(embeds), D,
+                                        B * plan.L, D, B * t_vis, L.stream_ptr()), "b200_embed_rows")
         new_labels = None if labels is None else torch.from_numpy(plan.labels).to(self.device)
         am = None if attention_mask is None else torch.from_numpy(plan.mask).to(self.device).to(attention_mask.dtype)
         pos = None if position_ids is None else torch.from_numpy(plan.pos).to(self.device)

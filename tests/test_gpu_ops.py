@@ -79,6 +79,56 @@ def test_gemm_epilogues(L, bn):
     assert rel_err(out, ref) < 5e-3
 
 
+# ---------------------------------------------------------------- decode-step GEMM --------------------------------
+@pytest.mark.parametrize("M", [1, 7, 32, 33, 64, 100, 128, 200, 256])
+@pytest.mark.parametrize("N,K", [(4096, 4096), (12288, 4096), (4096, 11008), (32000, 4096), (264, 72), (1024, 512)])
+def test_gemm_skinny_shapes(L, M, N, K):
+    a, w = rnd(M, K, seed=1), rnd(N, K, scale=1 / math.sqrt(K), seed=2)
+    assert rel_err(L.gemm_skinny(a, w), ref_gemm(a, w)) < 5e-3
+
+
+@pytest.mark.parametrize("splits", [1, 2, 3, 4, 8, 16])
+def test_gemm_skinny_splits_and_epilogues(L, splits):
+    M, N, K = 64, 1024, 2048
+    a, w = rnd(M, K, seed=3), rnd(N, K, scale=1 / math.sqrt(K), seed=4)
+    bias, res = rnd(N, seed=5), rnd(M, N, seed=6)
+    kw = dict(splits=splits)
+    assert rel_err(L.gemm_skinny(a, w, bias=bias, **kw), ref_gemm(a, w, bias)) < 5e-3
+    assert rel_err(L.gemm_skinny(a, w, bias=bias, act=1, **kw), ref_gemm(a, w, bias, act=1)) < 5e-3
+    assert rel_err(L.gemm_skinny(a, w, bias=bias, act=2, **kw), ref_gemm(a, w, bias, act=2)) < 5e-3
+    assert rel_err(L.gemm_skinny(a, w, act=3, **kw), ref_gemm(a, w, act=3)) < 5e-3
+    assert rel_err(L.gemm_skinny(a, w, bias=bias, residual=res, **kw), ref_gemm(a, w, bias, res)) < 5e-3
+    assert rel_err(L.gemm_skinny(a, w, bias=bias, out_fp32=True, **kw), ref_gemm(a, w, bias)) < 1e-5
+    x = res.clone()
+    L.gemm_skinny(a, w, out=x, bias=bias, residual=x, **kw)        # in-place residual, as the decoder uses it
+    assert rel_err(x, ref_gemm(a, w, bias, res)) < 5e-3
+
+
+def test_gemm_skinny_deterministic_and_reusable_workspace(L):
+    """Split-K partials are summed in split order by the last-arriving CTA: repeated launches are bit-identical, and
+    the tile counters are back at zero afterwards (the decode step reuses one workspace for every GEMM of a step)."""
+    M, N, K = 48, 4096, 11008
+    a, w = rnd(M, K, seed=7), rnd(N, K, scale=1 / math.sqrt(K), seed=8)
+    nb = L.lib().b200_gemm_skinny_workspace_bytes(M, N, K)
+    ws = torch.empty(nb, dtype=torch.uint8, device="cuda")
+    ws[:4096].zero_()
+    first = L.gemm_skinny(a, w, ws=ws)
+    for _ in range(5):
+        assert torch.equal(L.gemm_skinny(a, w, ws=ws), first)
+    torch.cuda.synchronize()
+    assert int(ws[:4096].view(torch.int32).abs().sum()) == 0
+    assert rel_err(first, ref_gemm(a, w)) < 5e-3
+    # same bits as the tiled prefill kernel up to fp32 summation order: compare in bf16 ulps
+    assert rel_err(first, L.gemm(a, w)) < 2e-3
+
+
+def test_gemm_skinny_bad_args(L):
+    with pytest.raises(L.B200Error):
+        L.gemm_skinny(rnd(300, 64), rnd(128, 64))     # M > 256
+    with pytest.raises(L.B200Error):
+        L.gemm_skinny(rnd(8, 60), rnd(128, 60))       # K not a multiple of 8
+
+
 def test_gemm_bad_args(L):
     with pytest.raises(L.B200Error):
         L.gemm(rnd(8, 60), rnd(16, 60))         # K not a multiple of 8

@@ -147,6 +147,48 @@ def perf():
         log(f"perf {name:24s} cuBLAS(torch.matmul): {ms*1e3:9.1f} us  {2.0*M*N*K/ms/1e9:8.1f} TFLOP/s")
 
 
+def skinny():
+    """Decode-step GEMM shapes with COLD weights: every launch reads a different copy out of a pool larger than L2
+    (in the decode step each weight matrix is read once per 13 GB pass)."""
+    shapes = [("qkv", 12288, 4096), ("o", 4096, 4096), ("gateup", 22016, 4096), ("down", 4096, 11008),
+              ("lm_head", 32000, 4096)]
+    for M in (64, 128):
+        tot_best = 0.0
+        for name, N, K in shapes:
+            copies = max(2, int(400e6 // (N * K * 2)) + 1)
+            ws_ = [torch.randn(N, K, device="cuda", dtype=torch.bfloat16) / math.sqrt(K) for _ in range(copies)]
+            a = torch.randn(M, K, device="cuda", dtype=torch.bfloat16)
+            out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+            nb = L.lib().b200_gemm_skinny_workspace_bytes(M, N, K) * 4
+            scratch = torch.zeros(nb, dtype=torch.uint8, device="cuda")
+            variants = [("tiled bn=0", lambda w: L.gemm(a, w, out=out)),
+                        ("tiled bn=128", lambda w: L.gemm(a, w, out=out, bn=128))]
+            for sp in (0, 1, 2, 4, 8, 16):
+                variants.append((f"skinny splits={sp}", lambda w, sp=sp: L.gemm_skinny(a, w, out=out, splits=sp, ws=scratch)))
+            variants.append(("cuBLAS", lambda w: torch.matmul(a, w.t(), out=out)))
+            best = 1e9
+            for vn, fn in variants:
+                for i in range(copies):
+                    fn(ws_[i])
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                iters = 3 * copies
+                e0.record()
+                for i in range(iters):
+                    fn(ws_[i % copies])
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / iters
+                gbs = (M * K + N * K + M * N) * 2 / ms / 1e6
+                if vn.startswith("skinny"):
+                    best = min(best, ms)
+                log(f"skinny M={M:4d} {name:8s} N={N} K={K} {vn:18s}: {ms*1e3:8.1f} us  {gbs:7.1f} GB/s")
+            tot_best += best * (32 if name != "lm_head" else 1)
+            del ws_
+        log(f"skinny M={M}: best-variant sum over 32 layers + lm_head = {tot_best:.2f} ms/step "
+            f"(13.2 GB at 6.45 TB/s = 2.05 ms)")
+
+
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "basic"
     t0 = time.time()
@@ -155,6 +197,9 @@ if __name__ == "__main__":
         r = basic()
     elif which == "epi":
         r = epi()
+    elif which == "skinny":
+        skinny()
+        r = True
     else:
         perf()
         r = True
