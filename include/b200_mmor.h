@@ -62,13 +62,12 @@ int b200_gemm_bf16(const void* A, int lda, const void* W, int ldw, void* C, int 
                    int bn_hint, b200_stream_t stream);
 
 /* Same contract for M <= 256 rows (the single-token decode step, model/llava_arch.py:192-201 -> HF LlamaDecoderLayer /
- * lm_head): weights are the tensor-core M operand and are streamed exactly once, K is split across CTAs and reduced in
- * split order inside the kernel (deterministic). No row_map. splits: 0 = auto. The first 4096 bytes of `workspace`
- * are tile counters and must be ZERO on entry (the kernel leaves them zero); size by the *_workspace_bytes call. */
-size_t b200_gemm_skinny_workspace_bytes(int M, int N, int K);
+ * lm_head), HBM bound: weights are the tensor-core M operand and are streamed exactly once; K is split over a
+ * thread-block cluster and reduced through distributed shared memory in split order (deterministic). No row_map.
+ * splits: 0 = auto, else 1/2/4/8. */
 int b200_gemm_bf16_skinny(const void* A, int lda, const void* W, int ldw, void* C, int ldc, int M, int N, int K,
                           const void* bias, const void* residual, int ldr, int act, int out_fp32, int splits,
-                          void* workspace, size_t workspace_bytes, b200_stream_t stream);
+                          b200_stream_t stream);
 
 /* y = LayerNorm(gather(x)[row] + add[row % period]) * gamma + beta  (HF CLIP LayerNorm eps 1e-5, BERT eps 1e-12).
  * row_map (source row per output row, <0 = zero row), add may be NULL. */
@@ -251,6 +250,34 @@ int b200_llama_decode_step(const b200_llama_weights* w, int32_t* tokens, int32_t
                            const b200_kv_cache* cache, int B, int ctx_bound, int32_t* finished, int eos_id, int pad_id,
                            int32_t* history, int hist_ld, void* logits_out, void* workspace, size_t workspace_bytes,
                            b200_stream_t stream);
+
+/* ============================================================================================================
+ * Training-side operators (fine-tune step)
+ * ========================================================================================================== */
+
+/* LLaVATrainer.compute_loss (train/llava_trainer.py:136-174): shifted cross-entropy of `logits` [B*L, V] against the
+ * UNshifted modified_labels [B, L] (row (b, l) is scored against label (b, l + 1); -100 = ignored) with per-class
+ * weights vocab_weight [V] (nn.CrossEntropyLoss(weight=...) semantics, NULL = unweighted):
+ *     loss_out[0] = sum_i w[y_i] nll_i / sum_i w[y_i],   loss_out[1] = sum_i w[y_i].
+ * dlogits (same dtype / shape as logits, may alias them, may be NULL) receives grad_scale * dloss/dlogits; rows
+ * without a label are zero-filled. Deterministic (fixed-order reductions). */
+size_t b200_weighted_ce_workspace_bytes(int B, int L);
+int b200_weighted_ce(const void* logits, int logits_fp32, int64_t ld, const int64_t* labels, const float* vocab_weight,
+                     int B, int L, int V, float grad_scale, void* dlogits, int64_t ldd, float* loss_out,
+                     void* workspace, size_t workspace_bytes, b200_stream_t stream);
+
+/* HF Trainer gradient clipping (max_grad_norm, README.md:151) + torch.optim.AdamW as configured by
+ * LLaVATrainer.create_optimizer (train/llava_trainer.py:191-278), on flat buffers.
+ * b200_grad_sq_norm: out2[0] (+)= sum(grad^2) over a bf16 gradient buffer (accumulate != 0 chains buffers),
+ * out2[1] = min(1, max_norm / (sqrt(out2[0]) + 1e-6)) (1 when max_norm <= 0). Deterministic two-stage sum.
+ * b200_adamw_step: one pass over fp32 master weights / m / v with bf16 gradients scaled by *clip_coef (device
+ * pointer, NULL = 1): decoupled weight decay, bias-corrected Adam update (step counts from 1), bf16 copy of the new
+ * weights written to `param` (may be NULL). */
+size_t b200_grad_norm_workspace_bytes(void);
+int b200_grad_sq_norm(const void* grad, int64_t n, int accumulate, float max_norm, float* out2, void* workspace,
+                      size_t workspace_bytes, b200_stream_t stream);
+int b200_adamw_step(float* master, void* param, const void* grad, float* m, float* v, int64_t n, float lr, float beta1,
+                    float beta2, float eps, float weight_decay, int step, const float* clip_coef, b200_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -76,8 +76,12 @@ _SIGS = {
     "b200_prof_family_name": (ctypes.c_char_p, [ci]),
     "b200_prof_collect": (ci, [vp, vp, vp, vp]),
     "b200_gemm_bf16": (ci, [vp, ci, vp, ci, vp, ci, ci, ci, ci, vp, vp, ci, vp, ci, ci, ci, vp]),
-    "b200_gemm_skinny_workspace_bytes": (sz, [ci, ci, ci]),
-    "b200_gemm_bf16_skinny": (ci, [vp, ci, vp, ci, vp, ci, ci, ci, ci, vp, vp, ci, ci, ci, ci, vp, sz, vp]),
+    "b200_gemm_bf16_skinny": (ci, [vp, ci, vp, ci, vp, ci, ci, ci, ci, vp, vp, ci, ci, ci, ci, vp]),
+    "b200_weighted_ce_workspace_bytes": (sz, [ci, ci]),
+    "b200_weighted_ce": (ci, [vp, ci, i64, vp, vp, ci, ci, ci, cf, vp, i64, vp, vp, sz, vp]),
+    "b200_grad_norm_workspace_bytes": (sz, []),
+    "b200_grad_sq_norm": (ci, [vp, i64, ci, cf, vp, vp, sz, vp]),
+    "b200_adamw_step": (ci, [vp, vp, vp, vp, vp, i64, cf, cf, cf, cf, cf, ci, vp, vp]),
     "b200_layernorm": (ci, [vp, i64, vp, vp, ci, vp, vp, cf, vp, i64, ci, ci, vp]),
     "b200_rmsnorm": (ci, [vp, i64, vp, cf, vp, i64, ci, ci, vp]),
     "b200_flash_attention": (ci, [vp, i64, i64, i64, vp, i64, i64, i64, vp, i64, i64, i64, vp, i64, i64, i64,
@@ -178,25 +182,51 @@ def gemm(a, w, out=None, bias=None, residual=None, row_map=None, act=ACT_NONE, o
     return out
 
 
-def gemm_skinny(a, w, out=None, bias=None, residual=None, act=ACT_NONE, out_fp32=False, splits=0, ws=None):
-    """Decode-step GEMM (M <= 256): out = epilogue(a @ w.T), weights streamed once, split-K reduced in the kernel.
-    ws: uint8 scratch whose first 4096 bytes are zero (allocated and cleared here when None)."""
+def gemm_skinny(a, w, out=None, bias=None, residual=None, act=ACT_NONE, out_fp32=False, splits=0):
+    """Decode-step GEMM (M <= 256): out = epilogue(a @ w.T), weights streamed once, K split over a cluster."""
     M, K = a.shape
     N = w.shape[0]
     assert w.shape[1] == K and a.stride(1) == 1 and w.stride(1) == 1
     n_out = N // 2 if act == ACT_SWIGLU else N
     if out is None:
         out = torch.empty((M, n_out), device=a.device, dtype=torch.float32 if out_fp32 else torch.bfloat16)
-    if ws is None:
-        nb = lib().b200_gemm_skinny_workspace_bytes(M, N, K) * (4 if splits > 8 else 1)
-        ws = torch.empty(max(int(nb), 4096), dtype=torch.uint8, device=a.device)
-        ws[:4096].zero_()
     ldr = residual.stride(0) if residual is not None else 0
     rc = lib().b200_gemm_bf16_skinny(ptr(a), a.stride(0), ptr(w), w.stride(0), ptr(out), out.stride(0), M, N, K,
-                                     ptr(bias), ptr(residual), ldr, act, int(out_fp32), splits, ptr(ws), ws.numel(),
-                                     stream_ptr())
+                                     ptr(bias), ptr(residual), ldr, act, int(out_fp32), splits, stream_ptr())
     check(rc, "b200_gemm_bf16_skinny")
     return out
+
+
+def weighted_ce(logits, labels, vocab_weight=None, grad_scale=1.0, want_grad=False, inplace=False):
+    """LLaVATrainer.compute_loss. logits (B, L, V) fp32/bf16, labels (B, L) int64 unshifted modified_labels.
+    Returns (loss 0-dim fp32 tensor, weight sum, dlogits or None)."""
+    B, Lq, V = logits.shape
+    assert logits.is_contiguous() and labels.is_contiguous() and labels.dtype == torch.int64
+    is32 = logits.dtype == torch.float32
+    dl = (logits if inplace else torch.empty_like(logits)) if want_grad else None
+    out = torch.empty(2, device=logits.device, dtype=torch.float32)
+    ws = torch.empty(int(lib().b200_weighted_ce_workspace_bytes(B, Lq)), dtype=torch.uint8, device=logits.device)
+    vw = None if vocab_weight is None else vocab_weight.to(device=logits.device, dtype=torch.float32).contiguous()
+    check(lib().b200_weighted_ce(ptr(logits), int(is32), V, ptr(labels), ptr(vw), B, Lq, V, float(grad_scale),
+                                 ptr(dl), V, ptr(out), ptr(ws), ws.numel(), stream_ptr()), "b200_weighted_ce")
+    return out[0], out[1], dl
+
+
+def grad_sq_norm(grad, out2=None, accumulate=False, max_norm=0.0):
+    """out2[0] (+)= sum(grad^2), out2[1] = clip coefficient for max_norm. grad: flat bf16 tensor."""
+    if out2 is None:
+        out2 = torch.zeros(2, device=grad.device, dtype=torch.float32)
+    ws = torch.empty(int(lib().b200_grad_norm_workspace_bytes()), dtype=torch.uint8, device=grad.device)
+    check(lib().b200_grad_sq_norm(ptr(grad), grad.numel(), int(accumulate), float(max_norm), ptr(out2), ptr(ws),
+                                  ws.numel(), stream_ptr()), "b200_grad_sq_norm")
+    return out2
+
+
+def adamw_step(master, param, grad, m, v, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, step=1,
+               clip_coef=None):
+    """Fused AdamW on flat buffers: master/m/v fp32, grad bf16, param bf16 copy (or None)."""
+    check(lib().b200_adamw_step(ptr(master), ptr(param), ptr(grad), ptr(m), ptr(v), master.numel(), lr, beta1, beta2,
+                                eps, weight_decay, int(step), ptr(clip_coef), stream_ptr()), "b200_adamw_step")
 
 
 def layernorm(x, gamma, beta, eps, row_map=None, add=None, out=None):

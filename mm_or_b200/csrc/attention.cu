@@ -14,6 +14,8 @@
 //  decode_attn_kernel    one new token per sequence against the bf16 KV cache (llava_arch.py:192-201 +
 //      HF LlamaAttention with past_key_values). One query row per (sequence, head): a pure HBM-bound
 //      stream over K and V with 16-byte vector loads; no tensor cores needed.
+#include <cstdlib>
+
 #include "common.h"
 #include "ptx.cuh"
 
@@ -236,12 +238,17 @@ __global__ void __launch_bounds__(kFaThreads) flash_attn_kernel(const AttnArgs a
   }
 }
 
+int flash_attn_tc(const AttnArgs& a, int head_dim, cudaStream_t stream);  // attention_sm100.cu
+
 int flash_attn(const AttnArgs& a, int head_dim, cudaStream_t stream) {
   if (a.B <= 0 || a.H <= 0 || a.Lq <= 0) return 0;
   dim3 grid((a.Lq + kFaBM - 1) / kFaBM, a.H, a.B);
   const double qk = static_cast<double>(a.B) * a.H * a.Lq * a.Lk * (a.causal ? 0.5 : 1.0);
   LaunchScope scope(kFamFlashAttn, stream,
                     2.0 * a.B * a.H * head_dim * (2.0 * a.Lq + 2.0 * a.Lk), 4.0 * qk * head_dim);
+  // the tcgen05 kernel is the product path; the mma.sync kernel below stays only as an A/B reference for bring-up
+  static const bool legacy = getenv("B200_FA_LEGACY") != nullptr;
+  if (!legacy) return flash_attn_tc(a, head_dim, stream);
   if (head_dim == 64) {
     constexpr int smem = (4 * kFaBN + kFaBM) * 64 * 2;
     static bool cfg = false;

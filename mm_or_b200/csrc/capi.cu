@@ -43,11 +43,10 @@ int b200_gemm_bf16(const void* A, int lda, const void* W, int ldw, void* C, int 
   return gemm_bf16_tn(static_cast<const bf16*>(A), lda, static_cast<const bf16*>(W), ldw, C, ldc, M, N, K, e,
                       bn_hint, static_cast<cudaStream_t>(stream));
 }
-size_t b200_gemm_skinny_workspace_bytes(int M, int N, int K) { return gemm_skinny_workspace_bytes(M, N, K); }
 
 int b200_gemm_bf16_skinny(const void* A, int lda, const void* W, int ldw, void* C, int ldc, int M, int N, int K,
                           const void* bias, const void* residual, int ldr, int act, int out_fp32, int splits,
-                          void* workspace, size_t workspace_bytes, b200_stream_t stream) {
+                          b200_stream_t stream) {
   GemmEpilogue e;
   e.bias = static_cast<const bf16*>(bias);
   e.residual = static_cast<const bf16*>(residual);
@@ -55,7 +54,31 @@ int b200_gemm_bf16_skinny(const void* A, int lda, const void* W, int ldw, void* 
   e.act = act;
   e.out_fp32 = out_fp32;
   return gemm_skinny(static_cast<const bf16*>(A), lda, static_cast<const bf16*>(W), ldw, C, ldc, M, N, K, e, splits,
-                     workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+                     static_cast<cudaStream_t>(stream));
+}
+
+size_t b200_weighted_ce_workspace_bytes(int B, int L) { return weighted_ce_workspace_bytes(B, L); }
+
+int b200_weighted_ce(const void* logits, int logits_fp32, int64_t ld, const int64_t* labels, const float* vocab_weight,
+                     int B, int L, int V, float grad_scale, void* dlogits, int64_t ldd, float* loss_out,
+                     void* workspace, size_t workspace_bytes, b200_stream_t stream) {
+  return weighted_ce(logits, logits_fp32, ld, reinterpret_cast<const long long*>(labels), vocab_weight, B, L, V,
+                     grad_scale, dlogits, ldd, loss_out, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+size_t b200_grad_norm_workspace_bytes(void) { return grad_norm_workspace_bytes(); }
+
+int b200_grad_sq_norm(const void* grad, int64_t n, int accumulate, float max_norm, float* out2, void* workspace,
+                      size_t workspace_bytes, b200_stream_t stream) {
+  return grad_sq_norm(static_cast<const bf16*>(grad), n, accumulate, max_norm, out2, workspace, workspace_bytes,
+                      static_cast<cudaStream_t>(stream));
+}
+
+int b200_adamw_step(float* master, void* param, const void* grad, float* m, float* v, int64_t n, float lr, float beta1,
+                    float beta2, float eps, float weight_decay, int step, const float* clip_coef,
+                    b200_stream_t stream) {
+  return adamw_step(master, static_cast<bf16*>(param), static_cast<const bf16*>(grad), m, v, n, lr, beta1, beta2, eps,
+                    weight_decay, step, clip_coef, static_cast<cudaStream_t>(stream));
 }
 
 int b200_layernorm(const void* x, int64_t ldx, const int32_t* row_map, const void* add, int period, const void* gamma,

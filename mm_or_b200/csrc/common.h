@@ -92,12 +92,21 @@ struct GemmEpilogue {
 int gemm_bf16_tn(const bf16* A, int lda, const bf16* B, int ldb, void* C, int ldc, int M, int N, int K,
                  const GemmEpilogue& epi, int bn_hint, cudaStream_t stream);
 
-// Decode-step GEMM (gemm_skinny.cu): M <= 256, weights streamed once, split-K with an in-kernel ordered reduction.
-// The first gemm_skinny_counter_bytes() of the workspace are per-tile arrival counters: zero on entry, zero on exit.
-size_t gemm_skinny_workspace_bytes(int M, int N, int K);
-static inline size_t gemm_skinny_counter_bytes() { return 4096; }
+// Decode-step GEMM (gemm_skinny.cu): M <= 256, weights streamed once, K split across a thread-block cluster and
+// reduced through distributed shared memory in split order. splits_hint: 0 = auto, else 1/2/4/8.
 int gemm_skinny(const bf16* A, int lda, const bf16* W, int ldw, void* C, int ldc, int M, int N, int K,
-                const GemmEpilogue& epi, int splits_hint, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+                const GemmEpilogue& epi, int splits_hint, cudaStream_t stream);
+
+// training-side kernels (train.cu)
+size_t weighted_ce_workspace_bytes(int Bn, int L);
+int weighted_ce(const void* logits, int is_fp32, long long ld, const long long* labels, const float* vocab_w, int Bn,
+                int L, int V, float grad_scale, void* dlogits, long long ldd, float* loss_out, void* workspace,
+                size_t workspace_bytes, cudaStream_t stream);
+size_t grad_norm_workspace_bytes();
+int grad_sq_norm(const bf16* grad, long long n, int accumulate, float max_norm, float* out2, void* workspace,
+                 size_t workspace_bytes, cudaStream_t stream);
+int adamw_step(float* master, bf16* param, const bf16* grad, float* m, float* v, long long n, float lr, float beta1,
+               float beta2, float eps, float weight_decay, int step, const float* clip_coef, cudaStream_t stream);
 
 // ---------------------------------------------------------------------------------------------
 // norms (norm.cu)

@@ -312,7 +312,8 @@ static EncodeTiledFn encode_fn() {
 
 // 2-D bf16 tensor map over a row-major [rows, cols] matrix with leading dimension ld (elements); box = box_rows x 64
 // elements, 128-byte swizzle, out-of-bounds elements read as zero.
-int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                 int l2_promotion = 2) {
   EncodeTiledFn fn = encode_fn();
   if (fn == nullptr) return fail(-6, "cuTensorMapEncodeTiled entry point not available");
   if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld * 2) % 16 != 0)
@@ -322,7 +323,10 @@ int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t col
   cuuint32_t box[2] = {64, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  l2_promotion == 0   ? CU_TENSOR_MAP_L2_PROMOTION_NONE
+                  : l2_promotion == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+                                      : CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(-6, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   return 0;

@@ -221,23 +221,25 @@ static size_t llama_prefill_ws(const b200_llama_weights* w, int Bn, int L, int a
   return s;
 }
 
-// scratch of the decode-step GEMMs (split-K partials + tile counters); p == nullptr selects the prefill kernel
-struct SkinnyWs {
-  void* p = nullptr;
-  size_t bytes = 0;
-};
-
-// nn.Linear dispatch: the weight-streaming kernel for the decode step (T <= 256 rows), the tiled one otherwise
+// nn.Linear dispatch for the decode step (T <= 256 rows, HBM bound). Measured on B200 with cold weights
+// (profiles/r1_skinny_gemm_notes.md): projections with few 128-row weight tiles (N = 4096: o_proj, down_proj) are
+// 1.3-1.9x faster on the split-K cluster kernel, which keeps two streaming CTAs on every SM; the wide ones (qkv,
+// gate_up, lm_head) already fill the chip with 128-column tiles of the tiled kernel.
 static int linear(const bf16* A, int lda, const bf16* W, int ldw, void* C, int ldc, int T, int N, int K,
-                  const GemmEpilogue& e, const SkinnyWs& sk, cudaStream_t st) {
-  if (sk.p != nullptr && T <= 256) return gemm_skinny(A, lda, W, ldw, C, ldc, T, N, K, e, 0, sk.p, sk.bytes, st);
+                  const GemmEpilogue& e, bool decode, cudaStream_t st) {
+  if (decode && T <= 256) {
+    const int n_tiles = (N + 127) / 128;
+    if (n_tiles * 2 <= num_sms()) return gemm_skinny(A, lda, W, ldw, C, ldc, T, N, K, e, 0, st);
+    if (T <= 128) return gemm_bf16_tn(A, lda, W, ldw, C, ldc, T, N, K, e, 128, st);
+  }
   return gemm_bf16_tn(A, lda, W, ldw, C, ldc, T, N, K, e, 0, st);
 }
 
 static int llama_layer(const b200_llama_weights* w, const b200_llama_layer& Ly, bf16* x, bf16* nbuf, bf16* qkv,
                        bf16* act, const int* kv_start, const int* kv_len, bf16* kc, bf16* vc, int cap, int Bn, int L,
                        int decode, const int* state, int ctx_bound, void* dec_ws, size_t dec_ws_bytes,
-                       const SkinnyWs& sk, cudaStream_t st) {
+                       cudaStream_t st) {
+  const bool sk = decode != 0;
   const int D = w->hidden, H = w->heads, T = Bn * L;
   B200_TRY(rmsnorm(x, D, B(Ly.attn_norm), w->rms_eps, nbuf, D, T, D, st));
   GemmEpilogue e;
@@ -319,7 +321,7 @@ static int llama_prefill(const b200_llama_weights* w, bf16* x, const int* kv_sta
     bf16* kc = static_cast<bf16*>(c->k) + l * c->layer_stride;
     bf16* vc = static_cast<bf16*>(c->v) + l * c->layer_stride;
     B200_TRY(llama_layer(w, w->layers[l], x, nbuf, qkv, act, kv_start, kv_len, kc, vc, c->cap, Bn, L, 0, nullptr, 0,
-                         nullptr, 0, SkinnyWs{}, st));
+                         nullptr, 0, st));
   }
   if (logits != nullptr) {
     GemmEpilogue e;
@@ -337,16 +339,6 @@ static int llama_prefill(const b200_llama_weights* w, bf16* x, const int* kv_sta
   return 0;
 }
 
-static size_t llama_skinny_ws(const b200_llama_weights* w, int Bn) {
-  if (Bn > 256) return 0;
-  const int D = w->hidden, F = w->ffn;
-  size_t m = gemm_skinny_workspace_bytes(Bn, 3 * D, D);
-  const size_t c[4] = {gemm_skinny_workspace_bytes(Bn, D, D), gemm_skinny_workspace_bytes(Bn, 2 * F, D),
-                       gemm_skinny_workspace_bytes(Bn, D, F), gemm_skinny_workspace_bytes(Bn, w->vocab, D)};
-  for (size_t v : c) m = v > m ? v : m;
-  return m;
-}
-
 static size_t llama_decode_ws(const b200_llama_weights* w, int Bn, int cap) {
   size_t s = 0;
   s += al(static_cast<size_t>(Bn) * w->hidden * 2) * 2;  // x, norm/context
@@ -354,7 +346,6 @@ static size_t llama_decode_ws(const b200_llama_weights* w, int Bn, int cap) {
   s += al(static_cast<size_t>(Bn) * w->ffn * 2);         // swiglu
   s += al(static_cast<size_t>(Bn) * w->vocab * 2);       // logits
   s += al(decode_attn_workspace_bytes(Bn, w->heads, 16));
-  s += al(llama_skinny_ws(w, Bn));
   (void)cap;
   return s;
 }
@@ -374,23 +365,17 @@ static int llama_decode_step(const b200_llama_weights* w, int* tokens, int* stat
   bf16* logits = a.take<bf16>(static_cast<size_t>(Bn) * w->vocab);
   const size_t dws_bytes = decode_attn_workspace_bytes(Bn, w->heads, 16);
   void* dws = a.take<uint8_t>(dws_bytes);
-  SkinnyWs sk;
-  sk.bytes = llama_skinny_ws(w, Bn);
-  if (sk.bytes > 0) {
-    sk.p = a.take<uint8_t>(sk.bytes);
-    B200_CUDA_OK(cudaMemsetAsync(sk.p, 0, gemm_skinny_counter_bytes(), st));  // split-K tile counters
-  }
   if (logits_out != nullptr) logits = static_cast<bf16*>(logits_out);
   B200_TRY(embed_rows(tokens, B(w->embed_tokens), x, D, Bn, D, w->vocab, st));
   for (int l = 0; l < w->n_layers; ++l) {
     bf16* kc = static_cast<bf16*>(c->k) + l * c->layer_stride;
     bf16* vc = static_cast<bf16*>(c->v) + l * c->layer_stride;
     B200_TRY(llama_layer(w, w->layers[l], x, nbuf, qkv, act, kv_start, nullptr, kc, vc, c->cap, Bn, 1, 1, state,
-                         ctx_bound, dws, dws_bytes, sk, st));
+                         ctx_bound, dws, dws_bytes, st));
   }
   B200_TRY(rmsnorm(x, D, B(w->final_norm), w->rms_eps, nbuf, D, Bn, D, st));
   GemmEpilogue e;
-  B200_TRY(linear(nbuf, D, B(w->lm_head), D, logits, w->vocab, Bn, w->vocab, D, e, sk, st));
+  B200_TRY(linear(nbuf, D, B(w->lm_head), D, logits, w->vocab, Bn, w->vocab, D, e, true, st));
   B200_TRY(argmax_rows(logits, 0, w->vocab, Bn, w->vocab, tokens, finished, eos_id, pad_id, history, hist_ld, 0,
                        state + 1, st));
   B200_TRY(bump_counters(state, st));

@@ -1,0 +1,325 @@
+// Training-side kernels of the MM2SG fine-tune step.
+//
+//  weighted_ce     LLaVATrainer.compute_loss (train/llava_trainer.py:136-174): shifted cross-entropy over
+//                  `modified_labels` with per-class weights, nn.CrossEntropyLoss(weight=vocab_weight) semantics:
+//                      loss = sum_i w[y_i] * nll_i / sum_i w[y_i]        over positions with y_i != -100
+//                  (vocab_weight[v] = 1 / (ln f_v + 1) for the listed pieces, min_w / 100 otherwise: train.py:1316-1322).
+//                  The reference materialises a contiguous shifted copy of the (B, L, 32000) logits and runs log_softmax
+//                  + nll_loss + the backward of both as separate kernels. Here one pass per supervised row computes
+//                  max / log-sum-exp with 16-byte loads, the weighted nll, and (optionally) writes
+//                  dlogits = w[y] / W * (softmax - onehot) * grad_scale in place of the logits; rows that carry no
+//                  label (prompt, visual tokens, padding, the last position) are only zero-filled. The shift is index
+//                  arithmetic (row (b, l) reads label (b, l + 1)). Reductions are two-stage in a fixed order, so the
+//                  loss is bit-deterministic.
+//  adamw / clip    LLaVATrainer.create_optimizer (train/llava_trainer.py:191-278) -> torch.optim.AdamW + HF Trainer
+//                  clip_grad_norm_(max_grad_norm = 0.1) (README.md:147-151): the reference runs for-each kernels with
+//                  >= 4 passes over params / grads / m / v. Here: one two-stage sum of squares over the flat gradient
+//                  buffer, then ONE pass that applies the clip coefficient (read from device memory, no host sync),
+//                  decoupled weight decay, the Adam update on fp32 master weights and writes the bf16 working copy.
+//                  HBM bound: 2 (grad) + 4 + 4 + 4 (read p, m, v) + 4 + 4 + 4 + 2 (write) = 28 B per parameter.
+#include "common.h"
+#include "ptx.cuh"
+
+namespace b200 {
+
+static constexpr int kCeThreads = 256;
+
+__device__ __forceinline__ float block_reduce(float v, float* red, bool is_max) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const float o = __shfl_xor_sync(0xffffffffu, v, off);
+    v = is_max ? fmaxf(v, o) : v + o;
+  }
+  __syncthreads();  // red may still be read from a previous call
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float r = red[0];
+  for (int w = 1; w < kCeThreads / 32; ++w) r = is_max ? fmaxf(r, red[w]) : r + red[w];
+  return r;
+}
+
+// stage 1 of the weight normaliser: W = sum of w[label] over supervised positions (fixed-order two-stage sum)
+__global__ void __launch_bounds__(kCeThreads) ce_weight_sum_kernel(const long long* __restrict__ labels,
+                                                                   const float* __restrict__ vocab_w, int Bn, int L,
+                                                                   int V, float* __restrict__ wsum) {
+  __shared__ float red[kCeThreads / 32];
+  float acc = 0.f;
+  const long long T = static_cast<long long>(Bn) * L;
+  for (long long i = threadIdx.x; i < T; i += kCeThreads) {  // single CTA: order independent of the grid
+    const int l = static_cast<int>(i % L);
+    if (l == L - 1) continue;
+    const long long y = labels[i + 1];
+    if (y >= 0 && y < V) acc += vocab_w ? vocab_w[y] : 1.f;
+  }
+  const float tot = block_reduce(acc, red, false);
+  if (threadIdx.x == 0) *wsum = tot;
+}
+
+template <typename T>
+__device__ __forceinline__ float ld_logit(const T* p, long long i);
+template <>
+__device__ __forceinline__ float ld_logit<float>(const float* p, long long i) {
+  return p[i];
+}
+template <>
+__device__ __forceinline__ float ld_logit<bf16>(const bf16* p, long long i) {
+  return __bfloat162float(p[i]);
+}
+template <typename T>
+__device__ __forceinline__ void st_logit(T* p, long long i, float v);
+template <>
+__device__ __forceinline__ void st_logit<float>(float* p, long long i, float v) {
+  p[i] = v;
+}
+template <>
+__device__ __forceinline__ void st_logit<bf16>(bf16* p, long long i, float v) {
+  p[i] = __float2bfloat16(v);
+}
+
+// one CTA per (b, l) row. row_loss[row] = w[y] * nll (0 for unsupervised rows).
+template <typename T>
+__global__ void __launch_bounds__(kCeThreads)
+    ce_row_kernel(const T* __restrict__ logits, long long ld, const long long* __restrict__ labels,
+                  const float* __restrict__ vocab_w, int L, int V, const float* __restrict__ wsum, float grad_scale,
+                  T* dlogits, long long ldd, float* __restrict__ row_loss) {
+  __shared__ float red[kCeThreads / 32];
+  const long long row = blockIdx.x;
+  const int l = static_cast<int>(row % L);
+  const long long y = (l == L - 1) ? -100 : labels[row + 1];
+  const bool live = y >= 0 && y < V;
+  T* drow = dlogits ? dlogits + row * ldd : nullptr;
+  if (!live) {
+    if (threadIdx.x == 0) row_loss[row] = 0.f;
+    if (drow != nullptr)
+      for (int i = threadIdx.x; i < V; i += kCeThreads) st_logit<T>(drow, i, 0.f);
+    return;
+  }
+  const T* xr = logits + row * ld;
+  float mx = -INFINITY;
+  for (int i = threadIdx.x; i < V; i += kCeThreads) mx = fmaxf(mx, ld_logit<T>(xr, i));
+  mx = block_reduce(mx, red, true);
+  float se = 0.f;
+  for (int i = threadIdx.x; i < V; i += kCeThreads) se += __expf(ld_logit<T>(xr, i) - mx);
+  se = block_reduce(se, red, false);
+  const float lse = mx + __logf(se);
+  const float w = vocab_w ? vocab_w[y] : 1.f;
+  if (threadIdx.x == 0) row_loss[row] = w * (lse - ld_logit<T>(xr, y));
+  if (drow != nullptr) {
+    const float W = *wsum;
+    const float coef = W > 0.f ? grad_scale * w / W : 0.f;
+    for (int i = threadIdx.x; i < V; i += kCeThreads) {
+      const float p = __expf(ld_logit<T>(xr, i) - lse);
+      st_logit<T>(drow, i, coef * (p - (i == y ? 1.f : 0.f)));
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kCeThreads) ce_finish_kernel(const float* __restrict__ row_loss, long long rows,
+                                                               const float* __restrict__ wsum,
+                                                               float* __restrict__ loss) {
+  __shared__ float red[kCeThreads / 32];
+  float acc = 0.f;
+  for (long long i = threadIdx.x; i < rows; i += kCeThreads) acc += row_loss[i];
+  const float tot = block_reduce(acc, red, false);
+  if (threadIdx.x == 0) {
+    const float W = *wsum;
+    loss[0] = W > 0.f ? tot / W : 0.f;  // no supervised token: torch returns nan; we return 0 and report W
+    loss[1] = W;
+  }
+}
+
+size_t weighted_ce_workspace_bytes(int Bn, int L) { return (static_cast<size_t>(Bn) * L + 64) * sizeof(float); }
+
+// logits [Bn*L, V] (row stride ld), labels [Bn, L] int64 (UNshifted modified_labels), vocab_w [V] fp32 or null.
+// loss_out[2] = {loss, sum of weights}. dlogits may be null (forward only) or alias logits.
+int weighted_ce(const void* logits, int is_fp32, long long ld, const long long* labels, const float* vocab_w, int Bn,
+                int L, int V, float grad_scale, void* dlogits, long long ldd, float* loss_out, void* workspace,
+                size_t workspace_bytes, cudaStream_t stream) {
+  if (Bn <= 0 || L <= 0) return fail(-2, "weighted_ce: empty batch");
+  if (workspace == nullptr || workspace_bytes < weighted_ce_workspace_bytes(Bn, L))
+    return fail(-2, "weighted_ce: workspace too small");
+  float* wsum = static_cast<float*>(workspace);
+  float* row_loss = wsum + 64;
+  const long long rows = static_cast<long long>(Bn) * L;
+  LaunchScope scope(kFamTrain, stream, (dlogits ? 3.0 : 2.0) * rows * V * (is_fp32 ? 4 : 2), 0.0, 3);
+  ce_weight_sum_kernel<<<1, kCeThreads, 0, stream>>>(labels, vocab_w, Bn, L, V, wsum);
+  if (is_fp32)
+    ce_row_kernel<float><<<static_cast<unsigned>(rows), kCeThreads, 0, stream>>>(
+        static_cast<const float*>(logits), ld, labels, vocab_w, L, V, wsum, grad_scale, static_cast<float*>(dlogits),
+        ldd, row_loss);
+  else
+    ce_row_kernel<bf16><<<static_cast<unsigned>(rows), kCeThreads, 0, stream>>>(
+        static_cast<const bf16*>(logits), ld, labels, vocab_w, L, V, wsum, grad_scale, static_cast<bf16*>(dlogits),
+        ldd, row_loss);
+  ce_finish_kernel<<<1, kCeThreads, 0, stream>>>(row_loss, rows, wsum, loss_out);
+  B200_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// gradient norm + fused AdamW
+// ---------------------------------------------------------------------------------------------------
+static constexpr int kOptThreads = 256;
+static constexpr int kNormBlocks = 1184;  // 8 per SM; fixed so that the two-stage sum has a fixed order
+
+__global__ void __launch_bounds__(kOptThreads) grad_sq_partial_kernel(const bf16* __restrict__ g, long long n,
+                                                                      float* __restrict__ partial) {
+  __shared__ float red[kOptThreads / 32];
+  float acc = 0.f;
+  const long long n8 = n / 8;
+  const uint4* g8 = reinterpret_cast<const uint4*>(g);
+  for (long long i = static_cast<long long>(blockIdx.x) * kOptThreads + threadIdx.x; i < n8;
+       i += static_cast<long long>(gridDim.x) * kOptThreads) {
+    const uint4 u = g8[i];
+    const float f[8] = {bf16lo(u.x), bf16hi(u.x), bf16lo(u.y), bf16hi(u.y),
+                        bf16lo(u.z), bf16hi(u.z), bf16lo(u.w), bf16hi(u.w)};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc += f[j] * f[j];
+  }
+  if (blockIdx.x == 0)
+    for (long long i = n8 * 8 + threadIdx.x; i < n; i += kOptThreads) {
+      const float f = __bfloat162float(g[i]);
+      acc += f * f;
+    }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if (lane == 0) red[warp] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < kOptThreads / 32; ++w) t += red[w];
+    partial[blockIdx.x] = t;
+  }
+}
+
+// out[0] += sum(partial) (accumulate = 1 chains several gradient buffers), out[1] = clip coefficient for max_norm
+__global__ void __launch_bounds__(kOptThreads) grad_norm_finish_kernel(const float* __restrict__ partial, int nblocks,
+                                                                       int accumulate, float max_norm,
+                                                                       float* __restrict__ out) {
+  __shared__ float red[kOptThreads / 32];
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < nblocks; i += kOptThreads) acc += partial[i];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if (lane == 0) red[warp] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = accumulate ? out[0] : 0.f;
+    for (int w = 0; w < kOptThreads / 32; ++w) t += red[w];
+    out[0] = t;
+    const float norm = sqrtf(t);
+    // torch.nn.utils.clip_grad_norm_: coef = max_norm / (norm + 1e-6), clamped to 1
+    out[1] = max_norm > 0.f ? fminf(1.f, max_norm / (norm + 1e-6f)) : 1.f;
+  }
+}
+
+size_t grad_norm_workspace_bytes() { return kNormBlocks * sizeof(float); }
+
+int grad_sq_norm(const bf16* grad, long long n, int accumulate, float max_norm, float* out2, void* workspace,
+                 size_t workspace_bytes, cudaStream_t stream) {
+  if (workspace == nullptr || workspace_bytes < grad_norm_workspace_bytes())
+    return fail(-2, "grad_sq_norm: workspace too small");
+  if ((reinterpret_cast<uintptr_t>(grad) & 15) != 0) return fail(-2, "grad_sq_norm: gradient buffer must be 16-byte aligned");
+  LaunchScope scope(kFamTrain, stream, 2.0 * n, 0.0, 2);
+  float* partial = static_cast<float*>(workspace);
+  grad_sq_partial_kernel<<<kNormBlocks, kOptThreads, 0, stream>>>(grad, n, partial);
+  grad_norm_finish_kernel<<<1, kOptThreads, 0, stream>>>(partial, kNormBlocks, accumulate, max_norm, out2);
+  B200_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+struct AdamArgs {
+  float* master;    // fp32 master weights
+  bf16* param;      // bf16 working copy (may be null)
+  const bf16* grad;
+  float* m;
+  float* v;
+  long long n;
+  float lr, beta1, beta2, eps, weight_decay;
+  float bc1, bc2_sqrt;       // 1 - beta1^t, sqrt(1 - beta2^t)
+  const float* clip;         // device pointer to the clip coefficient (out2 + 1 of grad_sq_norm) or null
+};
+
+__global__ void __launch_bounds__(kOptThreads) adamw_kernel(const AdamArgs a) {
+  const float clip = a.clip ? *a.clip : 1.f;
+  const float step_size = a.lr / a.bc1;
+  const float decay = 1.f - a.lr * a.weight_decay;
+  const long long n4 = a.n / 4;
+  for (long long i = static_cast<long long>(blockIdx.x) * kOptThreads + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * kOptThreads) {
+    const uint2 gu = reinterpret_cast<const uint2*>(a.grad)[i];
+    const float g[4] = {bf16lo(gu.x) * clip, bf16hi(gu.x) * clip, bf16lo(gu.y) * clip, bf16hi(gu.y) * clip};
+    float4 p = reinterpret_cast<float4*>(a.master)[i];
+    float4 m = reinterpret_cast<float4*>(a.m)[i];
+    float4 v = reinterpret_cast<float4*>(a.v)[i];
+    float* pp = &p.x;
+    float* mm = &m.x;
+    float* vv = &v.x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      pp[j] *= decay;                                            // decoupled weight decay (torch.optim.AdamW)
+      mm[j] = a.beta1 * mm[j] + (1.f - a.beta1) * g[j];
+      vv[j] = a.beta2 * vv[j] + (1.f - a.beta2) * g[j] * g[j];
+      const float denom = sqrtf(vv[j]) / a.bc2_sqrt + a.eps;
+      pp[j] -= step_size * mm[j] / denom;
+    }
+    reinterpret_cast<float4*>(a.master)[i] = p;
+    reinterpret_cast<float4*>(a.m)[i] = m;
+    reinterpret_cast<float4*>(a.v)[i] = v;
+    if (a.param != nullptr) {
+      uint2 o;
+      o.x = pack_bf16x2(p.x, p.y);
+      o.y = pack_bf16x2(p.z, p.w);
+      reinterpret_cast<uint2*>(a.param)[i] = o;
+    }
+  }
+  if (blockIdx.x == 0) {
+    for (long long i = n4 * 4 + threadIdx.x; i < a.n; i += kOptThreads) {
+      const float g = __bfloat162float(a.grad[i]) * clip;
+      float p = a.master[i] * decay;
+      const float m = a.beta1 * a.m[i] + (1.f - a.beta1) * g;
+      const float v = a.beta2 * a.v[i] + (1.f - a.beta2) * g * g;
+      p -= step_size * m / (sqrtf(v) / a.bc2_sqrt + a.eps);
+      a.master[i] = p;
+      a.m[i] = m;
+      a.v[i] = v;
+      if (a.param != nullptr) a.param[i] = __float2bfloat16(p);
+    }
+  }
+}
+
+int adamw_step(float* master, bf16* param, const bf16* grad, float* m, float* v, long long n, float lr, float beta1,
+               float beta2, float eps, float weight_decay, int step, const float* clip_coef, cudaStream_t stream) {
+  if (n <= 0) return 0;
+  if (step < 1) return fail(-2, "adamw_step: step counts from 1");
+  const uintptr_t al = reinterpret_cast<uintptr_t>(master) | reinterpret_cast<uintptr_t>(m) |
+                       reinterpret_cast<uintptr_t>(v);
+  if ((al & 15) != 0 || (reinterpret_cast<uintptr_t>(grad) & 7) != 0 || (reinterpret_cast<uintptr_t>(param) & 7) != 0)
+    return fail(-2, "adamw_step: buffers must be 16-byte (fp32) / 8-byte (bf16) aligned");
+  AdamArgs a;
+  a.master = master;
+  a.param = param;
+  a.grad = grad;
+  a.m = m;
+  a.v = v;
+  a.n = n;
+  a.lr = lr;
+  a.beta1 = beta1;
+  a.beta2 = beta2;
+  a.eps = eps;
+  a.weight_decay = weight_decay;
+  a.bc1 = 1.f - powf(beta1, static_cast<float>(step));
+  a.bc2_sqrt = sqrtf(1.f - powf(beta2, static_cast<float>(step)));
+  a.clip = clip_coef;
+  const long long want = (n / 4 + kOptThreads - 1) / kOptThreads;
+  const int grid = static_cast<int>(want < 1 ? 1 : (want > 8LL * num_sms() ? 8LL * num_sms() : want));
+  LaunchScope scope(kFamTrain, stream, 28.0 * n, 0.0);
+  adamw_kernel<<<grid, kOptThreads, 0, stream>>>(a);
+  B200_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace b200

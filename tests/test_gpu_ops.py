@@ -87,7 +87,7 @@ def test_gemm_skinny_shapes(L, M, N, K):
     assert rel_err(L.gemm_skinny(a, w), ref_gemm(a, w)) < 5e-3
 
 
-@pytest.mark.parametrize("splits", [1, 2, 3, 4, 8, 16])
+@pytest.mark.parametrize("splits", [0, 1, 2, 4, 8])
 def test_gemm_skinny_splits_and_epilogues(L, splits):
     M, N, K = 64, 1024, 2048
     a, w = rnd(M, K, seed=3), rnd(N, K, scale=1 / math.sqrt(K), seed=4)
@@ -104,22 +104,17 @@ def test_gemm_skinny_splits_and_epilogues(L, splits):
     assert rel_err(x, ref_gemm(a, w, bias, res)) < 5e-3
 
 
-def test_gemm_skinny_deterministic_and_reusable_workspace(L):
-    """Split-K partials are summed in split order by the last-arriving CTA: repeated launches are bit-identical, and
-    the tile counters are back at zero afterwards (the decode step reuses one workspace for every GEMM of a step)."""
+def test_gemm_skinny_deterministic(L):
+    """Split-K partials are summed in split order through distributed shared memory: repeated launches are
+    bit-identical, for every cluster size."""
     M, N, K = 48, 4096, 11008
     a, w = rnd(M, K, seed=7), rnd(N, K, scale=1 / math.sqrt(K), seed=8)
-    nb = L.lib().b200_gemm_skinny_workspace_bytes(M, N, K)
-    ws = torch.empty(nb, dtype=torch.uint8, device="cuda")
-    ws[:4096].zero_()
-    first = L.gemm_skinny(a, w, ws=ws)
-    for _ in range(5):
-        assert torch.equal(L.gemm_skinny(a, w, ws=ws), first)
-    torch.cuda.synchronize()
-    assert int(ws[:4096].view(torch.int32).abs().sum()) == 0
-    assert rel_err(first, ref_gemm(a, w)) < 5e-3
-    # same bits as the tiled prefill kernel up to fp32 summation order: compare in bf16 ulps
-    assert rel_err(first, L.gemm(a, w)) < 2e-3
+    for splits in (0, 1, 2, 4, 8):
+        first = L.gemm_skinny(a, w, splits=splits)
+        for _ in range(3):
+            assert torch.equal(L.gemm_skinny(a, w, splits=splits), first)
+        assert rel_err(first, ref_gemm(a, w)) < 5e-3
+        assert rel_err(first, L.gemm(a, w)) < 2e-3     # vs the tiled prefill kernel: fp32 summation order only
 
 
 def test_gemm_skinny_bad_args(L):
@@ -204,6 +199,40 @@ def test_flash_attention_causal_leftpad(L):
     # fewer queries than keys (last-layer pooler shape): Lq < Lk, non-causal
     out = L.flash_attention(q[:, :100], k, v)
     assert rel_err(out, ref_attn(q[:, :100], k, v)) < TOL_OP
+
+
+def test_flash_attention_rescale_and_long_keys(L):
+    """Scores whose running maximum jumps by far more than 2^8 between key tiles (the lazy-rescale path of the
+    tcgen05 kernel rescales the TMEM accumulator there), many key tiles, Lq != Lk with the causal offset."""
+    B, H, d = 2, 2, 128
+    Lq, Lk = 200, 1500
+    q, k, v = rnd(B, Lq, H, d, seed=11), rnd(B, Lk, H, d, seed=12), rnd(B, Lk, H, d, seed=13)
+    k = k.clone()
+    k[:, 700:] *= 6.0                    # later keys dominate: max rises tile after tile
+    k[:, 1300:] *= 3.0
+    q = (q * 2.0).contiguous()
+    assert rel_err(L.flash_attention(q, k, v), ref_attn(q, k, v)) < TOL_OP
+    assert rel_err(L.flash_attention(q, k, v, causal=True), ref_attn(q, k, v, causal=True)) < TOL_OP
+    d = 64
+    q, k, v = rnd(B, 577, H, d, seed=14) * 3, rnd(B, 577, H, d, seed=15) * 3, rnd(B, 577, H, d, seed=16)
+    assert rel_err(L.flash_attention(q, k, v), ref_attn(q, k, v)) < TOL_OP
+
+
+def test_flash_attention_kv_cache_layout(L):
+    """K / V read from the head-major KV-cache layout [B][H][cap][128] (row stride 128, head stride cap*128), Q and O
+    in the token-major qkv layout: the prefill call site of b200_llama_prefill."""
+    B, H, Lq, cap, d = 2, 3, 300, 384, 128
+    qkv = rnd(B, Lq, 3, H, d, seed=21)
+    kc, vc = rnd(B, H, cap, d, seed=22), rnd(B, H, cap, d, seed=23)
+    q = qkv[:, :, 0]
+    k, v = kc[:, :, :Lq].transpose(1, 2), vc[:, :, :Lq].transpose(1, 2)      # (B, Lq, H, d) views
+    start = torch.tensor([0, 37], device="cuda", dtype=torch.int32)
+    out = L.flash_attention(q, k, v, causal=True, kv_start=start)
+    ref = ref_attn(q, k, v, causal=True, kv_start=start)
+    for b in range(B):
+        s0 = int(start[b])
+        assert rel_err(out[b, s0:], ref[b, s0:]) < TOL_OP
+        assert float(out[b, :s0].float().abs().max()) == 0.0 if s0 else True   # fully masked rows: exact zeros
 
 
 @pytest.mark.parametrize("B,ctx,splits", [(5, 700, 0), (2, 1500, 4), (64, 300, 1), (1, 9, 0)])

@@ -1,0 +1,95 @@
+"""GPU parity tests of the training-side kernels through the C ABI: weighted shifted
+cross-entropy + its gradient against the oracle (oracle.weighted_ce restates LLaVATrainer.compute_loss,
+train/llava_trainer.py:143-167) and torch autograd, gradient-norm clipping and fused AdamW against
+torch.nn.utils.clip_grad_norm_ / torch.optim.AdamW in fp32. Floating point: tolerances stated per assertion."""
+import math
+
+import pytest
+import torch
+
+from oracle import mm2sg_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def L():
+    if not torch.cuda.is_available():
+        pytest.skip("needs CUDA")
+    from mm_or_b200 import _lib
+    _lib.lib()
+    return _lib
+
+
+def _ce_case(B, Lq, V, dtype, seed):
+    g = torch.Generator().manual_seed(seed)
+    logits = (torch.randn(B, Lq, V, generator=g) * 3).to(dtype)
+    labels = torch.randint(0, V, (B, Lq), generator=g)
+    labels[:, : Lq // 2] = -100                       # prompt + visual rows carry no label
+    labels[torch.rand(B, Lq, generator=g) < 0.2] = -100
+    w = torch.rand(V, generator=g) + 0.01
+    w[::7] *= 0.01                                    # "extra token" weights are 100x smaller (train.py:1322)
+    return logits, labels, w
+
+
+@pytest.mark.parametrize("dtype,V", [(torch.float32, 32000), (torch.bfloat16, 32000), (torch.float32, 517)])
+def test_weighted_ce_forward_backward(L, dtype, V):
+    B, Lq = 3, 40
+    logits, labels, w = _ce_case(B, Lq, V, dtype, seed=V)
+    ref_in = logits.float().clone().requires_grad_(True)
+    ref = O.weighted_ce(ref_in, labels, w)            # oracle restatement of compute_loss
+    ref.backward()
+    loss, wsum, dl = L.weighted_ce(logits.cuda(), labels.cuda(), w, want_grad=True)
+    sl = labels[:, 1:]
+    assert abs(float(wsum) - float(w[sl[sl >= 0]].sum())) < 1e-3 * float(wsum)
+    tol = 1e-5 if dtype == torch.float32 else 2e-3
+    assert abs(float(loss) - float(ref)) < tol * max(1.0, abs(float(ref)))
+    g = dl.float().cpu()
+    gtol = 1e-5 if dtype == torch.float32 else 1e-2   # bf16 gradients: one rounding to 8 mantissa bits
+    assert ((g - ref_in.grad).norm() / ref_in.grad.norm()).item() < gtol
+    assert float(g[:, -1].abs().max()) == 0.0         # last position scores nothing (shift)
+    assert float(g[:, : Lq // 2 - 1].abs().max()) == 0.0
+    # unweighted == plain shifted CE (HF LlamaForCausalLM loss), in place, with a gradient scale
+    loss2, _, dl2 = L.weighted_ce(logits.cuda().clone(), labels.cuda(), None, grad_scale=0.5, want_grad=True,
+                                  inplace=True)
+    ref2 = torch.nn.functional.cross_entropy(logits.float()[:, :-1].reshape(-1, V), labels[:, 1:].reshape(-1),
+                                             ignore_index=-100)
+    assert abs(float(loss2) - float(ref2)) < tol * max(1.0, abs(float(ref2)))
+
+
+def test_weighted_ce_deterministic_and_empty(L):
+    logits, labels, w = _ce_case(2, 64, 4096, torch.float32, seed=5)
+    a = L.weighted_ce(logits.cuda(), labels.cuda(), w)[0]
+    for _ in range(3):
+        assert torch.equal(L.weighted_ce(logits.cuda(), labels.cuda(), w)[0], a)
+    none = torch.full_like(labels, -100)
+    loss, wsum, dl = L.weighted_ce(logits.cuda(), none.cuda(), w, want_grad=True)
+    assert float(wsum) == 0.0 and float(loss) == 0.0 and float(dl.abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("n", [1, 7, 4096, 1_000_003])
+def test_grad_norm_and_adamw_match_torch(L, n):
+    g0 = torch.Generator().manual_seed(n)
+    p32 = torch.randn(n, generator=g0)
+    ref_p = p32.clone().requires_grad_(True)
+    opt = torch.optim.AdamW([ref_p], lr=2e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.05)
+    master, m, v = p32.clone().cuda(), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    param = torch.empty(n, device="cuda", dtype=torch.bfloat16)
+    for step in range(1, 4):
+        grad = (torch.randn(n, generator=g0) * (3.0 if step == 2 else 0.01)).to(torch.bfloat16)
+        ref_p.grad = grad.float().clone()
+        norm = torch.nn.utils.clip_grad_norm_([ref_p], 0.1)
+        opt.step()
+        out2 = L.grad_sq_norm(grad.cuda(), max_norm=0.1)
+        assert abs(math.sqrt(float(out2[0])) - float(norm)) < 1e-4 * max(1e-3, float(norm))
+        assert abs(float(out2[1]) - min(1.0, 0.1 / (float(norm) + 1e-6))) < 1e-5
+        L.adamw_step(master, param, grad.cuda(), m, v, lr=2e-3, weight_decay=0.05, step=step, clip_coef=out2[1:])
+        torch.cuda.synchronize()
+        assert ((master.cpu() - ref_p.detach()).abs().max() / ref_p.detach().abs().max()).item() < 2e-6
+        assert torch.equal(param.cpu(), master.cpu().to(torch.bfloat16))
+    # chained buffers accumulate into one norm
+    a, b = torch.randn(1000).to(torch.bfloat16).cuda(), torch.randn(3000).to(torch.bfloat16).cuda()
+    out2 = L.grad_sq_norm(a)
+    out2 = L.grad_sq_norm(b, out2=out2, accumulate=True, max_norm=1.0)
+    tot = float(a.float().pow(2).sum() + b.float().pow(2).sum())
+    assert abs(float(out2[0]) - tot) < 1e-4 * tot

@@ -147,24 +147,22 @@ def perf():
         log(f"perf {name:24s} cuBLAS(torch.matmul): {ms*1e3:9.1f} us  {2.0*M*N*K/ms/1e9:8.1f} TFLOP/s")
 
 
-def skinny():
+def skinny(ms=(64, 128)):
     """Decode-step GEMM shapes with COLD weights: every launch reads a different copy out of a pool larger than L2
     (in the decode step each weight matrix is read once per 13 GB pass)."""
     shapes = [("qkv", 12288, 4096), ("o", 4096, 4096), ("gateup", 22016, 4096), ("down", 4096, 11008),
               ("lm_head", 32000, 4096)]
-    for M in (64, 128):
+    for M in ms:
         tot_best = 0.0
         for name, N, K in shapes:
-            copies = max(2, int(400e6 // (N * K * 2)) + 1)
+            copies = max(2, int(300e6 // (N * K * 2)) + 1)
             ws_ = [torch.randn(N, K, device="cuda", dtype=torch.bfloat16) / math.sqrt(K) for _ in range(copies)]
             a = torch.randn(M, K, device="cuda", dtype=torch.bfloat16)
             out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
-            nb = L.lib().b200_gemm_skinny_workspace_bytes(M, N, K) * 4
-            scratch = torch.zeros(nb, dtype=torch.uint8, device="cuda")
             variants = [("tiled bn=0", lambda w: L.gemm(a, w, out=out)),
                         ("tiled bn=128", lambda w: L.gemm(a, w, out=out, bn=128))]
-            for sp in (0, 1, 2, 4, 8, 16):
-                variants.append((f"skinny splits={sp}", lambda w, sp=sp: L.gemm_skinny(a, w, out=out, splits=sp, ws=scratch)))
+            for sp in (0, 1, 2, 4, 8):
+                variants.append((f"skinny splits={sp}", lambda w, sp=sp: L.gemm_skinny(a, w, out=out, splits=sp)))
             variants.append(("cuBLAS", lambda w: torch.matmul(a, w.t(), out=out)))
             best = 1e9
             for vn, fn in variants:
@@ -199,6 +197,9 @@ if __name__ == "__main__":
         r = epi()
     elif which == "skinny":
         skinny()
+        r = True
+    elif which == "skinny64":
+        skinny((64,))
         r = True
     else:
         perf()

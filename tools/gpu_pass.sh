@@ -11,7 +11,7 @@ nvidia-smi --query-gpu=name,clocks.max.sm,clocks.max.mem,power.limit --format=cs
 
 if [[ $STAGES == *newtests* ]]; then
   # kernels that have never run on hardware: short leash
-  timeout 300 python -m pytest tests/test_gpu_ops.py -m gpu -x -q -k "${NEWTESTS:-skinny}" --timeout 120 2>&1 | tail -30 > gpurun_out/${TAG}_pytest_new.log
+  timeout 150 python -m pytest tests/test_gpu_ops.py tests/test_gpu_train_ops.py -m gpu -x -q -k "${NEWTESTS:-skinny}" --timeout 120 2>&1 | tail -30 > gpurun_out/${TAG}_pytest_new.log
   echo "new tests rc=${PIPESTATUS[0]}"; tail -15 gpurun_out/${TAG}_pytest_new.log
 fi
 
@@ -23,7 +23,13 @@ fi
 
 if [[ $STAGES == *skinny* ]]; then
   timeout 300 python tools/gpu_gemm_check.py skinny > gpurun_out/${TAG}_skinny_perf.log 2>&1
-  echo "skinny perf rc=$?"; grep -E "best-variant|splits=0|tiled bn=0|cuBLAS" gpurun_out/${TAG}_skinny_perf.log | tail -40
+  echo "skinny perf rc=$?"; grep -E "best-variant|splits=0|tiled bn=|cuBLAS" gpurun_out/${TAG}_skinny_perf.log | tail -40
+fi
+
+if [[ $STAGES == *attn* ]]; then
+  timeout 200 python tools/gpu_attn_check.py > gpurun_out/${TAG}_attn_perf.log 2>&1
+  B200_FA_LEGACY=1 timeout 200 python tools/gpu_attn_check.py >> gpurun_out/${TAG}_attn_perf.log 2>&1
+  echo "attn perf rc=$?"; cat gpurun_out/${TAG}_attn_perf.log | tail -20
 fi
 
 if [[ $STAGES == *bench* ]]; then
