@@ -42,7 +42,7 @@ def parse_args():
     p.add_argument("--steps", type=int, default=3)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    p.add_argument("--batch", type=int, default=64, help="samples per GPU per step")
+    p.add_argument("--batch", type=int, default=128, help="samples per GPU per step (KV cache: 0.56 GB per sample)")
     p.add_argument("--views", type=int, default=6)
     p.add_argument("--text-len", type=int, default=256)
     p.add_argument("--new-tokens", type=int, default=256)
@@ -310,7 +310,8 @@ def run_b200(args):
 
 
 def measured_traffic(kernel):
-    """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/traffic.json), or None."""
+    """DRAM bytes per launch of `kernel` next to its algorithmic bytes, from the committed `ncu --set full` capture
+    (profiles/traffic.json; taken at the capture's batch size, so compare the ratio), or None."""
     path = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(path):
         with open(path) as f:

@@ -56,6 +56,13 @@ __device__ __forceinline__ void tc_load(void* dst, const CUtensorMap* tm, uint64
   tma_load_4d(dst, tm, bar, c[0], c[1], c[2], c[3]);
 }
 
+// 2^x on the SFU (ex2.approx.ftz): -inf -> 0, no denormal fix-up code around it
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 template <int D>
 struct TcCfg {
   static constexpr int kPanels = D / 64;
@@ -229,11 +236,13 @@ __global__ void __launch_bounds__(kTcThreads, 2)
       const int kbase = (tile_begin + j) * kTcBN;
       const bool need_mask = (kbase < key_begin) || (kbase + kTcBN > key_end) ||
                              (a.causal && (kbase + kTcBN - 1 > q0 + qd * 32 + causal_off));
+      // scores stay unscaled in registers; the softmax scale is folded into one FFMA per element:
+      // p = 2^(s * scale_log2 - m)
       float s[64];
 #pragma unroll
       for (int c = 0; c < 32; ++c) {
-        s[c] = __uint_as_float(v0[c]) * a.scale_log2;
-        s[32 + c] = __uint_as_float(v1[c]) * a.scale_log2;
+        s[c] = __uint_as_float(v0[c]);
+        s[32 + c] = __uint_as_float(v1[c]);
       }
       if (need_mask) {
 #pragma unroll
@@ -243,24 +252,37 @@ __global__ void __launch_bounds__(kTcThreads, 2)
           if (!vis) s[c] = -INFINITY;
         }
       }
-      float tmax = s[0];
+      // four independent chains (a 64-deep dependent FMNMX chain would be latency bound)
+      float mx0 = fmaxf(s[0], s[1]), mx1 = fmaxf(s[2], s[3]), mx2 = fmaxf(s[4], s[5]), mx3 = fmaxf(s[6], s[7]);
 #pragma unroll
-      for (int c = 1; c < 64; ++c) tmax = fmaxf(tmax, s[c]);
+      for (int c = 8; c < 64; c += 8) {
+        mx0 = fmaxf(mx0, fmaxf(s[c], s[c + 1]));
+        mx1 = fmaxf(mx1, fmaxf(s[c + 2], s[c + 3]));
+        mx2 = fmaxf(mx2, fmaxf(s[c + 4], s[c + 5]));
+        mx3 = fmaxf(mx3, fmaxf(s[c + 6], s[c + 7]));
+      }
+      const float tmax = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * a.scale_log2;  // scale > 0: max commutes
       // lazy rescale: raise the running max only when it would otherwise let P exceed 2^8
       const bool raise = tmax > m_run + kRescaleThreshold;  // also true for the first visible key (m_run = -inf)
       const float m_new = raise ? tmax : m_run;
       const float msafe = (m_new == -INFINITY) ? 0.f : m_new;
-      const float alpha = raise ? exp2f(m_run - msafe) : 1.f;  // m_run = -inf -> 0
-      float rsum = 0.f;
+      const float alpha = raise ? fast_exp2(m_run - msafe) : 1.f;  // m_run = -inf -> 0
+      float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
       uint32_t pk[32];
 #pragma unroll
-      for (int c = 0; c < 32; ++c) {
-        const float p0 = exp2f(s[2 * c] - msafe);
-        const float p1 = exp2f(s[2 * c + 1] - msafe);
-        rsum += p0 + p1;
+      for (int c = 0; c < 32; c += 2) {
+        const float p0 = fast_exp2(fmaf(s[2 * c], a.scale_log2, -msafe));
+        const float p1 = fast_exp2(fmaf(s[2 * c + 1], a.scale_log2, -msafe));
+        const float p2 = fast_exp2(fmaf(s[2 * c + 2], a.scale_log2, -msafe));
+        const float p3 = fast_exp2(fmaf(s[2 * c + 3], a.scale_log2, -msafe));
+        rs0 += p0;
+        rs1 += p1;
+        rs2 += p2;
+        rs3 += p3;
         pk[c] = pack_bf16x2(p0, p1);
+        pk[c + 1] = pack_bf16x2(p2, p3);
       }
-      l_run = l_run * alpha + rsum;
+      l_run = l_run * alpha + ((rs0 + rs1) + (rs2 + rs3));
       m_run = m_new;
 
       if (j > 0) {

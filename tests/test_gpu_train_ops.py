@@ -36,9 +36,11 @@ def _ce_case(B, Lq, V, dtype, seed):
 def test_weighted_ce_forward_backward(L, dtype, V):
     B, Lq = 3, 40
     logits, labels, w = _ce_case(B, Lq, V, dtype, seed=V)
-    ref_in = logits.float().clone().requires_grad_(True)
-    ref = O.weighted_ce(ref_in, labels, w)            # oracle restatement of compute_loss
-    ref.backward()
+    with torch.enable_grad():                         # other test modules switch autograd off globally
+        ref_in = logits.float().clone().requires_grad_(True)
+        ref = O.weighted_ce(ref_in, labels, w)        # oracle restatement of compute_loss
+        ref.backward()
+    ref = ref.detach()
     loss, wsum, dl = L.weighted_ce(logits.cuda(), labels.cuda(), w, want_grad=True)
     sl = labels[:, 1:]
     assert abs(float(wsum) - float(w[sl[sl >= 0]].sum())) < 1e-3 * float(wsum)

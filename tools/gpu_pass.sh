@@ -52,7 +52,7 @@ fi
 if [[ $STAGES == *full* ]]; then
   # --set full on the kernels that carry the step; 2 decoder layers are enough to reach every kernel shape
   for spec in "gemm256vit gemm_bf16_tn_kernel.*256 40 4" "gemm256llm gemm_bf16_tn_kernel.*256 103 5" \
-              "flash128 flash_attn_kernel.*128 2 2" "flash64 flash_attn_kernel.*64 2 1" \
+              "flash128 flash_attn_tc_kernel.*128 2 2" "flash64 flash_attn_tc_kernel.*64 2 1" \
               "decattn decode_attn_kernel 2 2" "gemmskinny gemm_skinny_kernel 2 5"; do
     read name pat skip cnt <<< "$spec"
     timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base demangled \

@@ -60,11 +60,17 @@ def full(path):
             if k in hdr:
                 i = hdr.index(k)
                 print(f"  {k:70s} {r[i]:>18s} {units[i]}")
-        rd = float(r[hdr.index("dram__bytes_read.sum")].replace(",", ""))
-        wr = float(r[hdr.index("dram__bytes_write.sum")].replace(",", ""))
-        t = float(r[hdr.index("gpu__time_duration.sum")].replace(",", ""))
-        print(f"  => traffic {rd + wr:.2f} ({units[hdr.index('dram__bytes_read.sum')]}) in {t:.1f} "
-              f"{units[hdr.index('gpu__time_duration.sum')]}")
+        mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+        tmul = {"ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0, "usecond": 1e-6, "msecond": 1e-3, "nsecond": 1e-9,
+                "second": 1.0}
+
+        def val(key, table):
+            i = hdr.index(key)
+            return float(r[i].replace(",", "")) * table[units[i]]
+        traffic = val("dram__bytes_read.sum", mult) + val("dram__bytes_write.sum", mult)
+        t = val("gpu__time_duration.sum", tmul)
+        print(f"  => DRAM traffic {traffic / 1e6:.1f} MB in {t * 1e6:.1f} us = {traffic / t / 1e9:.0f} GB/s "
+              f"(under ncu: caches flushed before every replay)")
         print()
 
 
