@@ -255,6 +255,30 @@ int b200_llama_decode_step(const b200_llama_weights* w, int32_t* tokens, int32_t
  * Training-side operators (fine-tune step)
  * ========================================================================================================== */
 
+/* Backward building blocks of every nn.Linear / activation / norm on the path (autograd of the modules cited above;
+ * the reference gets them from torch autograd + cuBLAS).
+ * b200_gemm_bf16_ex: the GEMM of b200_gemm_bf16 with optionally TRANSPOSED operands read in place as MN-major
+ * tensor-core operands: a_transposed: A is stored [K, M]; w_transposed: W is stored [K, N]. With Y = X W^T:
+ *     dX[M,K] = dY[M,N] W[N,K]      -> (A = dY, W = W with w_transposed = 1, "N" = K, "K" = N)
+ *     dW[N,K] = dY^T[N,M] X[M,K]    -> (A = dY with a_transposed = 1, W = X with w_transposed = 1, "M" = N, "N" = K, "K" = M)
+ * accumulate != 0 (fp32 output only): C += result (gradient accumulation).
+ * b200_colsum: out[n] (+)= sum_m dy[m, n] (bias gradients), deterministic.
+ * b200_act_backward: dz = dy * act'(z) from the saved pre-activation z; act 1 quick_gelu, 2 gelu(erf), 3 SwiGLU
+ * (z = interleaved (gate, up) [M, 2F], dy [M, F], dz [M, 2F]); n_out = elements of dy.
+ * b200_norm_backward: LayerNorm (rms = 0) / RMSNorm (rms = 1) backward from the saved input x: dx bf16, dgamma / dbeta
+ * fp32 [D] ((+)= with accumulate; dbeta ignored for RMSNorm). D in {512, 1024, 4096}. */
+int b200_gemm_bf16_ex(const void* A, int lda, int a_transposed, const void* W, int ldw, int w_transposed, void* C, int ldc,
+                      int M, int N, int K, const void* bias, const void* residual, int ldr, int act, int out_fp32,
+                      int accumulate, int bn_hint, b200_stream_t stream);
+size_t b200_colsum_workspace_bytes(int N);
+int b200_colsum(const void* dy, int64_t ld, int M, int N, int accumulate, float* out, void* workspace,
+                size_t workspace_bytes, b200_stream_t stream);
+int b200_act_backward(const void* z, const void* dy, void* dz, int64_t n_out, int act, b200_stream_t stream);
+size_t b200_norm_backward_workspace_bytes(int M, int D);
+int b200_norm_backward(const void* x, const void* dy, const void* gamma, float eps, int M, int D, int rms, void* dx,
+                       float* dgamma, float* dbeta, int accumulate, void* workspace, size_t workspace_bytes,
+                       b200_stream_t stream);
+
 /* LLaVATrainer.compute_loss (train/llava_trainer.py:136-174): shifted cross-entropy of `logits` [B*L, V] against the
  * UNshifted modified_labels [B, L] (row (b, l) is scored against label (b, l + 1); -100 = ignored) with per-class
  * weights vocab_weight [V] (nn.CrossEntropyLoss(weight=...) semantics, NULL = unweighted):

@@ -77,6 +77,12 @@ _SIGS = {
     "b200_prof_collect": (ci, [vp, vp, vp, vp]),
     "b200_gemm_bf16": (ci, [vp, ci, vp, ci, vp, ci, ci, ci, ci, vp, vp, ci, vp, ci, ci, ci, vp]),
     "b200_gemm_bf16_skinny": (ci, [vp, ci, vp, ci, vp, ci, ci, ci, ci, vp, vp, ci, ci, ci, ci, vp]),
+    "b200_gemm_bf16_ex": (ci, [vp, ci, ci, vp, ci, ci, vp, ci, ci, ci, ci, vp, vp, ci, ci, ci, ci, ci, vp]),
+    "b200_colsum_workspace_bytes": (sz, [ci]),
+    "b200_colsum": (ci, [vp, i64, ci, ci, ci, vp, vp, sz, vp]),
+    "b200_act_backward": (ci, [vp, vp, vp, i64, ci, vp]),
+    "b200_norm_backward_workspace_bytes": (sz, [ci, ci]),
+    "b200_norm_backward": (ci, [vp, vp, vp, cf, ci, ci, ci, vp, vp, vp, ci, vp, sz, vp]),
     "b200_weighted_ce_workspace_bytes": (sz, [ci, ci]),
     "b200_weighted_ce": (ci, [vp, ci, i64, vp, vp, ci, ci, ci, cf, vp, i64, vp, vp, sz, vp]),
     "b200_grad_norm_workspace_bytes": (sz, []),
@@ -195,6 +201,53 @@ def gemm_skinny(a, w, out=None, bias=None, residual=None, act=ACT_NONE, out_fp32
                                      ptr(bias), ptr(residual), ldr, act, int(out_fp32), splits, stream_ptr())
     check(rc, "b200_gemm_bf16_skinny")
     return out
+
+
+def gemm_ex(a, w, a_t=False, w_t=False, out=None, out_fp32=False, accumulate=False, bn=0):
+    """General GEMM with transposed operands read in place: A is (M, K), or (K, M) when a_t; W is (N, K), or (K, N)
+    when w_t. out = A_eff @ W_eff.T, optionally accumulated into an fp32 `out`."""
+    M, K = (a.shape[1], a.shape[0]) if a_t else a.shape
+    N = w.shape[1] if w_t else w.shape[0]
+    assert (w.shape[0] if w_t else w.shape[1]) == K and a.stride(1) == 1 and w.stride(1) == 1
+    if out is None:
+        out = torch.empty((M, N), device=a.device, dtype=torch.float32 if out_fp32 else torch.bfloat16)
+    check(lib().b200_gemm_bf16_ex(ptr(a), a.stride(0), int(a_t), ptr(w), w.stride(0), int(w_t), ptr(out), out.stride(0),
+                                  M, N, K, None, None, 0, ACT_NONE, int(out.dtype == torch.float32), int(accumulate),
+                                  bn, stream_ptr()), "b200_gemm_bf16_ex")
+    return out
+
+
+def linear_backward(x, w, dy, dw=None, db=None, accumulate=False, need_dx=True):
+    """Backward of y = x @ w.T + b: returns (dx bf16 | None, dw fp32 (N, K), db fp32 (N,) | None)."""
+    dx = gemm_ex(dy, w, w_t=True) if need_dx else None                 # dX = dY W
+    dw = gemm_ex(dy, x, a_t=True, w_t=True, out=dw, out_fp32=True, accumulate=accumulate)   # dW = dY^T X
+    if db is not None or not accumulate:
+        N = w.shape[0]
+        if db is None:
+            db = torch.empty(N, device=x.device, dtype=torch.float32)
+        ws = torch.empty(int(lib().b200_colsum_workspace_bytes(N)), dtype=torch.uint8, device=x.device)
+        check(lib().b200_colsum(ptr(dy), dy.stride(0), dy.shape[0], N, int(accumulate), ptr(db), ptr(ws), ws.numel(),
+                                stream_ptr()), "b200_colsum")
+    return dx, dw, db
+
+
+def act_backward(z, dy, act):
+    dz = torch.empty_like(z)
+    check(lib().b200_act_backward(ptr(z), ptr(dy), ptr(dz), dy.numel(), act, stream_ptr()), "b200_act_backward")
+    return dz
+
+
+def norm_backward(x, dy, gamma, eps, rms=False, dgamma=None, dbeta=None, accumulate=False):
+    M, D = x.shape
+    dx = torch.empty_like(x)
+    if dgamma is None:
+        dgamma = torch.empty(D, device=x.device, dtype=torch.float32)
+    if dbeta is None and not rms:
+        dbeta = torch.empty(D, device=x.device, dtype=torch.float32)
+    ws = torch.empty(int(lib().b200_norm_backward_workspace_bytes(M, D)), dtype=torch.uint8, device=x.device)
+    check(lib().b200_norm_backward(ptr(x), ptr(dy), ptr(gamma), eps, M, D, int(rms), ptr(dx), ptr(dgamma), ptr(dbeta),
+                                   int(accumulate), ptr(ws), ws.numel(), stream_ptr()), "b200_norm_backward")
+    return dx, dgamma, dbeta
 
 
 def weighted_ce(logits, labels, vocab_weight=None, grad_scale=1.0, want_grad=False, inplace=False):

@@ -57,6 +57,41 @@ int b200_gemm_bf16_skinny(const void* A, int lda, const void* W, int ldw, void* 
                      static_cast<cudaStream_t>(stream));
 }
 
+int b200_gemm_bf16_ex(const void* A, int lda, int a_transposed, const void* W, int ldw, int w_transposed, void* C, int ldc,
+                      int M, int N, int K, const void* bias, const void* residual, int ldr, int act, int out_fp32,
+                      int accumulate, int bn_hint, b200_stream_t stream) {
+  GemmEpilogue e;
+  e.bias = static_cast<const bf16*>(bias);
+  e.residual = static_cast<const bf16*>(residual);
+  e.ldr = ldr;
+  e.act = act;
+  e.out_fp32 = out_fp32;
+  e.accumulate = accumulate;
+  return gemm_bf16_ex(static_cast<const bf16*>(A), lda, a_transposed, static_cast<const bf16*>(W), ldw, w_transposed, C,
+                      ldc, M, N, K, e, bn_hint, static_cast<cudaStream_t>(stream));
+}
+
+size_t b200_colsum_workspace_bytes(int N) { return colsum_workspace_bytes(N); }
+int b200_colsum(const void* dy, int64_t ld, int M, int N, int accumulate, float* out, void* workspace,
+                size_t workspace_bytes, b200_stream_t stream) {
+  return colsum(static_cast<const bf16*>(dy), ld, M, N, accumulate, out, workspace, workspace_bytes,
+                static_cast<cudaStream_t>(stream));
+}
+
+int b200_act_backward(const void* z, const void* dy, void* dz, int64_t n_out, int act, b200_stream_t stream) {
+  return act_backward(static_cast<const bf16*>(z), static_cast<const bf16*>(dy), static_cast<bf16*>(dz), n_out, act,
+                      static_cast<cudaStream_t>(stream));
+}
+
+size_t b200_norm_backward_workspace_bytes(int M, int D) { return norm_backward_workspace_bytes(M, D); }
+int b200_norm_backward(const void* x, const void* dy, const void* gamma, float eps, int M, int D, int rms, void* dx,
+                       float* dgamma, float* dbeta, int accumulate, void* workspace, size_t workspace_bytes,
+                       b200_stream_t stream) {
+  return norm_backward(static_cast<const bf16*>(x), static_cast<const bf16*>(dy), static_cast<const bf16*>(gamma), eps,
+                       M, D, rms, static_cast<bf16*>(dx), dgamma, dbeta, accumulate, workspace, workspace_bytes,
+                       static_cast<cudaStream_t>(stream));
+}
+
 size_t b200_weighted_ce_workspace_bytes(int B, int L) { return weighted_ce_workspace_bytes(B, L); }
 
 int b200_weighted_ce(const void* logits, int logits_fp32, int64_t ld, const int64_t* labels, const float* vocab_weight,

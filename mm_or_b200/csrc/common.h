@@ -82,6 +82,7 @@ struct GemmEpilogue {
   int res_group_stride = 0;  // (lets a compact (B*576)-row GEMM read its residual from a (B, S, D) tensor)
   int act = kActNone;
   int out_fp32 = 0;  // 0: C is bf16, 1: C is fp32
+  int accumulate = 0;  // fp32 output only: C += result
   // fused GEMM -> all-gather: when n_peers > 0 every bf16 output vector is stored to the same offset of each
   // peer_c[p] (peer-mapped device pointers over NVLink, this rank's own buffer included) instead of C.
   int n_peers = 0;
@@ -91,6 +92,11 @@ struct GemmEpilogue {
 // bn_hint: 0 = choose automatically, else one of 32/64/128/256
 int gemm_bf16_tn(const bf16* A, int lda, const bf16* B, int ldb, void* C, int ldc, int M, int N, int K,
                  const GemmEpilogue& epi, int bn_hint, cudaStream_t stream);
+
+// General form: a_mn / b_mn = 1 means the operand is stored transposed ([K, M] / [K, N]) and is read in place as an
+// MN-major tensor-core operand (backward GEMMs: dX = dY W uses b_mn, dW = dY^T X uses both).
+int gemm_bf16_ex(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, int b_mn, void* C, int ldc, int M, int N,
+                 int K, const GemmEpilogue& epi, int bn_hint, cudaStream_t stream);
 
 // Decode-step GEMM (gemm_skinny.cu): M <= 256, weights streamed once, K split across a thread-block cluster and
 // reduced through distributed shared memory in split order. splits_hint: 0 = auto, else 1/2/4/8.
@@ -105,6 +111,14 @@ int weighted_ce(const void* logits, int is_fp32, long long ld, const long long* 
 size_t grad_norm_workspace_bytes();
 int grad_sq_norm(const bf16* grad, long long n, int accumulate, float max_norm, float* out2, void* workspace,
                  size_t workspace_bytes, cudaStream_t stream);
+size_t colsum_workspace_bytes(int N);
+int colsum(const bf16* dy, long long ld, int M, int N, int accumulate, float* out, void* workspace,
+           size_t workspace_bytes, cudaStream_t stream);
+int act_backward(const bf16* z, const bf16* dy, bf16* dz, long long n_out, int act, cudaStream_t stream);
+size_t norm_backward_workspace_bytes(int M, int D);
+int norm_backward(const bf16* x, const bf16* dy, const bf16* gamma, float eps, int M, int D, int rms, bf16* dx,
+                  float* dgamma, float* dbeta, int accumulate, void* workspace, size_t workspace_bytes,
+                  cudaStream_t stream);
 int adamw_step(float* master, bf16* param, const bf16* grad, float* m, float* v, long long n, float lr, float beta1,
                float beta2, float eps, float weight_decay, int step, const float* clip_coef, cudaStream_t stream);
 

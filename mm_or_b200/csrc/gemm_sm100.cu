@@ -32,6 +32,9 @@ struct GemmArgs {
   int ldc;
   int M, N, K;
   int m_tiles, n_tiles;
+  // operand majors: 0 = K-major ([rows, K], the nn.Linear forward layout), 1 = MN-major (the matrix is stored
+  // [K, rows]: the transposed operands of the backward GEMMs dX = dY W and dW = dY^T X, read in place)
+  int a_mn, b_mn;
   GemmEpilogue epi;
 };
 
@@ -114,8 +117,20 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          tma_load_2d(smem_a + stage * Cfg::kStageBytesA, &tmA, &full_bar[stage], kb * kBK, mt * kBM);
-          tma_load_2d(smem_b + stage * Cfg::kStageBytesB, &tmB, &full_bar[stage], kb * kBK, nt * BN);
+          if (!g.a_mn) {
+            tma_load_2d(smem_a + stage * Cfg::kStageBytesA, &tmA, &full_bar[stage], kb * kBK, mt * kBM);
+          } else {  // [64 k rows][64 m] boxes, one 8 KB panel per 64 rows of the tile
+            for (int p = 0; p < kBM / 64; ++p)
+              tma_load_2d(smem_a + stage * Cfg::kStageBytesA + p * 8192, &tmA, &full_bar[stage], mt * kBM + p * 64,
+                          kb * kBK);
+          }
+          if (!g.b_mn) {
+            tma_load_2d(smem_b + stage * Cfg::kStageBytesB, &tmB, &full_bar[stage], kb * kBK, nt * BN);
+          } else {
+            for (int p = 0; p < BN / 64; ++p)
+              tma_load_2d(smem_b + stage * Cfg::kStageBytesB + p * 8192, &tmB, &full_bar[stage], nt * BN + p * 64,
+                          kb * kBK);
+          }
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1u;
@@ -126,7 +141,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN);
+      const uint32_t idesc = umma_idesc_bf16(kBM, BN, g.a_mn, g.b_mn);
+      // K-major: 16 k = 32 B inside the 128 B swizzle row (+2 in the addr>>4 field); MN-major: 16 k rows of 128 B
+      const uint32_t a_step = g.a_mn ? 128u : 2u, b_step = g.b_mn ? 128u : 2u;
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -138,13 +155,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after_sync();
-          const uint64_t da = umma_desc_kmajor_sw128(smem_u32(smem_a + stage * Cfg::kStageBytesA));
-          const uint64_t db = umma_desc_kmajor_sw128(smem_u32(smem_b + stage * Cfg::kStageBytesB));
+          const uint32_t sa = smem_u32(smem_a + stage * Cfg::kStageBytesA);
+          const uint32_t sb = smem_u32(smem_b + stage * Cfg::kStageBytesB);
+          const uint64_t da = g.a_mn ? umma_desc_mnmajor_sw128(sa, 8192) : umma_desc_kmajor_sw128(sa);
+          const uint64_t db = g.b_mn ? umma_desc_mnmajor_sw128(sb, 8192) : umma_desc_kmajor_sw128(sb);
 #pragma unroll
-          for (int k = 0; k < kBK / 16; ++k) {
-            // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in the (addr >> 4) field
-            umma_bf16_ss(d_addr, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-          }
+          for (int k = 0; k < kBK / 16; ++k)
+            umma_bf16_ss(d_addr, da + a_step * k, db + b_step * k, idesc, (kb | k) != 0 ? 1u : 0u);
           umma_commit(&empty_bar[stage]);  // stage reusable once these MMAs have read it
           if (++stage == kStages) {
             stage = 0;
@@ -250,9 +267,17 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
           float* crow = reinterpret_cast<float*>(g.C) + static_cast<size_t>(out_row) * g.ldc + n0;
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {
-            if (n0 + j4 * 4 < g.N)
-              *reinterpret_cast<float4*>(crow + j4 * 4) =
-                  make_float4(x[j4 * 4], x[j4 * 4 + 1], x[j4 * 4 + 2], x[j4 * 4 + 3]);
+            if (n0 + j4 * 4 < g.N) {
+              float4 o = make_float4(x[j4 * 4], x[j4 * 4 + 1], x[j4 * 4 + 2], x[j4 * 4 + 3]);
+              if (e.accumulate) {  // C += result (gradient accumulation over micro-batches)
+                const float4 old = *reinterpret_cast<const float4*>(crow + j4 * 4);
+                o.x += old.x;
+                o.y += old.y;
+                o.z += old.z;
+                o.w += old.w;
+              }
+              *reinterpret_cast<float4*>(crow + j4 * 4) = o;
+            }
           }
         } else {
           const size_t coff = static_cast<size_t>(out_row) * g.ldc + n0;
@@ -364,14 +389,18 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   return 0;
 }
 
-int gemm_bf16_tn(const bf16* A, int lda, const bf16* B, int ldb, void* C, int ldc, int M, int N, int K,
-                 const GemmEpilogue& epi, int bn_hint, cudaStream_t stream) {
+// A: [M, K] (a_mn = 0) or stored transposed [K, M] (a_mn = 1); B: [N, K] (b_mn = 0) or [K, N] (b_mn = 1).
+int gemm_bf16_ex(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, int b_mn, void* C, int ldc, int M, int N,
+                 int K, const GemmEpilogue& epi, int bn_hint, cudaStream_t stream) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
-  if (K % 8 != 0 || N % 8 != 0) return fail(-2, "gemm: K (%d) and N (%d) must be multiples of 8", K, N);
+  if (N % 8 != 0) return fail(-2, "gemm: N (%d) must be a multiple of 8", N);
+  if (!(a_mn && b_mn) && K % 8 != 0) return fail(-2, "gemm: K (%d) must be a multiple of 8 for a K-major operand", K);
+  if (a_mn && M % 8 != 0) return fail(-2, "gemm: M (%d) must be a multiple of 8 for a transposed A", M);
   if (epi.act == kActSwiGLU && (N % 16 != 0 || epi.out_fp32 || epi.residual))
     return fail(-2, "gemm: SwiGLU epilogue needs N %% 16 == 0, bf16 output and no residual");
   if (epi.n_peers < 0 || epi.n_peers > 8 || (epi.n_peers > 0 && (epi.out_fp32 || epi.act == kActSwiGLU)))
     return fail(-2, "gemm: peer stores need 1..8 peers, bf16 output and no SwiGLU pairing");
+  if (epi.accumulate && !epi.out_fp32) return fail(-2, "gemm: accumulation needs an fp32 output");
   const int m_tiles = (M + kBM - 1) / kBM;
   int bn = bn_hint;
   if (bn == 0) {
@@ -381,6 +410,7 @@ int gemm_bf16_tn(const bf16* A, int lda, const bf16* B, int ldb, void* C, int ld
     const int sms = num_sms();
     while (bn > 32 && m_tiles * ((N + bn - 1) / bn) < sms) bn >>= 1;
   }
+  if (b_mn && bn < 64) bn = 64;  // a transposed B tile is made of 64-column panels
   if (bn != 32 && bn != 64 && bn != 128 && bn != 256) return fail(-2, "gemm: unsupported BN %d", bn);
   GemmArgs g;
   g.C = C;
@@ -390,16 +420,29 @@ int gemm_bf16_tn(const bf16* A, int lda, const bf16* B, int ldb, void* C, int ld
   g.K = K;
   g.m_tiles = m_tiles;
   g.n_tiles = (N + bn - 1) / bn;
+  g.a_mn = a_mn ? 1 : 0;
+  g.b_mn = b_mn ? 1 : 0;
   g.epi = epi;
   CUtensorMap tmA, tmB;
-  B200_TRY(make_tmap_2d(&tmA, A, M, K, lda, kBM));
-  B200_TRY(make_tmap_2d(&tmB, B, N, K, ldb, bn));
+  if (a_mn)
+    B200_TRY(make_tmap_2d(&tmA, A, K, M, lda, 64));
+  else
+    B200_TRY(make_tmap_2d(&tmA, A, M, K, lda, kBM));
+  if (b_mn)
+    B200_TRY(make_tmap_2d(&tmB, B, K, N, ldb, 64));
+  else
+    B200_TRY(make_tmap_2d(&tmB, B, N, K, ldb, bn));
   switch (bn) {
     case 256: return launch_gemm<256>(tmA, tmB, g, stream);
     case 128: return launch_gemm<128>(tmA, tmB, g, stream);
     case 64: return launch_gemm<64>(tmA, tmB, g, stream);
     default: return launch_gemm<32>(tmA, tmB, g, stream);
   }
+}
+
+int gemm_bf16_tn(const bf16* A, int lda, const bf16* B, int ldb, void* C, int ldc, int M, int N, int K,
+                 const GemmEpilogue& epi, int bn_hint, cudaStream_t stream) {
+  return gemm_bf16_ex(A, lda, 0, B, ldb, 0, C, ldc, M, N, K, epi, bn_hint, stream);
 }
 
 }  // namespace b200

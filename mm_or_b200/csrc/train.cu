@@ -322,4 +322,257 @@ int adamw_step(float* master, bf16* param, const bf16* grad, float* m, float* v,
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// backward building blocks (bias gradient, activation / norm backward). Forward formulas: gemm_sm100.cu act_apply,
+// norm.cu; references: HF CLIPMLP quick_gelu, BertIntermediate gelu(erf), LlamaMLP silu(gate) * up, nn.LayerNorm,
+// LlamaRMSNorm (fp32 statistics).
+// ---------------------------------------------------------------------------------------------------
+static constexpr int kColSplit = 64;
+
+// db[n] (+)= sum_m dY[m, n]: two-stage, fixed order. stage 1: grid (ceil(N/256), kColSplit)
+__global__ void __launch_bounds__(256) colsum_partial_kernel(const bf16* __restrict__ dy, long long ld, int M, int N,
+                                                             float* __restrict__ partial) {
+  const int n = blockIdx.x * 256 + threadIdx.x;
+  if (n >= N) return;
+  const int rows = (M + kColSplit - 1) / kColSplit;
+  const int m0 = blockIdx.y * rows, m1 = min(M, m0 + rows);
+  float acc = 0.f;
+  for (int m = m0; m < m1; ++m) acc += __bfloat162float(dy[static_cast<long long>(m) * ld + n]);
+  partial[static_cast<long long>(blockIdx.y) * N + n] = acc;
+}
+__global__ void __launch_bounds__(256) colsum_finish_kernel(const float* __restrict__ partial, int N, int accumulate,
+                                                            float* __restrict__ out) {
+  const int n = blockIdx.x * 256 + threadIdx.x;
+  if (n >= N) return;
+  float acc = accumulate ? out[n] : 0.f;
+  for (int s = 0; s < kColSplit; ++s) acc += partial[static_cast<long long>(s) * N + n];
+  out[n] = acc;
+}
+
+size_t colsum_workspace_bytes(int N) { return static_cast<size_t>(kColSplit) * N * sizeof(float); }
+
+int colsum(const bf16* dy, long long ld, int M, int N, int accumulate, float* out, void* workspace,
+           size_t workspace_bytes, cudaStream_t stream) {
+  if (M <= 0 || N <= 0) return 0;
+  if (workspace == nullptr || workspace_bytes < colsum_workspace_bytes(N)) return fail(-2, "colsum: workspace too small");
+  LaunchScope scope(kFamTrain, stream, 2.0 * M * N, 0.0, 2);
+  float* partial = static_cast<float*>(workspace);
+  colsum_partial_kernel<<<dim3((N + 255) / 256, kColSplit), 256, 0, stream>>>(dy, ld, M, N, partial);
+  colsum_finish_kernel<<<(N + 255) / 256, 256, 0, stream>>>(partial, N, accumulate, out);
+  B200_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// dz = dy * act'(z) for the pre-activation z saved by the forward GEMM (act: kActQuickGelu / kActGeluErf), or for
+// SwiGLU: z = interleaved (gate, up) pairs [M, 2F], dy [M, F] -> dz [M, 2F] interleaved.
+__global__ void __launch_bounds__(256) act_backward_kernel(const bf16* __restrict__ z, const bf16* __restrict__ dy,
+                                                           bf16* __restrict__ dz, long long n_out, int act) {
+  const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;  // one output element of dy each
+  if (i >= n_out) return;
+  const float g = __bfloat162float(dy[i]);
+  if (act == kActSwiGLU) {
+    const float gate = __bfloat162float(z[2 * i]), up = __bfloat162float(z[2 * i + 1]);
+    const float sg = 1.f / (1.f + __expf(-gate));
+    const float silu = gate * sg;
+    dz[2 * i] = __float2bfloat16(g * up * (sg + silu * (1.f - sg)));   // d silu(x) = s + x s (1 - s)
+    dz[2 * i + 1] = __float2bfloat16(g * silu);
+    return;
+  }
+  const float x = __bfloat162float(z[i]);
+  float d;
+  if (act == kActQuickGelu) {
+    const float sg = 1.f / (1.f + __expf(-1.702f * x));
+    d = sg + 1.702f * x * sg * (1.f - sg);
+  } else {  // gelu(erf): Phi(x) + x phi(x)
+    d = 0.5f * (1.f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
+  }
+  dz[i] = __float2bfloat16(g * d);
+}
+
+int act_backward(const bf16* z, const bf16* dy, bf16* dz, long long n_out, int act, cudaStream_t stream) {
+  if (n_out <= 0) return 0;
+  if (act != kActQuickGelu && act != kActGeluErf && act != kActSwiGLU) return fail(-2, "act_backward: unknown act %d", act);
+  LaunchScope scope(kFamTrain, stream, (act == kActSwiGLU ? 10.0 : 6.0) * n_out, 0.0);
+  act_backward_kernel<<<static_cast<unsigned>((n_out + 255) / 256), 256, 0, stream>>>(z, dy, dz, n_out, act);
+  B200_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// LayerNorm / RMSNorm backward. One CTA walks a block of rows; every thread owns 8 * kVec fixed columns
+// (D = kThreads * 8 * kVec), so the dgamma / dbeta sums of the CTA's rows stay in registers; fp32 statistics are
+// recomputed from x with two block reductions per row:
+//   LN : xhat = (x - mean) rstd;  dx = rstd (dyg - mean(dyg) - xhat mean(dyg xhat)),  dyg = dy * gamma
+//   RMS: xhat = x rstd;           dx = rstd (dyg - xhat mean(dyg xhat))
+// Per-CTA dgamma / dbeta partials are summed in block order by norm_param_finish_kernel (deterministic).
+template <int kThreads>
+__device__ __forceinline__ void block_sum2(float& a, float& b, float (*red)[2]) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, off);
+    b += __shfl_xor_sync(0xffffffffu, b, off);
+  }
+  __syncthreads();
+  if (lane == 0) {
+    red[warp][0] = a;
+    red[warp][1] = b;
+  }
+  __syncthreads();
+  a = b = 0.f;
+#pragma unroll
+  for (int w = 0; w < kThreads / 32; ++w) {
+    a += red[w][0];
+    b += red[w][1];
+  }
+}
+
+template <int kThreads, int kVec, bool kRms>
+__global__ void __launch_bounds__(kThreads) norm_backward_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy,
+                                                                 const bf16* __restrict__ gamma, float eps, int M,
+                                                                 int D, bf16* __restrict__ dx,
+                                                                 float* __restrict__ pgamma, float* __restrict__ pbeta,
+                                                                 int rows_per_block) {
+  __shared__ float red[kThreads / 32][2];
+  float gm[kVec][8], dg[kVec][8], db[kVec][8];
+#pragma unroll
+  for (int i = 0; i < kVec; ++i) {
+    const uint4 g4 = __ldg(reinterpret_cast<const uint4*>(gamma) + i * kThreads + threadIdx.x);
+    const float t[8] = {bf16lo(g4.x), bf16hi(g4.x), bf16lo(g4.y), bf16hi(g4.y),
+                        bf16lo(g4.z), bf16hi(g4.z), bf16lo(g4.w), bf16hi(g4.w)};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      gm[i][j] = t[j];
+      dg[i][j] = db[i][j] = 0.f;
+    }
+  }
+  const int r0 = blockIdx.x * rows_per_block;
+  const int r1 = min(M, r0 + rows_per_block);
+  for (int row = r0; row < r1; ++row) {
+    const uint4* xp = reinterpret_cast<const uint4*>(x + static_cast<long long>(row) * D);
+    const uint4* gp = reinterpret_cast<const uint4*>(dy + static_cast<long long>(row) * D);
+    float xv[kVec][8], gv[kVec][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < kVec; ++i) {
+      const uint4 u = xp[i * kThreads + threadIdx.x], w = gp[i * kThreads + threadIdx.x];
+      const float a[8] = {bf16lo(u.x), bf16hi(u.x), bf16lo(u.y), bf16hi(u.y),
+                          bf16lo(u.z), bf16hi(u.z), bf16lo(u.w), bf16hi(u.w)};
+      const float b[8] = {bf16lo(w.x), bf16hi(w.x), bf16lo(w.y), bf16hi(w.y),
+                          bf16lo(w.z), bf16hi(w.z), bf16lo(w.w), bf16hi(w.w)};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        xv[i][j] = a[j];
+        gv[i][j] = b[j];
+        s1 += a[j];
+        s2 += a[j] * a[j];
+      }
+    }
+    block_sum2<kThreads>(s1, s2, red);
+    float mean = 0.f, rstd;
+    if (kRms) {
+      rstd = rsqrtf(s2 / D + eps);
+    } else {
+      mean = s1 / D;
+      float var = 0.f, dummy = 0.f;
+#pragma unroll
+      for (int i = 0; i < kVec; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float d = xv[i][j] - mean;
+          var += d * d;
+        }
+      block_sum2<kThreads>(var, dummy, red);
+      rstd = rsqrtf(var / D + eps);
+    }
+    float c1 = 0.f, c2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < kVec; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xhat = (xv[i][j] - mean) * rstd;
+        dg[i][j] += gv[i][j] * xhat;
+        db[i][j] += gv[i][j];
+        const float dyg = gv[i][j] * gm[i][j];
+        xv[i][j] = xhat;
+        gv[i][j] = dyg;
+        c1 += dyg;
+        c2 += dyg * xhat;
+      }
+    block_sum2<kThreads>(c1, c2, red);
+    c1 = kRms ? 0.f : c1 / D;
+    c2 /= D;
+    uint4* op = reinterpret_cast<uint4*>(dx + static_cast<long long>(row) * D);
+#pragma unroll
+    for (int i = 0; i < kVec; ++i) {
+      float y[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) y[j] = rstd * (gv[i][j] - c1 - xv[i][j] * c2);
+      uint4 o;
+      o.x = pack_bf16x2(y[0], y[1]);
+      o.y = pack_bf16x2(y[2], y[3]);
+      o.z = pack_bf16x2(y[4], y[5]);
+      o.w = pack_bf16x2(y[6], y[7]);
+      op[i * kThreads + threadIdx.x] = o;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < kVec; ++i) {
+    float* pgd = pgamma + static_cast<long long>(blockIdx.x) * D + (i * kThreads + threadIdx.x) * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) pgd[j] = dg[i][j];
+    if (!kRms && pbeta != nullptr) {
+      float* pbd = pbeta + static_cast<long long>(blockIdx.x) * D + (i * kThreads + threadIdx.x) * 8;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) pbd[j] = db[i][j];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) norm_param_finish_kernel(const float* __restrict__ partial, int blocks, int D,
+                                                                int accumulate, float* __restrict__ out) {
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= D) return;
+  float acc = accumulate ? out[c] : 0.f;
+  for (int b = 0; b < blocks; ++b) acc += partial[static_cast<long long>(b) * D + c];
+  out[c] = acc;
+}
+
+static constexpr int kNormBwdRows = 16;  // rows per CTA
+
+size_t norm_backward_workspace_bytes(int M, int D) {
+  const size_t blocks = (M + kNormBwdRows - 1) / kNormBwdRows;
+  return 2 * blocks * D * sizeof(float);
+}
+
+// dgamma / dbeta: fp32 [D], (+)= when accumulate. beta == rms -> dbeta ignored (pass nullptr).
+int norm_backward(const bf16* x, const bf16* dy, const bf16* gamma, float eps, int M, int D, int rms, bf16* dx,
+                  float* dgamma, float* dbeta, int accumulate, void* workspace, size_t workspace_bytes,
+                  cudaStream_t stream) {
+  if (M <= 0) return 0;
+  if (workspace == nullptr || workspace_bytes < norm_backward_workspace_bytes(M, D))
+    return fail(-2, "norm_backward: workspace too small");
+  const int blocks = (M + kNormBwdRows - 1) / kNormBwdRows;
+  float* pg = static_cast<float*>(workspace);
+  float* pb = pg + static_cast<size_t>(blocks) * D;
+  LaunchScope scope(kFamTrain, stream, 6.0 * M * D, 0.0, 3);
+#define B200_NB(T, V)                                                                                          \
+  if (rms)                                                                                                     \
+    norm_backward_kernel<T, V, true><<<blocks, T, 0, stream>>>(x, dy, gamma, eps, M, D, dx, pg, nullptr,      \
+                                                               kNormBwdRows);                                 \
+  else                                                                                                         \
+    norm_backward_kernel<T, V, false><<<blocks, T, 0, stream>>>(x, dy, gamma, eps, M, D, dx, pg, pb, kNormBwdRows);
+  switch (D) {
+    case 512: B200_NB(64, 1) break;
+    case 1024: B200_NB(128, 1) break;
+    case 4096: B200_NB(256, 2) break;
+    default: return fail(-2, "norm_backward: hidden size %d not supported (512 / 1024 / 4096)", D);
+  }
+#undef B200_NB
+  if (dgamma != nullptr) norm_param_finish_kernel<<<(D + 255) / 256, 256, 0, stream>>>(pg, blocks, D, accumulate, dgamma);
+  if (!rms && dbeta != nullptr)
+    norm_param_finish_kernel<<<(D + 255) / 256, 256, 0, stream>>>(pb, blocks, D, accumulate, dbeta);
+  B200_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 }  // namespace b200

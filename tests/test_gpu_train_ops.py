@@ -95,3 +95,77 @@ def test_grad_norm_and_adamw_match_torch(L, n):
     out2 = L.grad_sq_norm(b, out2=out2, accumulate=True, max_norm=1.0)
     tot = float(a.float().pow(2).sum() + b.float().pow(2).sum())
     assert abs(float(out2[0]) - tot) < 1e-4 * tot
+
+
+def rnd(*shape, scale=1.0, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return (torch.randn(*shape, generator=g, device="cuda") * scale).to(torch.bfloat16)
+
+
+def rel(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).norm() / (b.norm() + 1e-12)).item()
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 256, 128), (1000, 1024, 512), (3924, 4096, 11008), (577 * 2, 4096, 1024),
+                                   (40, 32000, 4096), (8, 64, 72)])
+def test_gemm_transposed_operands(L, M, N, K):
+    """The three operand layouts of a Linear's backward, read in place (MN-major tensor-core operands)."""
+    a, w = rnd(M, K, seed=1), rnd(N, K, scale=1 / math.sqrt(K), seed=2)
+    ref = a.float() @ w.float().t()
+    at, wt = a.t().contiguous(), w.t().contiguous()           # stored transposed: (K, M), (K, N)
+    assert rel(L.gemm_ex(a, wt, w_t=True), ref) < 5e-3
+    assert rel(L.gemm_ex(at, w, a_t=True), ref) < 5e-3
+    assert rel(L.gemm_ex(at, wt, a_t=True, w_t=True), ref) < 5e-3
+    acc = torch.ones(M, N, device="cuda", dtype=torch.float32)
+    L.gemm_ex(at, wt, a_t=True, w_t=True, out=acc, accumulate=True)
+    assert rel(acc - 1.0, ref) < 1e-4
+
+
+def test_linear_backward_matches_autograd(L):
+    M, N, K = 1200, 1024, 768
+    x, w, dy = rnd(M, K, seed=3), rnd(N, K, scale=0.05, seed=4), rnd(M, N, seed=5)
+    with torch.enable_grad():
+        xr, wr = x.float().requires_grad_(True), w.float().requires_grad_(True)
+        br = torch.zeros(N, device="cuda", requires_grad=True)
+        (torch.nn.functional.linear(xr, wr, br) * dy.float()).sum().backward()
+    dx, dw, db = L.linear_backward(x, w, dy)
+    assert rel(dx, xr.grad) < 5e-3 and rel(dw, wr.grad) < 1e-4 and rel(db, br.grad) < 1e-5
+    dx2, dw2, db2 = L.linear_backward(x, w, dy, dw=dw.clone(), db=db.clone(), accumulate=True)
+    assert rel(dw2, 2 * wr.grad) < 1e-4 and rel(db2, 2 * br.grad) < 1e-5
+
+
+@pytest.mark.parametrize("act", [1, 2, 3])
+def test_activation_backward(L, act):
+    M, F = 333, 1408
+    z = rnd(M, 2 * F if act == 3 else F, seed=6) * 2
+    dy = rnd(M, F, seed=7)
+    with torch.enable_grad():
+        zr = z.float().requires_grad_(True)
+        if act == 1:
+            y = zr * torch.sigmoid(1.702 * zr)
+        elif act == 2:
+            y = torch.nn.functional.gelu(zr)
+        else:
+            y = torch.nn.functional.silu(zr[:, 0::2]) * zr[:, 1::2]
+        (y * dy.float()).sum().backward()
+    assert rel(L.act_backward(z, dy, act), zr.grad) < 5e-3
+
+
+@pytest.mark.parametrize("D,rms", [(512, True), (1024, False), (4096, True), (4096, False)])
+def test_norm_backward(L, D, rms):
+    M = 777
+    x, dy, g = rnd(M, D, seed=8), rnd(M, D, seed=9), rnd(D, scale=0.1, seed=10) + 1
+    with torch.enable_grad():
+        xr, gr = x.float().requires_grad_(True), g.float().requires_grad_(True)
+        br = torch.zeros(D, device="cuda", requires_grad=True)
+        if rms:
+            y = gr * xr * torch.rsqrt(xr.pow(2).mean(-1, keepdim=True) + 1e-5)
+        else:
+            y = torch.nn.functional.layer_norm(xr, (D,), gr, br, 1e-5)
+        (y * dy.float()).sum().backward()
+    dx, dg, db = L.norm_backward(x, dy, g, 1e-5, rms=rms)
+    assert rel(dx, xr.grad) < 5e-3
+    assert rel(dg, gr.grad) < 1e-4
+    if not rms:
+        assert rel(db, br.grad) < 1e-4
