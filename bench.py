@@ -244,6 +244,9 @@ def run_b200(args):
     roof = None
     L_packed = args.text_len - 1 + 576
     if not args.no_roofline and rank == 0:
+        # rank 0 alone runs this extra, event-instrumented step: it must not enter the visual-token exchange (a
+        # collective), so the model is taken out of the process group for it -- the kernels timed are the same
+        model.set_process_group(None)
         L.prof_enable(True)
         model.generate(ids, images=images_dev, **dict(gen_kw, use_cuda_graph=False))
         fam = L.prof_collect()

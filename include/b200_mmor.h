@@ -90,6 +90,26 @@ int b200_flash_attention(const void* q, int64_t q_bs, int64_t q_rs, int64_t q_hs
                          const int32_t* kv_start, const int32_t* kv_len, int causal, float scale,
                          b200_stream_t stream);
 
+/* Training-time variant: additionally writes lse [B, H, Lq] fp32, the natural-log sum-exp of every query row's scaled
+ * scores (-inf for fully masked rows), which the attention backward pass needs (FlashAttention-2 saves the same,
+ * train/llama_flash_attn_monkey_patch.py:78-89 -> flash_attn_varlen_qkvpacked_func). */
+int b200_flash_attention_lse(const void* q, int64_t q_bs, int64_t q_rs, int64_t q_hs, const void* k, int64_t k_bs,
+                             int64_t k_rs, int64_t k_hs, const void* v, int64_t v_bs, int64_t v_rs, int64_t v_hs,
+                             void* o, int64_t o_bs, int64_t o_rs, int64_t o_hs, int B, int H, int Lq, int Lk,
+                             int head_dim, const int32_t* kv_start, const int32_t* kv_len, int causal, float scale,
+                             float* lse, b200_stream_t stream);
+
+/* Attention backward (autograd of the three attention sites; for the Llama layers the reference runs FlashAttention-2's
+ * backward behind train/llama_flash_attn_monkey_patch.py:78-89). P is recomputed from lse; dO has O's layout and
+ * dq / dk / dv have the layout (strides) of q / k / v. No atomics: bit-deterministic. workspace: *_workspace_bytes. */
+size_t b200_flash_attention_bwd_workspace_bytes(int B, int H, int Lq);
+int b200_flash_attention_bwd(const void* q, int64_t q_bs, int64_t q_rs, int64_t q_hs, const void* k, int64_t k_bs,
+                             int64_t k_rs, int64_t k_hs, const void* v, int64_t v_bs, int64_t v_rs, int64_t v_hs,
+                             const void* o, const void* d_o, int64_t o_bs, int64_t o_rs, int64_t o_hs, const float* lse,
+                             void* dq, void* dk, void* dv, int B, int H, int Lq, int Lk, int head_dim,
+                             const int32_t* kv_start, const int32_t* kv_len, int causal, float scale, void* workspace,
+                             size_t workspace_bytes, b200_stream_t stream);
+
 /* Single-token attention against the KV cache [B][H][cap][128] (decode step, model/llava_arch.py:192-201 + HF
  * LlamaAttention with past_key_values). ctx = slots in use; kv_start as above. splits: 0 = auto. */
 size_t b200_decode_attention_workspace_bytes(int B, int H, int ctx);

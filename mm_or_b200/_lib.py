@@ -92,6 +92,11 @@ _SIGS = {
     "b200_rmsnorm": (ci, [vp, i64, vp, cf, vp, i64, ci, ci, vp]),
     "b200_flash_attention": (ci, [vp, i64, i64, i64, vp, i64, i64, i64, vp, i64, i64, i64, vp, i64, i64, i64,
                                   ci, ci, ci, ci, ci, vp, vp, ci, cf, vp]),
+    "b200_flash_attention_lse": (ci, [vp, i64, i64, i64, vp, i64, i64, i64, vp, i64, i64, i64, vp, i64, i64, i64,
+                                      ci, ci, ci, ci, ci, vp, vp, ci, cf, vp, vp]),
+    "b200_flash_attention_bwd_workspace_bytes": (sz, [ci, ci, ci]),
+    "b200_flash_attention_bwd": (ci, [vp, i64, i64, i64, vp, i64, i64, i64, vp, i64, i64, i64, vp, vp, i64, i64, i64,
+                                      vp, vp, vp, vp, ci, ci, ci, ci, ci, vp, vp, ci, cf, vp, sz, vp]),
     "b200_decode_attention_workspace_bytes": (sz, [ci, ci, ci]),
     "b200_decode_attention": (ci, [vp, i64, vp, vp, vp, i64, ci, ci, ci, ci, vp, cf, ci, vp, sz, vp]),
     "b200_rope_kv_write": (ci, [vp, vp, vp, vp, ci, vp, vp, ci, ci, ci, ci, ci, vp]),
@@ -302,17 +307,44 @@ def rmsnorm(x, w, eps, out=None):
     return out
 
 
-def flash_attention(q, k, v, causal=False, kv_start=None, kv_len=None, scale=None):
-    """q (B, Lq, H, d), k/v (B, Lk, H, d) views with unit stride on d -> (B, Lq, H, d) bf16."""
+def flash_attention(q, k, v, causal=False, kv_start=None, kv_len=None, scale=None, return_lse=False):
+    """q (B, Lq, H, d), k/v (B, Lk, H, d) views with unit stride on d -> (B, Lq, H, d) bf16
+    (+ lse (B, H, Lq) fp32 when return_lse)."""
     B, Lq, H, d = q.shape
     Lk = k.shape[1]
     o = torch.empty((B, Lq, H, d), device=q.device, dtype=torch.bfloat16)
     scale = d ** -0.5 if scale is None else scale
+    if return_lse:
+        lse = torch.empty((B, H, Lq), device=q.device, dtype=torch.float32)
+        check(lib().b200_flash_attention_lse(ptr(q), q.stride(0), q.stride(1), q.stride(2), ptr(k), k.stride(0),
+                                             k.stride(1), k.stride(2), ptr(v), v.stride(0), v.stride(1), v.stride(2),
+                                             ptr(o), o.stride(0), o.stride(1), o.stride(2), B, H, Lq, Lk, d,
+                                             ptr(kv_start), ptr(kv_len), int(causal), scale, ptr(lse), stream_ptr()),
+              "b200_flash_attention_lse")
+        return o, lse
     check(lib().b200_flash_attention(ptr(q), q.stride(0), q.stride(1), q.stride(2), ptr(k), k.stride(0), k.stride(1),
                                      k.stride(2), ptr(v), v.stride(0), v.stride(1), v.stride(2), ptr(o), o.stride(0),
                                      o.stride(1), o.stride(2), B, H, Lq, Lk, d, ptr(kv_start), ptr(kv_len),
                                      int(causal), scale, stream_ptr()), "b200_flash_attention")
     return o
+
+
+def flash_attention_bwd(q, k, v, o, d_o, lse, causal=False, kv_start=None, kv_len=None, scale=None):
+    """Gradients (dq, dk, dv) of flash_attention; all tensors (B, L, H, d) views with unit stride on d, o and d_o
+    share a layout."""
+    B, Lq, H, d = q.shape
+    Lk = k.shape[1]
+    assert o.stride() == d_o.stride()
+    dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+    assert dq.stride() == q.stride() and dk.stride() == k.stride() and dv.stride() == v.stride()
+    scale = d ** -0.5 if scale is None else scale
+    ws = torch.empty(int(lib().b200_flash_attention_bwd_workspace_bytes(B, H, Lq)), dtype=torch.uint8, device=q.device)
+    check(lib().b200_flash_attention_bwd(ptr(q), q.stride(0), q.stride(1), q.stride(2), ptr(k), k.stride(0), k.stride(1),
+                                         k.stride(2), ptr(v), v.stride(0), v.stride(1), v.stride(2), ptr(o), ptr(d_o),
+                                         o.stride(0), o.stride(1), o.stride(2), ptr(lse), ptr(dq), ptr(dk), ptr(dv), B, H,
+                                         Lq, Lk, d, ptr(kv_start), ptr(kv_len), int(causal), scale, ptr(ws), ws.numel(),
+                                         stream_ptr()), "b200_flash_attention_bwd")
+    return dq, dk, dv
 
 
 def decode_attention(q, k_cache, v_cache, ctx, kv_start=None, splits=0):

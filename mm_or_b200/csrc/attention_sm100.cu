@@ -24,8 +24,7 @@
 //               Fully masked rows (left-padding queries) produce exact zeros, never NaN.
 // Two CTAs are resident per SM (<= 113 KB smem, <= 256 TMEM columns each), so one CTA's exponentials overlap the
 // other's MMAs as well.
-#include "common.h"
-#include "ptx.cuh"
+#include "attention_common.cuh"
 
 namespace b200 {
 
@@ -42,26 +41,10 @@ struct TcAttnArgs {
   const int* kv_len;
   int causal;
   float scale_log2;
+  float* lse;
   // tensor-map dimension (1..3) that carries the token / head / sample index, per tensor (dims are sorted by stride)
   int q_dim[3], k_dim[3], v_dim[3];
 };
-
-// issue one box load with (token, head, sample) routed to the tensor map's dimension order
-__device__ __forceinline__ void tc_load(void* dst, const CUtensorMap* tm, uint64_t* bar, const int (&dim)[3], int d0,
-                                        int token, int head, int sample) {
-  int c[4] = {d0, 0, 0, 0};
-  c[dim[0]] = token;
-  c[dim[1]] = head;
-  c[dim[2]] = sample;
-  tma_load_4d(dst, tm, bar, c[0], c[1], c[2], c[3]);
-}
-
-// 2^x on the SFU (ex2.approx.ftz): -inf -> 0, no denormal fix-up code around it
-__device__ __forceinline__ float fast_exp2(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
 
 template <int D>
 struct TcCfg {
@@ -313,7 +296,10 @@ __global__ void __launch_bounds__(kTcThreads, 2)
       if (lane == 0) mbar_arrive(p_full);
     }
 
-    // ---- epilogue: O / l -> bf16
+    // ---- epilogue: O / l -> bf16 (+ the row's log-sum-exp for the backward pass)
+    if (a.lse != nullptr && qi < a.Lq)
+      a.lse[(static_cast<long long>(b) * a.H + h) * a.Lq + qi] =
+          l_run > 0.f ? (m_run + log2f(l_run)) * 0.6931471805599453f : -INFINITY;
     bf16* orow = a.o + b * a.o_bs + static_cast<long long>(qi) * a.o_rs + h * a.o_hs;
     if (n_tiles > 0) {
       mbar_wait(p_free, (n_tiles - 1) & 1u);
@@ -352,62 +338,6 @@ __global__ void __launch_bounds__(kTcThreads, 2)
 // ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn4)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-// 4-D bf16 map over (d, then token / head / sample sorted by ascending stride -- cuTensorMapEncodeTiled wants every
-// stride to be a multiple of the previous one, which holds for all layouts on this path once sorted); box = 64 d x
-// box_rows tokens. dim_of[0..2] receive the tensor-map dimension (1..3) of token / head / sample.
-static int make_tmap_attn(CUtensorMap* out, const bf16* base, int D, int L, int H, int B, long long rs, long long hs,
-                          long long bs, int box_rows, int (&dim_of)[3]) {
-  static EncodeTiledFn4 fn = nullptr;
-  if (fn == nullptr) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
-        qres != cudaDriverEntryPointSuccess)
-      return fail(-6, "cuTensorMapEncodeTiled entry point not available");
-    fn = reinterpret_cast<EncodeTiledFn4>(p);
-  }
-  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (rs * 2) % 16 != 0 || (hs * 2) % 16 != 0 || (bs * 2) % 16 != 0)
-    return fail(-2, "flash_attn: q/k/v pointers and strides must be 16-byte aligned");
-  struct Dim {
-    long long extent, stride_b;
-    int role;  // 0 token, 1 head, 2 sample
-  } d[3] = {{L, rs * 2, 0}, {H, hs * 2, 1}, {B, bs * 2, 2}};
-  // an extent-1 dimension may come with any stride (even 0): park it last with a legal one
-  long long span = D * 2;
-  for (int i = 0; i < 3; ++i)
-    if (d[i].extent > 1 && d[i].stride_b * d[i].extent > span) span = d[i].stride_b * d[i].extent;
-  for (int i = 0; i < 3; ++i)
-    if (d[i].extent <= 1) d[i].stride_b = span;
-  for (int i = 0; i < 3; ++i)
-    for (int j = i + 1; j < 3; ++j)
-      if (d[j].stride_b < d[i].stride_b || (d[j].stride_b == d[i].stride_b && d[j].extent > d[i].extent)) {
-        const Dim t = d[i];
-        d[i] = d[j];
-        d[j] = t;
-      }
-  cuuint64_t dims[4] = {static_cast<cuuint64_t>(D), 0, 0, 0};
-  cuuint64_t strides[3];
-  cuuint32_t box[4] = {64, 1, 1, 1};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
-  for (int i = 0; i < 3; ++i) {
-    dims[i + 1] = static_cast<cuuint64_t>(d[i].extent);
-    strides[i] = static_cast<cuuint64_t>(d[i].stride_b);
-    dim_of[d[i].role] = i + 1;
-    if (d[i].role == 0) box[i + 1] = static_cast<cuuint32_t>(box_rows);
-  }
-  CUresult rc = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (rc != CUDA_SUCCESS)
-    return fail(-6, "cuTensorMapEncodeTiled (attention) failed with CUresult %d (strides %lld/%lld/%lld B)", (int)rc,
-                d[0].stride_b, d[1].stride_b, d[2].stride_b);
-  return 0;
-}
-
 template <int D>
 static int launch_tc(const AttnArgs& a, cudaStream_t stream) {
   using Cfg = TcCfg<D>;
@@ -434,6 +364,7 @@ static int launch_tc(const AttnArgs& a, cudaStream_t stream) {
   t.kv_len = a.kv_len;
   t.causal = a.causal;
   t.scale_log2 = a.scale_log2;
+  t.lse = a.lse;
   dim3 grid((a.Lq + kTcBM - 1) / kTcBM, a.H, a.B);
   flash_attn_tc_kernel<D><<<grid, kTcThreads, Cfg::kSmemBytes, stream>>>(tmQ, tmK, tmV, t);
   B200_CUDA_OK(cudaGetLastError());

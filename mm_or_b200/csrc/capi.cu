@@ -151,6 +151,64 @@ int b200_flash_attention(const void* q, int64_t q_bs, int64_t q_rs, int64_t q_hs
   return flash_attn(a, head_dim, static_cast<cudaStream_t>(stream));
 }
 
+int b200_flash_attention_lse(const void* q, int64_t q_bs, int64_t q_rs, int64_t q_hs, const void* k, int64_t k_bs,
+                             int64_t k_rs, int64_t k_hs, const void* v, int64_t v_bs, int64_t v_rs, int64_t v_hs,
+                             void* o, int64_t o_bs, int64_t o_rs, int64_t o_hs, int B, int H, int Lq, int Lk,
+                             int head_dim, const int32_t* kv_start, const int32_t* kv_len, int causal, float scale,
+                             float* lse, b200_stream_t stream) {
+  AttnArgs a{};
+  a.q = static_cast<const bf16*>(q);
+  a.k = static_cast<const bf16*>(k);
+  a.v = static_cast<const bf16*>(v);
+  a.o = static_cast<bf16*>(o);
+  a.q_bs = q_bs; a.q_rs = q_rs; a.q_hs = q_hs;
+  a.k_bs = k_bs; a.k_rs = k_rs; a.k_hs = k_hs;
+  a.v_bs = v_bs; a.v_rs = v_rs; a.v_hs = v_hs;
+  a.o_bs = o_bs; a.o_rs = o_rs; a.o_hs = o_hs;
+  a.B = B; a.H = H; a.Lq = Lq; a.Lk = Lk;
+  a.kv_start = kv_start;
+  a.kv_len = kv_len;
+  a.causal = causal;
+  a.scale_log2 = scale * 1.4426950408889634f;
+  a.lse = lse;
+  return flash_attn(a, head_dim, static_cast<cudaStream_t>(stream));
+}
+
+size_t b200_flash_attention_bwd_workspace_bytes(int B, int H, int Lq) { return flash_attn_bwd_workspace_bytes(B, H, Lq); }
+
+int b200_flash_attention_bwd(const void* q, int64_t q_bs, int64_t q_rs, int64_t q_hs, const void* k, int64_t k_bs,
+                             int64_t k_rs, int64_t k_hs, const void* v, int64_t v_bs, int64_t v_rs, int64_t v_hs,
+                             const void* o, const void* d_o, int64_t o_bs, int64_t o_rs, int64_t o_hs, const float* lse,
+                             void* dq, void* dk, void* dv, int B, int H, int Lq, int Lk, int head_dim,
+                             const int32_t* kv_start, const int32_t* kv_len, int causal, float scale, void* workspace,
+                             size_t workspace_bytes, b200_stream_t stream) {
+  AttnArgs a{};
+  a.q = static_cast<const bf16*>(q);
+  a.k = static_cast<const bf16*>(k);
+  a.v = static_cast<const bf16*>(v);
+  a.o = const_cast<bf16*>(static_cast<const bf16*>(o));
+  a.q_bs = q_bs; a.q_rs = q_rs; a.q_hs = q_hs;
+  a.k_bs = k_bs; a.k_rs = k_rs; a.k_hs = k_hs;
+  a.v_bs = v_bs; a.v_rs = v_rs; a.v_hs = v_hs;
+  a.o_bs = o_bs; a.o_rs = o_rs; a.o_hs = o_hs;
+  a.B = B; a.H = H; a.Lq = Lq; a.Lk = Lk;
+  a.kv_start = kv_start;
+  a.kv_len = kv_len;
+  a.causal = causal;
+  a.scale_log2 = scale * 1.4426950408889634f;
+  AttnBwdArgs g{};
+  g.d_o = static_cast<const bf16*>(d_o);
+  g.do_bs = o_bs; g.do_rs = o_rs; g.do_hs = o_hs;      // dO shares O's layout
+  g.lse = lse;
+  g.dq = static_cast<bf16*>(dq);
+  g.dk = static_cast<bf16*>(dk);
+  g.dv = static_cast<bf16*>(dv);
+  g.dq_bs = q_bs; g.dq_rs = q_rs; g.dq_hs = q_hs;      // gradients share their tensor's layout
+  g.dk_bs = k_bs; g.dk_rs = k_rs; g.dk_hs = k_hs;
+  g.dv_bs = v_bs; g.dv_rs = v_rs; g.dv_hs = v_hs;
+  return flash_attn_bwd(a, g, head_dim, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
 size_t b200_decode_attention_workspace_bytes(int B, int H, int ctx) {
   (void)ctx;
   return decode_attn_workspace_bytes(B, H, 16);

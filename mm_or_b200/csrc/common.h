@@ -149,8 +149,27 @@ struct AttnArgs {
   const int* kv_len;    // [B] number of valid keys counted from 0 (key padding) or null
   int causal;           // key j visible to query i iff j <= i + (Lk - Lq)
   float scale_log2;     // softmax scale * log2(e)
+  float* lse;           // optional [B, H, Lq] fp32: natural-log sum-exp of the scaled scores per query row (saved for
+                        // the backward pass; -inf for fully masked rows)
 };
 int flash_attn(const AttnArgs& a, int head_dim, cudaStream_t stream);
+
+// backward (attention_bwd_sm100.cu): the forward call's AttnArgs (q, k, v, o, masks, scale) plus dO, the saved lse and
+// the gradient outputs; strides as in AttnArgs
+struct AttnBwdArgs {
+  const bf16* d_o;
+  long long do_bs, do_rs, do_hs;
+  const float* lse;  // [B, H, Lq] from the forward
+  bf16* dq;
+  bf16* dk;
+  bf16* dv;
+  long long dq_bs, dq_rs, dq_hs;
+  long long dk_bs, dk_rs, dk_hs;
+  long long dv_bs, dv_rs, dv_hs;
+};
+size_t flash_attn_bwd_workspace_bytes(int B, int H, int Lq);
+int flash_attn_bwd(const AttnArgs& f, const AttnBwdArgs& g, int head_dim, void* workspace, size_t workspace_bytes,
+                   cudaStream_t stream);
 
 struct DecodeArgs {
   const bf16* q;  // [B, q_rs] with head h at h*128

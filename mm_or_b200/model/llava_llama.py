@@ -418,10 +418,14 @@ class LlavaLlamaForCausalLM:
         import torch.distributed as dist
         if exchange not in ("peer", "nccl"):
             raise ValueError(f"unknown exchange {exchange!r}")
+        if group is None:                 # back to single-GPU behaviour (keeps the symmetric buffer for a later re-join)
+            self._pg = None
+            return
         self._pg = group
         self._exchange = exchange
         self._decode_shift = int(decode_shift)
-        self._peer = None
+        if self._peer is not None and self._peer.group is not group:
+            self._peer = None
         if group is not None and dist.get_world_size(group) > 8:
             raise ValueError("one NVSwitch box: at most 8 ranks")
 

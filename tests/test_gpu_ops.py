@@ -218,6 +218,21 @@ def test_flash_attention_rescale_and_long_keys(L):
     assert rel_err(L.flash_attention(q, k, v), ref_attn(q, k, v)) < TOL_OP
 
 
+def test_flash_attention_lse(L):
+    B, H, Lq, d = 2, 3, 333, 128
+    q, k, v = rnd(B, Lq, H, d, seed=31), rnd(B, Lq, H, d, seed=32), rnd(B, Lq, H, d, seed=33)
+    start = torch.tensor([0, 100], device="cuda", dtype=torch.int32)
+    o, lse = L.flash_attention(q, k, v, causal=True, kv_start=start, return_lse=True)
+    s = torch.einsum("bqhd,bkhd->bhqk", q.float(), k.float()) / math.sqrt(d)
+    kj = torch.arange(Lq, device="cuda")
+    vis = (kj[None, :] <= kj[:, None])[None, None] & (kj[None, None, None, :] >= start[:, None, None, None].long())
+    ref = torch.logsumexp(s.masked_fill(~vis, float("-inf")), dim=-1)
+    live = torch.isfinite(ref)
+    assert torch.equal(torch.isfinite(lse), live)
+    assert float((lse[live] - ref[live]).abs().max()) < 2e-2
+    assert rel_err(o, L.flash_attention(q, k, v, causal=True, kv_start=start)) == 0.0
+
+
 def test_flash_attention_kv_cache_layout(L):
     """K / V read from the head-major KV-cache layout [B][H][cap][128] (row stride 128, head stride cap*128), Q and O
     in the token-major qkv layout: the prefill call site of b200_llama_prefill."""

@@ -169,3 +169,43 @@ def test_norm_backward(L, D, rms):
     assert rel(dg, gr.grad) < 1e-4
     if not rms:
         assert rel(db, br.grad) < 1e-4
+
+
+def _attn_ref(q, k, v, causal, kv_start, kv_len):
+    B, Lq, H, d = q.shape
+    Lk = k.shape[1]
+    s = torch.einsum("bqhd,bkhd->bhqk", q, k) / math.sqrt(d)
+    kj = torch.arange(Lk, device=q.device)
+    vis = torch.ones(B, 1, Lq, Lk, dtype=torch.bool, device=q.device)
+    if causal:
+        qi = torch.arange(Lq, device=q.device) + (Lk - Lq)
+        vis = vis & (kj[None, :] <= qi[:, None])[None, None]
+    if kv_start is not None:
+        vis = vis & (kj[None, None, None, :] >= kv_start[:, None, None, None].long())
+    if kv_len is not None:
+        vis = vis & (kj[None, None, None, :] < kv_len[:, None, None, None].long())
+    s = s.masked_fill(~vis, float("-inf"))
+    p = torch.softmax(s, dim=-1)
+    p = torch.nan_to_num(p, nan=0.0)                   # fully masked rows
+    return torch.einsum("bhqk,bkhd->bqhd", p, v)
+
+
+@pytest.mark.parametrize("d,H,Lq,Lk,causal", [(128, 2, 200, 200, True), (128, 2, 333, 333, False), (64, 3, 577, 577, False),
+                                              (128, 2, 150, 420, True), (64, 2, 64, 64, False)])
+def test_flash_attention_backward(L, d, H, Lq, Lk, causal):
+    B = 2
+    q, k, v = rnd(B, Lq, H, d, seed=41), rnd(B, Lk, H, d, seed=42), rnd(B, Lk, H, d, seed=43)
+    d_o = rnd(B, Lq, H, d, seed=44)
+    kv_start = torch.tensor([0, min(37, Lk // 3)], device="cuda", dtype=torch.int32) if causal else None
+    kv_len = None if causal else torch.tensor([Lk, max(1, Lk - 50)], device="cuda", dtype=torch.int32)
+    o, lse = L.flash_attention(q, k, v, causal=causal, kv_start=kv_start, kv_len=kv_len, return_lse=True)
+    dq, dk, dv = L.flash_attention_bwd(q, k, v, o, d_o, lse, causal=causal, kv_start=kv_start, kv_len=kv_len)
+    with torch.enable_grad():
+        qr, kr, vr = (t.float().requires_grad_(True) for t in (q, k, v))
+        (_attn_ref(qr, kr, vr, causal, kv_start, kv_len) * d_o.float()).sum().backward()
+    # bf16 P / dS operands and bf16 outputs: ~1e-2 relative (Frobenius) like the forward
+    assert rel(dv, vr.grad) < 1e-2, "dV"
+    assert rel(dk, kr.grad) < 1.5e-2, "dK"
+    assert rel(dq, qr.grad) < 1.5e-2, "dQ"
+    dq2, dk2, dv2 = L.flash_attention_bwd(q, k, v, o, d_o, lse, causal=causal, kv_start=kv_start, kv_len=kv_len)
+    assert torch.equal(dq, dq2) and torch.equal(dk, dk2) and torch.equal(dv, dv2)      # no atomics: deterministic

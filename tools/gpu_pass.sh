@@ -51,9 +51,14 @@ fi
 
 if [[ $STAGES == *full* ]]; then
   # --set full on the kernels that carry the step; 2 decoder layers are enough to reach every kernel shape
-  for spec in "gemm256vit gemm_bf16_tn_kernel.*256 40 4" "gemm256llm gemm_bf16_tn_kernel.*256 103 5" \
-              "flash128 flash_attn_tc_kernel.*128 2 2" "flash64 flash_attn_tc_kernel.*64 2 1" \
-              "decattn decode_attn_kernel 2 2" "gemmskinny gemm_skinny_kernel 2 5"; do
+  if [[ -n "$NCU_ONLY_FLASH" ]]; then
+    SPECS=("flash128 flash_attn_tc_kernel.*128 2 2" "flash64 flash_attn_tc_kernel.*64 2 1")
+  else
+    SPECS=("gemm256vit gemm_bf16_tn_kernel.*256 40 4" "gemm256llm gemm_bf16_tn_kernel.*256 103 5" \
+           "flash128 flash_attn_tc_kernel.*128 2 2" "flash64 flash_attn_tc_kernel.*64 2 1" \
+           "decattn decode_attn_kernel 2 2" "gemmskinny gemm_skinny_kernel 2 5")
+  fi
+  for spec in "${SPECS[@]}"; do
     read name pat skip cnt <<< "$spec"
     timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base demangled \
       -k regex:$pat --launch-skip $skip -c $cnt -f -o gpurun_out/${TAG}_${name} $NCU_CMD --layers 2 \
