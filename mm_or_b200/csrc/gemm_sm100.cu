@@ -395,7 +395,7 @@ int gemm_bf16_ex(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, int b
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   if (N % 8 != 0) return fail(-2, "gemm: N (%d) must be a multiple of 8", N);
   if (!(a_mn && b_mn) && K % 8 != 0) return fail(-2, "gemm: K (%d) must be a multiple of 8 for a K-major operand", K);
-  if (a_mn && M % 8 != 0) return fail(-2, "gemm: M (%d) must be a multiple of 8 for a transposed A", M);
+  // (a transposed operand only needs a 16-byte aligned leading dimension; make_tmap_2d checks it)
   if (epi.act == kActSwiGLU && (N % 16 != 0 || epi.out_fp32 || epi.residual))
     return fail(-2, "gemm: SwiGLU epilogue needs N %% 16 == 0, bf16 output and no residual");
   if (epi.n_peers < 0 || epi.n_peers > 8 || (epi.n_peers > 0 && (epi.out_fp32 || epi.act == kActSwiGLU)))

@@ -113,7 +113,12 @@ def test_gemm_transposed_operands(L, M, N, K):
     """The three operand layouts of a Linear's backward, read in place (MN-major tensor-core operands)."""
     a, w = rnd(M, K, seed=1), rnd(N, K, scale=1 / math.sqrt(K), seed=2)
     ref = a.float() @ w.float().t()
-    at, wt = a.t().contiguous(), w.t().contiguous()           # stored transposed: (K, M), (K, N)
+    def stored_t(x):                                          # (rows, cols) -> its transpose stored row-major with a
+        r, c = x.shape                                        # 16-byte aligned leading dimension
+        buf = torch.zeros(c, (r + 7) // 8 * 8, device="cuda", dtype=x.dtype)
+        buf[:, :r] = x.t()
+        return buf[:, :r]
+    at, wt = stored_t(a), stored_t(w)                         # stored transposed: (K, M), (K, N)
     assert rel(L.gemm_ex(a, wt, w_t=True), ref) < 5e-3
     assert rel(L.gemm_ex(at, w, a_t=True), ref) < 5e-3
     assert rel(L.gemm_ex(at, wt, a_t=True, w_t=True), ref) < 5e-3

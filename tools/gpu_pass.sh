@@ -16,7 +16,7 @@ if [[ $STAGES == *newtests* ]]; then
 fi
 
 if [[ $STAGES == *,tests* || $STAGES == tests* ]]; then
-  timeout 900 python -m pytest tests -m gpu -x -q --timeout 300 2>&1 | tail -30 > gpurun_out/${TAG}_pytest_gpu.log
+  timeout 900 python -m pytest tests -m gpu -q --timeout 300 2>&1 | tail -30 > gpurun_out/${TAG}_pytest_gpu.log
   echo "pytest rc=${PIPESTATUS[0]}"; tail -8 gpurun_out/${TAG}_pytest_gpu.log
   timeout 300 python __graft_entry__.py smoke 2>&1 | tail -3
 fi
