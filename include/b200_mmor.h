@@ -286,7 +286,8 @@ int b200_llama_decode_step(const b200_llama_weights* w, int32_t* tokens, int32_t
  * b200_act_backward: dz = dy * act'(z) from the saved pre-activation z; act 1 quick_gelu, 2 gelu(erf), 3 SwiGLU
  * (z = interleaved (gate, up) [M, 2F], dy [M, F], dz [M, 2F]); n_out = elements of dy.
  * b200_norm_backward: LayerNorm (rms = 0) / RMSNorm (rms = 1) backward from the saved input x: dx bf16, dgamma / dbeta
- * fp32 [D] ((+)= with accumulate; dbeta ignored for RMSNorm). D in {512, 1024, 4096}. */
+ * fp32 [D] ((+)= with accumulate; dbeta ignored for RMSNorm). `add` (bf16 [M, D], may be NULL, may alias dx) is added
+ * to dx: the gradient that reaches x through the residual connection around the norm. D in {512, 1024, 4096}. */
 int b200_gemm_bf16_ex(const void* A, int lda, int a_transposed, const void* W, int ldw, int w_transposed, void* C, int ldc,
                       int M, int N, int K, const void* bias, const void* residual, int ldr, int act, int out_fp32,
                       int accumulate, int bn_hint, b200_stream_t stream);
@@ -294,9 +295,17 @@ size_t b200_colsum_workspace_bytes(int N);
 int b200_colsum(const void* dy, int64_t ld, int M, int N, int accumulate, float* out, void* workspace,
                 size_t workspace_bytes, b200_stream_t stream);
 int b200_act_backward(const void* z, const void* dy, void* dz, int64_t n_out, int act, b200_stream_t stream);
+/* b200_swiglu_forward: h[m, j] = silu(z[m, 2j]) * z[m, 2j+1] from the stored pre-activation (training forward; the
+ * inference path fuses it into the GEMM epilogue). b200_rope_kv_backward: backward of b200_rope_kv_write -- dq (in
+ * place in dqkv) and dk (from the head-major cache layout) are rotated by -theta, dk / dv are gathered back into the
+ * token-major dqkv [B*Lq, 3*H*128]. */
+int b200_swiglu_forward(const void* z, void* h, int64_t n_out, b200_stream_t stream);
+int b200_rope_kv_backward(void* dqkv, const int32_t* kv_start, const float* cos_table, const float* sin_table,
+                          int max_pos, const void* dk_cache, const void* dv_cache, int B, int H, int Lq, int cap,
+                          b200_stream_t stream);
 size_t b200_norm_backward_workspace_bytes(int M, int D);
-int b200_norm_backward(const void* x, const void* dy, const void* gamma, float eps, int M, int D, int rms, void* dx,
-                       float* dgamma, float* dbeta, int accumulate, void* workspace, size_t workspace_bytes,
+int b200_norm_backward(const void* x, const void* dy, const void* gamma, float eps, int M, int D, int rms,
+                       const void* add, void* dx, float* dgamma, float* dbeta, int accumulate, void* workspace, size_t workspace_bytes,
                        b200_stream_t stream);
 
 /* LLaVATrainer.compute_loss (train/llava_trainer.py:136-174): shifted cross-entropy of `logits` [B*L, V] against the

@@ -81,8 +81,10 @@ _SIGS = {
     "b200_colsum_workspace_bytes": (sz, [ci]),
     "b200_colsum": (ci, [vp, i64, ci, ci, ci, vp, vp, sz, vp]),
     "b200_act_backward": (ci, [vp, vp, vp, i64, ci, vp]),
+    "b200_swiglu_forward": (ci, [vp, vp, i64, vp]),
+    "b200_rope_kv_backward": (ci, [vp, vp, vp, vp, ci, vp, vp, ci, ci, ci, ci, vp]),
     "b200_norm_backward_workspace_bytes": (sz, [ci, ci]),
-    "b200_norm_backward": (ci, [vp, vp, vp, cf, ci, ci, ci, vp, vp, vp, ci, vp, sz, vp]),
+    "b200_norm_backward": (ci, [vp, vp, vp, cf, ci, ci, ci, vp, vp, vp, vp, ci, vp, sz, vp]),
     "b200_weighted_ce_workspace_bytes": (sz, [ci, ci]),
     "b200_weighted_ce": (ci, [vp, ci, i64, vp, vp, ci, ci, ci, cf, vp, i64, vp, vp, sz, vp]),
     "b200_grad_norm_workspace_bytes": (sz, []),
@@ -236,13 +238,22 @@ def linear_backward(x, w, dy, dw=None, db=None, accumulate=False, need_dx=True):
     return dx, dw, db
 
 
+def swiglu_forward(z):
+    """(M, 2F) interleaved (gate, up) pre-activations -> (M, F)."""
+    M, F2 = z.shape
+    h = torch.empty((M, F2 // 2), device=z.device, dtype=torch.bfloat16)
+    check(lib().b200_swiglu_forward(ptr(z), ptr(h), h.numel(), stream_ptr()), "b200_swiglu_forward")
+    return h
+
+
 def act_backward(z, dy, act):
     dz = torch.empty_like(z)
     check(lib().b200_act_backward(ptr(z), ptr(dy), ptr(dz), dy.numel(), act, stream_ptr()), "b200_act_backward")
     return dz
 
 
-def norm_backward(x, dy, gamma, eps, rms=False, dgamma=None, dbeta=None, accumulate=False):
+def norm_backward(x, dy, gamma, eps, rms=False, dgamma=None, dbeta=None, accumulate=False, add=None):
+    """dx (+ add: the residual-branch gradient), dgamma, dbeta of LayerNorm / RMSNorm from the saved input x."""
     M, D = x.shape
     dx = torch.empty_like(x)
     if dgamma is None:
@@ -250,7 +261,8 @@ def norm_backward(x, dy, gamma, eps, rms=False, dgamma=None, dbeta=None, accumul
     if dbeta is None and not rms:
         dbeta = torch.empty(D, device=x.device, dtype=torch.float32)
     ws = torch.empty(int(lib().b200_norm_backward_workspace_bytes(M, D)), dtype=torch.uint8, device=x.device)
-    check(lib().b200_norm_backward(ptr(x), ptr(dy), ptr(gamma), eps, M, D, int(rms), ptr(dx), ptr(dgamma), ptr(dbeta),
+    check(lib().b200_norm_backward(ptr(x), ptr(dy), ptr(gamma), eps, M, D, int(rms), ptr(add), ptr(dx), ptr(dgamma),
+                                   ptr(dbeta),
                                    int(accumulate), ptr(ws), ws.numel(), stream_ptr()), "b200_norm_backward")
     return dx, dgamma, dbeta
 
@@ -329,13 +341,17 @@ def flash_attention(q, k, v, causal=False, kv_start=None, kv_len=None, scale=Non
     return o
 
 
-def flash_attention_bwd(q, k, v, o, d_o, lse, causal=False, kv_start=None, kv_len=None, scale=None):
+def flash_attention_bwd(q, k, v, o, d_o, lse, causal=False, kv_start=None, kv_len=None, scale=None, out=None):
     """Gradients (dq, dk, dv) of flash_attention; all tensors (B, L, H, d) views with unit stride on d, o and d_o
-    share a layout."""
+    share a layout; out = (dq, dk, dv) views with the strides of q / k / v (allocated here when None)."""
     B, Lq, H, d = q.shape
     Lk = k.shape[1]
     assert o.stride() == d_o.stride()
-    dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+    if out is None:
+        out = tuple(torch.empty(t.shape, device=t.device, dtype=t.dtype).as_strided(t.shape, t.stride())
+                    if t.is_contiguous() else None for t in (q, k, v))
+        assert all(t is not None for t in out), "pass out= for non-contiguous q / k / v views"
+    dq, dk, dv = out
     assert dq.stride() == q.stride() and dk.stride() == k.stride() and dv.stride() == v.stride()
     scale = d ** -0.5 if scale is None else scale
     ws = torch.empty(int(lib().b200_flash_attention_bwd_workspace_bytes(B, H, Lq)), dtype=torch.uint8, device=q.device)

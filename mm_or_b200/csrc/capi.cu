@@ -83,12 +83,24 @@ int b200_act_backward(const void* z, const void* dy, void* dz, int64_t n_out, in
                       static_cast<cudaStream_t>(stream));
 }
 
+int b200_swiglu_forward(const void* z, void* h, int64_t n_out, b200_stream_t stream) {
+  return swiglu_forward(static_cast<const bf16*>(z), static_cast<bf16*>(h), n_out, static_cast<cudaStream_t>(stream));
+}
+
+int b200_rope_kv_backward(void* dqkv, const int32_t* kv_start, const float* cos_table, const float* sin_table,
+                          int max_pos, const void* dk_cache, const void* dv_cache, int B, int H, int Lq, int cap,
+                          b200_stream_t stream) {
+  return rope_kv_backward(static_cast<bf16*>(dqkv), kv_start, cos_table, sin_table, max_pos,
+                          static_cast<const bf16*>(dk_cache), static_cast<const bf16*>(dv_cache), B, H, Lq, cap,
+                          static_cast<cudaStream_t>(stream));
+}
+
 size_t b200_norm_backward_workspace_bytes(int M, int D) { return norm_backward_workspace_bytes(M, D); }
-int b200_norm_backward(const void* x, const void* dy, const void* gamma, float eps, int M, int D, int rms, void* dx,
-                       float* dgamma, float* dbeta, int accumulate, void* workspace, size_t workspace_bytes,
+int b200_norm_backward(const void* x, const void* dy, const void* gamma, float eps, int M, int D, int rms,
+                       const void* add, void* dx, float* dgamma, float* dbeta, int accumulate, void* workspace, size_t workspace_bytes,
                        b200_stream_t stream) {
   return norm_backward(static_cast<const bf16*>(x), static_cast<const bf16*>(dy), static_cast<const bf16*>(gamma), eps,
-                       M, D, rms, static_cast<bf16*>(dx), dgamma, dbeta, accumulate, workspace, workspace_bytes,
+                       M, D, rms, static_cast<const bf16*>(add), static_cast<bf16*>(dx), dgamma, dbeta, accumulate, workspace, workspace_bytes,
                        static_cast<cudaStream_t>(stream));
 }
 

@@ -114,10 +114,13 @@ int grad_sq_norm(const bf16* grad, long long n, int accumulate, float max_norm, 
 size_t colsum_workspace_bytes(int N);
 int colsum(const bf16* dy, long long ld, int M, int N, int accumulate, float* out, void* workspace,
            size_t workspace_bytes, cudaStream_t stream);
+int swiglu_forward(const bf16* z, bf16* h, long long n_out, cudaStream_t stream);
+int rope_kv_backward(bf16* dqkv, const int* kv_start, const float* cos_t, const float* sin_t, int max_pos,
+                     const bf16* dk_cache, const bf16* dv_cache, int Bn, int H, int Lq, int cap, cudaStream_t stream);
 int act_backward(const bf16* z, const bf16* dy, bf16* dz, long long n_out, int act, cudaStream_t stream);
 size_t norm_backward_workspace_bytes(int M, int D);
-int norm_backward(const bf16* x, const bf16* dy, const bf16* gamma, float eps, int M, int D, int rms, bf16* dx,
-                  float* dgamma, float* dbeta, int accumulate, void* workspace, size_t workspace_bytes,
+int norm_backward(const bf16* x, const bf16* dy, const bf16* gamma, float eps, int M, int D, int rms, const bf16* add,
+                  bf16* dx, float* dgamma, float* dbeta, int accumulate, void* workspace, size_t workspace_bytes,
                   cudaStream_t stream);
 int adamw_step(float* master, bf16* param, const bf16* grad, float* m, float* v, long long n, float lr, float beta1,
                float beta2, float eps, float weight_decay, int step, const float* clip_coef, cudaStream_t stream);

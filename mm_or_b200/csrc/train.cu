@@ -398,6 +398,70 @@ int act_backward(const bf16* z, const bf16* dy, bf16* dz, long long n_out, int a
   return 0;
 }
 
+// h[m, j] = silu(z[m, 2j]) * z[m, 2j+1]: the SwiGLU of the training forward, which keeps the pre-activation z for
+// act_backward (the inference path fuses the same formula into the GEMM epilogue and never stores z)
+__global__ void __launch_bounds__(256) swiglu_forward_kernel(const bf16* __restrict__ z, bf16* __restrict__ h,
+                                                             long long n_out) {
+  const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= n_out) return;
+  const uint32_t gu = reinterpret_cast<const uint32_t*>(z)[i];
+  const float gate = bf16lo(gu), up = bf16hi(gu);
+  h[i] = __float2bfloat16(gate / (1.f + __expf(-gate)) * up);
+}
+
+int swiglu_forward(const bf16* z, bf16* h, long long n_out, cudaStream_t stream) {
+  if (n_out <= 0) return 0;
+  LaunchScope scope(kFamTrain, stream, 6.0 * n_out, 0.0);
+  swiglu_forward_kernel<<<static_cast<unsigned>((n_out + 255) / 256), 256, 0, stream>>>(z, h, n_out);
+  B200_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// Backward of rope_kv_write (misc.cu): gathers dK / dV from the head-major cache layout [B][H][cap][128] back into the
+// token-major dqkv [B*L, 3*H*128] and applies the inverse rotation (angle -theta) to dq (in place) and dk.
+__global__ void __launch_bounds__(128) rope_kv_backward_kernel(bf16* __restrict__ dqkv, const int* __restrict__ kv_start,
+                                                               const float* __restrict__ cos_t,
+                                                               const float* __restrict__ sin_t,
+                                                               const bf16* __restrict__ dkc, const bf16* __restrict__ dvc,
+                                                               int T, int H, int Lq, int cap, int max_pos) {
+  const long long w = blockIdx.x * 4ll + (threadIdx.x >> 5);  // one warp per (token, head)
+  if (w >= static_cast<long long>(T) * H) return;
+  const int lane = threadIdx.x & 31;
+  const int h = w % H;
+  const int tok = w / H;
+  const int b = tok / Lq, l = tok % Lq;
+  int p = l - (kv_start ? kv_start[b] : 0);
+  p = p < 0 ? 0 : (p >= max_pos ? max_pos - 1 : p);
+  const float2 cs = *reinterpret_cast<const float2*>(cos_t + static_cast<long long>(p) * 64 + lane * 2);
+  const float2 sn = *reinterpret_cast<const float2*>(sin_t + static_cast<long long>(p) * 64 + lane * 2);
+  bf16* row = dqkv + static_cast<long long>(tok) * 3 * H * 128;
+  const bf16* crow_k = dkc + ((static_cast<long long>(b) * H + h) * cap + l) * 128;
+  const bf16* crow_v = dvc + ((static_cast<long long>(b) * H + h) * cap + l) * 128;
+#pragma unroll
+  for (int which = 0; which < 2; ++which) {  // 0 = dq (in place), 1 = dk (from the cache layout)
+    bf16* dst = row + which * H * 128 + h * 128;
+    const bf16* src = which == 0 ? dst : crow_k;
+    const uint32_t lo = *reinterpret_cast<const uint32_t*>(src + lane * 2);
+    const uint32_t hi = *reinterpret_cast<const uint32_t*>(src + 64 + lane * 2);
+    const float x0 = bf16lo(lo), x1 = bf16hi(lo), y0 = bf16lo(hi), y1 = bf16hi(hi);
+    *reinterpret_cast<uint32_t*>(dst + lane * 2) = pack_bf16x2(x0 * cs.x + y0 * sn.x, x1 * cs.y + y1 * sn.y);
+    *reinterpret_cast<uint32_t*>(dst + 64 + lane * 2) = pack_bf16x2(y0 * cs.x - x0 * sn.x, y1 * cs.y - x1 * sn.y);
+  }
+  *reinterpret_cast<uint2*>(row + 2 * H * 128 + h * 128 + lane * 4) = *reinterpret_cast<const uint2*>(crow_v + lane * 4);
+}
+
+int rope_kv_backward(bf16* dqkv, const int* kv_start, const float* cos_t, const float* sin_t, int max_pos,
+                     const bf16* dk_cache, const bf16* dv_cache, int Bn, int H, int Lq, int cap, cudaStream_t stream) {
+  if (Bn <= 0 || Lq <= 0) return 0;
+  if (Lq > cap) return fail(-2, "rope_kv_backward: L %d exceeds the cache capacity %d", Lq, cap);
+  const long long warps = static_cast<long long>(Bn) * Lq * H;
+  LaunchScope scope(kFamTrain, stream, 10.0 * warps * 128, 0.0);
+  rope_kv_backward_kernel<<<static_cast<unsigned>((warps + 3) / 4), 128, 0, stream>>>(
+      dqkv, kv_start, cos_t, sin_t, dk_cache, dv_cache, Bn * Lq, H, Lq, cap, max_pos);
+  B200_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 // LayerNorm / RMSNorm backward. One CTA walks a block of rows; every thread owns 8 * kVec fixed columns
 // (D = kThreads * 8 * kVec), so the dgamma / dbeta sums of the CTA's rows stay in registers; fp32 statistics are
 // recomputed from x with two block reductions per row:
@@ -429,7 +493,8 @@ __device__ __forceinline__ void block_sum2(float& a, float& b, float (*red)[2]) 
 template <int kThreads, int kVec, bool kRms>
 __global__ void __launch_bounds__(kThreads) norm_backward_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy,
                                                                  const bf16* __restrict__ gamma, float eps, int M,
-                                                                 int D, bf16* __restrict__ dx,
+                                                                 int D, const bf16* __restrict__ add,
+                                                                 bf16* __restrict__ dx,
                                                                  float* __restrict__ pgamma, float* __restrict__ pbeta,
                                                                  int rows_per_block) {
   __shared__ float red[kThreads / 32][2];
@@ -502,11 +567,23 @@ __global__ void __launch_bounds__(kThreads) norm_backward_kernel(const bf16* __r
     c1 = kRms ? 0.f : c1 / D;
     c2 /= D;
     uint4* op = reinterpret_cast<uint4*>(dx + static_cast<long long>(row) * D);
+    const uint4* ap = add ? reinterpret_cast<const uint4*>(add + static_cast<long long>(row) * D) : nullptr;
 #pragma unroll
     for (int i = 0; i < kVec; ++i) {
       float y[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) y[j] = rstd * (gv[i][j] - c1 - xv[i][j] * c2);
+      if (ap != nullptr) {  // gradient arriving through the residual branch around the norm (may alias dx)
+        const uint4 u = ap[i * kThreads + threadIdx.x];
+        y[0] += bf16lo(u.x);
+        y[1] += bf16hi(u.x);
+        y[2] += bf16lo(u.y);
+        y[3] += bf16hi(u.y);
+        y[4] += bf16lo(u.z);
+        y[5] += bf16hi(u.z);
+        y[6] += bf16lo(u.w);
+        y[7] += bf16hi(u.w);
+      }
       uint4 o;
       o.x = pack_bf16x2(y[0], y[1]);
       o.y = pack_bf16x2(y[2], y[3]);
@@ -545,8 +622,8 @@ size_t norm_backward_workspace_bytes(int M, int D) {
 }
 
 // dgamma / dbeta: fp32 [D], (+)= when accumulate. beta == rms -> dbeta ignored (pass nullptr).
-int norm_backward(const bf16* x, const bf16* dy, const bf16* gamma, float eps, int M, int D, int rms, bf16* dx,
-                  float* dgamma, float* dbeta, int accumulate, void* workspace, size_t workspace_bytes,
+int norm_backward(const bf16* x, const bf16* dy, const bf16* gamma, float eps, int M, int D, int rms, const bf16* add,
+                  bf16* dx, float* dgamma, float* dbeta, int accumulate, void* workspace, size_t workspace_bytes,
                   cudaStream_t stream) {
   if (M <= 0) return 0;
   if (workspace == nullptr || workspace_bytes < norm_backward_workspace_bytes(M, D))
@@ -557,10 +634,11 @@ int norm_backward(const bf16* x, const bf16* dy, const bf16* gamma, float eps, i
   LaunchScope scope(kFamTrain, stream, 6.0 * M * D, 0.0, 3);
 #define B200_NB(T, V)                                                                                          \
   if (rms)                                                                                                     \
-    norm_backward_kernel<T, V, true><<<blocks, T, 0, stream>>>(x, dy, gamma, eps, M, D, dx, pg, nullptr,      \
+    norm_backward_kernel<T, V, true><<<blocks, T, 0, stream>>>(x, dy, gamma, eps, M, D, add, dx, pg, nullptr, \
                                                                kNormBwdRows);                                 \
   else                                                                                                         \
-    norm_backward_kernel<T, V, false><<<blocks, T, 0, stream>>>(x, dy, gamma, eps, M, D, dx, pg, pb, kNormBwdRows);
+    norm_backward_kernel<T, V, false><<<blocks, T, 0, stream>>>(x, dy, gamma, eps, M, D, add, dx, pg, pb,     \
+                                                                kNormBwdRows);
   switch (D) {
     case 512: B200_NB(64, 1) break;
     case 1024: B200_NB(128, 1) break;

@@ -1,0 +1,145 @@
+"""Teacher-forced forward + backward of the Llama decoder for the MM2SG fine-tune step.
+
+Reference: LlavaLlamaForCausalLM.forward (LLaVA/llava/model/language_model/llava_llama.py:54-106 -> HF LlamaForCausalLM
+with the FlashAttention-2 patch train/llama_flash_attn_monkey_patch.py:15-92) followed by LLaVATrainer.compute_loss
+(train/llava_trainer.py:136-174) and torch autograd. Here every tensor operation is a kernel of libb200mmor.so called
+through the C ABI (forward kernels of the inference path + the backward operators of train.cu / gemm_sm100.cu /
+attention_bwd_sm100.cu); torch only owns the memory. Activations are saved per layer (no recomputation):
+x_in, norm(x_in), qkv (q rotated), K / V in the head-major cache layout, attention context + log-sum-exp, x_mid,
+norm(x_mid), the SwiGLU pre-activation and its output.
+
+Right-padded batches (train.py:1185-1191): `lengths[b]` real rows, keys beyond them are masked, labels are -100 there.
+Gradients are returned in fp32 under the reference's parameter names (q/k/v and gate/up are split back out of the fused
+layouts), `accumulate=True` adds into an existing gradient dict (gradient accumulation over micro-batches).
+"""
+import ctypes
+
+import torch
+
+from .. import _lib as L
+
+BF = torch.bfloat16
+
+
+class LayerCache:
+    __slots__ = ("x_in", "a", "qkv", "kc", "vc", "ctx", "lse", "x_mid", "b", "z", "h")
+
+
+def _views(qkv, kc, vc, B, Lq, H):
+    """(B, L, H, 128) views of q (inside the token-major qkv) and of K / V (head-major caches)."""
+    q = qkv.view(B, Lq, 3, H, 128)[:, :, 0]
+    k = kc.transpose(1, 2)[:, :Lq]
+    v = vc.transpose(1, 2)[:, :Lq]
+    return q, k, v
+
+
+def forward_backward(model, embeds, labels, lengths, vocab_weight=None, grad_scale=1.0, grads=None, accumulate=False,
+                     need_input_grad=True):
+    """embeds (B, L, D) bf16 packed inputs_embeds, labels (B, L) int64 UNshifted modified_labels, lengths (B,) int32.
+    Returns (loss fp32 0-dim, weight sum, grads dict, d_embeds (B, L, D) bf16 or None)."""
+    cfg = model.config
+    lib = L.lib()
+    dev = embeds.device
+    B, Lq, D = embeds.shape
+    H, F, V = cfg.num_attention_heads, cfg.intermediate_size, cfg.vocab_size
+    T = B * Lq
+    layers, _, final_norm, rope_cos, rope_sin = model._keep[:5]
+    eps = cfg.rms_norm_eps
+    lengths = lengths.to(device=dev, dtype=torch.int32).contiguous()
+    labels = labels.to(dev).contiguous()
+    x = embeds.to(dev, BF).contiguous().view(T, D)
+
+    def rope_write(qkv, kc, vc):
+        L.check(lib.b200_rope_kv_write(L.ptr(qkv), None, L.ptr(rope_cos), L.ptr(rope_sin), cfg.max_position_embeddings,
+                                       L.ptr(kc), L.ptr(vc), B, H, Lq, 0, Lq, L.stream_ptr()), "b200_rope_kv_write")
+
+    # ---------------------------------------------------------------- forward
+    caches = []
+    for lt in layers:
+        c = LayerCache()
+        c.x_in = x
+        c.a = L.rmsnorm(x, lt["attn_norm"], eps)
+        c.qkv = L.gemm(c.a, lt["qkv_w"])
+        c.kc = torch.empty((B, H, Lq, 128), device=dev, dtype=BF)
+        c.vc = torch.empty((B, H, Lq, 128), device=dev, dtype=BF)
+        rope_write(c.qkv, c.kc, c.vc)
+        q, k, v = _views(c.qkv, c.kc, c.vc, B, Lq, H)
+        ctx, c.lse = L.flash_attention(q, k, v, causal=True, kv_len=lengths, return_lse=True)
+        c.ctx = ctx.view(T, D)
+        c.x_mid = L.gemm(c.ctx, lt["o_w"], residual=x)
+        c.b = L.rmsnorm(c.x_mid, lt["mlp_norm"], eps)
+        c.z = L.gemm(c.b, lt["gate_up_w"])                       # pre-activation kept for the backward
+        c.h = L.swiglu_forward(c.z)
+        x = L.gemm(c.h, lt["down_w"], residual=c.x_mid)
+        caches.append(c)
+    x_last = x
+    xf = L.rmsnorm(x_last, final_norm, eps)
+    logits = L.gemm(xf, model.lm_head)                           # bf16 like the reference's bf16 lm_head
+    loss, wsum, dlogits = L.weighted_ce(logits.view(B, Lq, V), labels, vocab_weight, grad_scale=grad_scale,
+                                        want_grad=True, inplace=True)
+    dlogits = dlogits.view(T, V)
+
+    # ---------------------------------------------------------------- backward
+    g = grads if grads is not None else {}
+
+    def slot(name, shape):
+        if name not in g:
+            g[name] = torch.zeros(shape, device=dev, dtype=torch.float32)
+            return g[name], False
+        return g[name], accumulate
+
+    def lin_bwd(x_saved, w, dy, name, need_dx=True):
+        dw, acc = slot(name, tuple(w.shape))
+        dx = L.gemm_ex(dy, w, w_t=True) if need_dx else None
+        L.gemm_ex(dy, x_saved, a_t=True, w_t=True, out=dw, accumulate=acc)
+        return dx
+
+    def norm_bwd(x_saved, dy, gamma, name, add=None):
+        dg, acc = slot(name, (D,))
+        dx, _, _ = L.norm_backward(x_saved, dy, gamma, eps, rms=True, dgamma=dg, accumulate=acc, add=add)
+        return dx
+
+    dxf = lin_bwd(xf, model.lm_head, dlogits, "lm_head.weight")
+    dx = norm_bwd(x_last, dxf, final_norm, "model.norm.weight")
+    for i in range(len(layers) - 1, -1, -1):
+        lt, c = layers[i], caches[i]
+        p = f"_fused.layers.{i}."
+        dh = lin_bwd(c.h, lt["down_w"], dx, p + "down_w")
+        dz = L.act_backward(c.z, dh, L.ACT_SWIGLU)
+        db = lin_bwd(c.b, lt["gate_up_w"], dz, p + "gate_up_w")
+        dx_mid = norm_bwd(c.x_mid, db, lt["mlp_norm"], f"model.layers.{i}.post_attention_layernorm.weight", add=dx)
+        dctx = lin_bwd(c.ctx, lt["o_w"], dx_mid, p + "o_w")
+        dqkv = torch.empty_like(c.qkv)
+        dkc, dvc = torch.empty_like(c.kc), torch.empty_like(c.vc)
+        q, k, v = _views(c.qkv, c.kc, c.vc, B, Lq, H)
+        dq, dk, dv = _views(dqkv, dkc, dvc, B, Lq, H)
+        L.flash_attention_bwd(q, k, v, c.ctx.view(B, Lq, H, 128), dctx.view(B, Lq, H, 128), c.lse, causal=True,
+                              kv_len=lengths, out=(dq, dk, dv))
+        L.check(lib.b200_rope_kv_backward(L.ptr(dqkv), None, L.ptr(rope_cos), L.ptr(rope_sin),
+                                          cfg.max_position_embeddings, L.ptr(dkc), L.ptr(dvc), B, H, Lq, Lq,
+                                          L.stream_ptr()), "b200_rope_kv_backward")
+        da = lin_bwd(c.a, lt["qkv_w"], dqkv, p + "qkv_w", need_dx=True)
+        need = need_input_grad or i > 0
+        dx = norm_bwd(c.x_in, da, lt["attn_norm"], f"model.layers.{i}.input_layernorm.weight", add=dx_mid) if need \
+            else None
+    d_embeds = dx.view(B, Lq, D) if dx is not None else None
+    return loss, wsum, g, d_embeds
+
+
+def unfuse_grads(g, cfg):
+    """Gradients of the fused layouts -> the reference's parameter names (q/k/v_proj, gate/up_proj, ...)."""
+    D, F = cfg.hidden_size, cfg.intermediate_size
+    out = {k: v for k, v in g.items() if not k.startswith("_fused.")}
+    for i in range(cfg.num_hidden_layers):
+        p, r = f"_fused.layers.{i}.", f"model.layers.{i}."
+        if p + "qkv_w" not in g:
+            continue
+        qkv = g[p + "qkv_w"]
+        for j, n in enumerate(("q", "k", "v")):
+            out[r + f"self_attn.{n}_proj.weight"] = qkv[j * D:(j + 1) * D]
+        out[r + "self_attn.o_proj.weight"] = g[p + "o_w"]
+        gu = g[p + "gate_up_w"].view(F, 2, D)
+        out[r + "mlp.gate_proj.weight"] = gu[:, 0]
+        out[r + "mlp.up_proj.weight"] = gu[:, 1]
+        out[r + "mlp.down_proj.weight"] = g[p + "down_w"]
+    return out

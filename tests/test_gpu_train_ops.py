@@ -214,3 +214,81 @@ def test_flash_attention_backward(L, d, H, Lq, Lk, causal):
     assert rel(dq, qr.grad) < 1.5e-2, "dQ"
     dq2, dk2, dv2 = L.flash_attention_bwd(q, k, v, o, d_o, lse, causal=causal, kv_start=kv_start, kv_len=kv_len)
     assert torch.equal(dq, dq2) and torch.equal(dk, dk2) and torch.equal(dv, dv2)      # no atomics: deterministic
+
+
+def test_rope_backward_and_swiglu_forward(L):
+    B, H, Lq = 2, 3, 37
+    D = H * 128
+    g = torch.Generator().manual_seed(3)
+    inv = 1.0 / (10000.0 ** (torch.arange(0, 128, 2, dtype=torch.float32) / 128))
+    fr = torch.outer(torch.arange(64, dtype=torch.float32), inv)
+    cos, sin = fr.cos().cuda().contiguous(), fr.sin().cuda().contiguous()
+    dqkv = rnd(B * Lq, 3 * D, seed=51)
+    dkc, dvc = rnd(B, H, Lq, 128, seed=52), rnd(B, H, Lq, 128, seed=53)
+    ref_q = dqkv.view(B, Lq, 3, H, 128)[:, :, 0].float().clone()
+    out = dqkv.clone()
+    L.check(L.lib().b200_rope_kv_backward(L.ptr(out), None, L.ptr(cos), L.ptr(sin), 64, L.ptr(dkc), L.ptr(dvc), B, H, Lq,
+                                          Lq, L.stream_ptr()), "rope_kv_backward")
+    o5 = out.view(B, Lq, 3, H, 128).float()
+    c = torch.cat([cos[:Lq], cos[:Lq]], -1)[None, :, None, :]
+    s = torch.cat([sin[:Lq], sin[:Lq]], -1)[None, :, None, :]
+
+    def inv_rot(u):                                       # transpose of u -> u cos + rotate_half(u) sin
+        rot_t = torch.cat([u[..., 64:], -u[..., :64]], -1)
+        return u * c + rot_t * s
+    assert rel(o5[:, :, 0], inv_rot(ref_q)) < 5e-3
+    assert rel(o5[:, :, 1], inv_rot(dkc.float().transpose(1, 2))) < 5e-3
+    assert torch.equal(out.view(B, Lq, 3, H, 128)[:, :, 2], dvc.transpose(1, 2))
+    z = rnd(100, 2 * 1408, seed=54)
+    ref = torch.nn.functional.silu(z.float()[:, 0::2]) * z.float()[:, 1::2]
+    assert rel(L.swiglu_forward(z), ref) < 5e-3
+
+
+def test_llama_train_step_matches_autograd(L):
+    """Decoder forward + weighted CE + full backward through the C ABI vs torch autograd over the CPU oracle
+    (oracle.llama_forward + oracle.weighted_ce) in fp32 on the same bf16-rounded weights, right-padded batch."""
+    import golden_cases as gc
+    from helpers import oracle_cfg
+    from mm_or_b200.model.llava_llama import LlavaLlamaForCausalLM
+    from mm_or_b200.train import llama as T
+    cfg = gc.small_config()
+    sd = gc.bf16_round(gc.small_weights(cfg))
+    model = LlavaLlamaForCausalLM(cfg).load_state_dict(sd)
+    B, Lq, D, V = 2, 48, cfg.hidden_size, cfg.vocab_size
+    g = torch.Generator().manual_seed(11)
+    emb = (torch.randn(B, Lq, D, generator=g) * 0.5).to(torch.bfloat16)
+    lengths = torch.tensor([Lq, 33], dtype=torch.int32)
+    labels = torch.randint(3, V, (B, Lq), generator=g)
+    labels[:, :20] = -100
+    labels[1, 33:] = -100
+    w = torch.rand(V, generator=g) + 0.05
+    emb_dev = emb.cuda()
+    emb_dev[1, 33:] = 0                                     # pad rows are zero vectors (llava_arch.py:317-338)
+    loss, wsum, grads, d_emb = T.forward_backward(model, emb_dev, labels.cuda(), lengths.cuda(), vocab_weight=w)
+    grads = T.unfuse_grads(grads, cfg)
+    # ---- oracle under autograd
+    ocfg = oracle_cfg(cfg).llm
+    with torch.enable_grad():
+        params = {k: v.clone().float().requires_grad_(True) for k, v in sd.items()
+                  if k.startswith("model.layers.") or k in ("model.norm.weight", "lm_head.weight")}
+        x = emb_dev.float().cpu().requires_grad_(True)
+        mask = torch.arange(Lq)[None, :] < lengths[:, None].long()
+        pos = torch.arange(Lq)[None, :].repeat(B, 1) * mask
+        logits, _ = O.llama_forward({**sd, **params}, x, mask, pos, ocfg)
+        ref_loss = O.weighted_ce(logits, labels, w)
+        ref_loss.backward()
+    assert abs(float(loss) - float(ref_loss)) < 3e-2 * abs(float(ref_loss))
+    worst = 0.0
+    for k, p in params.items():
+        r = rel(grads[k].cpu(), p.grad)
+        worst = max(worst, r)
+        assert r < 6e-2, (k, r)
+    live = mask[:, :, None].expand_as(x.grad)
+    assert rel(d_emb.float().cpu()[live], x.grad[live]) < 6e-2
+    # gradient accumulation: a second micro-batch doubles every gradient
+    _, _, grads2, _ = T.forward_backward(model, emb_dev, labels.cuda(), lengths.cuda(), vocab_weight=w,
+                                         grads={k: v.clone() for k, v in T.forward_backward(
+                                             model, emb_dev, labels.cuda(), lengths.cuda(), vocab_weight=w)[2].items()},
+                                         accumulate=True)
+    g2 = T.unfuse_grads(grads2, cfg)
+    assert rel(g2["lm_head.weight"].cpu(), 2 * params["lm_head.weight"].grad) < 6e-2

@@ -1,12 +1,16 @@
 #!/bin/bash
-# N-GPU pass (run with `gpurun --gpus N -- bash tools/gpu_dist.sh N`): 2-rank parity tests of the sharded path, then the
-# bench under torchrun exactly as the driver launches it.
+# N-GPU pass (run with `gpurun --gpus N -- bash tools/gpu_dist.sh N [tag] [tests|notests]`): 2-rank parity tests of the
+# sharded path, then the bench under torchrun exactly as the driver launches it. Every step has a hard timeout: a
+# multi-GPU hang is charged N x.
 N=${1:-2}
 TAG=${2:-r1_dist}
+MODE=${3:-tests}
 mkdir -p gpurun_out
-nvidia-smi topo -m > gpurun_out/${TAG}_topo.txt 2>&1
-timeout 600 python -m pytest tests/test_gpu_dist.py -m gpu -x -q --timeout 500 2>&1 | tail -30 > gpurun_out/${TAG}_pytest.log
-echo "dist pytest rc=${PIPESTATUS[0]}"; tail -12 gpurun_out/${TAG}_pytest.log
-timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29541 \
-  bench.py --gpus $N --steps 2 --warmup 3 --batch ${BATCH:-64} > gpurun_out/${TAG}_bench_n$N.json 2> gpurun_out/${TAG}_bench_n$N.err
+if [[ $MODE == tests ]]; then
+  timeout 300 python -m pytest tests/test_gpu_dist.py -m gpu -x -q --timeout 280 2>&1 | tail -30 > gpurun_out/${TAG}_pytest.log
+  echo "dist pytest rc=${PIPESTATUS[0]}"; tail -12 gpurun_out/${TAG}_pytest.log
+fi
+timeout ${BENCH_TIMEOUT:-300} python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29541 \
+  bench.py --gpus $N --steps ${STEPS:-2} --warmup 3 --batch ${BATCH:-64} --new-tokens ${NEWTOK:-256} \
+  > gpurun_out/${TAG}_bench_n$N.json 2> gpurun_out/${TAG}_bench_n$N.err
 echo "bench N=$N rc=$?"; tail -c 3500 gpurun_out/${TAG}_bench_n$N.json; tail -8 gpurun_out/${TAG}_bench_n$N.err
