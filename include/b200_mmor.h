@@ -300,6 +300,15 @@ int b200_act_backward(const void* z, const void* dy, void* dz, int64_t n_out, in
  * place in dqkv) and dk (from the head-major cache layout) are rotated by -theta, dk / dv are gathered back into the
  * token-major dqkv [B*Lq, 3*H*128]. */
 int b200_swiglu_forward(const void* z, void* h, int64_t n_out, b200_stream_t stream);
+/* y = act(z) elementwise from a stored pre-activation (act 1 quick_gelu, 2 gelu(erf)): training forward of the CLIP
+ * MLP, the pooler FFN and the mm_projector. b200_group_sum: out[i] (+)= sum_g x[g * slab + i], the gradient of a table
+ * that is broadcast over the batch (the pooler's position + token-type embeddings). */
+int b200_act_forward(const void* z, void* y, int64_t n, int act, b200_stream_t stream);
+/* out[r] = src[row_map[r]] (zeros when < 0) + add[r % period]: the pooler's pre-LayerNorm embedding sum
+ * (model/llava_arch.py:143-170 pad_embeddings + HF BertEmbeddings), materialised for the backward pass. */
+int b200_gather_add_rows(const void* src, int64_t ld_src, const int32_t* row_map, const void* add, int period, int rows,
+                         int D, void* out, b200_stream_t stream);
+int b200_group_sum(const void* x, int groups, int64_t slab, int accumulate, float* out, b200_stream_t stream);
 int b200_rope_kv_backward(void* dqkv, const int32_t* kv_start, const float* cos_table, const float* sin_table,
                           int max_pos, const void* dk_cache, const void* dv_cache, int B, int H, int Lq, int cap,
                           b200_stream_t stream);
@@ -321,16 +330,18 @@ int b200_weighted_ce(const void* logits, int logits_fp32, int64_t ld, const int6
 
 /* HF Trainer gradient clipping (max_grad_norm, README.md:151) + torch.optim.AdamW as configured by
  * LLaVATrainer.create_optimizer (train/llava_trainer.py:191-278), on flat buffers.
- * b200_grad_sq_norm: out2[0] (+)= sum(grad^2) over a bf16 gradient buffer (accumulate != 0 chains buffers),
+ * Gradients are bf16 (grad_fp32 = 0) or fp32 (grad_fp32 = 1, what the backward GEMMs accumulate into).
+ * b200_grad_sq_norm: out2[0] (+)= sum(grad^2) over a gradient buffer (accumulate != 0 chains buffers),
  * out2[1] = min(1, max_norm / (sqrt(out2[0]) + 1e-6)) (1 when max_norm <= 0). Deterministic two-stage sum.
  * b200_adamw_step: one pass over fp32 master weights / m / v with bf16 gradients scaled by *clip_coef (device
  * pointer, NULL = 1): decoupled weight decay, bias-corrected Adam update (step counts from 1), bf16 copy of the new
  * weights written to `param` (may be NULL). */
 size_t b200_grad_norm_workspace_bytes(void);
-int b200_grad_sq_norm(const void* grad, int64_t n, int accumulate, float max_norm, float* out2, void* workspace,
-                      size_t workspace_bytes, b200_stream_t stream);
-int b200_adamw_step(float* master, void* param, const void* grad, float* m, float* v, int64_t n, float lr, float beta1,
-                    float beta2, float eps, float weight_decay, int step, const float* clip_coef, b200_stream_t stream);
+int b200_grad_sq_norm(const void* grad, int grad_fp32, int64_t n, int accumulate, float max_norm, float* out2,
+                      void* workspace, size_t workspace_bytes, b200_stream_t stream);
+int b200_adamw_step(float* master, void* param, const void* grad, int grad_fp32, float* m, float* v, int64_t n, float lr,
+                    float beta1, float beta2, float eps, float weight_decay, int step, const float* clip_coef,
+                    b200_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -82,14 +82,17 @@ _SIGS = {
     "b200_colsum": (ci, [vp, i64, ci, ci, ci, vp, vp, sz, vp]),
     "b200_act_backward": (ci, [vp, vp, vp, i64, ci, vp]),
     "b200_swiglu_forward": (ci, [vp, vp, i64, vp]),
+    "b200_act_forward": (ci, [vp, vp, i64, ci, vp]),
+    "b200_gather_add_rows": (ci, [vp, i64, vp, vp, ci, ci, ci, vp, vp]),
+    "b200_group_sum": (ci, [vp, ci, i64, ci, vp, vp]),
     "b200_rope_kv_backward": (ci, [vp, vp, vp, vp, ci, vp, vp, ci, ci, ci, ci, vp]),
     "b200_norm_backward_workspace_bytes": (sz, [ci, ci]),
     "b200_norm_backward": (ci, [vp, vp, vp, cf, ci, ci, ci, vp, vp, vp, vp, ci, vp, sz, vp]),
     "b200_weighted_ce_workspace_bytes": (sz, [ci, ci]),
     "b200_weighted_ce": (ci, [vp, ci, i64, vp, vp, ci, ci, ci, cf, vp, i64, vp, vp, sz, vp]),
     "b200_grad_norm_workspace_bytes": (sz, []),
-    "b200_grad_sq_norm": (ci, [vp, i64, ci, cf, vp, vp, sz, vp]),
-    "b200_adamw_step": (ci, [vp, vp, vp, vp, vp, i64, cf, cf, cf, cf, cf, ci, vp, vp]),
+    "b200_grad_sq_norm": (ci, [vp, ci, i64, ci, cf, vp, vp, sz, vp]),
+    "b200_adamw_step": (ci, [vp, vp, vp, ci, vp, vp, i64, cf, cf, cf, cf, cf, ci, vp, vp]),
     "b200_layernorm": (ci, [vp, i64, vp, vp, ci, vp, vp, cf, vp, i64, ci, ci, vp]),
     "b200_rmsnorm": (ci, [vp, i64, vp, cf, vp, i64, ci, ci, vp]),
     "b200_flash_attention": (ci, [vp, i64, i64, i64, vp, i64, i64, i64, vp, i64, i64, i64, vp, i64, i64, i64,
@@ -210,7 +213,7 @@ def gemm_skinny(a, w, out=None, bias=None, residual=None, act=ACT_NONE, out_fp32
     return out
 
 
-def gemm_ex(a, w, a_t=False, w_t=False, out=None, out_fp32=False, accumulate=False, bn=0):
+def gemm_ex(a, w, a_t=False, w_t=False, out=None, out_fp32=False, accumulate=False, bn=0, residual=None):
     """General GEMM with transposed operands read in place: A is (M, K), or (K, M) when a_t; W is (N, K), or (K, N)
     when w_t. out = A_eff @ W_eff.T, optionally accumulated into an fp32 `out`."""
     M, K = (a.shape[1], a.shape[0]) if a_t else a.shape
@@ -218,9 +221,10 @@ def gemm_ex(a, w, a_t=False, w_t=False, out=None, out_fp32=False, accumulate=Fal
     assert (w.shape[0] if w_t else w.shape[1]) == K and a.stride(1) == 1 and w.stride(1) == 1
     if out is None:
         out = torch.empty((M, N), device=a.device, dtype=torch.float32 if out_fp32 else torch.bfloat16)
+    ldr = residual.stride(0) if residual is not None else 0
     check(lib().b200_gemm_bf16_ex(ptr(a), a.stride(0), int(a_t), ptr(w), w.stride(0), int(w_t), ptr(out), out.stride(0),
-                                  M, N, K, None, None, 0, ACT_NONE, int(out.dtype == torch.float32), int(accumulate),
-                                  bn, stream_ptr()), "b200_gemm_bf16_ex")
+                                  M, N, K, None, ptr(residual), ldr, ACT_NONE, int(out.dtype == torch.float32),
+                                  int(accumulate), bn, stream_ptr()), "b200_gemm_bf16_ex")
     return out
 
 
@@ -244,6 +248,53 @@ def swiglu_forward(z):
     h = torch.empty((M, F2 // 2), device=z.device, dtype=torch.bfloat16)
     check(lib().b200_swiglu_forward(ptr(z), ptr(h), h.numel(), stream_ptr()), "b200_swiglu_forward")
     return h
+
+
+def gather_add_rows(src, row_map, add, rows, period=None):
+    """out[r] = src[row_map[r]] (zero when < 0) + add[r % period]."""
+    D = src.shape[1]
+    out = torch.empty((rows, D), device=src.device, dtype=torch.bfloat16)
+    period = (add.shape[0] if add is not None else 1) if period is None else period
+    check(lib().b200_gather_add_rows(ptr(src), src.stride(0), ptr(row_map), ptr(add), period, rows, D, ptr(out),
+                                     stream_ptr()), "b200_gather_add_rows")
+    return out
+
+
+def embed_rows(ids, table, out=None, rows=None):
+    """out[r] = table[ids[r]] (ids >= 0), zeros (ids == -1), untouched (ids <= -2)."""
+    rows = ids.numel() if rows is None else rows
+    D = table.shape[1]
+    if out is None:
+        out = torch.empty((rows, D), device=table.device, dtype=torch.bfloat16)
+    check(lib().b200_embed_rows(ptr(ids), ptr(table), ptr(out), out.stride(0), rows, D, table.shape[0], stream_ptr()),
+          "b200_embed_rows")
+    return out
+
+
+def colsum(dy, out=None, accumulate=False):
+    M, N = dy.shape
+    if out is None:
+        out = torch.empty(N, device=dy.device, dtype=torch.float32)
+    ws = torch.empty(int(lib().b200_colsum_workspace_bytes(N)), dtype=torch.uint8, device=dy.device)
+    check(lib().b200_colsum(ptr(dy), dy.stride(0), M, N, int(accumulate), ptr(out), ptr(ws), ws.numel(), stream_ptr()),
+          "b200_colsum")
+    return out
+
+
+def act_forward(z, act):
+    y = torch.empty_like(z)
+    check(lib().b200_act_forward(ptr(z), ptr(y), z.numel(), act, stream_ptr()), "b200_act_forward")
+    return y
+
+
+def group_sum(x, out=None, accumulate=False):
+    """x (G, ...) bf16 -> fp32 sum over the leading dimension."""
+    G = x.shape[0]
+    slab = x[0].numel()
+    if out is None:
+        out = torch.empty(x.shape[1:], device=x.device, dtype=torch.float32)
+    check(lib().b200_group_sum(ptr(x), G, slab, int(accumulate), ptr(out), stream_ptr()), "b200_group_sum")
+    return out
 
 
 def act_backward(z, dy, act):
@@ -283,20 +334,21 @@ def weighted_ce(logits, labels, vocab_weight=None, grad_scale=1.0, want_grad=Fal
 
 
 def grad_sq_norm(grad, out2=None, accumulate=False, max_norm=0.0):
-    """out2[0] (+)= sum(grad^2), out2[1] = clip coefficient for max_norm. grad: flat bf16 tensor."""
+    """out2[0] (+)= sum(grad^2), out2[1] = clip coefficient for max_norm. grad: contiguous bf16 or fp32 tensor."""
     if out2 is None:
         out2 = torch.zeros(2, device=grad.device, dtype=torch.float32)
     ws = torch.empty(int(lib().b200_grad_norm_workspace_bytes()), dtype=torch.uint8, device=grad.device)
-    check(lib().b200_grad_sq_norm(ptr(grad), grad.numel(), int(accumulate), float(max_norm), ptr(out2), ptr(ws),
-                                  ws.numel(), stream_ptr()), "b200_grad_sq_norm")
+    check(lib().b200_grad_sq_norm(ptr(grad), int(grad.dtype == torch.float32), grad.numel(), int(accumulate),
+                                  float(max_norm), ptr(out2), ptr(ws), ws.numel(), stream_ptr()), "b200_grad_sq_norm")
     return out2
 
 
 def adamw_step(master, param, grad, m, v, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, step=1,
                clip_coef=None):
-    """Fused AdamW on flat buffers: master/m/v fp32, grad bf16, param bf16 copy (or None)."""
-    check(lib().b200_adamw_step(ptr(master), ptr(param), ptr(grad), ptr(m), ptr(v), master.numel(), lr, beta1, beta2,
-                                eps, weight_decay, int(step), ptr(clip_coef), stream_ptr()), "b200_adamw_step")
+    """Fused AdamW on flat buffers: master/m/v fp32, grad bf16 or fp32, param bf16 copy (or None)."""
+    check(lib().b200_adamw_step(ptr(master), ptr(param), ptr(grad), int(grad.dtype == torch.float32), ptr(m), ptr(v),
+                                master.numel(), lr, beta1, beta2, eps, weight_decay, int(step), ptr(clip_coef),
+                                stream_ptr()), "b200_adamw_step")
 
 
 def layernorm(x, gamma, beta, eps, row_map=None, add=None, out=None):

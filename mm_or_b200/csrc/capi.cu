@@ -83,6 +83,20 @@ int b200_act_backward(const void* z, const void* dy, void* dz, int64_t n_out, in
                       static_cast<cudaStream_t>(stream));
 }
 
+int b200_act_forward(const void* z, void* y, int64_t n, int act, b200_stream_t stream) {
+  return act_forward(static_cast<const bf16*>(z), static_cast<bf16*>(y), n, act, static_cast<cudaStream_t>(stream));
+}
+
+int b200_group_sum(const void* x, int groups, int64_t slab, int accumulate, float* out, b200_stream_t stream) {
+  return group_sum(static_cast<const bf16*>(x), groups, slab, accumulate, out, static_cast<cudaStream_t>(stream));
+}
+
+int b200_gather_add_rows(const void* src, int64_t ld_src, const int32_t* row_map, const void* add, int period, int rows,
+                         int D, void* out, b200_stream_t stream) {
+  return gather_add_rows(static_cast<const bf16*>(src), ld_src, row_map, static_cast<const bf16*>(add), period, rows, D,
+                         static_cast<bf16*>(out), static_cast<cudaStream_t>(stream));
+}
+
 int b200_swiglu_forward(const void* z, void* h, int64_t n_out, b200_stream_t stream) {
   return swiglu_forward(static_cast<const bf16*>(z), static_cast<bf16*>(h), n_out, static_cast<cudaStream_t>(stream));
 }
@@ -115,17 +129,17 @@ int b200_weighted_ce(const void* logits, int logits_fp32, int64_t ld, const int6
 
 size_t b200_grad_norm_workspace_bytes(void) { return grad_norm_workspace_bytes(); }
 
-int b200_grad_sq_norm(const void* grad, int64_t n, int accumulate, float max_norm, float* out2, void* workspace,
-                      size_t workspace_bytes, b200_stream_t stream) {
-  return grad_sq_norm(static_cast<const bf16*>(grad), n, accumulate, max_norm, out2, workspace, workspace_bytes,
+int b200_grad_sq_norm(const void* grad, int grad_fp32, int64_t n, int accumulate, float max_norm, float* out2,
+                      void* workspace, size_t workspace_bytes, b200_stream_t stream) {
+  return grad_sq_norm(grad, grad_fp32, n, accumulate, max_norm, out2, workspace, workspace_bytes,
                       static_cast<cudaStream_t>(stream));
 }
 
-int b200_adamw_step(float* master, void* param, const void* grad, float* m, float* v, int64_t n, float lr, float beta1,
-                    float beta2, float eps, float weight_decay, int step, const float* clip_coef,
+int b200_adamw_step(float* master, void* param, const void* grad, int grad_fp32, float* m, float* v, int64_t n, float lr,
+                    float beta1, float beta2, float eps, float weight_decay, int step, const float* clip_coef,
                     b200_stream_t stream) {
-  return adamw_step(master, static_cast<bf16*>(param), static_cast<const bf16*>(grad), m, v, n, lr, beta1, beta2, eps,
-                    weight_decay, step, clip_coef, static_cast<cudaStream_t>(stream));
+  return adamw_step(master, static_cast<bf16*>(param), grad, grad_fp32, m, v, n, lr, beta1, beta2, eps, weight_decay,
+                    step, clip_coef, static_cast<cudaStream_t>(stream));
 }
 
 int b200_layernorm(const void* x, int64_t ldx, const int32_t* row_map, const void* add, int period, const void* gamma,

@@ -109,11 +109,15 @@ int weighted_ce(const void* logits, int is_fp32, long long ld, const long long* 
                 int L, int V, float grad_scale, void* dlogits, long long ldd, float* loss_out, void* workspace,
                 size_t workspace_bytes, cudaStream_t stream);
 size_t grad_norm_workspace_bytes();
-int grad_sq_norm(const bf16* grad, long long n, int accumulate, float max_norm, float* out2, void* workspace,
-                 size_t workspace_bytes, cudaStream_t stream);
+int grad_sq_norm(const void* grad, int grad_fp32, long long n, int accumulate, float max_norm, float* out2,
+                 void* workspace, size_t workspace_bytes, cudaStream_t stream);
 size_t colsum_workspace_bytes(int N);
 int colsum(const bf16* dy, long long ld, int M, int N, int accumulate, float* out, void* workspace,
            size_t workspace_bytes, cudaStream_t stream);
+int act_forward(const bf16* z, bf16* y, long long n, int act, cudaStream_t stream);
+int group_sum(const bf16* x, int groups, long long slab, int accumulate, float* out, cudaStream_t stream);
+int gather_add_rows(const bf16* src, long long ld_src, const int* row_map, const bf16* add, int period, int rows, int D,
+                    bf16* out, cudaStream_t stream);
 int swiglu_forward(const bf16* z, bf16* h, long long n_out, cudaStream_t stream);
 int rope_kv_backward(bf16* dqkv, const int* kv_start, const float* cos_t, const float* sin_t, int max_pos,
                      const bf16* dk_cache, const bf16* dv_cache, int Bn, int H, int Lq, int cap, cudaStream_t stream);
@@ -122,8 +126,9 @@ size_t norm_backward_workspace_bytes(int M, int D);
 int norm_backward(const bf16* x, const bf16* dy, const bf16* gamma, float eps, int M, int D, int rms, const bf16* add,
                   bf16* dx, float* dgamma, float* dbeta, int accumulate, void* workspace, size_t workspace_bytes,
                   cudaStream_t stream);
-int adamw_step(float* master, bf16* param, const bf16* grad, float* m, float* v, long long n, float lr, float beta1,
-               float beta2, float eps, float weight_decay, int step, const float* clip_coef, cudaStream_t stream);
+int adamw_step(float* master, bf16* param, const void* grad, int grad_fp32, float* m, float* v, long long n, float lr,
+               float beta1, float beta2, float eps, float weight_decay, int step, const float* clip_coef,
+               cudaStream_t stream);
 
 // ---------------------------------------------------------------------------------------------
 // norms (norm.cu)

@@ -163,25 +163,19 @@ int weighted_ce(const void* logits, int is_fp32, long long ld, const long long* 
 static constexpr int kOptThreads = 256;
 static constexpr int kNormBlocks = 1184;  // 8 per SM; fixed so that the two-stage sum has a fixed order
 
-__global__ void __launch_bounds__(kOptThreads) grad_sq_partial_kernel(const bf16* __restrict__ g, long long n,
+__device__ __forceinline__ float grad_at(const bf16* g, long long i) { return __bfloat162float(g[i]); }
+__device__ __forceinline__ float grad_at(const float* g, long long i) { return g[i]; }
+
+template <typename GT>
+__global__ void __launch_bounds__(kOptThreads) grad_sq_partial_kernel(const GT* __restrict__ g, long long n,
                                                                       float* __restrict__ partial) {
   __shared__ float red[kOptThreads / 32];
   float acc = 0.f;
-  const long long n8 = n / 8;
-  const uint4* g8 = reinterpret_cast<const uint4*>(g);
-  for (long long i = static_cast<long long>(blockIdx.x) * kOptThreads + threadIdx.x; i < n8;
+  for (long long i = static_cast<long long>(blockIdx.x) * kOptThreads + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * kOptThreads) {
-    const uint4 u = g8[i];
-    const float f[8] = {bf16lo(u.x), bf16hi(u.x), bf16lo(u.y), bf16hi(u.y),
-                        bf16lo(u.z), bf16hi(u.z), bf16lo(u.w), bf16hi(u.w)};
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc += f[j] * f[j];
+    const float f = grad_at(g, i);
+    acc += f * f;
   }
-  if (blockIdx.x == 0)
-    for (long long i = n8 * 8 + threadIdx.x; i < n; i += kOptThreads) {
-      const float f = __bfloat162float(g[i]);
-      acc += f * f;
-    }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
@@ -218,23 +212,26 @@ __global__ void __launch_bounds__(kOptThreads) grad_norm_finish_kernel(const flo
 
 size_t grad_norm_workspace_bytes() { return kNormBlocks * sizeof(float); }
 
-int grad_sq_norm(const bf16* grad, long long n, int accumulate, float max_norm, float* out2, void* workspace,
-                 size_t workspace_bytes, cudaStream_t stream) {
+int grad_sq_norm(const void* grad, int grad_fp32, long long n, int accumulate, float max_norm, float* out2,
+                 void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   if (workspace == nullptr || workspace_bytes < grad_norm_workspace_bytes())
     return fail(-2, "grad_sq_norm: workspace too small");
-  if ((reinterpret_cast<uintptr_t>(grad) & 15) != 0) return fail(-2, "grad_sq_norm: gradient buffer must be 16-byte aligned");
-  LaunchScope scope(kFamTrain, stream, 2.0 * n, 0.0, 2);
+  LaunchScope scope(kFamTrain, stream, (grad_fp32 ? 4.0 : 2.0) * n, 0.0, 2);
   float* partial = static_cast<float*>(workspace);
-  grad_sq_partial_kernel<<<kNormBlocks, kOptThreads, 0, stream>>>(grad, n, partial);
+  if (grad_fp32)
+    grad_sq_partial_kernel<float><<<kNormBlocks, kOptThreads, 0, stream>>>(static_cast<const float*>(grad), n, partial);
+  else
+    grad_sq_partial_kernel<bf16><<<kNormBlocks, kOptThreads, 0, stream>>>(static_cast<const bf16*>(grad), n, partial);
   grad_norm_finish_kernel<<<1, kOptThreads, 0, stream>>>(partial, kNormBlocks, accumulate, max_norm, out2);
   B200_CUDA_OK(cudaGetLastError());
   return 0;
 }
 
+template <typename GT>
 struct AdamArgs {
   float* master;    // fp32 master weights
   bf16* param;      // bf16 working copy (may be null)
-  const bf16* grad;
+  const GT* grad;
   float* m;
   float* v;
   long long n;
@@ -243,63 +240,30 @@ struct AdamArgs {
   const float* clip;         // device pointer to the clip coefficient (out2 + 1 of grad_sq_norm) or null
 };
 
-__global__ void __launch_bounds__(kOptThreads) adamw_kernel(const AdamArgs a) {
+template <typename GT>
+__global__ void __launch_bounds__(kOptThreads) adamw_kernel(const AdamArgs<GT> a) {
   const float clip = a.clip ? *a.clip : 1.f;
   const float step_size = a.lr / a.bc1;
   const float decay = 1.f - a.lr * a.weight_decay;
-  const long long n4 = a.n / 4;
-  for (long long i = static_cast<long long>(blockIdx.x) * kOptThreads + threadIdx.x; i < n4;
+  for (long long i = static_cast<long long>(blockIdx.x) * kOptThreads + threadIdx.x; i < a.n;
        i += static_cast<long long>(gridDim.x) * kOptThreads) {
-    const uint2 gu = reinterpret_cast<const uint2*>(a.grad)[i];
-    const float g[4] = {bf16lo(gu.x) * clip, bf16hi(gu.x) * clip, bf16lo(gu.y) * clip, bf16hi(gu.y) * clip};
-    float4 p = reinterpret_cast<float4*>(a.master)[i];
-    float4 m = reinterpret_cast<float4*>(a.m)[i];
-    float4 v = reinterpret_cast<float4*>(a.v)[i];
-    float* pp = &p.x;
-    float* mm = &m.x;
-    float* vv = &v.x;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      pp[j] *= decay;                                            // decoupled weight decay (torch.optim.AdamW)
-      mm[j] = a.beta1 * mm[j] + (1.f - a.beta1) * g[j];
-      vv[j] = a.beta2 * vv[j] + (1.f - a.beta2) * g[j] * g[j];
-      const float denom = sqrtf(vv[j]) / a.bc2_sqrt + a.eps;
-      pp[j] -= step_size * mm[j] / denom;
-    }
-    reinterpret_cast<float4*>(a.master)[i] = p;
-    reinterpret_cast<float4*>(a.m)[i] = m;
-    reinterpret_cast<float4*>(a.v)[i] = v;
-    if (a.param != nullptr) {
-      uint2 o;
-      o.x = pack_bf16x2(p.x, p.y);
-      o.y = pack_bf16x2(p.z, p.w);
-      reinterpret_cast<uint2*>(a.param)[i] = o;
-    }
-  }
-  if (blockIdx.x == 0) {
-    for (long long i = n4 * 4 + threadIdx.x; i < a.n; i += kOptThreads) {
-      const float g = __bfloat162float(a.grad[i]) * clip;
-      float p = a.master[i] * decay;
-      const float m = a.beta1 * a.m[i] + (1.f - a.beta1) * g;
-      const float v = a.beta2 * a.v[i] + (1.f - a.beta2) * g * g;
-      p -= step_size * m / (sqrtf(v) / a.bc2_sqrt + a.eps);
-      a.master[i] = p;
-      a.m[i] = m;
-      a.v[i] = v;
-      if (a.param != nullptr) a.param[i] = __float2bfloat16(p);
-    }
+    const float g = grad_at(a.grad, i) * clip;
+    float p = a.master[i] * decay;                               // decoupled weight decay (torch.optim.AdamW)
+    const float m = a.beta1 * a.m[i] + (1.f - a.beta1) * g;
+    const float v = a.beta2 * a.v[i] + (1.f - a.beta2) * g * g;
+    p -= step_size * m / (sqrtf(v) / a.bc2_sqrt + a.eps);
+    a.master[i] = p;
+    a.m[i] = m;
+    a.v[i] = v;
+    if (a.param != nullptr) a.param[i] = __float2bfloat16(p);
   }
 }
 
-int adamw_step(float* master, bf16* param, const bf16* grad, float* m, float* v, long long n, float lr, float beta1,
-               float beta2, float eps, float weight_decay, int step, const float* clip_coef, cudaStream_t stream) {
-  if (n <= 0) return 0;
-  if (step < 1) return fail(-2, "adamw_step: step counts from 1");
-  const uintptr_t al = reinterpret_cast<uintptr_t>(master) | reinterpret_cast<uintptr_t>(m) |
-                       reinterpret_cast<uintptr_t>(v);
-  if ((al & 15) != 0 || (reinterpret_cast<uintptr_t>(grad) & 7) != 0 || (reinterpret_cast<uintptr_t>(param) & 7) != 0)
-    return fail(-2, "adamw_step: buffers must be 16-byte (fp32) / 8-byte (bf16) aligned");
-  AdamArgs a;
+template <typename GT>
+static int adamw_launch(float* master, bf16* param, const GT* grad, float* m, float* v, long long n, float lr,
+                        float beta1, float beta2, float eps, float weight_decay, int step, const float* clip_coef,
+                        cudaStream_t stream) {
+  AdamArgs<GT> a;
   a.master = master;
   a.param = param;
   a.grad = grad;
@@ -314,12 +278,24 @@ int adamw_step(float* master, bf16* param, const bf16* grad, float* m, float* v,
   a.bc1 = 1.f - powf(beta1, static_cast<float>(step));
   a.bc2_sqrt = sqrtf(1.f - powf(beta2, static_cast<float>(step)));
   a.clip = clip_coef;
-  const long long want = (n / 4 + kOptThreads - 1) / kOptThreads;
-  const int grid = static_cast<int>(want < 1 ? 1 : (want > 8LL * num_sms() ? 8LL * num_sms() : want));
-  LaunchScope scope(kFamTrain, stream, 28.0 * n, 0.0);
-  adamw_kernel<<<grid, kOptThreads, 0, stream>>>(a);
+  const long long want = (n + kOptThreads - 1) / kOptThreads;
+  const int grid = static_cast<int>(want < 1 ? 1 : (want > 16LL * num_sms() ? 16LL * num_sms() : want));
+  LaunchScope scope(kFamTrain, stream, (26.0 + sizeof(GT)) * n, 0.0);
+  adamw_kernel<GT><<<grid, kOptThreads, 0, stream>>>(a);
   B200_CUDA_OK(cudaGetLastError());
   return 0;
+}
+
+int adamw_step(float* master, bf16* param, const void* grad, int grad_fp32, float* m, float* v, long long n, float lr,
+               float beta1, float beta2, float eps, float weight_decay, int step, const float* clip_coef,
+               cudaStream_t stream) {
+  if (n <= 0) return 0;
+  if (step < 1) return fail(-2, "adamw_step: step counts from 1");
+  if (grad_fp32)
+    return adamw_launch<float>(master, param, static_cast<const float*>(grad), m, v, n, lr, beta1, beta2, eps,
+                               weight_decay, step, clip_coef, stream);
+  return adamw_launch<bf16>(master, param, static_cast<const bf16*>(grad), m, v, n, lr, beta1, beta2, eps, weight_decay,
+                            step, clip_coef, stream);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -413,6 +389,83 @@ int swiglu_forward(const bf16* z, bf16* h, long long n_out, cudaStream_t stream)
   if (n_out <= 0) return 0;
   LaunchScope scope(kFamTrain, stream, 6.0 * n_out, 0.0);
   swiglu_forward_kernel<<<static_cast<unsigned>((n_out + 255) / 256), 256, 0, stream>>>(z, h, n_out);
+  B200_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// y = act(z) elementwise (quick_gelu / gelu-erf) from the stored pre-activation: training forward of the CLIP MLP, the
+// BERT pooler FFN and the mm_projector (the inference path fuses the activation into the GEMM epilogue)
+__global__ void __launch_bounds__(256) act_forward_kernel(const bf16* __restrict__ z, bf16* __restrict__ y, long long n,
+                                                          int act) {
+  const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= n) return;
+  const float x = __bfloat162float(z[i]);
+  const float r = act == kActQuickGelu ? x / (1.f + __expf(-1.702f * x))
+                                       : 0.5f * x * (1.f + erff(x * 0.70710678118654752f));
+  y[i] = __float2bfloat16(r);
+}
+
+int act_forward(const bf16* z, bf16* y, long long n, int act, cudaStream_t stream) {
+  if (n <= 0) return 0;
+  if (act != kActQuickGelu && act != kActGeluErf) return fail(-2, "act_forward: unknown act %d", act);
+  LaunchScope scope(kFamTrain, stream, 4.0 * n, 0.0);
+  act_forward_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(z, y, n, act);
+  B200_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// out[r, :] (+)= sum_g x[g, r, :] over `groups` slabs of [rows, D]: gradient of a table broadcast over the batch
+// (BERT position + token-type embeddings of the image pooler). Fixed summation order.
+__global__ void __launch_bounds__(256) group_sum_kernel(const bf16* __restrict__ x, int groups, long long slab,
+                                                        int accumulate, float* __restrict__ out) {
+  const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= slab) return;
+  float acc = accumulate ? out[i] : 0.f;
+  for (int g = 0; g < groups; ++g) acc += __bfloat162float(x[g * slab + i]);
+  out[i] = acc;
+}
+
+int group_sum(const bf16* x, int groups, long long slab, int accumulate, float* out, cudaStream_t stream) {
+  if (groups <= 0 || slab <= 0) return 0;
+  LaunchScope scope(kFamTrain, stream, 2.0 * groups * slab, 0.0);
+  group_sum_kernel<<<static_cast<unsigned>((slab + 255) / 256), 256, 0, stream>>>(x, groups, slab, accumulate, out);
+  B200_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// out[r] = src[row_map[r]] (zero row when row_map[r] < 0) + add[r % period]: the pooler's pre-LayerNorm embedding sum
+// (gathered patch features + position / token-type embeddings), materialised for the backward of its LayerNorm
+// (the inference path fuses the same gather + add into the LayerNorm kernel, norm.cu)
+__global__ void __launch_bounds__(128) gather_add_rows_kernel(const bf16* __restrict__ src, long long ld_src,
+                                                              const int* __restrict__ row_map,
+                                                              const bf16* __restrict__ add, int period, int rows, int D,
+                                                              bf16* __restrict__ out) {
+  const int r = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const int sr = row_map ? row_map[r] : r;
+  const uint4* sp = sr >= 0 ? reinterpret_cast<const uint4*>(src + static_cast<long long>(sr) * ld_src) : nullptr;
+  const uint4* ap = add ? reinterpret_cast<const uint4*>(add + static_cast<long long>(r % period) * D) : nullptr;
+  uint4* op = reinterpret_cast<uint4*>(out + static_cast<long long>(r) * D);
+  for (int i = lane; i < D / 8; i += 32) {
+    const uint4 u = sp ? sp[i] : make_uint4(0, 0, 0, 0);
+    const uint4 a = ap ? __ldg(ap + i) : make_uint4(0, 0, 0, 0);
+    uint4 o;
+    o.x = pack_bf16x2(bf16lo(u.x) + bf16lo(a.x), bf16hi(u.x) + bf16hi(a.x));
+    o.y = pack_bf16x2(bf16lo(u.y) + bf16lo(a.y), bf16hi(u.y) + bf16hi(a.y));
+    o.z = pack_bf16x2(bf16lo(u.z) + bf16lo(a.z), bf16hi(u.z) + bf16hi(a.z));
+    o.w = pack_bf16x2(bf16lo(u.w) + bf16lo(a.w), bf16hi(u.w) + bf16hi(a.w));
+    op[i] = o;
+  }
+}
+
+int gather_add_rows(const bf16* src, long long ld_src, const int* row_map, const bf16* add, int period, int rows, int D,
+                    bf16* out, cudaStream_t stream) {
+  if (rows <= 0) return 0;
+  if (D % 8 != 0 || ld_src % 8 != 0) return fail(-2, "gather_add_rows: D and the source stride must be multiples of 8");
+  LaunchScope scope(kFamTrain, stream, 4.0 * rows * D, 0.0);
+  gather_add_rows_kernel<<<(rows + 3) / 4, 128, 0, stream>>>(src, ld_src, row_map, add, period > 0 ? period : 1, rows,
+                                                             D, out);
   B200_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -1,0 +1,268 @@
+"""Forward with saved activations + backward of the visual side of MM2SG for the fine-tune step: the trainable CLIP layers,
+the BERT image pooler and the mlp2x_gelu projector (SURVEY.md 8a rows a1-a6 under training, a12 trainable set:
+"mm_projector, image_pooler, last 12 CLIP layers", train.py:1257-1261).
+
+Reference: the same modules as the inference path (clip_encoder.py:29-51 -> HF CLIPEncoderLayer,
+multimodal_projector/builder.py:46-53,169-190 -> HF BertLayer) under torch autograd, dropout fixed to 0 (SURVEY.md 7,
+"Dropout in training parity"). Every tensor operation here is a kernel of libb200mmor.so called through the C ABI;
+torch owns the memory. The frozen CLIP layers run through the inference stage entry point (b200_vit_forward).
+
+Not covered yet (raise / documented in DESIGN.md): gradients of the seg-mask CNN and of the audio projection, point
+clouds, dropout > 0.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from .. import _lib as L
+from ..synth import POOLER_GEOMETRY
+
+BF = torch.bfloat16
+VIT = "model.vision_tower.vision_tower.vision_model."
+POOL = "model.image_pooler.bert."
+
+
+class _Grads:
+    """fp32 gradient store keyed by the reference's parameter names; `accumulate` adds into existing entries."""
+
+    def __init__(self, store, accumulate, device):
+        self.g = store if store is not None else {}
+        self.accumulate = accumulate
+        self.device = device
+
+    def slot(self, name, shape):
+        if name not in self.g:
+            self.g[name] = torch.zeros(shape, device=self.device, dtype=torch.float32)
+            return self.g[name], False
+        return self.g[name], self.accumulate
+
+
+def _lin_bwd(G, x_saved, w, dy, wname, bname=None, need_dx=True, residual=None):
+    """Backward of y = x w^T (+ b): dW, db into the store; returns dx (+ residual, fused in the GEMM epilogue)."""
+    dw, acc = G.slot(wname, tuple(w.shape))
+    L.gemm_ex(dy, x_saved, a_t=True, w_t=True, out=dw, accumulate=acc)
+    if bname is not None:
+        db, accb = G.slot(bname, (w.shape[0],))
+        L.colsum(dy, out=db, accumulate=accb)
+    return L.gemm_ex(dy, w, w_t=True, residual=residual) if need_dx else None
+
+
+def _ln_bwd(G, x_saved, dy, gamma, eps, gname, bname, add=None):
+    dg, acc = G.slot(gname, (gamma.numel(),))
+    db, _ = G.slot(bname, (gamma.numel(),))
+    dx, _, _ = L.norm_backward(x_saved, dy, gamma, eps, rms=False, dgamma=dg, dbeta=db, accumulate=acc, add=add)
+    return dx
+
+
+def _heads(t, n, tokens, heads, hd):
+    """(n * tokens, 3 * heads * hd) fused qkv -> three (n, tokens, heads, hd) views."""
+    v5 = t.view(n, tokens, 3, heads, hd)
+    return v5[:, :, 0], v5[:, :, 1], v5[:, :, 2]
+
+
+# =====================================================================================================================
+# CLIP ViT: frozen prefix through the stage entry point, trainable layers op by op
+# =====================================================================================================================
+class VitCache:
+    __slots__ = ("layers", "n_img", "first")
+
+
+def vit_forward(tower, pixels, first_trainable):
+    """pixels (N, 3, S, S) -> hidden (N, 1 + P, D) after layer n_run (CLS row kept) + cache for vit_backward.
+    Layers [0, first_trainable) are frozen and run fused; layers [first_trainable, n_run) save their activations."""
+    n_run = tower.n_layers_run()
+    first = max(0, min(first_trainable, n_run))
+    lib = L.lib()
+    pixels = pixels.to(device=tower.device, dtype=BF).contiguous()
+    N = pixels.shape[0]
+    T, D = tower.num_patches + 1, tower.hidden_size
+    H = tower.cfg["num_attention_heads"]
+    hd = D // H
+    eps = tower.cfg.get("layer_norm_eps", 1e-5)
+    w = L.VitWeights.from_buffer_copy(tower._w)
+    w.n_layers = first
+    x = torch.empty((N, T, D), device=tower.device, dtype=BF)
+    nb = lib.b200_vit_workspace_bytes(ctypes.byref(w), N)
+    ws = tower._ws.get(nb, tower.device)
+    L.check(lib.b200_vit_forward(ctypes.byref(w), L.ptr(pixels), L.ptr(x), N, L.ptr(ws), ws.numel(), L.stream_ptr()),
+            "b200_vit_forward")
+    x = x.view(N * T, D)
+    cache = VitCache()
+    cache.layers, cache.n_img, cache.first = [], N, first
+    for l in range(first, n_run):
+        lt = tower._keep[1][l]
+        c = {"x": x}
+        c["a"] = L.layernorm(x, lt["ln1_w"], lt["ln1_b"], eps)
+        c["qkv"] = L.gemm(c["a"], lt["qkv_w"], bias=lt["qkv_b"])
+        q, k, v = _heads(c["qkv"], N, T, H, hd)
+        ctx, c["lse"] = L.flash_attention(q, k, v, scale=1.0, return_lse=True)   # q is pre-scaled in qkv_w
+        c["ctx"] = ctx.view(N * T, D)
+        c["x1"] = L.gemm(c["ctx"], lt["out_w"], bias=lt["out_b"], residual=x)
+        c["m"] = L.layernorm(c["x1"], lt["ln2_w"], lt["ln2_b"], eps)
+        c["z"] = L.gemm(c["m"], lt["fc1_w"], bias=lt["fc1_b"])
+        c["h"] = L.act_forward(c["z"], L.ACT_QUICK_GELU)
+        x = L.gemm(c["h"], lt["fc2_w"], bias=lt["fc2_b"], residual=c["x1"])
+        cache.layers.append(c)
+    return x.view(N, T, D), cache
+
+
+def vit_backward(tower, cache, d_hidden, grads=None, accumulate=False):
+    """d_hidden (N, 1 + P, D) bf16 -> gradients of the trainable CLIP layers under the reference's names."""
+    G = _Grads(grads, accumulate, tower.device)
+    N = cache.n_img
+    T, D = tower.num_patches + 1, tower.hidden_size
+    H = tower.cfg["num_attention_heads"]
+    hd = D // H
+    eps = tower.cfg.get("layer_norm_eps", 1e-5)
+    scale = hd ** -0.5
+    dx = d_hidden.to(BF).contiguous().view(N * T, D)
+    for idx in range(len(cache.layers) - 1, -1, -1):
+        l = cache.first + idx
+        lt, c = tower._keep[1][l], cache.layers[idx]
+        p = VIT + f"encoder.layers.{l}."
+        f = "_fused." + p
+        dh = _lin_bwd(G, c["h"], lt["fc2_w"], dx, p + "mlp.fc2.weight", p + "mlp.fc2.bias")
+        dz = L.act_backward(c["z"], dh, L.ACT_QUICK_GELU)
+        dm = _lin_bwd(G, c["m"], lt["fc1_w"], dz, p + "mlp.fc1.weight", p + "mlp.fc1.bias")
+        dx1 = _ln_bwd(G, c["x1"], dm, lt["ln2_w"], eps, p + "layer_norm2.weight", p + "layer_norm2.bias", add=dx)
+        dctx = _lin_bwd(G, c["ctx"], lt["out_w"], dx1, p + "self_attn.out_proj.weight", p + "self_attn.out_proj.bias")
+        dqkv = torch.empty_like(c["qkv"])
+        q, k, v = _heads(c["qkv"], N, T, H, hd)
+        L.flash_attention_bwd(q, k, v, c["ctx"].view(N, T, H, hd), dctx.view(N, T, H, hd), c["lse"], scale=1.0,
+                              out=_heads(dqkv, N, T, H, hd))
+        need_dx = idx > 0
+        da = _lin_bwd(G, c["a"], lt["qkv_w"], dqkv, f + "qkv_w", f + "qkv_b", need_dx=True)
+        dx = _ln_bwd(G, c["x"], da, lt["ln1_w"], eps, p + "layer_norm1.weight", p + "layer_norm1.bias", add=dx1)
+        if not need_dx:
+            dx = None
+        # the fused qkv weight holds q_proj * head_dim^-0.5: dL/dW_q(reference) = scale * dL/dW_q(fused)
+        qkv_w, qkv_b = G.g[f + "qkv_w"], G.g[f + "qkv_b"]
+        for j, n in enumerate(("q_proj", "k_proj", "v_proj")):
+            s = scale if j == 0 else 1.0
+            for src, suffix in ((qkv_w, ".weight"), (qkv_b, ".bias")):
+                dst, acc = G.slot(p + f"self_attn.{n}" + suffix, tuple(src[j * D:(j + 1) * D].shape))
+                part = src[j * D:(j + 1) * D]
+                dst.copy_(part * s if not acc else dst + part * s)
+        del G.g[f + "qkv_w"], G.g[f + "qkv_b"]
+    return G.g
+
+
+# =====================================================================================================================
+# image pooler (BERT, post-LN) and projector
+# =====================================================================================================================
+def pooler_forward(pooler, hidden, split_sizes):
+    """hidden (N_img, 1 + P, D) (CLS rows skipped through the gather map, llava_arch.py:143-170), split_sizes [V_b]
+    -> pooled (B, keep, D) + cache."""
+    g = pooler.geo
+    D, H = g["hidden"], g["heads"]
+    hd = D // H
+    keep, eps = g["keep"], g["eps"]
+    dev = pooler.device
+    N, T, _ = hidden.shape
+    P = T - 1
+    B = len(split_sizes)
+    vmax = max(split_sizes)
+    S = vmax * P
+    gmap = np.full((B, vmax, P), -1, dtype=np.int32)
+    img0 = np.concatenate([[0], np.cumsum(split_sizes)[:-1]])
+    base = np.arange(P, dtype=np.int32)[None, :] + 1
+    for b, vb in enumerate(split_sizes):
+        gmap[b, :vb] = (img0[b] + np.arange(vb, dtype=np.int32))[:, None] * T + base
+    kv_len = torch.as_tensor(np.asarray(split_sizes, dtype=np.int32) * P).to(dev)
+    t, layers_w, _ = pooler._keep
+    cache = {"gmap": gmap, "B": B, "S": S, "N": N, "T": T, "kv_len": kv_len, "layers": []}
+    gm = torch.as_tensor(gmap.reshape(-1)).to(dev)
+    u = L.gather_add_rows(hidden.reshape(N * T, D), gm, t["pos_type"], B * S, period=S)
+    cache["u"] = u
+    e = L.layernorm(u, t["emb_ln_w"], t["emb_ln_b"], eps)
+    for lt in layers_w:
+        c = {"e": e}
+        c["qkv"] = L.gemm(e, lt["qkv_w"], bias=lt["qkv_b"])
+        q, k, v = _heads(c["qkv"], B, S, H, hd)
+        ctx, c["lse"] = L.flash_attention(q, k, v, kv_len=kv_len, return_lse=True)
+        c["ctx"] = ctx.view(B * S, D)
+        c["y1"] = L.gemm(c["ctx"], lt["ao_w"], bias=lt["ao_b"], residual=e)
+        c["e1"] = L.layernorm(c["y1"], lt["ao_ln_w"], lt["ao_ln_b"], eps)
+        c["z"] = L.gemm(c["e1"], lt["fc1_w"], bias=lt["fc1_b"])
+        c["h"] = L.act_forward(c["z"], L.ACT_GELU)
+        c["y2"] = L.gemm(c["h"], lt["fc2_w"], bias=lt["fc2_b"], residual=c["e1"])
+        e = L.layernorm(c["y2"], lt["out_ln_w"], lt["out_ln_b"], eps)
+        cache["layers"].append(c)
+    pooled = e.view(B, S, D)[:, :keep]
+    return pooled, cache
+
+
+def pooler_backward(pooler, cache, d_pooled, grads=None, accumulate=False):
+    """d_pooled (B, keep, D) -> (d_hidden (N_img, 1 + P, D) bf16, grads)."""
+    G = _Grads(grads, accumulate, pooler.device)
+    g = pooler.geo
+    D, H = g["hidden"], g["heads"]
+    hd = D // H
+    keep, eps = g["keep"], g["eps"]
+    B, S, N, T = cache["B"], cache["S"], cache["N"], cache["T"]
+    t, layers_w, _ = pooler._keep
+    de = torch.zeros((B, S, D), device=pooler.device, dtype=BF)
+    de[:, :keep] = d_pooled.to(BF)                    # rows >= keep of the last layer are not consumed (builder.py:175)
+    de = de.view(B * S, D)
+    for i in range(len(layers_w) - 1, -1, -1):
+        lt, c = layers_w[i], cache["layers"][i]
+        p = POOL + f"encoder.layer.{i}."
+        f = "_fused." + p
+        dy2 = _ln_bwd(G, c["y2"], de, lt["out_ln_w"], eps, p + "output.LayerNorm.weight", p + "output.LayerNorm.bias")
+        dh = _lin_bwd(G, c["h"], lt["fc2_w"], dy2, p + "output.dense.weight", p + "output.dense.bias")
+        dz = L.act_backward(c["z"], dh, L.ACT_GELU)
+        de1 = _lin_bwd(G, c["e1"], lt["fc1_w"], dz, p + "intermediate.dense.weight", p + "intermediate.dense.bias",
+                       residual=dy2)                                       # + the residual branch y2 = ... + e1
+        dy1 = _ln_bwd(G, c["y1"], de1, lt["ao_ln_w"], eps, p + "attention.output.LayerNorm.weight",
+                      p + "attention.output.LayerNorm.bias")
+        dctx = _lin_bwd(G, c["ctx"], lt["ao_w"], dy1, p + "attention.output.dense.weight",
+                        p + "attention.output.dense.bias")
+        dqkv = torch.empty_like(c["qkv"])
+        q, k, v = _heads(c["qkv"], B, S, H, hd)
+        L.flash_attention_bwd(q, k, v, c["ctx"].view(B, S, H, hd), dctx.view(B, S, H, hd), c["lse"],
+                              kv_len=cache["kv_len"], out=_heads(dqkv, B, S, H, hd))
+        de = _lin_bwd(G, c["e"], lt["qkv_w"], dqkv, f + "qkv_w", f + "qkv_b", residual=dy1)   # y1 = ... + e
+        qkv_w, qkv_b = G.g[f + "qkv_w"], G.g[f + "qkv_b"]
+        for j, n in enumerate(("query", "key", "value")):
+            for src, suffix in ((qkv_w, ".weight"), (qkv_b, ".bias")):
+                part = src[j * D:(j + 1) * D]
+                dst, acc = G.slot(p + f"attention.self.{n}" + suffix, tuple(part.shape))
+                dst.copy_(part if not acc else dst + part)
+        del G.g[f + "qkv_w"], G.g[f + "qkv_b"]
+    du = _ln_bwd(G, cache["u"], de, t["emb_ln_w"], eps, POOL + "embeddings.LayerNorm.weight",
+                 POOL + "embeddings.LayerNorm.bias")
+    # u = gather(hidden) + position[s] + token_type[0]: table gradients are sums over the batch (and over s)
+    dpos, acc = G.slot(POOL + "embeddings.position_embeddings.weight", (t["pos_type"].shape[0], D))
+    if not acc:
+        dpos.zero_()
+    L.group_sum(du.view(B, S, D), out=dpos[:S], accumulate=acc)
+    dtt, acct = G.slot(POOL + "embeddings.token_type_embeddings.weight", (2, D))
+    if not acct:
+        dtt.zero_()
+    L.colsum(du, out=dtt[0], accumulate=acct)
+    # scatter back to the tower's hidden rows (every source row is used at most once; CLS rows get zeros)
+    inv = np.full(N * T, -1, dtype=np.int32)
+    gm = cache["gmap"].reshape(-1)
+    used = gm >= 0
+    inv[gm[used]] = np.nonzero(used)[0].astype(np.int32)
+    d_hidden = L.embed_rows(torch.as_tensor(inv).to(pooler.device), du, rows=N * T)
+    return d_hidden.view(N, T, D), G.g
+
+
+def projector_forward(proj, tokens):
+    """tokens (n, 1024) -> (n, hidden) + cache (mlp2x_gelu, multimodal_projector/builder.py:46-53)."""
+    c = {"x": tokens}
+    c["z"] = L.gemm(tokens, proj.t["0.weight"], bias=proj.t["0.bias"])
+    c["h"] = L.act_forward(c["z"], L.ACT_GELU)
+    out = L.gemm(c["h"], proj.t["2.weight"], bias=proj.t["2.bias"])
+    return out, c
+
+
+def projector_backward(proj, cache, d_out, grads=None, accumulate=False, need_dx=True):
+    G = _Grads(grads, accumulate, d_out.device)
+    dh = _lin_bwd(G, cache["h"], proj.t["2.weight"], d_out, "model.mm_projector.2.weight", "model.mm_projector.2.bias")
+    dz = L.act_backward(cache["z"], dh, L.ACT_GELU)
+    dx = _lin_bwd(G, cache["x"], proj.t["0.weight"], dz, "model.mm_projector.0.weight", "model.mm_projector.0.bias",
+                  need_dx=need_dx)
+    return dx, G.g

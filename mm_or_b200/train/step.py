@@ -1,0 +1,126 @@
+"""One MM2SG fine-tune step on B200 (BASELINE.json configs[4]): multimodal forward, class-weighted shifted CE, backward
+through the decoder / projector / image pooler / trainable CLIP layers, gradient-norm clipping and AdamW.
+
+Reference: LLaVATrainer (LLaVA/llava/train/llava_trainer.py:134-278) = HF Trainer.training_step over
+LlavaLlamaForCausalLM.forward + compute_loss, torch autograd, clip_grad_norm_(max_grad_norm), torch.optim.AdamW with
+the four parameter groups of create_optimizer ({decay, no decay} x {projector, rest}; no-decay = norm weights and
+biases), lr / mm_projector_lr from the training arguments (README.md:147-151: lr 2e-5, wd 0, max_grad_norm 0.1).
+Everything numeric runs in libb200mmor.so through the C ABI; master weights, m and v are fp32 under the reference's
+parameter names, and the model's fused bf16 working copies are rebuilt from them after every update.
+
+Frozen here (documented in DESIGN.md): embed_tokens, CLIP embeddings and the CLIP layers below
+`first_trainable_clip_layer`, the seg-mask CNN and the audio projection (no backward kernels yet).
+"""
+import numpy as np
+import torch
+
+from .. import _lib as L
+from ..model.pack import plan_pack
+from . import encoder as E
+from . import llama as T
+
+BF = torch.bfloat16
+
+
+def default_trainable(name, first_clip_layer):
+    if name.startswith("model.layers.") or name in ("model.norm.weight", "lm_head.weight"):
+        return True
+    if name.startswith("model.mm_projector."):
+        return True
+    if name.startswith("model.image_pooler.bert."):
+        # word_embeddings (vocab_size = 1) and the BertPooler head are never used by the path (builder.py:173-175)
+        return not ("word_embeddings" in name or ".pooler." in name)
+    p = E.VIT + "encoder.layers."
+    if name.startswith(p):
+        return int(name[len(p):].split(".")[0]) >= first_clip_layer
+    return False
+
+
+def no_decay(name):
+    """create_optimizer's decay filter: LayerNorm / RMSNorm weights and all biases are not decayed."""
+    return name.endswith(".bias") or "norm" in name.lower() or "layrnorm" in name.lower()
+
+
+class FineTuner:
+    def __init__(self, model, state_dict, lr=2e-5, mm_projector_lr=None, betas=(0.9, 0.999), eps=1e-8,
+                 weight_decay=0.0, max_grad_norm=0.1, first_trainable_clip_layer=12, vocab_weight=None,
+                 trainable=None):
+        self.model = model
+        self.dev = model.device
+        self.first_clip = first_trainable_clip_layer
+        self.lr, self.proj_lr = lr, (mm_projector_lr if mm_projector_lr is not None else lr)
+        self.betas, self.eps, self.wd, self.max_norm = betas, eps, weight_decay, max_grad_norm
+        self.vocab_weight = vocab_weight
+        pick = trainable if trainable is not None else (lambda n: default_trainable(n, first_trainable_clip_layer))
+        # the full reference-named state dict in bf16 on the device: the source the fused layouts are rebuilt from
+        self.sd = {k: v.detach().to(self.dev, BF).contiguous() for k, v in state_dict.items()}
+        n_run = model.get_vision_tower().n_layers_run()     # CLIP layers past the selected hidden state are dead
+        self.names = sorted(k for k in self.sd if pick(k) and self._has_backward(k, n_run))
+        self.master = {k: state_dict[k].detach().to(self.dev, torch.float32).contiguous().clone() for k in self.names}
+        self.m = {k: torch.zeros_like(v) for k, v in self.master.items()}
+        self.v = {k: torch.zeros_like(v) for k, v in self.master.items()}
+        self.step_count = 0
+        self.last_grads = None
+
+    @staticmethod
+    def _has_backward(name, n_run):
+        if name.startswith("model.image_pooler.") and not name.startswith("model.image_pooler.bert."):
+            return False                                     # seg-mask CNN / audio projection: no backward kernels yet
+        p = E.VIT + "encoder.layers."
+        if name.startswith(p):
+            return int(name[len(p):].split(".")[0]) < n_run
+        return True
+
+    # ------------------------------------------------------------------------------------------------------------
+    def forward_backward(self, input_ids, labels, attention_mask, images, grads=None, accumulate=False):
+        """Returns (loss, weight sum, grads under the reference's names)."""
+        model, dev = self.model, self.dev
+        cfg = model.config
+        tower, pooler, proj = model.get_vision_tower(), model.get_image_pooler(), model.get_model().mm_projector
+        keep, Dv, D = pooler.geo["keep"], pooler.geo["hidden"], cfg.hidden_size
+        concat, split = model._images_to_batch(images)
+        B = len(split)
+        hidden, vc = E.vit_forward(tower, concat, self.first_clip)
+        pooled, pc = E.pooler_forward(pooler, hidden, split)
+        vis, prc = E.projector_forward(proj, pooled.reshape(B * keep, Dv).contiguous())
+        plan = plan_pack(input_ids.cpu().numpy(), None if attention_mask is None else attention_mask.cpu().numpy(),
+                         None if labels is None else labels.cpu().numpy(), keep, "right",
+                         getattr(cfg, "tokenizer_model_max_length", None))
+        Lq = plan.L
+        src = plan.src.reshape(B, Lq).astype(np.int64)
+        text_ids = np.where(src >= -1, src, -2).astype(np.int32)
+        vis_ids = np.where(src <= -2, np.arange(B)[:, None] * keep + (-2 - src), -2).astype(np.int32)
+        embeds = torch.empty((B * Lq, D), device=dev, dtype=BF)
+        L.embed_rows(torch.as_tensor(text_ids.reshape(-1)).to(dev), model.model.embed_tokens, out=embeds)
+        L.embed_rows(torch.as_tensor(vis_ids.reshape(-1)).to(dev), vis, out=embeds)
+        loss, wsum, g, d_emb = T.forward_backward(model, embeds.view(B, Lq, D), torch.from_numpy(plan.labels).to(dev),
+                                                  torch.from_numpy(plan.lengths).to(dev), self.vocab_weight,
+                                                  grads=grads, accumulate=accumulate)
+        # pack backward: visual rows of d_embeds back to the projector output (truncated tokens get zeros)
+        d_vis = L.embed_rows(torch.as_tensor(plan.row_map).to(dev), d_emb.reshape(B * Lq, D), rows=B * keep)
+        dx, g = E.projector_backward(proj, prc, d_vis, grads=g, accumulate=accumulate)
+        d_hidden, g = E.pooler_backward(pooler, pc, dx.view(B, keep, Dv), grads=g, accumulate=accumulate)
+        g = E.vit_backward(tower, vc, d_hidden, grads=g, accumulate=accumulate)
+        return loss, wsum, g
+
+    def optimizer_step(self, grads):
+        """clip_grad_norm_(max_grad_norm) over the trainable set + AdamW; rebuilds the fused bf16 working weights."""
+        g = T.unfuse_grads(grads, self.model.config)
+        self.step_count += 1
+        out2 = torch.zeros(2, device=self.dev, dtype=torch.float32)
+        for i, k in enumerate(self.names):
+            L.grad_sq_norm(g[k].contiguous(), out2=out2, accumulate=i > 0, max_norm=self.max_norm)
+        clip = out2[1:]
+        for k in self.names:
+            lr = self.proj_lr if k.startswith("model.mm_projector.") else self.lr
+            wd = 0.0 if no_decay(k) else self.wd
+            L.adamw_step(self.master[k], self.sd[k], g[k].contiguous(), self.m[k], self.v[k], lr, self.betas[0],
+                         self.betas[1], self.eps, wd, self.step_count, clip_coef=clip)
+        self.model.load_state_dict(self.sd, device=self.dev)
+        return out2
+
+    def train_step(self, input_ids, labels, attention_mask, images):
+        loss, wsum, grads = self.forward_backward(input_ids, labels, attention_mask, images)
+        self.last_grads = grads
+        norm_sq = self.optimizer_step(grads)
+        return loss, norm_sq

@@ -292,3 +292,121 @@ def test_llama_train_step_matches_autograd(L):
                                          accumulate=True)
     g2 = T.unfuse_grads(grads2, cfg)
     assert rel(g2["lm_head.weight"].cpu(), 2 * params["lm_head.weight"].grad) < 6e-2
+
+
+def test_encoder_train_backward_matches_autograd(L):
+    """Trainable CLIP layer + BERT image pooler + mm_projector: forward with saved activations and backward through
+    the C ABI vs torch autograd over the oracle (fp32, same bf16-rounded weights, views [2, 1] so that one sample is
+    padded with a zero view and masked)."""
+    import golden_cases as gc
+    from helpers import oracle_cfg
+    from mm_or_b200.model.llava_llama import LlavaLlamaForCausalLM
+    from mm_or_b200.train import encoder as E
+    cfg = gc.small_config()
+    sd = gc.bf16_round(gc.small_weights(cfg))
+    model = LlavaLlamaForCausalLM(cfg).load_state_dict(sd)
+    tower, pooler, proj = model.get_vision_tower(), model.get_image_pooler(), model.get_model().mm_projector
+    ocfg = oracle_cfg(cfg)
+    g = torch.Generator().manual_seed(21)
+    views = [2, 1]
+    pixels = torch.randn(sum(views), 3, 336, 336, generator=g).to(torch.bfloat16)
+    B, keep = len(views), 576
+    hidden, vc = E.vit_forward(tower, pixels.cuda(), first_trainable=1)
+    pooled, pc = E.pooler_forward(pooler, hidden, views)
+    out, prc = E.projector_forward(proj, pooled.reshape(B * keep, -1).contiguous())
+    d_out = (torch.randn(B * keep, cfg.hidden_size, generator=g) * 0.1).to(torch.bfloat16)
+    dx, grads = E.projector_backward(proj, prc, d_out.cuda())
+    d_hidden, grads = E.pooler_backward(pooler, pc, dx.view(B, keep, -1), grads=grads)
+    grads = E.vit_backward(tower, vc, d_hidden, grads=grads)
+    # ---- oracle under autograd
+    train_prefixes = ("model.vision_tower.vision_tower.vision_model.encoder.layers.1.", "model.image_pooler.bert.e",
+                      "model.mm_projector.")
+    with torch.enable_grad():
+        params = {k: v.clone().float().requires_grad_(True) for k, v in sd.items() if k.startswith(train_prefixes)
+                  and "word_embeddings" not in k}
+        sdp = {**sd, **params}
+        feats = O.clip_tower_forward(sdp, pixels.float(), ocfg.vit)
+        per_sample, i0 = [], 0
+        for vb in views:
+            per_sample.append(feats[i0:i0 + vb])
+            i0 += vb
+        emb, mask = O.pad_embeddings(per_sample)
+        ref_pooled = O.bert_pooler_forward(sdp, emb, mask, ocfg.pooler)
+        ref_out = O.mm_projector(sdp, ref_pooled).reshape(B * keep, -1)
+        (ref_out * d_out.float()).sum().backward()
+    assert rel(out.cpu(), ref_out.detach()) < 2e-2
+    checked = 0
+    for k, p in params.items():
+        if p.grad is None or float(p.grad.abs().max()) == 0.0:
+            continue
+        assert k in grads, k
+        gg = grads[k].cpu()
+        if k.endswith("position_embeddings.weight"):
+            S = max(views) * keep
+            assert float(gg[S:].abs().max()) == 0.0
+        if k.endswith(("k_proj.bias", "key.bias")):
+            # softmax is invariant to a constant added to every key: the exact gradient is zero and autograd only
+            # returns rounding noise, so bound ours against the query-bias gradient instead
+            qk = k.replace("k_proj", "q_proj").replace("key", "query")
+            assert float(gg.norm()) < 2e-2 * float(params[qk].grad.norm()), (k, float(gg.norm()))
+            continue
+        r = rel(gg, p.grad)
+        assert r < 8e-2, (k, r)
+        checked += 1
+    assert checked >= 40
+
+
+def test_fine_tune_step_end_to_end(L):
+    """Whole MM2SG fine-tune step (config 5 at test size): loss and gradients vs torch autograd over the oracle's
+    multimodal forward + weighted CE; optimizer plumbing vs torch clip_grad_norm_ + AdamW fed with the same gradients;
+    the loss goes down over a few steps on a fixed batch."""
+    import golden_cases as gc
+    from helpers import oracle_cfg
+    from mm_or_b200.model.llava_llama import LlavaLlamaForCausalLM
+    from mm_or_b200.train.step import FineTuner
+    cfg = gc.small_config()
+    cfg.tokenizer_padding_side = "right"
+    sd = gc.bf16_round(gc.small_weights(cfg))
+    model = LlavaLlamaForCausalLM(cfg).load_state_dict(sd)
+    case = gc.make_case(cfg, "train_right")
+    g0 = torch.Generator().manual_seed(9)
+    w = torch.rand(cfg.vocab_size, generator=g0) + 0.05
+    ft = FineTuner(model, sd, lr=1e-3, weight_decay=0.01, max_grad_norm=0.1, first_trainable_clip_layer=1, vocab_weight=w)
+    loss, wsum, grads = ft.forward_backward(case["input_ids"], case["labels"], case["attention_mask"], case["images"])
+    from mm_or_b200.train import llama as T
+    grads_named = T.unfuse_grads(grads, cfg)
+    ocfg = oracle_cfg(cfg)
+    with torch.enable_grad():
+        params = {k: sd[k].clone().float().requires_grad_(True) for k in ft.names}
+        ref = O.multimodal_prefill({**sd, **params}, ocfg, case["input_ids"], case["attention_mask"], case["images"],
+                                   labels=case["labels"], padding_side="right")
+        ref_loss = O.weighted_ce(ref["logits"], ref["modified_labels"], w)
+        ref_loss.backward()
+    assert abs(float(loss) - float(ref_loss.detach())) < 3e-2 * abs(float(ref_loss.detach()))
+    bad = []
+    for k in ft.names:
+        pg = params[k].grad
+        if pg is None or k.endswith(("k_proj.bias", "key.bias")) or float(pg.norm()) < 1e-7:
+            continue
+        r = rel(grads_named[k].cpu(), pg)
+        if r > 0.12:
+            bad.append((k, r))
+    assert not bad, bad[:8]
+    # ---- optimizer plumbing: same gradients into torch's clip + AdamW
+    tp = {k: sd[k].clone().float().cuda().requires_grad_(True) for k in ft.names}
+    decay = [tp[k] for k in ft.names if not (k.endswith(".bias") or "norm" in k.lower() or "layrnorm" in k.lower())]
+    nodecay = [tp[k] for k in ft.names if (k.endswith(".bias") or "norm" in k.lower() or "layrnorm" in k.lower())]
+    opt = torch.optim.AdamW([{"params": decay, "weight_decay": 0.01}, {"params": nodecay, "weight_decay": 0.0}],
+                            lr=1e-3, betas=(0.9, 0.999), eps=1e-8)
+    for k in ft.names:
+        tp[k].grad = grads_named[k].clone()
+    torch.nn.utils.clip_grad_norm_(list(tp.values()), 0.1)
+    opt.step()
+    ft.optimizer_step(grads)
+    for k in ft.names:
+        assert (ft.master[k] - tp[k].detach()).abs().max().item() < 2e-6 + 1e-5 * tp[k].detach().abs().max().item(), k
+    # ---- a few more steps on the same batch: the loss must go down
+    first = float(loss)
+    for _ in range(4):
+        last, _ = ft.train_step(case["input_ids"], case["labels"], case["attention_mask"], case["images"])
+    assert float(last) < first
