@@ -1,15 +1,7 @@
-// Attention kernels of the MM2SG hot path.
+// Attention entry points of the MM2SG hot path.
 //
-//  flash_attn_kernel<D>  fused softmax(Q K^T * scale + mask) V for the three "many queries" sites:
-//      - CLIP ViT-L self-attention, S = 577, 16 heads x 64, no mask     (HF CLIPAttention via clip_encoder.py:48)
-//      - BERT image-pooler self-attention, S = V*576, 8 heads x 128, key-padding mask
-//                                                                       (multimodal_projector/builder.py:173)
-//      - Llama prefill self-attention, 32 heads x 128, causal + left-pad mask
-//                                                 (HF LlamaAttention via llava_llama.py:93; training uses the
-//                                                  varlen FlashAttention-2 patch llama_flash_attn_monkey_patch.py:78)
-//    The reference materialises the S x S score matrix in HBM; here scores never leave registers
-//    (online softmax, fp32 statistics). Round-1 implementation: bf16 mma.sync.m16n8k16 with cp.async
-//    double-buffered K/V tiles; the tcgen05 version is the planned replacement (DESIGN.md "next").
+//  flash_attn            softmax(Q K^T * scale + mask) V for the three "many queries" sites (CLIP ViT-L, BERT image pooler,
+//      Llama prefill / training): forwards to the tcgen05 kernel in attention_sm100.cu.
 //
 //  decode_attn_kernel    one new token per sequence against the bf16 KV cache (llava_arch.py:192-201 +
 //      HF LlamaAttention with past_key_values). One query row per (sequence, head): a pure HBM-bound
@@ -21,255 +13,14 @@
 
 namespace b200 {
 
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool pred) {
-  const uint32_t s = smem_u32(smem);
-  const int sz = pred ? 16 : 0;  // src-size 0 => zero fill
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(sz) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* smem) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
-               : "r"(smem_u32(smem)));
-}
-__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* smem) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
-               : "r"(smem_u32(smem)));
-}
-__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-
-static constexpr int kFaBM = 64;  // query rows per CTA (16 per warp)
-static constexpr int kFaBN = 64;  // keys per tile
-static constexpr int kFaThreads = 128;
-
-// smem tile [rows][D] bf16 with the 16-byte chunk index XOR-swizzled by (row & 7): conflict-free ldmatrix
-template <int D>
-__device__ __forceinline__ bf16* tile_ptr(bf16* base, int row, int chunk) {
-  return base + row * D + ((chunk ^ (row & 7)) << 3);
-}
-
-template <int D>
-__device__ __forceinline__ void load_tile_async(bf16* smem, const bf16* g, long long row_stride, int row0,
-                                                int rows_valid_end) {
-  // 64 rows x D elements, 16 B per cp.async
-  constexpr int kChunks = D / 8;
-  for (int i = threadIdx.x; i < kFaBN * kChunks; i += kFaThreads) {
-    const int r = i / kChunks, c = i % kChunks;
-    const int gr = row0 + r;
-    const bool ok = gr < rows_valid_end;
-    const bf16* src = g + static_cast<long long>(ok ? gr : 0) * row_stride + c * 8;
-    cp_async16(tile_ptr<D>(smem, r, c), src, ok);
-  }
-}
-
-template <int D>
-__global__ void __launch_bounds__(kFaThreads) flash_attn_kernel(const AttnArgs a) {
-  extern __shared__ __align__(16) uint8_t fa_smem[];
-  bf16* sK = reinterpret_cast<bf16*>(fa_smem);             // [2][64][D]
-  bf16* sV = sK + 2 * kFaBN * D;                           // [2][64][D]
-  bf16* sQ = sV + 2 * kFaBN * D;                           // [64][D]
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int g = lane >> 2, t = lane & 3;
-  const int q0 = blockIdx.x * kFaBM;
-  const int h = blockIdx.y, b = blockIdx.z;
-
-  const bf16* qg = a.q + b * a.q_bs + h * a.q_hs;
-  const bf16* kg = a.k + b * a.k_bs + h * a.k_hs;
-  const bf16* vg = a.v + b * a.v_bs + h * a.v_hs;
-
-  int key_begin = a.kv_start ? a.kv_start[b] : 0;
-  int key_end = a.kv_len ? min(a.kv_len[b], a.Lk) : a.Lk;
-  const int causal_off = a.Lk - a.Lq;
-  if (a.causal) key_end = min(key_end, q0 + kFaBM - 1 + causal_off + 1);
-  const int tile_begin = key_begin / kFaBN;
-  const int tile_end = (key_end + kFaBN - 1) / kFaBN;  // exclusive
-
-  // ---- load Q tile, first K/V tile
-  load_tile_async<D>(sQ, qg, a.q_rs, q0, a.Lq);
-  if (tile_begin < tile_end) {
-    load_tile_async<D>(sK, kg, a.k_rs, tile_begin * kFaBN, key_end);
-    load_tile_async<D>(sV, vg, a.v_rs, tile_begin * kFaBN, key_end);
-  }
-  cp_async_commit();
-  cp_async_wait<0>();
-  __syncthreads();
-
-  // Q fragments: 16 rows x D per warp
-  uint32_t qf[D / 16][4];
-#pragma unroll
-  for (int ks = 0; ks < D / 16; ++ks) {
-    const int r = warp * 16 + (lane & 7) + 8 * ((lane >> 3) & 1);
-    const int c = ks * 2 + (lane >> 4);
-    ldmatrix_x4(qf[ks], tile_ptr<D>(sQ, r, c));
-  }
-
-  float o[D / 8][4];
-#pragma unroll
-  for (int i = 0; i < D / 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
-  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
-  const int qi0 = q0 + warp * 16 + g, qi1 = qi0 + 8;
-
-  for (int tile = tile_begin; tile < tile_end; ++tile) {
-    const int buf = (tile - tile_begin) & 1;
-    bf16* cK = sK + buf * kFaBN * D;
-    bf16* cV = sV + buf * kFaBN * D;
-    // prefetch next tile into the other buffer
-    if (tile + 1 < tile_end) {
-      load_tile_async<D>(sK + (buf ^ 1) * kFaBN * D, kg, a.k_rs, (tile + 1) * kFaBN, key_end);
-      load_tile_async<D>(sV + (buf ^ 1) * kFaBN * D, vg, a.v_rs, (tile + 1) * kFaBN, key_end);
-    }
-    cp_async_commit();
-
-    // ---- S = Q K^T  (16 x 64 per warp)
-    float s[kFaBN / 8][4];
-#pragma unroll
-    for (int i = 0; i < kFaBN / 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
-#pragma unroll
-    for (int ks = 0; ks < D / 16; ++ks) {
-#pragma unroll
-      for (int np = 0; np < kFaBN / 16; ++np) {
-        uint32_t kf[4];
-        const int r = np * 16 + (lane & 7) + 8 * (lane >> 4);
-        const int c = ks * 2 + ((lane >> 3) & 1);
-        ldmatrix_x4(kf, tile_ptr<D>(cK, r, c));
-        mma_bf16_16816(s[np * 2], qf[ks], kf[0], kf[1]);
-        mma_bf16_16816(s[np * 2 + 1], qf[ks], kf[2], kf[3]);
-      }
-    }
-
-    // ---- mask + online softmax
-    const int kbase = tile * kFaBN;
-    const bool need_mask = (kbase < key_begin) || (kbase + kFaBN > key_end) ||
-                           (a.causal && (kbase + kFaBN - 1 > q0 + warp * 16 + causal_off));
-    float mx0 = m0, mx1 = m1;
-#pragma unroll
-    for (int i = 0; i < kFaBN / 8; ++i) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float val = s[i][j] * a.scale_log2;
-        if (need_mask) {
-          const int kj = kbase + i * 8 + 2 * t + (j & 1);
-          const int qi = (j < 2) ? qi0 : qi1;
-          const bool vis = kj >= key_begin && kj < key_end && (!a.causal || kj <= qi + causal_off);
-          if (!vis) val = -INFINITY;
-        }
-        s[i][j] = val;
-      }
-      mx0 = fmaxf(mx0, fmaxf(s[i][0], s[i][1]));
-      mx1 = fmaxf(mx1, fmaxf(s[i][2], s[i][3]));
-    }
-    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
-    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
-    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-    const float ms0 = (mx0 == -INFINITY) ? 0.f : mx0;  // fully-masked rows must not produce NaN
-    const float ms1 = (mx1 == -INFINITY) ? 0.f : mx1;
-    const float corr0 = exp2f(m0 - ms0), corr1 = exp2f(m1 - ms1);  // m = -inf -> 0
-    m0 = mx0;
-    m1 = mx1;
-    float rs0 = 0.f, rs1 = 0.f;
-#pragma unroll
-    for (int i = 0; i < kFaBN / 8; ++i) {
-      s[i][0] = exp2f(s[i][0] - ms0);
-      s[i][1] = exp2f(s[i][1] - ms0);
-      s[i][2] = exp2f(s[i][2] - ms1);
-      s[i][3] = exp2f(s[i][3] - ms1);
-      rs0 += s[i][0] + s[i][1];
-      rs1 += s[i][2] + s[i][3];
-    }
-    l0 = l0 * corr0 + rs0;
-    l1 = l1 * corr1 + rs1;
-#pragma unroll
-    for (int i = 0; i < D / 8; ++i) {
-      o[i][0] *= corr0;
-      o[i][1] *= corr0;
-      o[i][2] *= corr1;
-      o[i][3] *= corr1;
-    }
-
-    // ---- O += P V
-#pragma unroll
-    for (int ks = 0; ks < kFaBN / 16; ++ks) {
-      uint32_t pf[4];
-      pf[0] = pack_bf16x2(s[2 * ks][0], s[2 * ks][1]);
-      pf[1] = pack_bf16x2(s[2 * ks][2], s[2 * ks][3]);
-      pf[2] = pack_bf16x2(s[2 * ks + 1][0], s[2 * ks + 1][1]);
-      pf[3] = pack_bf16x2(s[2 * ks + 1][2], s[2 * ks + 1][3]);
-#pragma unroll
-      for (int np = 0; np < D / 16; ++np) {
-        uint32_t vf[4];
-        const int r = ks * 16 + (lane & 7) + 8 * ((lane >> 3) & 1);
-        const int c = np * 2 + (lane >> 4);
-        ldmatrix_x4_trans(vf, tile_ptr<D>(cV, r, c));
-        mma_bf16_16816(o[np * 2], pf, vf[0], vf[1]);
-        mma_bf16_16816(o[np * 2 + 1], pf, vf[2], vf[3]);
-      }
-    }
-    cp_async_wait<0>();
-    __syncthreads();
-  }
-
-  // ---- finalize
-  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
-  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
-  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-  const float inv0 = l0 > 0.f ? 1.f / l0 : 0.f;
-  const float inv1 = l1 > 0.f ? 1.f / l1 : 0.f;
-  bf16* og = a.o + b * a.o_bs + h * a.o_hs;
-#pragma unroll
-  for (int i = 0; i < D / 8; ++i) {
-    const int col = i * 8 + 2 * t;
-    if (qi0 < a.Lq)
-      *reinterpret_cast<uint32_t*>(og + qi0 * a.o_rs + col) = pack_bf16x2(o[i][0] * inv0, o[i][1] * inv0);
-    if (qi1 < a.Lq)
-      *reinterpret_cast<uint32_t*>(og + qi1 * a.o_rs + col) = pack_bf16x2(o[i][2] * inv1, o[i][3] * inv1);
-  }
-}
-
 int flash_attn_tc(const AttnArgs& a, int head_dim, cudaStream_t stream);  // attention_sm100.cu
 
+// prefill / ViT / pooler attention: the tcgen05 kernel of attention_sm100.cu (this wrapper only does the accounting)
 int flash_attn(const AttnArgs& a, int head_dim, cudaStream_t stream) {
   if (a.B <= 0 || a.H <= 0 || a.Lq <= 0) return 0;
-  dim3 grid((a.Lq + kFaBM - 1) / kFaBM, a.H, a.B);
   const double qk = static_cast<double>(a.B) * a.H * a.Lq * a.Lk * (a.causal ? 0.5 : 1.0);
-  LaunchScope scope(kFamFlashAttn, stream,
-                    2.0 * a.B * a.H * head_dim * (2.0 * a.Lq + 2.0 * a.Lk), 4.0 * qk * head_dim);
-  // the tcgen05 kernel is the product path; the mma.sync kernel below stays only as an A/B reference for bring-up
-  static const bool legacy = getenv("B200_FA_LEGACY") != nullptr;
-  if (!legacy) return flash_attn_tc(a, head_dim, stream);
-  if (head_dim == 64) {
-    constexpr int smem = (4 * kFaBN + kFaBM) * 64 * 2;
-    static bool cfg = false;
-    if (!cfg) {
-      B200_CUDA_OK(cudaFuncSetAttribute(flash_attn_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      cfg = true;
-    }
-    flash_attn_kernel<64><<<grid, kFaThreads, smem, stream>>>(a);
-  } else if (head_dim == 128) {
-    constexpr int smem = (4 * kFaBN + kFaBM) * 128 * 2;
-    static bool cfg = false;
-    if (!cfg) {
-      B200_CUDA_OK(cudaFuncSetAttribute(flash_attn_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      cfg = true;
-    }
-    flash_attn_kernel<128><<<grid, kFaThreads, smem, stream>>>(a);
-  } else {
-    return fail(-2, "flash_attn: head_dim %d not supported (64 or 128)", head_dim);
-  }
-  B200_CUDA_OK(cudaGetLastError());
-  return 0;
+  LaunchScope scope(kFamFlashAttn, stream, 2.0 * a.B * a.H * head_dim * (2.0 * a.Lq + 2.0 * a.Lk), 4.0 * qk * head_dim);
+  return flash_attn_tc(a, head_dim, stream);
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -62,6 +62,20 @@ def all_gather_objects_equal(value, group=None):
     return all(g == got[0] for g in got), got
 
 
+def average_gradients(grads, names, group=None):
+    """Sum every named gradient over the ranks (all_reduce, NCCL on GPUs / gloo in the CPU tests) and divide by the
+    world size. Contiguous tensors are reduced in place (no extra copy of a 27 GB gradient set); a strided view is
+    replaced by a reduced contiguous copy. Returns the dict restricted to `names`."""
+    world = dist.get_world_size(group)
+    out = {}
+    for k in names:
+        t = grads[k] if grads[k].is_contiguous() else grads[k].contiguous()
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        t /= world
+        grads[k] = out[k] = t
+    return out
+
+
 class PeerGather:
     """Symmetric (world, B_local, T, D) bf16 buffer on every rank with every peer's base pointer, for the fused
     projector-GEMM + all-gather epilogue. Needs CUDA, NVLink peer access and torch symmetric memory."""

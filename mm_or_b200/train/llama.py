@@ -122,6 +122,7 @@ def forward_backward(model, embeds, labels, lengths, vocab_weight=None, grad_sca
         need = need_input_grad or i > 0
         dx = norm_bwd(c.x_in, da, lt["attn_norm"], f"model.layers.{i}.input_layernorm.weight", add=dx_mid) if need \
             else None
+        caches[i] = c = None      # this layer's saved activations are dead: let the allocator reuse them for gradients
     d_embeds = dx.view(B, Lq, D) if dx is not None else None
     return loss, wsum, g, d_embeds
 

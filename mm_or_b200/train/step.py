@@ -61,6 +61,13 @@ class FineTuner:
         self.v = {k: torch.zeros_like(v) for k, v in self.master.items()}
         self.step_count = 0
         self.last_grads = None
+        self.group = None
+
+    def set_process_group(self, group):
+        """Data-parallel fine-tuning: every rank runs forward_backward on its own samples; gradients
+        are summed over ranks with ncclAllReduce and divided by the world size before clipping / AdamW, which keeps
+        the replicas bit-identical (the reference gets the same from DeepSpeed ZeRO-2 / DDP)."""
+        self.group = group
 
     @staticmethod
     def _has_backward(name, n_run):
@@ -105,6 +112,9 @@ class FineTuner:
 
     def optimizer_step(self, grads):
         """clip_grad_norm_(max_grad_norm) over the trainable set + AdamW; rebuilds the fused bf16 working weights."""
+        if self.group is not None:
+            from ..dist import average_gradients
+            average_gradients(grads, list(grads), self.group)      # in place on the (contiguous) fused gradients
         g = T.unfuse_grads(grads, self.model.config)
         self.step_count += 1
         out2 = torch.zeros(2, device=self.dev, dtype=torch.float32)
@@ -116,6 +126,8 @@ class FineTuner:
             wd = 0.0 if no_decay(k) else self.wd
             L.adamw_step(self.master[k], self.sd[k], g[k].contiguous(), self.m[k], self.v[k], lr, self.betas[0],
                          self.betas[1], self.eps, wd, self.step_count, clip_coef=clip)
+        # drop the old fused working copies before rebuilding them (13.5 GB at 7B)
+        self.model._keep = self.model._w = self.model.lm_head = None
         self.model.load_state_dict(self.sd, device=self.dev)
         return out2
 

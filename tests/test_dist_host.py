@@ -66,6 +66,11 @@ def _worker(rank, world, port, q):
         sel = torch.from_numpy(vis_ids >= 0)
         packed[sel] = rows[torch.from_numpy(vis_ids[vis_ids >= 0])]
         assert torch.equal(packed[:, 2:2 + T], everyone[owner])
+        # data-parallel fine-tuning: gradients are averaged over ranks, identically on every rank
+        grads = {"a": torch.full((4, 3), float(rank + 1)), "b": torch.arange(6.0).view(2, 3).t() * (rank + 1)}
+        avg = D.average_gradients(grads, ["a", "b"])
+        assert torch.allclose(avg["a"], torch.full((4, 3), (1 + world) / 2.0))
+        assert torch.allclose(avg["b"], torch.arange(6.0).view(2, 3).t() * (1 + world) / 2.0)
         q.put((rank, "ok"))
     except Exception as e:  # surfaced by the parent
         q.put((rank, repr(e)))

@@ -1,5 +1,6 @@
 """GPU timing of the attention kernels on the shapes of the MM2SG path (ViT, pooler, prefill, decode).
-Run on a B200:  python tools/gpu_attn_check.py          (B200_FA_LEGACY=1 selects the mma.sync reference kernel)"""
+Run on a B200:  python tools/gpu_attn_check.py   (torch SDPA is timed beside it as a reference point; the round-1
+mma.sync kernel this replaced is recorded in profiles/r1_attention_perf.log)"""
 import math
 import os
 import sys
@@ -24,7 +25,7 @@ def timeit(fn, iters=10):
 
 
 def main():
-    tag = "legacy mma.sync" if os.environ.get("B200_FA_LEGACY") else "tcgen05"
+    tag = "tcgen05"
     shapes = [("vit 96 img", 96, 577, 577, 16, 64, False), ("pooler l1 B=16", 16, 3456, 3456, 8, 128, False),
               ("pooler l2 B=16", 16, 576, 3456, 8, 128, False), ("prefill B=16", 16, 831, 831, 32, 128, True)]
     for name, B, Lq, Lk, H, d, causal in shapes:

@@ -28,7 +28,6 @@ fi
 
 if [[ $STAGES == *attn* ]]; then
   timeout 200 python tools/gpu_attn_check.py > gpurun_out/${TAG}_attn_perf.log 2>&1
-  B200_FA_LEGACY=1 timeout 200 python tools/gpu_attn_check.py >> gpurun_out/${TAG}_attn_perf.log 2>&1
   echo "attn perf rc=$?"; cat gpurun_out/${TAG}_attn_perf.log | tail -20
 fi
 
