@@ -641,7 +641,12 @@ class LlavaLlamaForCausalLM:
                 kv_len = _i32(am.sum(1).astype(np.int32), self.device)
         cache = KVCache(self.config.num_hidden_layers, B, self.config.num_attention_heads, Lq, self.device)
         logits = self._prefill(inputs_embeds, kv_start, kv_len, cache, all_logits=True, logits_fp32=True)
-        out = ModelOutput(loss=None, logits=logits, past_key_values=cache if use_cache else None,
+        loss = None
+        if labels is not None:
+            # HF LlamaForCausalLM.forward: mean shifted CE over labels != -100 (the trainer then recomputes its
+            # class-weighted loss from output['modified_labels'], llava_trainer.py:153-169)
+            loss = L.weighted_ce(logits, labels.to(self.device).contiguous(), None)[0]
+        out = ModelOutput(loss=loss, logits=logits, past_key_values=cache if use_cache else None,
                           hidden_states=None, attentions=None)
         out["modified_labels"] = labels
         return out

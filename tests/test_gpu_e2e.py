@@ -88,6 +88,11 @@ def test_forward_logits(env, name):
     assert rel_err(rows[mm], g["logits_rows"].float()[mm]) < TOL_E2E
     if "modified_labels" in g:
         assert torch.equal(out["modified_labels"].cpu(), g["modified_labels"])   # integer work: exact
+        # HF-style .loss: mean shifted CE over the supervised positions
+        V = ref["logits"].shape[-1]
+        ref_loss = torch.nn.functional.cross_entropy(ref["logits"][:, :-1].reshape(-1, V).float(),
+                                                     ref["modified_labels"][:, 1:].reshape(-1), ignore_index=-100)
+        assert abs(float(out.loss) - float(ref_loss)) < 2e-2 * abs(float(ref_loss))
 
 
 @pytest.mark.parametrize("name", ["infer_left", "extras_left"])
