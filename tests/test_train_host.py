@@ -1,0 +1,69 @@
+"""CPU tests of the fine-tune host logic (mm_or_b200/train): parameter-group rules of the reference's
+create_optimizer (LLaVA/llava/train/llava_trainer.py:191-278), the default trainable set of the MM2SG recipe
+(train.py:1257-1261) and the un-fusing of gradients from the kernels' fused weight layouts."""
+import torch
+
+from mm_or_b200.config import LlavaConfig
+from mm_or_b200.train import llama as T
+from mm_or_b200.train.step import FineTuner, default_trainable, no_decay
+
+VIT = "model.vision_tower.vision_tower.vision_model."
+
+
+def test_no_decay_matches_reference_groups():
+    # decay = parameters outside LayerNorm-type modules whose name has no "bias" (llava_trainer.py:205-206;
+    # LlamaRMSNorm is registered in ALL_LAYERNORM_LAYERS by HF)
+    decayed = ["model.layers.3.self_attn.q_proj.weight", "model.layers.0.mlp.down_proj.weight", "lm_head.weight",
+               "model.mm_projector.0.weight", "model.image_pooler.bert.embeddings.position_embeddings.weight",
+               "model.image_pooler.bert.encoder.layer.1.intermediate.dense.weight",
+               VIT + "encoder.layers.20.mlp.fc1.weight"]
+    not_decayed = ["model.layers.3.input_layernorm.weight", "model.layers.3.post_attention_layernorm.weight",
+                   "model.norm.weight", "model.mm_projector.2.bias", VIT + "encoder.layers.20.layer_norm1.weight",
+                   VIT + "encoder.layers.20.self_attn.k_proj.bias", VIT + "pre_layrnorm.weight",
+                   "model.image_pooler.bert.embeddings.LayerNorm.weight",
+                   "model.image_pooler.bert.encoder.layer.0.attention.output.LayerNorm.bias"]
+    assert not any(no_decay(n) for n in decayed)
+    assert all(no_decay(n) for n in not_decayed)
+
+
+def test_default_trainable_set():
+    yes = ["model.layers.0.self_attn.v_proj.weight", "model.norm.weight", "lm_head.weight", "model.mm_projector.0.bias",
+           "model.image_pooler.bert.encoder.layer.0.output.dense.weight", VIT + "encoder.layers.12.mlp.fc2.bias",
+           VIT + "encoder.layers.22.layer_norm2.weight"]
+    no = ["model.embed_tokens.weight", VIT + "encoder.layers.11.mlp.fc2.bias", VIT + "embeddings.class_embedding",
+          VIT + "pre_layrnorm.weight", "model.image_pooler.bert.embeddings.word_embeddings.weight",
+          "model.image_pooler.bert.pooler.dense.weight"]
+    assert all(default_trainable(n, 12) for n in yes)
+    assert not any(default_trainable(n, 12) for n in no)
+    # layers past the selected hidden state never run; seg-mask / audio modules have no backward kernels yet
+    assert not FineTuner._has_backward(VIT + "encoder.layers.23.mlp.fc1.weight", 23)
+    assert FineTuner._has_backward(VIT + "encoder.layers.22.mlp.fc1.weight", 23)
+    assert not FineTuner._has_backward("model.image_pooler.segmasks_encoder.conv1.weight", 23)
+    assert not FineTuner._has_backward("model.image_pooler.project_audio.weight", 23)
+
+
+def test_unfuse_grads_inverts_the_fused_layouts():
+    cfg = LlavaConfig(hidden_size=16, intermediate_size=24, num_hidden_layers=2, num_attention_heads=2, vocab_size=32)
+    D, F = cfg.hidden_size, cfg.intermediate_size
+    g = torch.Generator().manual_seed(0)
+    ref, fused = {}, {}
+    for i in range(cfg.num_hidden_layers):
+        r = f"model.layers.{i}."
+        for n in ("q", "k", "v", "o"):
+            ref[r + f"self_attn.{n}_proj.weight"] = torch.randn(D, D, generator=g)
+        ref[r + "mlp.gate_proj.weight"] = torch.randn(F, D, generator=g)
+        ref[r + "mlp.up_proj.weight"] = torch.randn(F, D, generator=g)
+        ref[r + "mlp.down_proj.weight"] = torch.randn(D, F, generator=g)
+        ref[r + "input_layernorm.weight"] = torch.randn(D, generator=g)
+        f = f"_fused.layers.{i}."
+        # the layouts load_state_dict builds: qkv concatenated, gate/up row-interleaved
+        fused[f + "qkv_w"] = torch.cat([ref[r + f"self_attn.{n}_proj.weight"] for n in ("q", "k", "v")])
+        fused[f + "o_w"] = ref[r + "self_attn.o_proj.weight"]
+        fused[f + "gate_up_w"] = torch.stack([ref[r + "mlp.gate_proj.weight"], ref[r + "mlp.up_proj.weight"]],
+                                             dim=1).reshape(2 * F, D)
+        fused[f + "down_w"] = ref[r + "mlp.down_proj.weight"]
+        fused[r + "input_layernorm.weight"] = ref[r + "input_layernorm.weight"]
+    out = T.unfuse_grads(fused, cfg)
+    assert set(out) == set(ref)
+    for k in ref:
+        assert torch.equal(out[k], ref[k]), k
