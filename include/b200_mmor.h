@@ -272,6 +272,23 @@ int b200_llama_decode_step(const b200_llama_weights* w, int32_t* tokens, int32_t
                            b200_stream_t stream);
 
 /* ============================================================================================================
+ * Image preprocessing in front of the tower: mm_utils.py:14-40 expand2square + process_images ->
+ * HF CLIPImageProcessor.preprocess (PIL BICUBIC resize, centre crop, rescale, normalise) -> bf16.
+ * images: device [n, H, W, 3] uint8 RGB. pad_to_square: paste on a max(H, W) square of background_rgb (HOST uint8[3])
+ * like expand2square. The canvas is resized to resized_h x resized_w with Pillow's two-pass antialiased bicubic --
+ * bounds_* [out, 2] int32 (first source index, taps) and coeffs_* [out, ksize_*] int32 22-bit fixed point are the
+ * DEVICE tables of Pillow's precompute_coeffs / normalize_coeffs_8bpc (NULL for an axis that keeps its size) -- then
+ * centre-cropped to crop x crop, rescaled by 1/255, normalised with mean / std (HOST float[3]) in float32 and written
+ * as bf16 [n, 3, crop, crop]. Bit-exact with the host path (integer resampling, IEEE float tail).
+ * ========================================================================================================== */
+size_t b200_preprocess_workspace_bytes(int n, int canvas_h, int resized_w);
+int b200_preprocess_images(const uint8_t* images, int n, int H, int W, int pad_to_square, const uint8_t* background_rgb,
+                           const int32_t* bounds_x, const int32_t* coeffs_x, int ksize_x, const int32_t* bounds_y,
+                           const int32_t* coeffs_y, int ksize_y, int resized_h, int resized_w, int crop,
+                           const float* mean, const float* std, void* out, void* workspace, size_t workspace_bytes,
+                           b200_stream_t stream);
+
+/* ============================================================================================================
  * Training-side operators (fine-tune step)
  * ========================================================================================================== */
 

@@ -108,6 +108,8 @@ _SIGS = {
     "b200_embed_rows": (ci, [vp, vp, vp, i64, ci, ci, ci, vp]),
     "b200_argmax": (ci, [vp, ci, i64, ci, ci, vp, vp, ci, ci, vp]),
     "b200_patchify": (ci, [vp, vp, ci, ci, ci, ci, ci, vp]),
+    "b200_preprocess_workspace_bytes": (sz, [ci, ci, ci]),
+    "b200_preprocess_images": (ci, [vp, ci, ci, ci, ci, vp, vp, vp, ci, vp, vp, ci, ci, ci, ci, vp, vp, vp, vp, sz, vp]),
     "b200_vit_workspace_bytes": (sz, [_P(VitWeights), ci]),
     "b200_vit_forward": (ci, [_P(VitWeights), vp, vp, ci, vp, sz, vp]),
     "b200_pooler_workspace_bytes": (sz, [_P(PoolerWeights), ci, ci]),

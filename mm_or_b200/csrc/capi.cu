@@ -280,4 +280,18 @@ int b200_patchify(const void* pixels, void* cols, int N, int C, int S, int P, in
                          static_cast<cudaStream_t>(stream));
 }
 
+size_t b200_preprocess_workspace_bytes(int n, int canvas_h, int resized_w) {
+  return preprocess_workspace_bytes(n, canvas_h, resized_w);
+}
+
+int b200_preprocess_images(const uint8_t* images, int n, int H, int W, int pad_to_square, const uint8_t* background_rgb,
+                           const int32_t* bounds_x, const int32_t* coeffs_x, int ksize_x, const int32_t* bounds_y,
+                           const int32_t* coeffs_y, int ksize_y, int resized_h, int resized_w, int crop,
+                           const float* mean, const float* std, void* out, void* workspace, size_t workspace_bytes,
+                           b200_stream_t stream) {
+  return preprocess_images(images, n, H, W, pad_to_square, background_rgb, bounds_x, coeffs_x, ksize_x, bounds_y,
+                           coeffs_y, ksize_y, resized_h, resized_w, crop, mean, std, static_cast<bf16*>(out), workspace,
+                           workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

@@ -216,4 +216,11 @@ int segmask_forward(const uint8_t* cls, int n_maps, const bf16* emb, const bf16*
                     const bf16* const* conv_b, bf16* out, long long out_ld, const int* out_row_map, void* workspace,
                     size_t workspace_bytes, cudaStream_t stream);
 
+// image preprocessing (preprocess.cu)
+size_t preprocess_workspace_bytes(int n, int canvas_h, int res_w);
+int preprocess_images(const uint8_t* img, int n, int H, int W, int pad, const uint8_t* bg, const int* bx, const int* kx,
+                      int ksize_x, const int* by, const int* ky, int ksize_y, int res_h, int res_w, int out,
+                      const float* mean, const float* stdv, bf16* dst, void* workspace, size_t workspace_bytes,
+                      cudaStream_t stream);
+
 }  // namespace b200

@@ -1,0 +1,66 @@
+"""Image preprocessing.
+CPU: the oracle's restatement of Pillow's antialiased bicubic resample (and the product's coefficient tables) are
+pinned bit-exactly against the Pillow installed here -- Pillow is the third-party code the reference's
+CLIPImageProcessor (transformers 4.31) resizes with; expand2square / centre-crop geometry against the reference's
+own functions restated in the oracle.
+GPU: b200_preprocess_images through the C ABI equals the oracle bit for bit (integer resampling, IEEE float tail)."""
+import numpy as np
+import pytest
+import torch
+from PIL import Image
+
+from mm_or_b200 import preprocess as PP
+from oracle import preprocess_oracle as PO
+
+SIZES = [(48, 64, 21, 21), (64, 48, 21, 30), (200, 333, 336, 336), (37, 37, 336, 336), (100, 50, 7, 3),
+         (768, 1024, 336, 448)]
+
+
+@pytest.mark.parametrize("H,W,oh,ow", SIZES)
+def test_oracle_resize_equals_pillow(H, W, oh, ow):
+    rng = np.random.default_rng(H * 1000 + W)
+    img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    ref = np.asarray(Image.fromarray(img).resize((ow, oh), resample=Image.BICUBIC))
+    assert np.array_equal(PO.resize_bicubic_u8(img, oh, ow), ref)
+
+
+@pytest.mark.parametrize("n_in,n_out", [(2048, 336), (1536, 336), (336, 336), (100, 336), (577, 13), (4, 9)])
+def test_product_tables_equal_oracle_tables(n_in, n_out):
+    b0, k0 = PO.resample_coeffs(n_in, n_out)
+    b1, k1 = PP.resample_tables(n_in, n_out)
+    assert np.array_equal(b0, b1) and np.array_equal(k0, k1)
+    assert k1.dtype == np.int32 and abs(int(k1[n_out // 2].sum()) - (1 << 22)) <= k1.shape[1]
+
+
+def test_expand2square_and_pipeline_shapes():
+    img = np.arange(6 * 10 * 3, dtype=np.uint8).reshape(6, 10, 3)
+    sq = PO.expand2square(img)
+    assert sq.shape == (10, 10, 3)
+    assert np.array_equal(sq[2:8], img) and tuple(sq[0, 0]) == (122, 116, 104) and tuple(sq[9, 9]) == (122, 116, 104)
+    tall = PO.expand2square(img.transpose(1, 0, 2).copy())
+    assert np.array_equal(tall[:, 2:8], img.transpose(1, 0, 2))
+    out = PO.clip_preprocess(np.full((30, 40, 3), 255, dtype=np.uint8), size=16)
+    assert out.shape == (3, 16, 16) and out.dtype == np.float32
+    # a white row of the image normalises to (1 - mean) / std exactly
+    assert out[0, 8, 8] == np.float32((np.float32(1.0) - np.float32(PO.CLIP_MEAN[0])) / np.float32(PO.CLIP_STD[0]))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("H,W,pad,size", [(1536, 2048, True, 336), (2048, 1536, True, 336), (480, 640, False, 336),
+                                          (336, 336, True, 336), (100, 150, True, 64), (300, 200, False, 224)])
+def test_gpu_preprocess_bit_exact(H, W, pad, size):
+    if not torch.cuda.is_available():
+        pytest.skip("needs CUDA")
+    rng = np.random.default_rng(H + 7 * W)
+    frames = [rng.integers(0, 256, (H, W, 3), dtype=np.uint8) for _ in range(3)]
+    proc = PP.GpuImageProcessor(size=size)
+    out = proc.preprocess(frames, pad=pad)
+    assert out.shape == (3, 3, size, size) and out.dtype == torch.bfloat16
+    for i, f in enumerate(frames):
+        ref = torch.from_numpy(PO.clip_preprocess(f, size=size, pad=pad)).to(torch.bfloat16)
+        assert torch.equal(out[i].cpu(), ref), f"frame {i}"
+    # PIL input and the process_images mirror (mm_utils.py:29-40): one sample with 3 views -> (1, 3, 3, S, S)
+    class Cfg:
+        image_aspect_ratio = "pad" if pad else None
+    stacked = PP.process_images([Image.fromarray(f) for f in frames], proc, Cfg)
+    assert stacked.shape == (1, 3, 3, size, size) and torch.equal(stacked[0], out)
