@@ -298,7 +298,8 @@ int b200_preprocess_images(const uint8_t* images, int n, int H, int W, int pad_t
  * tensor-core operands: a_transposed: A is stored [K, M]; w_transposed: W is stored [K, N]. With Y = X W^T:
  *     dX[M,K] = dY[M,N] W[N,K]      -> (A = dY, W = W with w_transposed = 1, "N" = K, "K" = N)
  *     dW[N,K] = dY^T[N,M] X[M,K]    -> (A = dY with a_transposed = 1, W = X with w_transposed = 1, "M" = N, "N" = K, "K" = M)
- * accumulate != 0 (fp32 output only): C += result (gradient accumulation).
+ * accumulate != 0 (fp32 output only): C += result (gradient accumulation). scale multiplies the accumulator before
+ * bias / activation / residual (the LoRA alpha / r factor; 1 otherwise).
  * b200_colsum: out[n] (+)= sum_m dy[m, n] (bias gradients), deterministic.
  * b200_act_backward: dz = dy * act'(z) from the saved pre-activation z; act 1 quick_gelu, 2 gelu(erf), 3 SwiGLU
  * (z = interleaved (gate, up) [M, 2F], dy [M, F], dz [M, 2F]); n_out = elements of dy.
@@ -307,7 +308,7 @@ int b200_preprocess_images(const uint8_t* images, int n, int H, int W, int pad_t
  * to dx: the gradient that reaches x through the residual connection around the norm. D in {512, 1024, 4096}. */
 int b200_gemm_bf16_ex(const void* A, int lda, int a_transposed, const void* W, int ldw, int w_transposed, void* C, int ldc,
                       int M, int N, int K, const void* bias, const void* residual, int ldr, int act, int out_fp32,
-                      int accumulate, int bn_hint, b200_stream_t stream);
+                      int accumulate, float scale, int bn_hint, b200_stream_t stream);
 size_t b200_colsum_workspace_bytes(int N);
 int b200_colsum(const void* dy, int64_t ld, int M, int N, int accumulate, float* out, void* workspace,
                 size_t workspace_bytes, b200_stream_t stream);

@@ -77,7 +77,7 @@ _SIGS = {
     "b200_prof_collect": (ci, [vp, vp, vp, vp]),
     "b200_gemm_bf16": (ci, [vp, ci, vp, ci, vp, ci, ci, ci, ci, vp, vp, ci, vp, ci, ci, ci, vp]),
     "b200_gemm_bf16_skinny": (ci, [vp, ci, vp, ci, vp, ci, ci, ci, ci, vp, vp, ci, ci, ci, ci, vp]),
-    "b200_gemm_bf16_ex": (ci, [vp, ci, ci, vp, ci, ci, vp, ci, ci, ci, ci, vp, vp, ci, ci, ci, ci, ci, vp]),
+    "b200_gemm_bf16_ex": (ci, [vp, ci, ci, vp, ci, ci, vp, ci, ci, ci, ci, vp, vp, ci, ci, ci, ci, cf, ci, vp]),
     "b200_colsum_workspace_bytes": (sz, [ci]),
     "b200_colsum": (ci, [vp, i64, ci, ci, ci, vp, vp, sz, vp]),
     "b200_act_backward": (ci, [vp, vp, vp, i64, ci, vp]),
@@ -215,7 +215,7 @@ def gemm_skinny(a, w, out=None, bias=None, residual=None, act=ACT_NONE, out_fp32
     return out
 
 
-def gemm_ex(a, w, a_t=False, w_t=False, out=None, out_fp32=False, accumulate=False, bn=0, residual=None):
+def gemm_ex(a, w, a_t=False, w_t=False, out=None, out_fp32=False, accumulate=False, bn=0, residual=None, scale=1.0):
     """General GEMM with transposed operands read in place: A is (M, K), or (K, M) when a_t; W is (N, K), or (K, N)
     when w_t. out = A_eff @ W_eff.T, optionally accumulated into an fp32 `out`."""
     M, K = (a.shape[1], a.shape[0]) if a_t else a.shape
@@ -226,7 +226,7 @@ def gemm_ex(a, w, a_t=False, w_t=False, out=None, out_fp32=False, accumulate=Fal
     ldr = residual.stride(0) if residual is not None else 0
     check(lib().b200_gemm_bf16_ex(ptr(a), a.stride(0), int(a_t), ptr(w), w.stride(0), int(w_t), ptr(out), out.stride(0),
                                   M, N, K, None, ptr(residual), ldr, ACT_NONE, int(out.dtype == torch.float32),
-                                  int(accumulate), bn, stream_ptr()), "b200_gemm_bf16_ex")
+                                  int(accumulate), float(scale), bn, stream_ptr()), "b200_gemm_bf16_ex")
     return out
 
 

@@ -59,8 +59,9 @@ int b200_gemm_bf16_skinny(const void* A, int lda, const void* W, int ldw, void* 
 
 int b200_gemm_bf16_ex(const void* A, int lda, int a_transposed, const void* W, int ldw, int w_transposed, void* C, int ldc,
                       int M, int N, int K, const void* bias, const void* residual, int ldr, int act, int out_fp32,
-                      int accumulate, int bn_hint, b200_stream_t stream) {
+                      int accumulate, float scale, int bn_hint, b200_stream_t stream) {
   GemmEpilogue e;
+  e.scale = scale;
   e.bias = static_cast<const bf16*>(bias);
   e.residual = static_cast<const bf16*>(residual);
   e.ldr = ldr;

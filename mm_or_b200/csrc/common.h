@@ -83,6 +83,7 @@ struct GemmEpilogue {
   int act = kActNone;
   int out_fp32 = 0;  // 0: C is bf16, 1: C is fp32
   int accumulate = 0;  // fp32 output only: C += result
+  float scale = 1.f;   // accumulator is multiplied by this before bias / activation / residual (LoRA alpha / r)
   // fused GEMM -> all-gather: when n_peers > 0 every bf16 output vector is stored to the same offset of each
   // peer_c[p] (peer-mapped device pointers over NVLink, this rank's own buffer included) instead of C.
   int n_peers = 0;

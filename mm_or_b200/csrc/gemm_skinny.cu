@@ -70,7 +70,7 @@ __device__ __forceinline__ float ld_dsmem_f32(uint32_t local_addr, uint32_t cta)
 __device__ __forceinline__ void sk_store(const SkinnyArgs& g, float val, float bias, int m, int n, bool live,
                                          int lane) {
   const GemmEpilogue& e = g.epi;
-  val += bias;
+  val = val * e.scale + bias;
   if (e.act == kActSwiGLU) {
     const float other = __shfl_xor_sync(0xffffffffu, val, 1);  // lane 2i: gate, lane 2i+1: up
     if (live && (lane & 1) == 0) {

@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         if (!ok || n0 >= g.N) continue;
         float x[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
+        for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]) * e.scale;
         if (e.bias != nullptr) {
 #pragma unroll
           for (int j8 = 0; j8 < 4; ++j8) {

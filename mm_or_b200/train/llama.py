@@ -22,7 +22,7 @@ BF = torch.bfloat16
 
 
 class LayerCache:
-    __slots__ = ("x_in", "a", "qkv", "kc", "vc", "ctx", "lse", "x_mid", "b", "z", "h")
+    __slots__ = ("x_in", "a", "qkv", "kc", "vc", "ctx", "lse", "x_mid", "b", "z", "h", "t")
 
 
 def _views(qkv, kc, vc, B, Lq, H):
@@ -34,8 +34,10 @@ def _views(qkv, kc, vc, B, Lq, H):
 
 
 def forward_backward(model, embeds, labels, lengths, vocab_weight=None, grad_scale=1.0, grads=None, accumulate=False,
-                     need_input_grad=True):
+                     need_input_grad=True, lora=None, train_base=True):
     """embeds (B, L, D) bf16 packed inputs_embeds, labels (B, L) int64 UNshifted modified_labels, lengths (B,) int32.
+    lora: a train.lora.LoraState -- adapters on the seven linears of every layer (gradients under `_lora.*` keys);
+    train_base = False freezes the base Linear weights (the QLoRA / LoRA recipe), norms and lm_head follow it too.
     Returns (loss fp32 0-dim, weight sum, grads dict, d_embeds (B, L, D) bf16 or None)."""
     cfg = model.config
     lib = L.lib()
@@ -53,24 +55,35 @@ def forward_backward(model, embeds, labels, lengths, vocab_weight=None, grad_sca
         L.check(lib.b200_rope_kv_write(L.ptr(qkv), None, L.ptr(rope_cos), L.ptr(rope_sin), cfg.max_position_embeddings,
                                        L.ptr(kc), L.ptr(vc), B, H, Lq, 0, Lq, L.stream_ptr()), "b200_rope_kv_write")
 
+    def lin_fwd(i, fname, x_in, w, residual=None, keep=None):
+        """y = x w^T (+ residual) (+ LoRA: (alpha / r) * (x A_cat^T) B_blk^T added in place)."""
+        y = L.gemm(x_in, w, residual=residual)
+        if lora is not None:
+            a_cat, b_blk = lora.fused[i][fname]
+            t = L.gemm(x_in, a_cat)
+            L.gemm_ex(t, b_blk, out=y, residual=y, scale=lora.scale)
+            keep[fname] = t
+        return y
+
     # ---------------------------------------------------------------- forward
     caches = []
-    for lt in layers:
+    for i, lt in enumerate(layers):
         c = LayerCache()
+        c.t = {}
         c.x_in = x
         c.a = L.rmsnorm(x, lt["attn_norm"], eps)
-        c.qkv = L.gemm(c.a, lt["qkv_w"])
+        c.qkv = lin_fwd(i, "qkv_w", c.a, lt["qkv_w"], keep=c.t)
         c.kc = torch.empty((B, H, Lq, 128), device=dev, dtype=BF)
         c.vc = torch.empty((B, H, Lq, 128), device=dev, dtype=BF)
         rope_write(c.qkv, c.kc, c.vc)
         q, k, v = _views(c.qkv, c.kc, c.vc, B, Lq, H)
         ctx, c.lse = L.flash_attention(q, k, v, causal=True, kv_len=lengths, return_lse=True)
         c.ctx = ctx.view(T, D)
-        c.x_mid = L.gemm(c.ctx, lt["o_w"], residual=x)
+        c.x_mid = lin_fwd(i, "o_w", c.ctx, lt["o_w"], residual=x, keep=c.t)
         c.b = L.rmsnorm(c.x_mid, lt["mlp_norm"], eps)
-        c.z = L.gemm(c.b, lt["gate_up_w"])                       # pre-activation kept for the backward
+        c.z = lin_fwd(i, "gate_up_w", c.b, lt["gate_up_w"], keep=c.t)   # pre-activation kept for the backward
         c.h = L.swiglu_forward(c.z)
-        x = L.gemm(c.h, lt["down_w"], residual=c.x_mid)
+        x = lin_fwd(i, "down_w", c.h, lt["down_w"], residual=c.x_mid, keep=c.t)
         caches.append(c)
     x_last = x
     xf = L.rmsnorm(x_last, final_norm, eps)
@@ -88,27 +101,43 @@ def forward_backward(model, embeds, labels, lengths, vocab_weight=None, grad_sca
             return g[name], False
         return g[name], accumulate
 
-    def lin_bwd(x_saved, w, dy, name, need_dx=True):
-        dw, acc = slot(name, tuple(w.shape))
+    def lin_bwd(x_saved, w, dy, name, need_dx=True, layer=None, fname=None, t=None):
         dx = L.gemm_ex(dy, w, w_t=True) if need_dx else None
-        L.gemm_ex(dy, x_saved, a_t=True, w_t=True, out=dw, accumulate=acc)
+        if train_base or layer is None:
+            dw, acc = slot(name, tuple(w.shape))
+            L.gemm_ex(dy, x_saved, a_t=True, w_t=True, out=dw, accumulate=acc)
+        if lora is not None and layer is not None:
+            a_cat, b_blk = lora.fused[layer][fname]
+            dt = L.gemm_ex(dy, b_blk, w_t=True, scale=lora.scale)                       # (T, g r)
+            db, accb = slot(f"_lora.layers.{layer}.{fname}.B", tuple(b_blk.shape))
+            L.gemm_ex(dy, t, a_t=True, w_t=True, out=db, accumulate=accb, scale=lora.scale)
+            da, acca = slot(f"_lora.layers.{layer}.{fname}.A", tuple(a_cat.shape))
+            L.gemm_ex(dt, x_saved, a_t=True, w_t=True, out=da, accumulate=acca)
+            if need_dx:
+                L.gemm_ex(dt, a_cat, w_t=True, out=dx, residual=dx)
         return dx
 
     def norm_bwd(x_saved, dy, gamma, name, add=None):
-        dg, acc = slot(name, (D,))
+        if train_base:
+            dg, acc = slot(name, (D,))
+        else:                                      # frozen gain: the kernel still needs somewhere to put dgamma
+            dg, acc = torch.empty(D, device=dev, dtype=torch.float32), False
         dx, _, _ = L.norm_backward(x_saved, dy, gamma, eps, rms=True, dgamma=dg, accumulate=acc, add=add)
         return dx
 
-    dxf = lin_bwd(xf, model.lm_head, dlogits, "lm_head.weight")
+    if train_base:
+        dxf = lin_bwd(xf, model.lm_head, dlogits, "lm_head.weight")
+    else:
+        dxf = L.gemm_ex(dlogits, model.lm_head, w_t=True)
     dx = norm_bwd(x_last, dxf, final_norm, "model.norm.weight")
     for i in range(len(layers) - 1, -1, -1):
         lt, c = layers[i], caches[i]
         p = f"_fused.layers.{i}."
-        dh = lin_bwd(c.h, lt["down_w"], dx, p + "down_w")
+        dh = lin_bwd(c.h, lt["down_w"], dx, p + "down_w", layer=i, fname="down_w", t=c.t.get("down_w"))
         dz = L.act_backward(c.z, dh, L.ACT_SWIGLU)
-        db = lin_bwd(c.b, lt["gate_up_w"], dz, p + "gate_up_w")
+        db = lin_bwd(c.b, lt["gate_up_w"], dz, p + "gate_up_w", layer=i, fname="gate_up_w", t=c.t.get("gate_up_w"))
         dx_mid = norm_bwd(c.x_mid, db, lt["mlp_norm"], f"model.layers.{i}.post_attention_layernorm.weight", add=dx)
-        dctx = lin_bwd(c.ctx, lt["o_w"], dx_mid, p + "o_w")
+        dctx = lin_bwd(c.ctx, lt["o_w"], dx_mid, p + "o_w", layer=i, fname="o_w", t=c.t.get("o_w"))
         dqkv = torch.empty_like(c.qkv)
         dkc, dvc = torch.empty_like(c.kc), torch.empty_like(c.vc)
         q, k, v = _views(c.qkv, c.kc, c.vc, B, Lq, H)
@@ -118,7 +147,7 @@ def forward_backward(model, embeds, labels, lengths, vocab_weight=None, grad_sca
         L.check(lib.b200_rope_kv_backward(L.ptr(dqkv), None, L.ptr(rope_cos), L.ptr(rope_sin),
                                           cfg.max_position_embeddings, L.ptr(dkc), L.ptr(dvc), B, H, Lq, Lq,
                                           L.stream_ptr()), "b200_rope_kv_backward")
-        da = lin_bwd(c.a, lt["qkv_w"], dqkv, p + "qkv_w", need_dx=True)
+        da = lin_bwd(c.a, lt["qkv_w"], dqkv, p + "qkv_w", need_dx=True, layer=i, fname="qkv_w", t=c.t.get("qkv_w"))
         need = need_input_grad or i > 0
         dx = norm_bwd(c.x_in, da, lt["attn_norm"], f"model.layers.{i}.input_layernorm.weight", add=dx_mid) if need \
             else None

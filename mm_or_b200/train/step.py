@@ -44,19 +44,31 @@ def no_decay(name):
 class FineTuner:
     def __init__(self, model, state_dict, lr=2e-5, mm_projector_lr=None, betas=(0.9, 0.999), eps=1e-8,
                  weight_decay=0.0, max_grad_norm=0.1, first_trainable_clip_layer=12, vocab_weight=None,
-                 trainable=None):
+                 trainable=None, lora=None):
+        """lora: a train.lora.LoraState -> the reference's LoRA recipe (train.py:1159-1175): the decoder's base
+        weights, norms and lm_head are frozen, the adapters train next to mm_projector / image_pooler / CLIP layers."""
         self.model = model
         self.dev = model.device
         self.first_clip = first_trainable_clip_layer
         self.lr, self.proj_lr = lr, (mm_projector_lr if mm_projector_lr is not None else lr)
         self.betas, self.eps, self.wd, self.max_norm = betas, eps, weight_decay, max_grad_norm
         self.vocab_weight = vocab_weight
+        self.lora = lora
         pick = trainable if trainable is not None else (lambda n: default_trainable(n, first_trainable_clip_layer))
+        if lora is not None:
+            base_pick = pick
+            pick = lambda n: base_pick(n) and not (n.startswith("model.layers.") or n in ("model.norm.weight",
+                                                                                         "lm_head.weight"))
         # the full reference-named state dict in bf16 on the device: the source the fused layouts are rebuilt from
         self.sd = {k: v.detach().to(self.dev, BF).contiguous() for k, v in state_dict.items()}
         n_run = model.get_vision_tower().n_layers_run()     # CLIP layers past the selected hidden state are dead
         self.names = sorted(k for k in self.sd if pick(k) and self._has_backward(k, n_run))
         self.master = {k: state_dict[k].detach().to(self.dev, torch.float32).contiguous().clone() for k in self.names}
+        if lora is not None:                       # adapters: masters from the LoraState, same optimizer
+            for k in lora.names():
+                self.sd[k] = lora.sd[k]
+                self.master[k] = lora.sd[k].float().clone()
+            self.names = sorted(self.names + lora.names())
         self.m = {k: torch.zeros_like(v) for k, v in self.master.items()}
         self.v = {k: torch.zeros_like(v) for k, v in self.master.items()}
         self.step_count = 0
@@ -102,7 +114,8 @@ class FineTuner:
         L.embed_rows(torch.as_tensor(vis_ids.reshape(-1)).to(dev), vis, out=embeds)
         loss, wsum, g, d_emb = T.forward_backward(model, embeds.view(B, Lq, D), torch.from_numpy(plan.labels).to(dev),
                                                   torch.from_numpy(plan.lengths).to(dev), self.vocab_weight,
-                                                  grads=grads, accumulate=accumulate)
+                                                  grads=grads, accumulate=accumulate, lora=self.lora,
+                                                  train_base=self.lora is None)
         # pack backward: visual rows of d_embeds back to the projector output (truncated tokens get zeros)
         d_vis = L.embed_rows(torch.as_tensor(plan.row_map).to(dev), d_emb.reshape(B * Lq, D), rows=B * keep)
         dx, g = E.projector_backward(proj, prc, d_vis, grads=g, accumulate=accumulate)
@@ -116,6 +129,8 @@ class FineTuner:
             from ..dist import average_gradients
             average_gradients(grads, list(grads), self.group)      # in place on the (contiguous) fused gradients
         g = T.unfuse_grads(grads, self.model.config)
+        if self.lora is not None:
+            g.update(self.lora.unfuse_grads(grads))
         self.step_count += 1
         out2 = torch.zeros(2, device=self.dev, dtype=torch.float32)
         for i, k in enumerate(self.names):
@@ -126,10 +141,21 @@ class FineTuner:
             wd = 0.0 if no_decay(k) else self.wd
             L.adamw_step(self.master[k], self.sd[k], g[k].contiguous(), self.m[k], self.v[k], lr, self.betas[0],
                          self.betas[1], self.eps, wd, self.step_count, clip_coef=clip)
+        if self.lora is not None:
+            self.lora.refuse()                     # adapters changed; the decoder's base weights did not
+            self._reload_encoder()
+            return out2
         # drop the old fused working copies before rebuilding them (13.5 GB at 7B)
         self.model._keep = self.model._w = self.model.lm_head = None
         self.model.load_state_dict(self.sd, device=self.dev)
         return out2
+
+    def _reload_encoder(self):
+        """Rebuild only the vision-side fused weights (tower, pooler, projector) from the updated bf16 tensors."""
+        m = self.model.model
+        m.vision_tower.load_weights(self.sd, self.dev)
+        m.image_pooler.load_weights(self.sd, self.dev)
+        m.mm_projector.load_weights(self.sd, self.dev)
 
     def train_step(self, input_ids, labels, attention_mask, images):
         loss, wsum, grads = self.forward_backward(input_ids, labels, attention_mask, images)

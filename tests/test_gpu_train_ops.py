@@ -410,3 +410,51 @@ def test_fine_tune_step_end_to_end(L):
     for _ in range(4):
         last, _ = ft.train_step(case["input_ids"], case["labels"], case["attention_mask"], case["images"])
     assert float(last) < first
+
+
+def test_lora_decoder_step_matches_autograd(L):
+    """LoRA adapters on the seven linears of every decoder layer (peft semantics, base frozen): adapter gradients vs
+    torch autograd over the oracle evaluated on W + (alpha / r) B A; merged weights reproduce the adapted forward."""
+    import golden_cases as gc
+    from helpers import oracle_cfg
+    from mm_or_b200.model.llava_llama import LlavaLlamaForCausalLM
+    from mm_or_b200.train import llama as T
+    from mm_or_b200.train.lora import FUSED, LoraState, param_name
+    cfg = gc.small_config()
+    sd = gc.bf16_round(gc.small_weights(cfg))
+    model = LlavaLlamaForCausalLM(cfg).load_state_dict(sd)
+    lora = LoraState(cfg, r=8, alpha=16, seed=3, init_b="random")
+    B, Lq, D, V = 2, 40, cfg.hidden_size, cfg.vocab_size
+    g = torch.Generator().manual_seed(12)
+    emb = (torch.randn(B, Lq, D, generator=g) * 0.5).to(torch.bfloat16).cuda()
+    lengths = torch.tensor([Lq, 31], dtype=torch.int32)
+    emb[1, 31:] = 0
+    labels = torch.randint(3, V, (B, Lq), generator=g)
+    labels[:, :15] = -100
+    labels[1, 31:] = -100
+    w = torch.rand(V, generator=g) + 0.05
+    loss, _, grads, d_emb = T.forward_backward(model, emb, labels.cuda(), lengths.cuda(), vocab_weight=w, lora=lora,
+                                               train_base=False)
+    assert not any(k.startswith("_fused.") or k == "lm_head.weight" for k in grads)      # base is frozen
+    lg = lora.unfuse_grads(grads)
+    ocfg = oracle_cfg(cfg).llm
+    with torch.enable_grad():
+        ad = {k: v.float().cpu().requires_grad_(True) for k, v in lora.sd.items()}
+        eff = dict(sd)
+        for i in range(cfg.num_hidden_layers):
+            for projs, module in FUSED.values():
+                for p in projs:
+                    k = f"model.layers.{i}.{module}.{p}.weight"
+                    eff[k] = sd[k] + lora.scale * (ad[param_name(i, module, p, "B")] @ ad[param_name(i, module, p, "A")])
+        mask = torch.arange(Lq)[None, :] < lengths[:, None].long()
+        pos = torch.arange(Lq)[None, :].repeat(B, 1) * mask
+        logits, _ = O.llama_forward(eff, emb.float().cpu(), mask, pos, ocfg)
+        ref_loss = O.weighted_ce(logits, labels, w)
+        ref_loss.backward()
+    assert abs(float(loss) - float(ref_loss.detach())) < 3e-2 * abs(float(ref_loss.detach()))
+    for k, p in ad.items():
+        assert rel(lg[k].cpu(), p.grad) < 8e-2, (k, rel(lg[k].cpu(), p.grad))
+    # merge_and_unload: the merged weights give the same loss through the plain (adapter-free) path
+    merged = LlavaLlamaForCausalLM(cfg).load_state_dict(lora.merged_state_dict(sd))
+    loss2, _, _, _ = T.forward_backward(merged, emb, labels.cuda(), lengths.cuda(), vocab_weight=w)
+    assert abs(float(loss2) - float(loss)) < 2e-2 * abs(float(loss))

@@ -67,3 +67,38 @@ def test_unfuse_grads_inverts_the_fused_layouts():
     assert set(out) == set(ref)
     for k in ref:
         assert torch.equal(out[k], ref[k]), k
+
+
+def test_lora_fused_adapters_equal_per_projection_adapters():
+    """B_blk A_cat of a fused weight == the per-projection B_j A_j laid out like the fused base weight (q|k|v
+    concatenated, gate / up row-interleaved), and unfuse_grads is the inverse mapping of the fusing."""
+    from mm_or_b200.train.lora import FUSED, LoraState, param_name
+    cfg = LlavaConfig(hidden_size=16, intermediate_size=24, num_hidden_layers=2, num_attention_heads=2, vocab_size=32)
+    st = LoraState(cfg, r=8, alpha=16, device="cpu", seed=1, init_b="random")
+    assert st.scale == 2.0 and len(st.names()) == 2 * 7 * 2
+    D, F, r = cfg.hidden_size, cfg.intermediate_size, 8
+    for i in range(2):
+        delta = {p: st.sd[param_name(i, m, p, "B")].float() @ st.sd[param_name(i, m, p, "A")].float()
+                 for projs, m in FUSED.values() for p in projs}
+        a, b = st.fused[i]["qkv_w"]
+        assert torch.allclose(b.float() @ a.float(), torch.cat([delta["q_proj"], delta["k_proj"], delta["v_proj"]]))
+        a, b = st.fused[i]["gate_up_w"]
+        want = torch.stack([delta["gate_proj"], delta["up_proj"]], dim=1).reshape(2 * F, D)
+        assert torch.allclose(b.float() @ a.float(), want)
+        a, b = st.fused[i]["down_w"]
+        assert torch.allclose(b.float() @ a.float(), delta["down_proj"])
+    # gradient un-fusing: pretend the fused tensors themselves are the gradients
+    g = {}
+    for i in range(2):
+        for fname in FUSED:
+            a, b = st.fused[i][fname]
+            g[f"_lora.layers.{i}.{fname}.A"], g[f"_lora.layers.{i}.{fname}.B"] = a.float(), b.float()
+    back = st.unfuse_grads(g)
+    assert set(back) == set(st.sd)
+    for k in st.sd:
+        assert torch.equal(back[k], st.sd[k].float()), k
+    merged = st.merged_state_dict({f"model.layers.{i}.{m}.{p}.weight": torch.zeros(st.shapes[p])
+                                   for i in range(2) for projs, m in FUSED.values() for p in projs})
+    k = "model.layers.1.mlp.up_proj.weight"
+    assert torch.allclose(merged[k], 2.0 * st.sd[param_name(1, "mlp", "up_proj", "B")].float()
+                          @ st.sd[param_name(1, "mlp", "up_proj", "A")].float())
