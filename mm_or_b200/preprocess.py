@@ -82,7 +82,7 @@ class GpuImageProcessor:
             for im in images:
                 if hasattr(im, "convert"):                              # PIL
                     im = np.asarray(im.convert("RGB"))
-                frames.append(torch.as_tensor(np.ascontiguousarray(im)) if not torch.is_tensor(im) else im)
+                frames.append(torch.as_tensor(np.array(im, copy=True)) if not torch.is_tensor(im) else im)
             batch = torch.stack(frames)
         else:
             batch = images if torch.is_tensor(images) else torch.as_tensor(np.ascontiguousarray(images))

