@@ -269,7 +269,15 @@ def run_b200(args):
             peak = pk["hbm"]
             roof = {"bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
                     "frac": round(ach / peak, 4)}
-        roof.update({"kernel": name, "traffic": measured_traffic(name), "peak_source": pk["source"],
+        # DRAM bytes per launch: the ncu capture's measured / algorithmic ratio (taken at the capture's batch size)
+        # applied to this run's algorithmic bytes per launch
+        cap = measured_traffic(name)
+        traffic = None
+        if cap is not None and not tensor_bound:
+            traffic = round(cap["ratio"] * top["bytes"] / n_launch)
+        elif cap is not None:
+            traffic = round(cap["dram_bytes_per_launch"])
+        roof.update({"kernel": name, "traffic": traffic, "traffic_capture": cap, "peak_source": pk["source"],
                      "launches": top["launches"], "avg_launch_us": round(top["ms"] * 1e3 / n_launch, 2),
                      "share_of_step": round(top["ms"] / total_ms, 4),
                      "families": {k: {"ms": round(v["ms"], 2), "launches": v["launches"],
