@@ -25,6 +25,114 @@ def _stub(name, **kw):
     return m
 
 
+def _install_ptv3_stubs():
+    """Functional stand-ins for the four third-party packages PointTransformerV3 (multimodal_projector/
+    pointtransformerv3.py) needs and this container lacks or cannot run on CPU. Each restates the PUBLISHED semantics of
+    the one entry point the reference calls -- deliberately written naively (Python dict lookups, per-sequence loops)
+    and independently of oracle/ptv3_oracle.py, so that the golden run cross-checks the oracle's vectorised versions:
+      spconv.pytorch (spconv-cu117 2.x, README.md:110): SparseConvTensor(features, indices[b,x,y,z], spatial_shape,
+        batch_size) / .replace_feature; SubMConv3d(in, out, kernel_size, bias, indice_key, padding): submanifold
+        convolution = cross-correlation evaluated at the active sites only, centred kernel whatever `padding` says,
+        weight layout (out, k0, k1, k2, in) (spconv 2.x KRSC), bias (out,);
+      torch_scatter.segment_csr(src, indptr, reduce): out[i] = reduce(src[indptr[i]:indptr[i+1]]);
+      flash_attn.flash_attn_varlen_qkvpacked_func(qkv(total,3,H,D) fp16, cu_seqlens, max_seqlen, dropout_p,
+        softmax_scale): per-sequence non-causal softmax(q k^T * scale) v, fp32 accumulation, fp16 result;
+      addict.Dict: dict with attribute access whose constructor re-wraps nested dicts in the same class.
+    """
+    import torch
+    import torch.nn as nn
+
+    class SparseConvTensor:
+        def __init__(self, features, indices, spatial_shape, batch_size):
+            self.features, self.indices = features, indices
+            self.spatial_shape, self.batch_size = spatial_shape, batch_size
+
+        def replace_feature(self, feature):
+            return SparseConvTensor(feature, self.indices, self.spatial_shape, self.batch_size)
+
+    class SubMConv3d(nn.Module):
+        def __init__(self, in_channels, out_channels, kernel_size, bias=True, indice_key=None, padding=0, **kw):
+            super().__init__()
+            k = kernel_size
+            self.k = k
+            self.weight = nn.Parameter(torch.empty(out_channels, k, k, k, in_channels))
+            nn.init.kaiming_uniform_(self.weight.view(out_channels, -1), a=5 ** 0.5)
+            self.bias = nn.Parameter(torch.zeros(out_channels)) if bias else None
+
+        def forward(self, x):
+            idx = x.indices.tolist()
+            site = {tuple(v): i for i, v in enumerate(idx)}
+            assert len(site) == len(idx), "duplicate voxels: submanifold convolution is undefined"
+            k, c = self.k, self.k // 2
+            out = x.features.new_zeros(len(idx), self.weight.shape[0])
+            for a in range(k):
+                for b_ in range(k):
+                    for d in range(k):
+                        dst, src = [], []
+                        for i, (bi, px, py, pz) in enumerate(idx):
+                            j = site.get((bi, px + a - c, py + b_ - c, pz + d - c))
+                            if j is not None:
+                                dst.append(i)
+                                src.append(j)
+                        if dst:
+                            out[dst] += x.features[src] @ self.weight[:, a, b_, d, :].t()
+            if self.bias is not None:
+                out = out + self.bias
+            return x.replace_feature(out)
+
+    sp = _stub("spconv")
+    sp.pytorch = _stub("spconv.pytorch", SubMConv3d=SubMConv3d, SparseConvTensor=SparseConvTensor,
+                       modules=types.SimpleNamespace(is_spconv_module=lambda m: isinstance(m, SubMConv3d)))
+
+    def segment_csr(src, indptr, reduce="sum"):
+        outs = []
+        for i in range(len(indptr) - 1):
+            seg = src[int(indptr[i]):int(indptr[i + 1])]
+            outs.append({"max": lambda s: s.max(0).values, "min": lambda s: s.min(0).values,
+                         "mean": lambda s: s.mean(0), "sum": lambda s: s.sum(0)}[reduce](seg))
+        return torch.stack(outs)
+
+    _stub("torch_scatter", segment_csr=segment_csr)
+
+    def flash_attn_varlen_qkvpacked_func(qkv, cu_seqlens, max_seqlen, dropout_p=0.0, softmax_scale=None, **kw):
+        assert qkv.dtype == torch.float16 and dropout_p == 0
+        out = torch.empty_like(qkv[:, 0])
+        cu = cu_seqlens.tolist()
+        for s, e in zip(cu[:-1], cu[1:]):
+            assert e - s <= max_seqlen
+            q, k, v = (qkv[s:e, i].float().transpose(0, 1) for i in range(3))       # (H, n, D)
+            p = torch.softmax(q @ k.transpose(1, 2) * softmax_scale, dim=-1)
+            out[s:e] = (p @ v).transpose(0, 1).to(torch.float16)
+        return out
+
+    _stub("flash_attn", flash_attn_varlen_qkvpacked_func=flash_attn_varlen_qkvpacked_func)
+
+    class Dict(dict):
+        def __init__(self, *args, **kwargs):
+            super().__init__()
+            for a in args:
+                if a:
+                    for k, v in (a.items() if isinstance(a, dict) else a):
+                        self[k] = self._hook(v)
+            for k, v in kwargs.items():
+                self[k] = self._hook(v)
+
+        @classmethod
+        def _hook(cls, v):
+            return cls(v) if isinstance(v, dict) and not isinstance(v, cls) else v
+
+        def __getattr__(self, k):
+            try:
+                return self[k]
+            except KeyError:
+                raise AttributeError(k)
+
+        def __setattr__(self, k, v):
+            self[k] = v
+
+    _stub("addict", Dict=Dict)
+
+
 _loaded = None
 
 
@@ -39,17 +147,8 @@ def load_reference(vit_cfg_kwargs):
     if _loaded is None:
         _stub("matplotlib")
         _stub("matplotlib.pyplot")
-        _stub("torch_scatter")
         _stub("torchinfo", summary=lambda *a, **k: None)
-
-        class _SubM(nn.Module):
-            def __init__(self, *a, **k):
-                super().__init__()
-
-        sp = _stub("spconv")
-        sp.pytorch = _stub("spconv.pytorch", SubMConv3d=_SubM, SparseConvTensor=object,
-                           modules=types.SimpleNamespace(is_spconv_module=lambda m: isinstance(m, _SubM)))
-        _stub("addict", Dict=type("Dict", (dict,), {}))
+        _install_ptv3_stubs()
 
         class DropPath(nn.Module):
             def __init__(self, p=0.0):
@@ -121,3 +220,13 @@ def build_reference_model(cfg, state_dict):
            and "token_type_ids" not in k]
     assert not bad, f"hot-path tensors not provided: {bad[:8]}"
     return model
+
+
+def load_reference_pooler():
+    """Returns (multimodal_projector.builder module, serialization package) of the reference, importable without the
+    rest of LLaVA being constructed: used by tests/golden/make_ptv3_golden.py for the point-cloud branch."""
+    load_reference(dict(hidden_size=64, intermediate_size=128, num_hidden_layers=1, num_attention_heads=2,
+                        image_size=28, patch_size=14, projection_dim=32))
+    from llava.model.multimodal_projector import builder as proj_builder
+    from llava.model.multimodal_projector import serialization
+    return proj_builder, serialization
