@@ -361,6 +361,83 @@ int b200_adamw_step(float* master, void* param, const void* grad, int grad_fp32,
                     float beta1, float beta2, float eps, float weight_decay, int step, const float* clip_coef,
                     b200_stream_t stream);
 
+/* ============================================================================================================
+ * Point-cloud branch of the image pooler: PointTransformerV3 in cls_mode, fp32  (ptv3.cu)
+ * Replaces ImageEmbeddingPooler._encode_pc (model/multimodal_projector/builder.py:93-148) and what it calls:
+ * Point.serialization / sparsify (model/multimodal_projector/pointtransformerv3.py:84-177), the serialization codes
+ * (model/multimodal_projector/serialization/{default,z_order,hilbert}.py), spconv SubMConv3d (:549,:768),
+ * SerializedAttention over flash-attn varlen (:443-494), SerializedPooling over torch_scatter.segment_csr (:643-713).
+ * The host (mm_or_b200/model/point_transformer.py) keeps every level sorted by z-order code; all feature tensors are
+ * fp32 row-major [points, channels]; index tensors are int32; codes are int64.
+ * ========================================================================================================== */
+
+/* grid = trunc((xyz - min over ALL points) / grid_size) in IEEE fp32 (pointtransformerv3.py:96-98).
+ * pts [n, ld] (xyz first), min3 [3] out, grid [n, 3] out, max_out [1] out = largest grid coordinate (the host derives
+ * the serialization depth from it, :101-103). */
+int b200_pc_grid_coords(const float* pts, int ld, int n, float grid_size, float* min3, int32_t* grid,
+                        int32_t* max_out, b200_stream_t stream);
+
+/* code[i] = batch[i] << 3*depth | key(grid[i])  (serialization/default.py:9-25); order 0 "z", 1 "z-trans", 2 "hilbert",
+ * 3 "hilbert-trans". Bit-exact with the reference's int64 codes. */
+int b200_pc_encode(const int32_t* grid, const int32_t* batch, int n, int depth, int order, int64_t* code,
+                   b200_stream_t stream);
+
+/* order = argsort(code) (stable, unsigned, low `bits` bits), code_sorted = code[order]  (pointtransformerv3.py:118). */
+size_t b200_pc_argsort_workspace_bytes(int n);
+int b200_pc_argsort(const int64_t* code, int n, int bits, int64_t* code_sorted, int32_t* order, void* workspace,
+                    size_t workspace_bytes, b200_stream_t stream);
+
+/* dst[i, 0:width] = src[idx[i], 0:width] over 4-byte elements (the physical re-ordering into z-order). */
+int b200_pc_gather_rows(const void* src, int ld_src, const int32_t* idx, int n, int width, void* dst, int ld_dst,
+                        b200_stream_t stream);
+
+/* Submanifold-convolution neighbour table (spconv indice pairs): nbr[i, t] = row of the active voxel at
+ * grid[i] + tap(t) - ksize/2, taps (a, b, c) row-major over (x, y, z), -1 where absent. zcode: sorted "z" codes of
+ * the rows. ksize 3 or 5. dup_flag[0] is set to 1 when two rows share a voxel (undefined for spconv too). */
+int b200_pc_neighbors(const int64_t* zcode, const int32_t* grid, const int32_t* batch, int n, int depth, int ksize,
+                      int32_t* nbr, int32_t* dup_flag, b200_stream_t stream);
+
+/* SerializedPooling plan (pointtransformerv3.py:655-701): clusters are the runs of equal zcode >> 3*pooling_depth.
+ * seg_start [n+1] out (first n_out+1 entries valid), n_out [1] out (device), grid_out [n, 3] / batch_out [n] out
+ * (first n_out rows valid): grid >> pooling_depth and batch of each cluster. */
+int b200_pc_pool_plan(const int64_t* zcode, const int32_t* grid, const int32_t* batch, int n, int pooling_depth,
+                      int32_t* seg_start, int32_t* n_out, int32_t* grid_out, int32_t* batch_out,
+                      b200_stream_t stream);
+
+/* off[b] = first row of cloud b, b = 0..n_clouds (batch sorted ascending). */
+int b200_pc_cloud_offsets(const int32_t* batch, int n, int n_clouds, int32_t* off, b200_stream_t stream);
+
+/* Gather-GEMM: C[m, :] = epilogue(sum_t A[idx[m, t], 0:K] . W[t*K:(t+1)*K, 0:N]); idx NULL = plain Linear (taps 1).
+ * W is [taps*K, N] row-major (the loader transposes nn.Linear / SubMConv3d weights once). Epilogue: + bias[N],
+ * * scale[N] + shift[N] (BatchNorm1d in eval mode, folded), act 0 none / 2 GELU(erf), + residual[M, ldr]; C fp32, or
+ * bf16 when out_bf16 (project_pc writes the pooler's token rows). */
+int b200_pc_gemm_f32(const float* A, int lda, const int32_t* idx, int taps, const float* W, const float* bias,
+                     const float* scale, const float* shift, int act, const float* residual, int ldr, void* C, int ldc,
+                     int out_bf16, int M, int N, int K, b200_stream_t stream);
+
+/* out = residual + LayerNorm(x) * gamma + beta (nn.LayerNorm, biased variance; residual may be NULL). */
+int b200_pc_layernorm_f32(const float* x, int ld, const float* gamma, const float* beta, float eps,
+                          const float* residual, int ldr, float* out, int ldo, int M, int C, b200_stream_t stream);
+
+/* Serialized patch attention with flash-attn varlen semantics (q, k, v and the output rounded to fp16, fp32 softmax).
+ * qkv [n, ld] = (q | k | v) of `channels` each, head h at h*16; order [n] = serialized order of the block; patches
+ * [n_patches, 4] = (q_begin, q_len, k_begin, k_len) in positions of `order` (get_padding_and_inverse,
+ * pointtransformerv3.py:385-441: a topped-up last patch has q = its own points, k = the cloud's last patch_size
+ * points). out [n, ldo], row r written by the patch that owns r. head_dim must be 16. */
+int b200_pc_patch_attention(const float* qkv, int ld, const int32_t* order, const int32_t* patches, int n_patches,
+                            int max_q_len, int channels, int heads, float scale, float* out, int ldo,
+                            b200_stream_t stream);
+
+/* out[s, c] = act((max over rows seg_start[s] .. seg_start[s+1]-1 of x[., c]) * scale[c] + shift[c])
+ * (torch_scatter.segment_csr(reduce="max") + BatchNorm1d + GELU, pointtransformerv3.py:686-713). */
+int b200_pc_segment_max(const float* x, int ld, const int32_t* seg_start, int n_seg, int C, const float* scale,
+                        const float* shift, int act, float* out, int ldo, b200_stream_t stream);
+
+/* out[row_map[b], :] = mean of rows cloud_off[b] .. cloud_off[b+1]-1 (AdaptiveAvgPool1d(1), builder.py:139-144). */
+int b200_pc_cloud_mean(const float* x, int ld, const int32_t* cloud_off, int n_clouds, int C, const int32_t* row_map,
+                       float* out, int ldo, b200_stream_t stream);
+
+
 #ifdef __cplusplus
 }
 #endif

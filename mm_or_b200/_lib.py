@@ -124,7 +124,23 @@ _SIGS = {
     "b200_llama_decode_workspace_bytes": (sz, [_P(LlamaWeights), ci, ci]),
     "b200_llama_decode_step": (ci, [_P(LlamaWeights), vp, vp, vp, _P(KvCache), ci, ci, vp, ci, ci, vp, ci, vp, vp,
                                     sz, vp]),
+    # point-cloud branch (ptv3.cu)
+    "b200_pc_grid_coords": (ci, [vp, ci, ci, cf, vp, vp, vp, vp]),
+    "b200_pc_encode": (ci, [vp, vp, ci, ci, ci, vp, vp]),
+    "b200_pc_argsort_workspace_bytes": (sz, [ci]),
+    "b200_pc_argsort": (ci, [vp, ci, ci, vp, vp, vp, sz, vp]),
+    "b200_pc_gather_rows": (ci, [vp, ci, vp, ci, ci, vp, ci, vp]),
+    "b200_pc_neighbors": (ci, [vp, vp, vp, ci, ci, ci, vp, vp, vp]),
+    "b200_pc_pool_plan": (ci, [vp, vp, vp, ci, ci, vp, vp, vp, vp, vp]),
+    "b200_pc_cloud_offsets": (ci, [vp, ci, ci, vp, vp]),
+    "b200_pc_gemm_f32": (ci, [vp, ci, vp, ci, vp, vp, vp, vp, ci, vp, ci, vp, ci, ci, ci, ci, ci, vp]),
+    "b200_pc_layernorm_f32": (ci, [vp, ci, vp, vp, cf, vp, ci, vp, ci, ci, ci, vp]),
+    "b200_pc_patch_attention": (ci, [vp, ci, vp, vp, ci, ci, ci, ci, cf, vp, ci, vp]),
+    "b200_pc_segment_max": (ci, [vp, ci, vp, ci, ci, vp, vp, ci, vp, ci, vp]),
+    "b200_pc_cloud_mean": (ci, [vp, ci, vp, ci, ci, vp, vp, ci, vp]),
 }
+
+PC_SYMBOLS = sorted(k for k in _SIGS if k.startswith("b200_pc_"))
 
 EXPORTED_SYMBOLS = ["b200_last_error"] + sorted(_SIGS)
 

@@ -50,6 +50,7 @@ enum KernelFamily : int {
   kFamSegmask,
   kFamMisc,
   kFamTrain,        // backward / loss / optimizer kernels
+  kFamPointCloud,   // PointTransformerV3 operators (ptv3.cu)
   kFamCount
 };
 struct LaunchScope {

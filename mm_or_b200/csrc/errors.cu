@@ -94,7 +94,8 @@ int b200_prof_family_count(void) { return kFamCount; }
 
 const char* b200_prof_family_name(int family) {
   static const char* names[kFamCount] = {"gemm",  "gemm_skinny", "flash_attn", "decode_attn", "norm",  "rope_kv",
-                                         "embed", "argmax",      "patchify",   "segmask",     "misc",  "train"};
+                                         "embed", "argmax",      "patchify",   "segmask",     "misc",  "train",
+                                         "pointcloud"};
   return family >= 0 && family < kFamCount ? names[family] : "";
 }
 

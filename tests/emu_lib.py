@@ -1,0 +1,61 @@
+"""TEST INFRASTRUCTURE: builds and loads tests/emu/_build/libb200emu.so -- mm_or_b200/csrc/ptv3.cu compiled with g++
+-DB200_EMU against the CUDA-kernel emulator of tests/emu/cuda_emu.h -- and binds it like mm_or_b200/_lib.py binds the real
+library, so that the CPU test-suite executes the SAME kernel source (and the same host orchestration,
+mm_or_b200/model/point_transformer.py) against the oracle. Never imported by the product."""
+import ctypes
+import os
+import subprocess
+
+import torch
+
+from mm_or_b200 import _lib as L
+from mm_or_b200.model.point_transformer import PcOps
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+EMU = os.path.join(HERE, "emu")
+SRC = os.path.join(HERE, "..", "mm_or_b200", "csrc", "ptv3.cu")
+OUT = os.path.join(EMU, "_build", "libb200emu.so")
+_lib = None
+
+
+def build():
+    deps = [SRC, os.path.join(EMU, "cuda_emu.h"), os.path.join(EMU, "emu_common.h"), os.path.join(EMU, "emu_support.cpp")]
+    if os.path.exists(OUT) and os.path.getmtime(OUT) >= max(os.path.getmtime(d) for d in deps):
+        return OUT
+    os.makedirs(os.path.dirname(OUT), exist_ok=True)
+    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-DB200_EMU", "-I" + EMU, "-x", "c++", SRC, "-x", "c++",
+           os.path.join(EMU, "emu_support.cpp"), "-o", OUT]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("emulator build failed:\n" + r.stderr)
+    return OUT
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        cdll = ctypes.CDLL(build())
+        cdll.b200_last_error.restype = ctypes.c_char_p
+        for name in L.PC_SYMBOLS:
+            fn = getattr(cdll, name)
+            fn.restype, fn.argtypes = L._SIGS[name]
+        assert cdll.b200_emu_marker() == 1
+        _lib = cdll
+    return _lib
+
+
+def ops():
+    """PcOps over the emulator: host tensors, host pointers."""
+    cdll = lib()
+
+    def ptr(t):
+        if t is None:
+            return None
+        assert not t.is_cuda
+        return ctypes.c_void_p(t.data_ptr())
+
+    def check(rc, what=""):
+        if rc != 0:
+            raise RuntimeError(f"{what} failed with code {rc}: {cdll.b200_last_error().decode()}")
+
+    return PcOps(cdll, torch.device("cpu"), ptr, lambda: None, check)
