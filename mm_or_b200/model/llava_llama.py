@@ -175,8 +175,8 @@ class CLIPVisionTower:
 # image pooler (+ audio / seg-mask tokens) and projector
 # =====================================================================================================================
 class ImageEmbeddingPooler:
-    """Mirror of ImageEmbeddingPooler (multimodal_projector/builder.py:61-190); point clouds are not supported yet
-    (PointTransformerV3 is deferred) and raise NotImplementedError."""
+    """Mirror of ImageEmbeddingPooler (multimodal_projector/builder.py:61-190): BERT pooler over the views' tokens plus
+    the point-cloud (PointTransformerV3, model/point_transformer.py), audio and seg-mask tokens."""
 
     def __init__(self):
         self.embedding_dim = POOLER_GEOMETRY["hidden"]
@@ -229,6 +229,11 @@ class ImageEmbeddingPooler:
             self._seg = (sw, s)
         self._keep = (t, keep, layers)
         self.device = torch.device(device)
+        # point-cloud branch: present when the checkpoint carries it (builder.py:82-85 always constructs it)
+        self.point_transformer = None
+        if POOL + "point_transformer.project_pc.weight" in sd:
+            from .point_transformer import PointTransformerV3
+            self.point_transformer = PointTransformerV3().load_weights(sd, POOL + "point_transformer.", device)
 
     @staticmethod
     def num_extra_tokens(pc, audio, segmasks):
@@ -239,8 +244,11 @@ class ImageEmbeddingPooler:
         """BERT pooler over gathered rows of `src` + extra modality tokens -> (B, T_vis, hidden)."""
         if self._w is None:
             raise L.B200Error("image pooler weights not loaded")
-        if pc is not None:
-            raise NotImplementedError("point-cloud tokens (PointTransformerV3) are not implemented in this build")
+        if pc is not None and self.point_transformer is None:
+            raise L.B200Error("point clouds were passed but the checkpoint has no model.image_pooler.point_transformer.* "
+                              "weights")
+        if pc is not None and len(pc) != B:
+            raise ValueError(f"pc must hold one entry (tensor or None) per sample: got {len(pc)} for batch {B}")
         g = self.geo
         keep, D = g["keep"], g["hidden"]
         if S < keep:
@@ -256,6 +264,9 @@ class ImageEmbeddingPooler:
                                             L.ptr(kv_len[s:]), n, S, keep, L.ptr(out[s:]), T, L.ptr(ws), ws.numel(),
                                             L.stream_ptr()), "b200_pooler_forward")
         t = keep
+        if pc is not None:                                            # _encode_pc (builder.py:93-148), fp32 -> bf16 (:177)
+            self.point_transformer(pc, out=out[:, t])
+            t += 1
         if audio is not None:                                         # _encode_audio (builder.py:150-159)
             feats = torch.zeros((B, 512), dtype=BF)
             for i, a in enumerate(audio):

@@ -124,6 +124,31 @@ class PcOps:
                   self.ptr(out), out.stride(0))
 
 
+def weight_specs(geometry=None, prefix=""):
+    """[(name, shape, kind)] of PointTransformerV3(cls_mode=True) under the reference's state_dict names
+    (pointtransformerv3.py:864-919); kind: w weight, b bias, g norm gain, m / v BatchNorm running mean / variance."""
+    g = dict(GEOMETRY if geometry is None else geometry)
+    bn = lambda p, c: [(p + "weight", (c,), "g"), (p + "bias", (c,), "b"), (p + "running_mean", (c,), "m"),
+                       (p + "running_var", (c,), "v")]
+    lin = lambda p, i, o: [(p + "weight", (o, i), "w"), (p + "bias", (o,), "b")]
+    ln = lambda p, c: [(p + "weight", (c,), "g"), (p + "bias", (c,), "b")]
+    c0 = g["enc_channels"][0]
+    out = [(prefix + "embedding.stem.conv.weight", (c0, 5, 5, 5, g["in_channels"]), "w")]
+    out += bn(prefix + "embedding.stem.norm.", c0)
+    for s, nb in enumerate(g["enc_depths"]):
+        C = g["enc_channels"][s]
+        p = prefix + f"enc.enc{s}."
+        if s > 0:
+            out += lin(p + "down.proj.", g["enc_channels"][s - 1], C) + bn(p + "down.norm.0.", C)
+        for i in range(nb):
+            q = p + f"block{i}."
+            out += [(q + "cpe.0.weight", (C, 3, 3, 3, C), "w"), (q + "cpe.0.bias", (C,), "b")]
+            out += lin(q + "cpe.1.", C, C) + ln(q + "cpe.2.", C) + ln(q + "norm1.0.", C)
+            out += lin(q + "attn.qkv.", C, 3 * C) + lin(q + "attn.proj.", C, C) + ln(q + "norm2.0.", C)
+            out += lin(q + "mlp.0.fc1.", C, g["mlp_ratio"] * C) + lin(q + "mlp.0.fc2.", g["mlp_ratio"] * C, C)
+    return out + lin(prefix + "project_pc.", g["enc_channels"][-1], g["project_pc_dim"])
+
+
 def patch_descriptors(counts, K):
     """(q_begin, q_len, k_begin, k_len) per patch in positions of a serialized order: the padding rule of
     SerializedAttention.get_padding_and_inverse (pointtransformerv3.py:385-441) without materialising pad / unpad: a
@@ -163,7 +188,9 @@ class PointTransformerV3:
         g = self.geo
         self.ops = ops if ops is not None else PcOps.cuda(device)
         dev = self.ops.device
-        f32 = lambda k: sd[prefix + k].detach().to(torch.float32)
+        # the reference casts the whole pooler (parameters AND BatchNorm buffers) to bf16 at load (model/builder.py:166)
+        # and widens PTv3 back to fp32 at call time (multimodal_projector/builder.py:95): values are bf16-rounded
+        f32 = lambda k: sd[prefix + k].detach().to(torch.bfloat16).to(torch.float32)
         put = lambda t: t.contiguous().to(dev)
 
         def lin(p):      # nn.Linear (out, in) -> [in, out]

@@ -199,11 +199,15 @@ def encode_segmasks(sd, segmasks, dtype) -> torch.Tensor:
     return out
 
 
-def pooler_with_extras(sd, emb, mask, cfg: PoolerCfg, audio=None, segmasks=None) -> torch.Tensor:
-    """ImageEmbeddingPooler.forward (builder.py:169-190) without the point-cloud branch (PTv3 deferred).
-    Token order: pooled[0:keep], audio, seg0, seg1, seg2."""
+def pooler_with_extras(sd, emb, mask, cfg: PoolerCfg, audio=None, segmasks=None, pc=None) -> torch.Tensor:
+    """ImageEmbeddingPooler.forward (builder.py:169-190). Token order: pooled[0:keep], pc, audio, seg0, seg1, seg2.
+    The point-cloud token is computed in fp32 with autocast off and cast to the pooler dtype (builder.py:176-177)."""
     out = bert_pooler_forward(sd, emb, mask, cfg)
     extra = []
+    if pc is not None:
+        from . import ptv3_oracle
+        extra.append(ptv3_oracle.encode_pc({k: v.float() for k, v in sd.items() if k.startswith(ptv3_oracle.PT)},
+                                           pc).to(out.dtype).unsqueeze(1))
     if audio is not None:
         extra.append(encode_audio(sd, audio, len(out), out.dtype).unsqueeze(1))
     if segmasks is not None:
@@ -216,13 +220,14 @@ def mm_projector(sd, x: torch.Tensor) -> torch.Tensor:
     return _lin(F.gelu(_lin(x, sd, "model.mm_projector.0")), sd, "model.mm_projector.2")
 
 
-def encode_images_pooled(sd, images: List[torch.Tensor], cfg: Mm2sgCfg, audio=None, segmasks=None) -> torch.Tensor:
+def encode_images_pooled(sd, images: List[torch.Tensor], cfg: Mm2sgCfg, audio=None, segmasks=None,
+                         pc=None) -> torch.Tensor:
     """llava_arch.py:172-183 for the `type(images) is list or ndim == 5` branch (:203-207)."""
     concat = torch.cat([im for im in images], dim=0)
     feats = clip_tower_forward(sd, concat, cfg.vit)
     split = torch.split(feats, [im.shape[0] for im in images], dim=0)
     emb, mask = pad_embeddings(list(split))
-    pooled = pooler_with_extras(sd, emb, mask, cfg.pooler, audio, segmasks)
+    pooled = pooler_with_extras(sd, emb, mask, cfg.pooler, audio, segmasks, pc)
     return mm_projector(sd, pooled)
 
 
@@ -359,8 +364,8 @@ def llama_forward(sd, x: torch.Tensor, mask: torch.Tensor, pos: torch.Tensor, cf
 #     model.generate(do_sample=False) (scene_graph_prediction_model.py:221-231; decode-step inputs llava_arch.py:192-201)
 # ----------------------------------------------------------------------------------------------------------------
 def multimodal_prefill(sd, cfg: Mm2sgCfg, input_ids, attention_mask, images, labels=None, audio=None, segmasks=None,
-                       padding_side="right", max_len=None, last_only=False):
-    visual = encode_images_pooled(sd, images, cfg, audio, segmasks)
+                       padding_side="right", max_len=None, last_only=False, pc=None):
+    visual = encode_images_pooled(sd, images, cfg, audio, segmasks, pc)
     src, mlabels, mask, pos = pack_plan(input_ids, attention_mask, labels, visual.shape[1], padding_side, max_len)
     emb = pack_embeds(sd, src, visual)
     logits, kv = llama_forward(sd, emb, mask, pos, cfg.llm, last_only=last_only)
