@@ -292,7 +292,8 @@ __global__ void cloud_offsets_kernel(const int* __restrict__ batch, int n, int n
 // gather-GEMM, fp32:  C[m, :] = epilogue( sum_{t < taps} A[idx[m, t], 0:K] . W[t*K : (t+1)*K, 0:N] )
 //   idx == nullptr: taps = 1, row m itself; idx < 0: the tap is absent. W is [taps*K, N] row-major (N contiguous).
 //   epilogue: (+ bias) -> (* scale + shift: folded BatchNorm) -> (GELU) -> (+ residual); fp32 or bf16 store.
-// 64 x 64 tile, 16-deep K slices over the flattened (tap, channel) axis, 256 threads, 4 x 4 outputs per thread.
+// Generic kernel (any shape): 64 x 64 tile, 16-deep K slices over the flattened (tap, channel) axis, 256 threads,
+// 4 x 4 outputs per thread. The network's own shapes take gather_gemm_tiled_kernel below.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int GM = 64, GN = 64, GK = 16;
 
@@ -355,6 +356,108 @@ __global__ void __launch_bounds__(256) gather_gemm_kernel(
   }
 }
 
+// Fast path of the same contract for the shapes the network produces (K, lda, N multiples of 4, 16-byte aligned A / W):
+// 128 x BN tile (BN = 32 / 64 / 128 by output width), one (tap, 16-channel) slice per step so the gathered row index is
+// read once per slice and never divided, 128-bit global and shared loads, 8 x (BN / 16) outputs per thread laid out so
+// that the shared-memory reads of a quarter-warp are contiguous (no bank conflicts).
+constexpr int TM = 128, TK = 16;
+
+template <int BN>
+__global__ void __launch_bounds__(256) gather_gemm_tiled_kernel(
+    const float* __restrict__ A, int lda, const int* __restrict__ idx, int taps, const float* __restrict__ W,
+    const float* __restrict__ bias, const float* __restrict__ scale, const float* __restrict__ shift, int act,
+    const float* __restrict__ residual, int ldr, void* __restrict__ Cout, int ldc, int out_bf16, int M, int N, int K) {
+  constexpr int NH = BN == 128 ? 2 : 1;  // column halves per thread
+  constexpr int CW = BN / 16 / NH;       // contiguous columns per half: 4, 4, 2
+  __shared__ __align__(16) float As[TK][TM + 4];
+  __shared__ __align__(16) float Bs[TK][BN];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.y * TM, n0 = blockIdx.x * BN;
+  const int tx = tid % 16, ty = tid / 16;
+  const int lr = tid / 2, lh = tid % 2;  // loader: row lr of the tile, channels lh*8 .. lh*8+7 of the slice
+  const int lm = m0 + lr;
+  float acc[8][NH * CW];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+#pragma unroll
+    for (int j = 0; j < NH * CW; ++j) acc[i][j] = 0.f;
+  }
+
+  for (int t = 0; t < taps; ++t) {
+    int row = -1;
+    if (lm < M) row = idx ? idx[(size_t)lm * taps + t] : lm;
+    const float* arow = row >= 0 ? A + (size_t)row * lda : nullptr;
+    const float* wt = W + (size_t)t * K * N;
+    for (int k0 = 0; k0 < K; k0 += TK) {
+      float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+      int ka = k0 + lh * 8;
+      if (arow) {
+        if (ka < K) a0 = *reinterpret_cast<const float4*>(arow + ka);
+        if (ka + 4 < K) a1 = *reinterpret_cast<const float4*>(arow + ka + 4);
+      }
+      As[lh * 8 + 0][lr] = a0.x;
+      As[lh * 8 + 1][lr] = a0.y;
+      As[lh * 8 + 2][lr] = a0.z;
+      As[lh * 8 + 3][lr] = a0.w;
+      As[lh * 8 + 4][lr] = a1.x;
+      As[lh * 8 + 5][lr] = a1.y;
+      As[lh * 8 + 6][lr] = a1.z;
+      As[lh * 8 + 7][lr] = a1.w;
+      for (int v = tid; v < TK * BN / 4; v += 256) {
+        int kk = v / (BN / 4), c4 = v % (BN / 4);
+        int nn = n0 + c4 * 4;
+        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k0 + kk < K && nn < N) b = *reinterpret_cast<const float4*>(wt + (size_t)(k0 + kk) * N + nn);
+        *reinterpret_cast<float4*>(&Bs[kk][c4 * 4]) = b;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int kk = 0; kk < TK; ++kk) {
+        float a[8], b[NH * CW];
+        float4 x0 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+        float4 x1 = *reinterpret_cast<const float4*>(&As[kk][64 + ty * 4]);
+        a[0] = x0.x; a[1] = x0.y; a[2] = x0.z; a[3] = x0.w;
+        a[4] = x1.x; a[5] = x1.y; a[6] = x1.z; a[7] = x1.w;
+        if constexpr (CW == 4) {
+#pragma unroll
+          for (int h = 0; h < NH; ++h) {
+            float4 y = *reinterpret_cast<const float4*>(&Bs[kk][h * 64 + tx * 4]);
+            b[h * 4 + 0] = y.x; b[h * 4 + 1] = y.y; b[h * 4 + 2] = y.z; b[h * 4 + 3] = y.w;
+          }
+        } else {
+          float2 y = *reinterpret_cast<const float2*>(&Bs[kk][tx * 2]);
+          b[0] = y.x; b[1] = y.y;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+#pragma unroll
+          for (int j = 0; j < NH * CW; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+      }
+      __syncthreads();
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    int m = m0 + (i / 4) * 64 + ty * 4 + (i % 4);
+    if (m >= M) continue;
+#pragma unroll
+    for (int h = 0; h < NH; ++h)
+#pragma unroll
+      for (int j = 0; j < CW; ++j) {
+        int nn = n0 + h * 64 + tx * CW + j;
+        if (nn >= N) continue;
+        float v = acc[i][h * CW + j];
+        if (bias) v += bias[nn];
+        if (scale) v = v * scale[nn] + shift[nn];
+        if (act == 2) v = gelu_erf(v);
+        if (residual) v += residual[(size_t)m * ldr + nn];
+        if (out_bf16) reinterpret_cast<uint16_t*>(Cout)[(size_t)m * ldc + nn] = bf16_bits(v);
+        else reinterpret_cast<float*>(Cout)[(size_t)m * ldc + nn] = v;
+      }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // LayerNorm, fp32, one warp per row: out = (residual) + (x - mean) / sqrt(var + eps) * gamma + beta  (biased variance)
 // ---------------------------------------------------------------------------------------------------------------
@@ -388,36 +491,46 @@ __global__ void layernorm_f32_kernel(const float* __restrict__ x, int ld, const 
 // serialized patch attention (SerializedAttention.forward, pointtransformerv3.py:443-494, flash-attn varlen semantics):
 // patch p = {q_begin, q_len, k_begin, k_len} in positions of the serialized order; queries and keys are the rows
 // order[pos]; q, k, v are rounded to fp16, scores / softmax / PV accumulate in fp32, the output is rounded to fp16.
-// grid (q tiles of 128, heads, patches), 128 threads, one query per thread, 128-key tiles of K and V in shared memory.
+// grid (q tiles of 256, heads, patches), 128 threads, two queries per thread (each K / V row read from shared memory
+// feeds 2 x 16 FMAs), 128-key tiles of K and V in shared memory, online softmax over chunks of 8 keys.
 // head_dim is fixed at 16 (every PTv3 stage: channels / heads = 16).
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int AD = 16, AT = 128;
+constexpr int AD = 16, AT = 128, AQ = 2;  // head_dim, threads (= keys per shared tile), queries per thread
 
 __global__ void __launch_bounds__(AT) patch_attention_kernel(const float* __restrict__ qkv, int ld,
                                                             const int* __restrict__ order,
                                                             const int* __restrict__ patches, int C, float scale,
                                                             float* __restrict__ out, int ldo) {
-  __shared__ float Ks[AT][AD];
-  __shared__ float Vs[AT][AD];
+  __shared__ __align__(16) float Ks[AT][AD];
+  __shared__ __align__(16) float Vs[AT][AD];
   const int* pd = patches + (size_t)blockIdx.z * 4;
   const int q_begin = pd[0], q_len = pd[1], k_begin = pd[2], k_len = pd[3];
   const int h = blockIdx.y;
-  const int qi = blockIdx.x * AT + threadIdx.x;
-  if ((int)(blockIdx.x * AT) >= q_len) return;  // whole block out of range (uniform)
-  const bool active = qi < q_len;
-  int qrow = active ? order[q_begin + qi] : 0;
-  float q[AD], o[AD];
-  for (int d = 0; d < AD; ++d) {
-    q[d] = active ? round_f16(qkv[(size_t)qrow * ld + h * AD + d]) : 0.f;
-    o[d] = 0.f;
+  const int q0 = blockIdx.x * (AT * AQ);
+  if (q0 >= q_len) return;  // whole block out of range (uniform)
+  bool active[AQ];
+  int qrow[AQ];
+  float q[AQ][AD], o[AQ][AD], m[AQ], l[AQ];
+#pragma unroll
+  for (int u = 0; u < AQ; ++u) {
+    int qi = q0 + u * AT + threadIdx.x;
+    active[u] = qi < q_len;
+    qrow[u] = active[u] ? order[q_begin + qi] : 0;
+    m[u] = -INFINITY;
+    l[u] = 0.f;
+#pragma unroll
+    for (int d = 0; d < AD; ++d) {
+      q[u][d] = active[u] ? round_f16(qkv[(size_t)qrow[u] * ld + h * AD + d]) : 0.f;
+      o[u][d] = 0.f;
+    }
   }
-  float m = -INFINITY, l = 0.f;
   for (int k0 = 0; k0 < k_len; k0 += AT) {
     int kj = k0 + threadIdx.x;
     if (kj < k_len) {
       int krow = order[k_begin + kj];
       const float* kp = qkv + (size_t)krow * ld + C + h * AD;
       const float* vp = qkv + (size_t)krow * ld + 2 * C + h * AD;
+#pragma unroll
       for (int d = 0; d < AD; ++d) {
         Ks[threadIdx.x][d] = round_f16(kp[d]);
         Vs[threadIdx.x][d] = round_f16(vp[d]);
@@ -426,36 +539,59 @@ __global__ void __launch_bounds__(AT) patch_attention_kernel(const float* __rest
     __syncthreads();
     int nk = k_len - k0 < AT ? k_len - k0 : AT;
     for (int c0 = 0; c0 < nk; c0 += 8) {
-      float s[8];
-      float cm = -INFINITY;
+      float s[AQ][8];
+      float cm[AQ];
+#pragma unroll
+      for (int u = 0; u < AQ; ++u) cm[u] = -INFINITY;
+#pragma unroll
       for (int j = 0; j < 8; ++j) {
-        float a = -INFINITY;
-        if (c0 + j < nk) {
-          a = 0.f;
-          for (int d = 0; d < AD; ++d) a = fmaf(q[d], Ks[c0 + j][d], a);
-          a *= scale;
-        }
-        s[j] = a;
-        cm = fmaxf(cm, a);
-      }
-      float mn = fmaxf(m, cm);
-      float alpha = expf(m - mn);  // m = -inf on the first chunk: exp(-inf) = 0
-      l *= alpha;
-      for (int d = 0; d < AD; ++d) o[d] *= alpha;
-      for (int j = 0; j < 8; ++j) {
-        if (c0 + j < nk) {
-          float p = expf(s[j] - mn);
-          l += p;
-          for (int d = 0; d < AD; ++d) o[d] = fmaf(p, Vs[c0 + j][d], o[d]);
+        bool ok = c0 + j < nk;
+        float kd[AD];
+#pragma unroll
+        for (int d = 0; d < AD; ++d) kd[d] = Ks[ok ? c0 + j : c0][d];
+#pragma unroll
+        for (int u = 0; u < AQ; ++u) {
+          float a = 0.f;
+#pragma unroll
+          for (int d = 0; d < AD; ++d) a = fmaf(q[u][d], kd[d], a);
+          a = ok ? a * scale : -INFINITY;
+          s[u][j] = a;
+          cm[u] = fmaxf(cm[u], a);
         }
       }
-      m = mn;
+#pragma unroll
+      for (int u = 0; u < AQ; ++u) {
+        float mn = fmaxf(m[u], cm[u]);
+        float alpha = expf(m[u] - mn);  // m = -inf on the first chunk: exp(-inf) = 0
+        l[u] *= alpha;
+#pragma unroll
+        for (int d = 0; d < AD; ++d) o[u][d] *= alpha;
+        m[u] = mn;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s[u][j] = expf(s[u][j] - mn);  // exp(-inf) = 0 for the keys past the end
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float vd[AD];
+        int kr = c0 + j < nk ? c0 + j : c0;
+#pragma unroll
+        for (int d = 0; d < AD; ++d) vd[d] = Vs[kr][d];
+#pragma unroll
+        for (int u = 0; u < AQ; ++u) {
+          l[u] += s[u][j];
+#pragma unroll
+          for (int d = 0; d < AD; ++d) o[u][d] = fmaf(s[u][j], vd[d], o[u][d]);
+        }
+      }
     }
     __syncthreads();
   }
-  if (active) {
-    float inv = 1.0f / l;
-    for (int d = 0; d < AD; ++d) out[(size_t)qrow * ldo + h * AD + d] = round_f16(o[d] * inv);
+#pragma unroll
+  for (int u = 0; u < AQ; ++u) {
+    if (!active[u]) continue;
+    float inv = 1.0f / l[u];
+#pragma unroll
+    for (int d = 0; d < AD; ++d) out[(size_t)qrow[u] * ldo + h * AD + d] = round_f16(o[u][d] * inv);
   }
 }
 
@@ -630,9 +766,26 @@ int b200_pc_gemm_f32(const float* A, int lda, const int32_t* idx, int taps, cons
     return fail(-2, "b200_pc_gemm_f32: bad argument (M=%d N=%d K=%d taps=%d act=%d)", M, N, K, taps, act);
   double flops = 2.0 * M * N * (double)K * taps;
   LaunchScope ls(kFamPointCloud, stream, 4.0 * ((double)M * K * taps + (double)K * taps * N + (double)M * N), flops);
-  dim3 grid((N + GN - 1) / GN, (M + GM - 1) / GM);
-  B200_LAUNCH(gather_gemm_kernel, grid, dim3(256), 0, stream, A, lda, idx, taps, W, bias, scale, shift, act, residual,
-              ldr, C, ldc, out_bf16, M, N, K);
+  bool fast = K % 4 == 0 && lda % 4 == 0 && N % 4 == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0 &&
+              (reinterpret_cast<uintptr_t>(W) & 15) == 0;
+  if (fast) {
+    int bn = N <= 32 ? 32 : (N <= 64 ? 64 : 128);
+    dim3 grid((N + bn - 1) / bn, (M + TM - 1) / TM);
+    if (bn == 32) {
+      B200_LAUNCH(gather_gemm_tiled_kernel<32>, grid, dim3(256), 0, stream, A, lda, idx, taps, W, bias, scale, shift,
+                  act, residual, ldr, C, ldc, out_bf16, M, N, K);
+    } else if (bn == 64) {
+      B200_LAUNCH(gather_gemm_tiled_kernel<64>, grid, dim3(256), 0, stream, A, lda, idx, taps, W, bias, scale, shift,
+                  act, residual, ldr, C, ldc, out_bf16, M, N, K);
+    } else {
+      B200_LAUNCH(gather_gemm_tiled_kernel<128>, grid, dim3(256), 0, stream, A, lda, idx, taps, W, bias, scale, shift,
+                  act, residual, ldr, C, ldc, out_bf16, M, N, K);
+    }
+  } else {  // odd shapes (the stem: K = 6) take the generic kernel
+    dim3 grid((N + GN - 1) / GN, (M + GM - 1) / GM);
+    B200_LAUNCH(gather_gemm_kernel, grid, dim3(256), 0, stream, A, lda, idx, taps, W, bias, scale, shift, act,
+                residual, ldr, C, ldc, out_bf16, M, N, K);
+  }
   PC_CHECK_LAUNCH("b200_pc_gemm_f32");
   return 0;
 }
@@ -658,7 +811,7 @@ int b200_pc_patch_attention(const float* qkv, int ld, const int32_t* order, cons
     return fail(-2, "b200_pc_patch_attention: bad argument (patches=%d channels=%d heads=%d; head_dim must be %d)",
                 n_patches, channels, heads, AD);
   LaunchScope ls(kFamPointCloud, stream, 0.0, 4.0 * n_patches * (double)max_q_len * max_q_len * channels);
-  dim3 grid((max_q_len + AT - 1) / AT, heads, n_patches);
+  dim3 grid((max_q_len + AT * AQ - 1) / (AT * AQ), heads, n_patches);
   B200_LAUNCH(patch_attention_kernel, grid, dim3(AT), 0, stream, qkv, ld, order, patches, channels, scale, out, ldo);
   PC_CHECK_LAUNCH("b200_pc_patch_attention");
   return 0;

@@ -26,6 +26,14 @@ struct dim3 {
 struct uint3_emu {
   unsigned x, y, z;
 };
+struct alignas(16) float4 {
+  float x, y, z, w;
+};
+struct alignas(8) float2 {
+  float x, y;
+};
+inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+#define __align__(n) __attribute__((aligned(n)))
 typedef void* cudaStream_t;
 typedef int cudaError_t;
 enum { cudaSuccess = 0 };

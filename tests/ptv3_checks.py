@@ -117,6 +117,31 @@ def check_gather_gemm_epilogues(ops):
     assert rel(ops.gemm(d(a), d(w), M, K, N, idx=d(idx), taps=taps), acc) < 1e-5
 
 
+def check_gather_gemm_tiled_shapes(ops):
+    """The fast path (K, N multiples of 4): every tile width, partial tiles in M and N, absent taps, every epilogue."""
+    d = lambda t: t.to(ops.device)
+    g = torch.Generator().manual_seed(3)
+    for M, K, N, taps in [(300, 32, 32, 27), (129, 64, 64, 27), (257, 32, 96, 1), (140, 128, 128, 1), (70, 256, 256, 3),
+                          (33, 512, 1024, 1), (200, 36, 44, 2), (5, 8, 4, 1)]:
+        a = torch.randn(M, K, generator=g)
+        w = torch.randn(taps * K, N, generator=g) / (taps * K) ** 0.5
+        idx = torch.randint(-1, M, (M, taps), generator=g).to(torch.int32) if taps > 1 else None
+        bias, scale, shift = torch.randn(N, generator=g), torch.rand(N, generator=g) + 0.5, torch.randn(N, generator=g)
+        res = torch.randn(M, N, generator=g)
+        acc = torch.zeros(M, N)
+        for t in range(taps):
+            if idx is None:
+                acc += a @ w
+            else:
+                ok = idx[:, t] >= 0
+                acc[ok] += a[idx[ok, t].long()] @ w[t * K:(t + 1) * K]
+        ref = torch.nn.functional.gelu((acc + bias) * scale + shift) + res
+        got = ops.gemm(d(a), d(w), M, K, N, idx=None if idx is None else d(idx), taps=taps, bias=d(bias),
+                       bn=(d(scale), d(shift)), act=2, residual=d(res))
+        assert rel(got, ref) < 1e-5, (M, K, N, taps)
+        assert rel(ops.gemm(d(a), d(w), M, K, N, idx=None if idx is None else d(idx), taps=taps), acc) < 1e-5
+
+
 def check_layernorm_segment_max_cloud_mean(ops):
     d = lambda t: t.to(ops.device)
     g = torch.Generator().manual_seed(1)
@@ -141,25 +166,27 @@ def check_layernorm_segment_max_cloud_mean(ops):
 def check_patch_attention_matches_flash_semantics(ops):
     d = lambda t: t.to(ops.device)
     g = torch.Generator().manual_seed(2)
-    K, C, H = 64, 32, 2                         # small patch size: the kernel takes patches, not K
-    counts = [150, 40, 64]
-    n = sum(counts)
-    qkv = torch.randn(n, 3 * C, generator=g) * 2
-    off, order = 0, []
-    for c in counts:                            # a serialized order: a permutation inside each cloud
-        order.append(off + torch.randperm(c, generator=g))
-        off += c
-    order = torch.cat(order).to(torch.int32)
-    pat = PT.patch_descriptors(counts, K)
-    got = ops.patch_attention(d(qkv), d(order), d(torch.tensor(pat, dtype=torch.int32)), len(pat),
-                              max(p[1] for p in pat), n, C, H).cpu()
-    pad, unpad, cu = P.patch_plan(counts, K)
-    inverse = torch.empty(n, dtype=torch.long)
-    inverse[order.long()] = torch.arange(n)
-    q = qkv[order.long()[pad]]
-    ref = P.varlen_attention_fp16(q.half().reshape(-1, 3, H, C // H), cu, H, (C // H) ** -0.5).float()[unpad[inverse]]
-    assert rel(got, ref) < 1e-3                 # both rounded to fp16 at the end: differences are 1-ulp fp16 flips
-    assert (got - ref).abs().max().item() < 4e-3
+    # small patch sizes: the kernel takes patch descriptors, not K. (K, cloud sizes): one short patch, full patches, a
+    # topped-up last patch; 300 exercises the second query of a thread and partial key tiles
+    for K, counts, C, H in [(64, [150, 40, 64], 32, 2), (300, [700, 150, 300], 64, 4)]:
+        n = sum(counts)
+        qkv = torch.randn(n, 3 * C, generator=g) * 2
+        off, order = 0, []
+        for c in counts:                            # a serialized order: a permutation inside each cloud
+            order.append(off + torch.randperm(c, generator=g))
+            off += c
+        order = torch.cat(order).to(torch.int32)
+        pat = PT.patch_descriptors(counts, K)
+        got = ops.patch_attention(d(qkv), d(order), d(torch.tensor(pat, dtype=torch.int32)), len(pat),
+                                  max(p[1] for p in pat), n, C, H).cpu()
+        pad, unpad, cu = P.patch_plan(counts, K)
+        inverse = torch.empty(n, dtype=torch.long)
+        inverse[order.long()] = torch.arange(n)
+        q = qkv[order.long()[pad]]
+        ref = P.varlen_attention_fp16(q.half().reshape(-1, 3, H, C // H), cu, H, (C // H) ** -0.5).float()
+        ref = ref[unpad[inverse]]
+        assert rel(got, ref) < 1e-3                 # both rounded to fp16 at the end: differences are 1-ulp fp16 flips
+        assert (got - ref).abs().max().item() < 4e-3
 
 
 def make_model(ops):
@@ -203,5 +230,6 @@ def check_bad_inputs_raise(ops):
 
 
 ALL = [check_grid_coords_and_codes_bit_exact, check_argsort_neighbors_pool_plan, check_gather_gemm_epilogues,
+       check_gather_gemm_tiled_shapes,
        check_layernorm_segment_max_cloud_mean, check_patch_attention_matches_flash_semantics,
        check_encode_pc_matches_oracle_and_reference_fixture, check_bad_inputs_raise]
