@@ -14,8 +14,24 @@ from mm_or_b200.model.point_transformer import PcOps
 HERE = os.path.dirname(os.path.abspath(__file__))
 EMU = os.path.join(HERE, "emu")
 SRC = os.path.join(HERE, "..", "mm_or_b200", "csrc", "ptv3.cu")
-OUT = os.path.join(EMU, "_build", "libb200emu.so")
 _lib = None
+
+
+def _cpu_has_fma():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("flags"):
+                    return " fma " in line + " "
+    except OSError:
+        pass
+    return False
+
+
+# fmaf() without -mfma is a libm call per multiply-add: build with the host's FMA instructions when it has them (the
+# library name carries the choice, so a build made on another machine is never picked up by mistake)
+FMA = _cpu_has_fma()
+OUT = os.path.join(EMU, "_build", "libb200emu_fma.so" if FMA else "libb200emu.so")
 
 
 def build():
@@ -23,7 +39,8 @@ def build():
     if os.path.exists(OUT) and os.path.getmtime(OUT) >= max(os.path.getmtime(d) for d in deps):
         return OUT
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
-    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-DB200_EMU", "-I" + EMU, "-x", "c++", SRC, "-x", "c++",
+    cmd = ["g++", "-O2"] + (["-mfma"] if FMA else []) + ["-std=c++17", "-fPIC", "-shared", "-DB200_EMU", "-I" + EMU,
+           "-x", "c++", SRC, "-x", "c++",
            os.path.join(EMU, "emu_support.cpp"), "-o", OUT]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:

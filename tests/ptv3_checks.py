@@ -220,6 +220,28 @@ def check_encode_pc_matches_oracle_and_reference_fixture(ops):
     assert [lv.n for lv in levels] == [fx[f"enc{s}"]["feat"].shape[0] for s in range(5)]
 
 
+def check_edge_cases_match_oracle(ops):
+    """All clouds missing; a single point; 1024 and 1025 points (exactly one patch / one full + a one-point patch that
+    attends to the last 1024 points); ragged batch order (cloud, None, None, cloud)."""
+    model, sd = make_model(ops)
+    bias = sd[P.PT + "project_pc.bias"].to(torch.bfloat16)
+    out = model([None, None])
+    assert eq(out, torch.stack([bias, bias]))
+    cases = [[P.synth_cloud(1, seed=30, box=(4, 4, 2))],
+             P.dedupe_clouds([P.synth_cloud(1024, seed=31, box=(30, 30, 2))]),
+             P.dedupe_clouds([P.synth_cloud(1031, seed=32, box=(30, 30, 2)), None, None,
+                              P.synth_cloud(60, seed=33, box=(8, 8, 2))])]
+    while len(cases[2][0]) > 1025:                       # trim to exactly 1025 points after de-duplication
+        cases[2][0] = cases[2][0][:1025]
+        cases[2] = P.dedupe_clouds(cases[2])
+    for clouds in cases:
+        torch.manual_seed(5)
+        got = model(clouds)
+        torch.manual_seed(5)
+        ref = P.encode_pc(sd, clouds)
+        assert rel(got, ref) < 4e-3, [None if c is None else len(c) for c in clouds]      # one bf16 rounding
+
+
 def check_bad_inputs_raise(ops):
     model, _ = make_model(ops)
     c = P.synth_cloud(200, seed=8, box=(10, 10, 3))
@@ -232,4 +254,4 @@ def check_bad_inputs_raise(ops):
 ALL = [check_grid_coords_and_codes_bit_exact, check_argsort_neighbors_pool_plan, check_gather_gemm_epilogues,
        check_gather_gemm_tiled_shapes,
        check_layernorm_segment_max_cloud_mean, check_patch_attention_matches_flash_semantics,
-       check_encode_pc_matches_oracle_and_reference_fixture, check_bad_inputs_raise]
+       check_encode_pc_matches_oracle_and_reference_fixture, check_edge_cases_match_oracle, check_bad_inputs_raise]
