@@ -438,6 +438,27 @@ int b200_pc_cloud_mean(const float* x, int ld, const int32_t* cloud_off, int n_c
                        float* out, int ldo, b200_stream_t stream);
 
 
+/* ---- fine-tuning of the small modality encoders and of embed_tokens (train_extras.cu) ----
+ * Seg-mask CNN (model/multimodal_projector/segmentation_map_feature_extractor.py:53-75) under training: the forward keeps
+ * every activation (fp32, `acts`), the backward is what torch autograd computes for the reference
+ * (`image_pooler.segmasks_encoder.*` is trainable, train/train.py:1257-1261): d_conv_w[l] [Cout, Cin, 3, 3], d_conv_b[l]
+ * [Cout], d_emb [30, 8], all fp32, overwritten or (accumulate) added to. d_out: bf16 token-gradient rows, map n reads
+ * row row_map[n] (or n), < 0 = no gradient. d_conv_w / d_conv_b are HOST arrays of 5 device pointers. */
+size_t b200_segmask_train_acts_bytes(int n_maps);
+int b200_segmask_forward_train(const b200_segmask_weights* w, const uint8_t* cls, int n_maps, void* acts,
+                               size_t acts_bytes, void* out, int64_t out_ld, const int32_t* out_row_map,
+                               b200_stream_t stream);
+size_t b200_segmask_backward_workspace_bytes(int n_maps);
+int b200_segmask_backward(const b200_segmask_weights* w, const uint8_t* cls, int n_maps, const void* acts,
+                          const void* d_out, int64_t d_ld, const int32_t* row_map, float* const* d_conv_w,
+                          float* const* d_conv_b, float* d_emb, int accumulate, void* workspace, size_t workspace_bytes,
+                          b200_stream_t stream);
+/* nn.Embedding backward for embed_tokens (language_model/llava_llama.py:93 -> HF LlamaModel.embed_tokens under autograd):
+ * d_table[seg_token[s], :] (+)= sum of the bf16 rows d_rows[row_list[j]] for j in [seg_start[s], seg_start[s+1]); the
+ * host groups the text rows by token id, so the sum order is fixed. */
+int b200_embed_grad(const void* d_rows, int64_t ld, const int32_t* row_list, const int32_t* seg_start,
+                    const int32_t* seg_token, int n_seg, int D, float* d_table, int accumulate, b200_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

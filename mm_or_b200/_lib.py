@@ -138,9 +138,18 @@ _SIGS = {
     "b200_pc_patch_attention": (ci, [vp, ci, vp, vp, ci, ci, ci, ci, cf, vp, ci, vp]),
     "b200_pc_segment_max": (ci, [vp, ci, vp, ci, ci, vp, vp, ci, vp, ci, vp]),
     "b200_pc_cloud_mean": (ci, [vp, ci, vp, ci, ci, vp, vp, ci, vp]),
+    # fine-tuning of the seg-mask CNN and embed_tokens (train_extras.cu)
+    "b200_segmask_train_acts_bytes": (sz, [ci]),
+    "b200_segmask_forward_train": (ci, [_P(SegmaskWeights), vp, ci, vp, sz, vp, i64, vp, vp]),
+    "b200_segmask_backward_workspace_bytes": (sz, [ci]),
+    "b200_segmask_backward": (ci, [_P(SegmaskWeights), vp, ci, vp, vp, i64, vp, _P(vp), _P(vp), vp, ci, vp, sz, vp]),
+    "b200_embed_grad": (ci, [vp, i64, vp, vp, vp, ci, ci, vp, ci, vp]),
 }
 
 PC_SYMBOLS = sorted(k for k in _SIGS if k.startswith("b200_pc_"))
+# entry points whose kernels also build for the host against the test-only kernel emulator (tests/emu/)
+EMULATABLE_SYMBOLS = PC_SYMBOLS + ["b200_segmask_train_acts_bytes", "b200_segmask_forward_train",
+                                   "b200_segmask_backward_workspace_bytes", "b200_segmask_backward", "b200_embed_grad"]
 
 EXPORTED_SYMBOLS = ["b200_last_error"] + sorted(_SIGS)
 
@@ -471,3 +480,62 @@ def prof_collect():
     check(lib().b200_prof_collect(ms, by, fl, la), "b200_prof_collect")
     return {lib().b200_prof_family_name(i).decode(): dict(ms=ms[i], bytes=by[i], flops=fl[i], launches=la[i])
             for i in range(n)}
+
+
+# ---- fine-tuning of the seg-mask CNN and embed_tokens (train_extras.cu) -------------------------------------------
+def segmask_forward_train(weights, cls, out, out_ld, row_map, cdll=None, ptr_fn=None, stream_fn=None):
+    """Forward of the seg-mask CNN that keeps its activations. weights: SegmaskWeights; cls (n, 32, 32) uint8.
+    Writes the bf16 token rows into `out` and returns the activation buffer for segmask_backward."""
+    cdll, ptr_fn, stream_fn = cdll or lib(), ptr_fn or ptr, stream_fn or stream_ptr
+    n = cls.shape[0]
+    acts = torch.empty(int(cdll.b200_segmask_train_acts_bytes(n)), dtype=torch.uint8, device=cls.device)
+    rc = cdll.b200_segmask_forward_train(ctypes.byref(weights), ptr_fn(cls), n, ptr_fn(acts), acts.numel(), ptr_fn(out),
+                                         out_ld, ptr_fn(row_map), stream_fn())
+    _check_with(cdll, rc, "b200_segmask_forward_train")
+    return acts
+
+
+def segmask_backward(weights, cls, acts, d_out, d_ld, row_map, d_conv_w, d_conv_b, d_emb, accumulate=False, cdll=None,
+                     ptr_fn=None, stream_fn=None):
+    """d_conv_w / d_conv_b: lists of 5 fp32 tensors, d_emb (30, 8) fp32: overwritten, or added to when accumulate."""
+    cdll, ptr_fn, stream_fn = cdll or lib(), ptr_fn or ptr, stream_fn or stream_ptr
+    n = cls.shape[0]
+    ws = torch.empty(int(cdll.b200_segmask_backward_workspace_bytes(n)), dtype=torch.uint8, device=cls.device)
+    pw = (ctypes.c_void_p * 5)(*[ptr_fn(t).value for t in d_conv_w])
+    pb = (ctypes.c_void_p * 5)(*[ptr_fn(t).value for t in d_conv_b])
+    rc = cdll.b200_segmask_backward(ctypes.byref(weights), ptr_fn(cls), n, ptr_fn(acts), ptr_fn(d_out), d_ld,
+                                    ptr_fn(row_map), pw, pb, ptr_fn(d_emb), int(accumulate), ptr_fn(ws), ws.numel(),
+                                    stream_fn())
+    _check_with(cdll, rc, "b200_segmask_backward")
+
+
+def embed_grad(d_rows, token_of_row, d_table, accumulate=False, cdll=None, ptr_fn=None, stream_fn=None):
+    """nn.Embedding backward: d_table[token] (+)= sum of the bf16 rows of d_rows whose token_of_row equals token
+    (token_of_row: host int array, < 0 = row carries no token). Rows are grouped by token on the host (stable), so the
+    summation order is fixed."""
+    import numpy as np
+    cdll, ptr_fn, stream_fn = cdll or lib(), ptr_fn or ptr, stream_fn or stream_ptr
+    tok = np.asarray(token_of_row).reshape(-1)
+    rows = np.nonzero(tok >= 0)[0]
+    if rows.size == 0:
+        return d_table
+    order = rows[np.argsort(tok[rows], kind="stable")]
+    sorted_tok = tok[order]
+    heads = np.nonzero(np.concatenate([[True], sorted_tok[1:] != sorted_tok[:-1]]))[0]
+    seg_start = np.concatenate([heads, [len(order)]]).astype(np.int32)
+    seg_token = sorted_tok[heads].astype(np.int32)
+    if int(seg_token.max()) >= d_table.shape[0]:
+        raise B200Error("embed_grad: token id outside the embedding table")
+    dev = d_rows.device
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a)).to(dev)
+    rc = cdll.b200_embed_grad(ptr_fn(d_rows), d_rows.stride(0), ptr_fn(t(order.astype(np.int32))), ptr_fn(t(seg_start)),
+                              ptr_fn(t(seg_token)), len(seg_token), d_rows.shape[1], ptr_fn(d_table), int(accumulate),
+                              stream_fn())
+    _check_with(cdll, rc, "b200_embed_grad")
+    return d_table
+
+
+def _check_with(cdll, rc, what):
+    if rc != 0:
+        msg = cdll.b200_last_error()
+        raise B200Error(f"{what} failed with code {rc}: {msg.decode() if msg else '?'}")

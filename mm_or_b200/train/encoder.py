@@ -7,8 +7,9 @@ multimodal_projector/builder.py:46-53,169-190 -> HF BertLayer) under torch autog
 "Dropout in training parity"). Every tensor operation here is a kernel of libb200mmor.so called through the C ABI;
 torch owns the memory. The frozen CLIP layers run through the inference stage entry point (b200_vit_forward).
 
-Not covered yet (raise / documented in DESIGN.md): gradients of the seg-mask CNN and of the audio projection, point
-clouds, dropout > 0.
+The extra-modality tokens of the pooler (builder.py:176-189) are covered by extras_forward / extras_backward: the audio
+projection and the seg-mask CNN train (csrc/train_extras.cu); the point-cloud token is computed but PointTransformerV3
+stays frozen (its training path -- BatchNorm batch statistics, drop-path -- is not built). Dropout > 0 is not covered.
 """
 import ctypes
 
@@ -248,6 +249,87 @@ def pooler_backward(pooler, cache, d_pooled, grads=None, accumulate=False):
     inv[gm[used]] = np.nonzero(used)[0].astype(np.int32)
     d_hidden = L.embed_rows(torch.as_tensor(inv).to(pooler.device), du, rows=N * T)
     return d_hidden.view(N, T, D), G.g
+
+
+# =====================================================================================================================
+# extra-modality tokens: pc (frozen), audio (Linear 512 -> 1024), seg-masks (5-layer CNN)   builder.py:93-167,176-189
+# =====================================================================================================================
+POOLX = "model.image_pooler."
+_SEG_CH = (8, 64, 128, 256, 512, 1024)
+_K_PAD = 64        # the weight-gradient GEMM contracts over the batch: padded with zero rows to one full K tile
+
+
+def extras_forward(pooler, tokens, keep, pc=None, audio=None, segmasks=None):
+    """tokens (B, T, D) bf16 whose [:, :keep] already holds the pooled image tokens: fills the extra tokens in the
+    pooler's fixed order pc, audio, seg0..2 (a modality contributes its slot(s) to every sample as soon as its kwarg is
+    not None) and returns the cache extras_backward needs."""
+    B, T, D = tokens.shape
+    dev = tokens.device
+    t = keep
+    cache = {}
+    if pc is not None:
+        if pooler.point_transformer is None:
+            raise L.B200Error("point clouds were passed but the checkpoint has no point_transformer weights")
+        pooler.point_transformer(pc, out=tokens[:, t])
+        t += 1
+    if audio is not None:                                                  # _encode_audio (builder.py:150-159)
+        rows = max(_K_PAD, -(-B // _K_PAD) * _K_PAD)
+        feats = torch.zeros((rows, 512), dtype=BF)
+        for i, a in enumerate(audio):
+            if a is not None:
+                feats[i] = a.detach().to("cpu", BF)
+        feats = feats.to(dev)
+        L.gemm(feats[:B], pooler.audio_w, out=tokens.view(B * T, D)[t::T], bias=pooler.audio_b)
+        cache["audio"] = (feats, t)
+        t += 1
+    if segmasks is not None:                                               # _encode_segmasks (builder.py:161-167)
+        if pooler._seg is None:
+            raise L.B200Error("seg-mask encoder weights not loaded")
+        tokens[:, t:t + 3].zero_()
+        maps, rows = [], []
+        for i, sm in enumerate(segmasks):
+            if sm is not None:
+                for j, m in enumerate(sm):
+                    if tuple(m.shape) != (32, 32):
+                        raise AssertionError(f"Expected input size (batch_size, 32, 32), but got {tuple(m.shape)}")
+                    maps.append(m.detach().to("cpu", torch.uint8))
+                    rows.append(i * T + t + j)
+        if maps:
+            cls = torch.stack(maps).contiguous().to(dev)
+            rm = torch.as_tensor(np.asarray(rows, dtype=np.int32)).to(dev)
+            acts = L.segmask_forward_train(pooler._seg[0], cls, tokens, D, rm)
+            cache["seg"] = (cls, rm, acts)
+        t += 3
+    if t != T:
+        raise ValueError(f"token buffer holds {T} tokens but the modalities passed need {t}")
+    return cache
+
+
+def extras_backward(pooler, cache, d_tokens, grads=None, accumulate=False):
+    """d_tokens (B, T, D) bf16, gradient w.r.t. the pooler's output tokens -> gradients of project_audio and of the
+    seg-mask CNN under the reference's names. A modality that is absent from the batch leaves no entry (its parameters
+    are skipped by the optimizer step, like parameters whose .grad is None in torch)."""
+    G = _Grads(grads, accumulate, d_tokens.device)
+    B, T, D = d_tokens.shape
+    if "audio" in cache:
+        feats, t = cache["audio"]
+        dy = torch.zeros((feats.shape[0], D), device=d_tokens.device, dtype=BF)
+        dy[:B] = d_tokens[:, t]
+        _lin_bwd(G, feats, pooler.audio_w, dy, POOLX + "project_audio.weight", POOLX + "project_audio.bias",
+                 need_dx=False)
+    if "seg" in cache:
+        cls, rm, acts = cache["seg"]
+        p = POOLX + "segmasks_encoder."
+        dW, dB = [], []
+        acc = False
+        for i in range(5):
+            w, acc = G.slot(p + f"conv{i + 1}.weight", (_SEG_CH[i + 1], _SEG_CH[i], 3, 3))
+            b, _ = G.slot(p + f"conv{i + 1}.bias", (_SEG_CH[i + 1],))
+            dW.append(w)
+            dB.append(b)
+        dE, _ = G.slot(p + "embedding.weight", (30, 8))
+        L.segmask_backward(pooler._seg[0], cls, acts, d_tokens.view(B * T, D), D, rm, dW, dB, dE, accumulate=acc)
+    return G.g
 
 
 def projector_forward(proj, tokens):

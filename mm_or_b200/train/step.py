@@ -8,8 +8,9 @@ biases), lr / mm_projector_lr from the training arguments (README.md:147-151: lr
 Everything numeric runs in libb200mmor.so through the C ABI; master weights, m and v are fp32 under the reference's
 parameter names, and the model's fused bf16 working copies are rebuilt from them after every update.
 
-Frozen here (documented in DESIGN.md): embed_tokens, CLIP embeddings and the CLIP layers below
-`first_trainable_clip_layer`, the seg-mask CNN and the audio projection (no backward kernels yet).
+Frozen here (documented in DESIGN.md): CLIP embeddings and the CLIP layers below `first_trainable_clip_layer`,
+PointTransformerV3 (its token is computed, its training path is not built), and embed_tokens unless
+`train_embed_tokens=True` (full fine-tuning; the reference's LoRA recipe keeps it frozen).
 """
 import numpy as np
 import torch
@@ -30,6 +31,8 @@ def default_trainable(name, first_clip_layer):
     if name.startswith("model.image_pooler.bert."):
         # word_embeddings (vocab_size = 1) and the BertPooler head are never used by the path (builder.py:173-175)
         return not ("word_embeddings" in name or ".pooler." in name)
+    if name.startswith("model.image_pooler.project_audio.") or name.startswith("model.image_pooler.segmasks_encoder."):
+        return True                                          # the whole image_pooler trains (train.py:1257-1261)
     p = E.VIT + "encoder.layers."
     if name.startswith(p):
         return int(name[len(p):].split(".")[0]) >= first_clip_layer
@@ -44,7 +47,7 @@ def no_decay(name):
 class FineTuner:
     def __init__(self, model, state_dict, lr=2e-5, mm_projector_lr=None, betas=(0.9, 0.999), eps=1e-8,
                  weight_decay=0.0, max_grad_norm=0.1, first_trainable_clip_layer=12, vocab_weight=None,
-                 trainable=None, lora=None):
+                 trainable=None, lora=None, train_embed_tokens=False):
         """lora: a train.lora.LoraState -> the reference's LoRA recipe (train.py:1159-1175): the decoder's base
         weights, norms and lm_head are frozen, the adapters train next to mm_projector / image_pooler / CLIP layers."""
         self.model = model
@@ -54,7 +57,10 @@ class FineTuner:
         self.betas, self.eps, self.wd, self.max_norm = betas, eps, weight_decay, max_grad_norm
         self.vocab_weight = vocab_weight
         self.lora = lora
-        pick = trainable if trainable is not None else (lambda n: default_trainable(n, first_trainable_clip_layer))
+        self.train_embed = bool(train_embed_tokens) and lora is None
+        pick = trainable if trainable is not None else (
+            lambda n: default_trainable(n, first_trainable_clip_layer) or
+            (self.train_embed and n == "model.embed_tokens.weight"))
         if lora is not None:
             base_pick = pick
             pick = lambda n: base_pick(n) and not (n.startswith("model.layers.") or n in ("model.norm.weight",
@@ -83,16 +89,18 @@ class FineTuner:
 
     @staticmethod
     def _has_backward(name, n_run):
-        if name.startswith("model.image_pooler.") and not name.startswith("model.image_pooler.bert."):
-            return False                                     # seg-mask CNN / audio projection: no backward kernels yet
+        if name.startswith("model.image_pooler.point_transformer."):
+            return False                                     # PointTransformerV3 stays frozen (no training path)
         p = E.VIT + "encoder.layers."
         if name.startswith(p):
             return int(name[len(p):].split(".")[0]) < n_run
         return True
 
     # ------------------------------------------------------------------------------------------------------------
-    def forward_backward(self, input_ids, labels, attention_mask, images, grads=None, accumulate=False):
-        """Returns (loss, weight sum, grads under the reference's names)."""
+    def forward_backward(self, input_ids, labels, attention_mask, images, grads=None, accumulate=False, pc=None,
+                         audio=None, segmasks=None):
+        """Returns (loss, weight sum, grads under the reference's names). pc / audio / segmasks as in
+        LlavaLlamaForCausalLM.forward (llava_llama.py:54-70): lists with one entry (or None) per sample."""
         model, dev = self.model, self.dev
         cfg = model.config
         tower, pooler, proj = model.get_vision_tower(), model.get_image_pooler(), model.get_model().mm_projector
@@ -100,15 +108,23 @@ class FineTuner:
         concat, split = model._images_to_batch(images)
         B = len(split)
         hidden, vc = E.vit_forward(tower, concat, self.first_clip)
-        pooled, pc = E.pooler_forward(pooler, hidden, split)
-        vis, prc = E.projector_forward(proj, pooled.reshape(B * keep, Dv).contiguous())
+        pooled, pcache = E.pooler_forward(pooler, hidden, split)
+        Tv = keep + pooler.num_extra_tokens(pc, audio, segmasks)              # tokens per sample (builder.py:176-189)
+        if Tv == keep:
+            tokens, xcache = pooled.reshape(B * keep, Dv).contiguous(), {}
+        else:
+            tok3 = torch.empty((B, Tv, Dv), device=dev, dtype=BF)
+            tok3[:, :keep] = pooled
+            xcache = E.extras_forward(pooler, tok3, keep, pc, audio, segmasks)
+            tokens = tok3.view(B * Tv, Dv)
+        vis, prc = E.projector_forward(proj, tokens)
         plan = plan_pack(input_ids.cpu().numpy(), None if attention_mask is None else attention_mask.cpu().numpy(),
-                         None if labels is None else labels.cpu().numpy(), keep, "right",
+                         None if labels is None else labels.cpu().numpy(), Tv, "right",
                          getattr(cfg, "tokenizer_model_max_length", None))
         Lq = plan.L
         src = plan.src.reshape(B, Lq).astype(np.int64)
         text_ids = np.where(src >= -1, src, -2).astype(np.int32)
-        vis_ids = np.where(src <= -2, np.arange(B)[:, None] * keep + (-2 - src), -2).astype(np.int32)
+        vis_ids = np.where(src <= -2, np.arange(B)[:, None] * Tv + (-2 - src), -2).astype(np.int32)
         embeds = torch.empty((B * Lq, D), device=dev, dtype=BF)
         L.embed_rows(torch.as_tensor(text_ids.reshape(-1)).to(dev), model.model.embed_tokens, out=embeds)
         L.embed_rows(torch.as_tensor(vis_ids.reshape(-1)).to(dev), vis, out=embeds)
@@ -117,9 +133,18 @@ class FineTuner:
                                                   grads=grads, accumulate=accumulate, lora=self.lora,
                                                   train_base=self.lora is None)
         # pack backward: visual rows of d_embeds back to the projector output (truncated tokens get zeros)
-        d_vis = L.embed_rows(torch.as_tensor(plan.row_map).to(dev), d_emb.reshape(B * Lq, D), rows=B * keep)
+        d_vis = L.embed_rows(torch.as_tensor(plan.row_map).to(dev), d_emb.reshape(B * Lq, D), rows=B * Tv)
+        if self.train_embed:                                   # nn.Embedding backward over the text rows
+            dst, acc = E._Grads(g, accumulate, dev).slot("model.embed_tokens.weight",
+                                                         tuple(model.model.embed_tokens.shape))
+            if not acc:
+                dst.zero_()
+            L.embed_grad(d_emb.reshape(B * Lq, D), text_ids.reshape(-1), dst, accumulate=True)
         dx, g = E.projector_backward(proj, prc, d_vis, grads=g, accumulate=accumulate)
-        d_hidden, g = E.pooler_backward(pooler, pc, dx.view(B, keep, Dv), grads=g, accumulate=accumulate)
+        dx3 = dx.view(B, Tv, Dv)
+        if xcache:
+            g = E.extras_backward(pooler, xcache, dx3, grads=g, accumulate=accumulate)
+        d_hidden, g = E.pooler_backward(pooler, pcache, dx3[:, :keep], grads=g, accumulate=accumulate)
         g = E.vit_backward(tower, vc, d_hidden, grads=g, accumulate=accumulate)
         return loss, wsum, g
 
@@ -133,10 +158,13 @@ class FineTuner:
             g.update(self.lora.unfuse_grads(grads))
         self.step_count += 1
         out2 = torch.zeros(2, device=self.dev, dtype=torch.float32)
-        for i, k in enumerate(self.names):
+        # parameters that received no gradient this step (a modality absent from the batch) are skipped by the norm and
+        # by AdamW, like parameters whose .grad is None in torch
+        names = [k for k in self.names if k in g]
+        for i, k in enumerate(names):
             L.grad_sq_norm(g[k].contiguous(), out2=out2, accumulate=i > 0, max_norm=self.max_norm)
         clip = out2[1:]
-        for k in self.names:
+        for k in names:
             lr = self.proj_lr if k.startswith("model.mm_projector.") else self.lr
             wd = 0.0 if no_decay(k) else self.wd
             L.adamw_step(self.master[k], self.sd[k], g[k].contiguous(), self.m[k], self.v[k], lr, self.betas[0],
@@ -157,8 +185,9 @@ class FineTuner:
         m.image_pooler.load_weights(self.sd, self.dev)
         m.mm_projector.load_weights(self.sd, self.dev)
 
-    def train_step(self, input_ids, labels, attention_mask, images):
-        loss, wsum, grads = self.forward_backward(input_ids, labels, attention_mask, images)
+    def train_step(self, input_ids, labels, attention_mask, images, pc=None, audio=None, segmasks=None):
+        loss, wsum, grads = self.forward_backward(input_ids, labels, attention_mask, images, pc=pc, audio=audio,
+                                                  segmasks=segmasks)
         self.last_grads = grads
         norm_sq = self.optimizer_step(grads)
         return loss, norm_sq

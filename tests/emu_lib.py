@@ -1,4 +1,4 @@
-"""TEST INFRASTRUCTURE: builds and loads tests/emu/_build/libb200emu.so -- mm_or_b200/csrc/ptv3.cu compiled with g++
+"""TEST INFRASTRUCTURE: builds and loads tests/emu/_build/libb200emu.so -- mm_or_b200/csrc/{ptv3,train_extras}.cu compiled with g++
 -DB200_EMU against the CUDA-kernel emulator of tests/emu/cuda_emu.h -- and binds it like mm_or_b200/_lib.py binds the real
 library, so that the CPU test-suite executes the SAME kernel source (and the same host orchestration,
 mm_or_b200/model/point_transformer.py) against the oracle. Never imported by the product."""
@@ -13,7 +13,8 @@ from mm_or_b200.model.point_transformer import PcOps
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 EMU = os.path.join(HERE, "emu")
-SRC = os.path.join(HERE, "..", "mm_or_b200", "csrc", "ptv3.cu")
+CSRC = os.path.join(HERE, "..", "mm_or_b200", "csrc")
+SRCS = [os.path.join(CSRC, "ptv3.cu"), os.path.join(CSRC, "train_extras.cu")]
 _lib = None
 
 
@@ -35,13 +36,15 @@ OUT = os.path.join(EMU, "_build", "libb200emu_fma.so" if FMA else "libb200emu.so
 
 
 def build():
-    deps = [SRC, os.path.join(EMU, "cuda_emu.h"), os.path.join(EMU, "emu_common.h"), os.path.join(EMU, "emu_support.cpp")]
+    deps = SRCS + [os.path.join(EMU, "cuda_emu.h"), os.path.join(EMU, "emu_common.h"),
+                   os.path.join(EMU, "emu_support.cpp"), os.path.join(HERE, "..", "include", "b200_mmor.h")]
     if os.path.exists(OUT) and os.path.getmtime(OUT) >= max(os.path.getmtime(d) for d in deps):
         return OUT
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
-    cmd = ["g++", "-O2"] + (["-mfma"] if FMA else []) + ["-std=c++17", "-fPIC", "-shared", "-DB200_EMU", "-I" + EMU,
-           "-x", "c++", SRC, "-x", "c++",
-           os.path.join(EMU, "emu_support.cpp"), "-o", OUT]
+    cmd = ["g++", "-O2"] + (["-mfma"] if FMA else []) + ["-std=c++17", "-fPIC", "-shared", "-DB200_EMU", "-I" + EMU]
+    for src in SRCS + [os.path.join(EMU, "emu_support.cpp")]:
+        cmd += ["-x", "c++", src]
+    cmd += ["-o", OUT]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("emulator build failed:\n" + r.stderr)
@@ -53,7 +56,7 @@ def lib():
     if _lib is None:
         cdll = ctypes.CDLL(build())
         cdll.b200_last_error.restype = ctypes.c_char_p
-        for name in L.PC_SYMBOLS:
+        for name in L.EMULATABLE_SYMBOLS:
             fn = getattr(cdll, name)
             fn.restype, fn.argtypes = L._SIGS[name]
         assert cdll.b200_emu_marker() == 1

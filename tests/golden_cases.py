@@ -41,8 +41,15 @@ CASES = {
 }
 
 
+# cases without a recorded fixture (compared against the oracle only)
+EXTRA_CASES = {
+    "train_extras_right": dict(batch=3, views=[2, 1, 2], text_len=22, jitter=5, image_pos=4, audio=True, segmasks=True,
+                               side="right", labels=True, seed=4),
+}
+
+
 def make_case(cfg, name, dtype=torch.float32):
-    c = CASES[name]
+    c = CASES[name] if name in CASES else EXTRA_CASES[name]
     b = synth_batch(cfg, c["batch"], max(c["views"]), c["text_len"], seed=c["seed"], jitter=c["jitter"],
                     image_pos=c["image_pos"], audio=c["audio"], segmasks=c["segmasks"], dtype=dtype)
     b["images"] = [im[:v].contiguous() for im, v in zip(b["images"], c["views"])]

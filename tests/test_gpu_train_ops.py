@@ -399,7 +399,8 @@ def test_fine_tune_step_end_to_end(L):
     opt = torch.optim.AdamW([{"params": decay, "weight_decay": 0.01}, {"params": nodecay, "weight_decay": 0.0}],
                             lr=1e-3, betas=(0.9, 0.999), eps=1e-8)
     for k in ft.names:
-        tp[k].grad = grads_named[k].clone()
+        if k in grads_named:           # modalities absent from the batch (audio / seg-masks) leave no gradient,
+            tp[k].grad = grads_named[k].clone()   # like .grad = None in torch: skipped by clip and AdamW
     torch.nn.utils.clip_grad_norm_(list(tp.values()), 0.1)
     opt.step()
     ft.optimizer_step(grads)

@@ -25,8 +25,11 @@ def test_codes_match_reference_fixture(ops, order):
 def test_product_never_uses_the_emulator():
     """The emulator library lives under tests/ and the product binding only ever opens libb200mmor.so."""
     import inspect
+    import re
     from mm_or_b200 import _lib as L
     from mm_or_b200.model import point_transformer as PT
-    assert "emu" not in inspect.getsource(L) .lower().replace("enumerate", "")
+    src = inspect.getsource(L)
+    assert "libb200emu" not in src and "emu_lib" not in src
+    assert re.findall(r"CDLL\((\w+)\)", src) == ["LIB_PATH"]
     assert "tests" not in inspect.getsource(PT.PcOps.cuda)
     assert L.LIB_PATH.endswith("libb200mmor.so")

@@ -29,17 +29,20 @@ def test_no_decay_matches_reference_groups():
 def test_default_trainable_set():
     yes = ["model.layers.0.self_attn.v_proj.weight", "model.norm.weight", "lm_head.weight", "model.mm_projector.0.bias",
            "model.image_pooler.bert.encoder.layer.0.output.dense.weight", VIT + "encoder.layers.12.mlp.fc2.bias",
-           VIT + "encoder.layers.22.layer_norm2.weight"]
+           VIT + "encoder.layers.22.layer_norm2.weight", "model.image_pooler.project_audio.weight",
+           "model.image_pooler.segmasks_encoder.conv3.bias", "model.image_pooler.segmasks_encoder.embedding.weight"]
     no = ["model.embed_tokens.weight", VIT + "encoder.layers.11.mlp.fc2.bias", VIT + "embeddings.class_embedding",
           VIT + "pre_layrnorm.weight", "model.image_pooler.bert.embeddings.word_embeddings.weight",
-          "model.image_pooler.bert.pooler.dense.weight"]
+          "model.image_pooler.bert.pooler.dense.weight",
+          "model.image_pooler.point_transformer.enc.enc0.block0.attn.qkv.weight"]
     assert all(default_trainable(n, 12) for n in yes)
     assert not any(default_trainable(n, 12) for n in no)
-    # layers past the selected hidden state never run; seg-mask / audio modules have no backward kernels yet
+    # layers past the selected hidden state never run; PointTransformerV3 has no training path (stays frozen)
     assert not FineTuner._has_backward(VIT + "encoder.layers.23.mlp.fc1.weight", 23)
     assert FineTuner._has_backward(VIT + "encoder.layers.22.mlp.fc1.weight", 23)
-    assert not FineTuner._has_backward("model.image_pooler.segmasks_encoder.conv1.weight", 23)
-    assert not FineTuner._has_backward("model.image_pooler.project_audio.weight", 23)
+    assert FineTuner._has_backward("model.image_pooler.segmasks_encoder.conv1.weight", 23)
+    assert FineTuner._has_backward("model.image_pooler.project_audio.weight", 23)
+    assert not FineTuner._has_backward("model.image_pooler.point_transformer.project_pc.weight", 23)
 
 
 def test_unfuse_grads_inverts_the_fused_layouts():
