@@ -528,8 +528,11 @@ def embed_grad(d_rows, token_of_row, d_table, accumulate=False, cdll=None, ptr_f
         raise B200Error("embed_grad: token id outside the embedding table")
     dev = d_rows.device
     t = lambda a: torch.as_tensor(np.ascontiguousarray(a)).to(dev)
-    rc = cdll.b200_embed_grad(ptr_fn(d_rows), d_rows.stride(0), ptr_fn(t(order.astype(np.int32))), ptr_fn(t(seg_start)),
-                              ptr_fn(t(seg_token)), len(seg_token), d_rows.shape[1], ptr_fn(d_table), int(accumulate),
+    # the index tensors must outlive the launch: a temporary freed inside the call expression hands its block to the
+    # next allocation, and all three arrays would alias
+    row_list, seg_start_d, seg_token_d = t(order.astype(np.int32)), t(seg_start), t(seg_token)
+    rc = cdll.b200_embed_grad(ptr_fn(d_rows), d_rows.stride(0), ptr_fn(row_list), ptr_fn(seg_start_d),
+                              ptr_fn(seg_token_d), len(seg_token), d_rows.shape[1], ptr_fn(d_table), int(accumulate),
                               stream_fn())
     _check_with(cdll, rc, "b200_embed_grad")
     return d_table

@@ -580,11 +580,11 @@ class LlavaLlamaForCausalLM:
             text_ids = np.where(src >= -1, src, -2).astype(np.int32)
             vis_ids = np.where(src <= -2, np.arange(B)[:, None] * t_vis + (-2 - src), -2).astype(np.int32)
             lib = L.lib()
-            L.check(lib.b200_embed_rows(L.ptr(_i32(text_ids.reshape(-1), self.device)), L.ptr(self.model.embed_tokens),
-                                        L.ptr(embeds), D, B * plan.L, D, self.config.vocab_size, L.stream_ptr()),
-                    "b200_embed_rows")
-            L.check(lib.b200_embed_rows(L.ptr(_i32(vis_ids.reshape(-1), self.device)), L.ptr(vis), L.ptr(embeds), D,
-                                        B * plan.L, D, B * t_vis, L.stream_ptr()), "b200_embed_rows")
+            text_dev, vis_dev = _i32(text_ids.reshape(-1), self.device), _i32(vis_ids.reshape(-1), self.device)
+            L.check(lib.b200_embed_rows(L.ptr(text_dev), L.ptr(self.model.embed_tokens), L.ptr(embeds), D, B * plan.L, D,
+                                        self.config.vocab_size, L.stream_ptr()), "b200_embed_rows")
+            L.check(lib.b200_embed_rows(L.ptr(vis_dev), L.ptr(vis), L.ptr(embeds), D, B * plan.L, D, B * t_vis,
+                                        L.stream_ptr()), "b200_embed_rows")
         new_labels = None if labels is None else torch.from_numpy(plan.labels).to(self.device)
         am = None if attention_mask is None else torch.from_numpy(plan.mask).to(self.device).to(attention_mask.dtype)
         pos = None if position_ids is None else torch.from_numpy(plan.pos).to(self.device)
