@@ -65,3 +65,8 @@ def test_generate_with_point_clouds_matches_oracle():
     toks, ref_lg = O.greedy_decode(sd, ocfg, ref["logits"][:, -1], ref["kv"], ref["mask"], 3, stop_on_eos=False)
     assert rel_err(lg, ref_lg) < TOL_E2E
     assert out.shape[1] == case["input_ids"].shape[1] + 3
+    # the same batch was recorded from the reference's own forward (tests/golden/make_pc_golden.py)
+    import os
+    fx = torch.load(os.path.join(gc.GOLDEN_DIR, "pc_left.pt"))
+    assert fx["shuffle_seed"] == 77 and [None if c is None else len(c) for c in pcs] == fx["n_points"]
+    assert rel_err(lg[:, :3], fx["greedy_logits"][:, :3].float()) < TOL_E2E

@@ -82,3 +82,31 @@ def test_explicit_perms_equal_global_rng():
     a = P.encode_pc(sd, clouds)
     b = P.encode_pc(sd, clouds, perms=perms)
     assert torch.equal(a, b)
+
+
+def test_full_model_with_point_clouds_matches_reference_fixture():
+    """pc + audio + seg-masks through the whole oracle (token order pooled, pc, audio, seg x 3; prefill logits; greedy
+    continuation) against tests/golden/pc_left.pt, recorded from the reference's own LlavaLlamaForCausalLM.forward
+    (tests/golden/make_pc_golden.py)."""
+    from helpers import oracle_cfg
+    from oracle import mm2sg_oracle as O
+    fx = torch.load(os.path.join(gc.GOLDEN_DIR, "pc_left.pt"))
+    cfg = gc.small_config()
+    sd = gc.small_weights(cfg)
+    sd.update(P.synth_weights())
+    sd = gc.bf16_round(sd)
+    case = gc.make_case(cfg, "extras_left")
+    pcs = P.dedupe_clouds([P.synth_cloud(1300, seed=21), None, P.synth_cloud(300, seed=22, box=(16, 16, 3))])
+    assert [None if c is None else len(c) for c in pcs] == fx["n_points"]
+    torch.manual_seed(fx["shuffle_seed"])
+    with torch.no_grad():
+        out = O.multimodal_prefill(sd, oracle_cfg(cfg), case["input_ids"], case["attention_mask"], case["images"],
+                                   audio=case["audio"], segmasks=case["segmasks"], pc=pcs, padding_side="left")
+        toks, lg = O.greedy_decode(sd, oracle_cfg(cfg), out["logits"][:, -1], out["kv"], out["mask"],
+                                   fx["greedy_ids"].shape[1], stop_on_eos=False)
+    rel = lambda a, b: ((a.float() - b.float()).norm() / b.float().norm()).item()
+    assert out["visual"].shape[1] == 581
+    assert rel(out["visual"][:, 570:], fx["visual_tail"]) < TOL_F32
+    assert rel(out["logits"][:, -1], fx["logits_last"]) < TOL_F32
+    assert torch.equal(toks, fx["greedy_ids"])
+    assert rel(lg, fx["greedy_logits"]) < 1e-3                      # fp16-compressed fixture
