@@ -1,0 +1,71 @@
+"""GPU parity cases named after BASELINE.json's configs, at the small parity configuration (the headline configs[1] is
+what bench.py measures at full size; configs[3] / [4] are covered by tests/test_gpu_dist.py and
+tests/test_gpu_train_ops.py):
+  configs[0]  single 336x336 frame (list form, one view) -> greedy 32 tokens
+  configs[2]  6-view RGB + depth + seg-mask renderings (18 encoder passes per sample) + audio embedding + seg-mask
+              class maps, fused multimodal token pack. Mapping: the reference has no depth-image or
+              seg-mask-image input, so the 18 frames go through the ViT (checked against the oracle frame by frame),
+              the 6 RGB views through the pooler, and audio / 32x32 class maps give the 1 + 3 extra tokens (T_vis = 580).
+"""
+import pytest
+import torch
+
+import golden_cases as gc
+from helpers import TOL_E2E, TOL_STAGE, oracle_cfg, rel_err
+from mm_or_b200.synth import synth_batch
+from oracle import mm2sg_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def env():
+    torch.set_grad_enabled(False)
+    from mm_or_b200.model.llava_llama import LlavaLlamaForCausalLM
+    cfg = gc.small_config()
+    sd = gc.bf16_round(gc.small_weights(cfg))
+    model = LlavaLlamaForCausalLM(cfg).load_state_dict(sd)
+    model.config.tokenizer_padding_side = "left"
+    return cfg, oracle_cfg(cfg), sd, model
+
+
+def test_config0_single_frame_greedy_32(env):
+    cfg, ocfg, sd, model = env
+    b = synth_batch(cfg, 1, 1, 64, seed=50, jitter=0, image_pos=40)
+    ids, images = b["input_ids"], b["images"]                      # images: list with one (1, 3, 336, 336) tensor
+    assert images[0].shape[0] == 1 and int((ids == -200).sum()) == 1
+    steps = 32
+    out, lg = model.generate(ids, images=images, do_sample=False, use_cache=True, max_new_tokens=steps,
+                             stop_on_eos=False, return_logits=True)
+    ref = O.multimodal_prefill(sd, ocfg, ids, b["attention_mask"], images, padding_side="left")
+    toks, ref_lg = O.greedy_decode(sd, ocfg, ref["logits"][:, -1], ref["kv"], ref["mask"], steps, stop_on_eos=False)
+    assert out.shape == (1, ids.shape[1] + steps) and torch.equal(out[:, :ids.shape[1]].cpu(), ids)
+    assert rel_err(lg, ref_lg) < TOL_E2E
+    err = (lg.cpu().float() - ref_lg).abs().max().item()
+    top2 = ref_lg.topk(2, -1).values
+    safe = (top2[..., 0] - top2[..., 1]) > 2 * err
+    assert torch.equal(out[:, ids.shape[1]:].cpu()[safe], toks[safe])
+
+
+def test_config2_rgb_depth_seg_audio_pack(env):
+    cfg, ocfg, sd, model = env
+    B, V = 2, 6
+    b = synth_batch(cfg, B, V, 24, seed=51, jitter=3, image_pos=5, audio=True, segmasks=True)
+    extra = synth_batch(cfg, B, 2 * V, 24, seed=52)["images"]      # the depth and seg-mask renderings: 12 more frames
+    frames = torch.cat([torch.cat([rgb, ex], 0) for rgb, ex in zip(b["images"], extra)], 0)     # (B * 18, 3, S, S)
+    assert frames.shape[0] == B * 18
+    feats = model.get_vision_tower()(frames.cuda())
+    ref_feats = O.clip_tower_forward(sd, frames, ocfg.vit)
+    assert feats.shape == ref_feats.shape == (B * 18, 576, 1024)
+    assert rel_err(feats, ref_feats) < TOL_STAGE
+    # RGB views + audio + class maps through pooler, projector and pack
+    out, lg = model.generate(b["input_ids"], images=b["images"], audio=b["audio"], segmasks=b["segmasks"],
+                             max_new_tokens=4, stop_on_eos=False, return_logits=True)
+    ref = O.multimodal_prefill(sd, ocfg, b["input_ids"], b["attention_mask"], b["images"], audio=b["audio"],
+                               segmasks=b["segmasks"], padding_side="left")
+    assert ref["visual"].shape[1] == 580
+    toks, ref_lg = O.greedy_decode(sd, ocfg, ref["logits"][:, -1], ref["kv"], ref["mask"], 4, stop_on_eos=False)
+    assert rel_err(lg, ref_lg) < TOL_E2E
+    pooled = model.encode_images_pooled(torch.cat(b["images"], 0).cuda(), [V] * B, None, b["audio"], b["segmasks"])
+    visual = model.get_model().mm_projector(pooled)
+    assert visual.shape == ref["visual"].shape and rel_err(visual, ref["visual"]) < TOL_STAGE
