@@ -76,6 +76,24 @@ def average_gradients(grads, names, group=None):
     return out
 
 
+def align_optional_gradients(grads, optional, group=None):
+    """Gradients of modality-specific parameters (audio projection, seg-mask CNN, embed_tokens) exist only on ranks
+    whose local batch carried the modality. After this call every rank holds the same keys, so the per-key collectives
+    of average_gradients line up: a gradient present on ANY rank exists everywhere (zeros where the local batch did not
+    produce it -- what DDP does for parameters unused on a rank), one present nowhere stays absent everywhere (the
+    optimizer skips it, like .grad = None). `optional`: {name: shape}."""
+    names = sorted(optional)
+    if not names:
+        return grads
+    dev = next(iter(grads.values())).device if grads else torch.device("cpu")
+    flags = torch.tensor([1 if k in grads else 0 for k in names], dtype=torch.int32, device=dev)
+    dist.all_reduce(flags, op=dist.ReduceOp.MAX, group=group)
+    for k, f in zip(names, flags.tolist()):
+        if f and k not in grads:
+            grads[k] = torch.zeros(tuple(optional[k]), dtype=torch.float32, device=dev)
+    return grads
+
+
 class PeerGather:
     """Symmetric (world, B_local, T, D) bf16 buffer on every rank with every peer's base pointer, for the fused
     projector-GEMM + all-gather epilogue. Needs CUDA, NVLink peer access and torch symmetric memory."""

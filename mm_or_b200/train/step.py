@@ -151,8 +151,12 @@ class FineTuner:
     def optimizer_step(self, grads):
         """clip_grad_norm_(max_grad_norm) over the trainable set + AdamW; rebuilds the fused bf16 working weights."""
         if self.group is not None:
-            from ..dist import average_gradients
-            average_gradients(grads, list(grads), self.group)      # in place on the (contiguous) fused gradients
+            from ..dist import align_optional_gradients, average_gradients
+            optional = {k: tuple(v.shape) for k, v in self.master.items()
+                        if k == "model.embed_tokens.weight" or k.startswith(("model.image_pooler.project_audio.",
+                                                                             "model.image_pooler.segmasks_encoder."))}
+            align_optional_gradients(grads, optional, self.group)  # ranks whose batch lacked a modality contribute zeros
+            average_gradients(grads, sorted(grads), self.group)    # in place on the (contiguous) fused gradients
         g = T.unfuse_grads(grads, self.model.config)
         if self.lora is not None:
             g.update(self.lora.unfuse_grads(grads))

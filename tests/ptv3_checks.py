@@ -242,6 +242,35 @@ def check_edge_cases_match_oracle(ops):
         assert rel(got, ref) < 4e-3, [None if c is None else len(c) for c in clouds]      # one bf16 rounding
 
 
+def check_entry_points_reject_bad_arguments(ops):
+    """Every b200_pc_* entry point returns -2 and leaves a message (no launch) for arguments it cannot serve."""
+    d = lambda t: t.to(ops.device)
+    lib, p, st = ops.lib, ops.ptr, ops.stream
+    f32, i32, i64 = (lambda *s: d(torch.zeros(*s))), (lambda *s: d(torch.zeros(*s, dtype=torch.int32))), \
+        (lambda *s: d(torch.zeros(*s, dtype=torch.int64)))
+    x, g, b, c = f32(8, 6), i32(8, 3), i32(8), i64(8)
+    bad = [
+        lib.b200_pc_grid_coords(p(x), 6, 0, 0.01, p(f32(3)), p(g), p(i32(1)), st()),            # n = 0
+        lib.b200_pc_grid_coords(p(x), 6, 8, 0.0, p(f32(3)), p(g), p(i32(1)), st()),             # grid size 0
+        lib.b200_pc_encode(p(g), p(b), 8, 17, 0, p(c), st()),                                   # depth > 16
+        lib.b200_pc_encode(p(g), p(b), 8, 4, 4, p(c), st()),                                    # unknown order
+        lib.b200_pc_argsort(p(c), 8, 12, p(c), p(b), p(f32(1)), 4, st()),                       # workspace too small
+        lib.b200_pc_neighbors(p(c), p(g), p(b), 8, 4, 4, p(i32(8, 64)), p(i32(1)), st()),       # kernel size 4
+        lib.b200_pc_pool_plan(p(c), p(g), p(b), 8, 5, p(i32(9)), p(i32(1)), p(g), p(b), st()),  # pooling depth 5
+        lib.b200_pc_gemm_f32(p(x), 6, None, 2, p(f32(12, 4)), None, None, None, 0, None, 0, p(f32(8, 4)), 4, 0, 8, 4, 6,
+                             st()),                                                             # taps without indices
+        lib.b200_pc_gemm_f32(p(x), 6, None, 1, p(f32(6, 4)), None, None, None, 1, None, 0, p(f32(8, 4)), 4, 0, 8, 4, 6,
+                             st()),                                                             # unsupported activation
+        lib.b200_pc_layernorm_f32(p(x), 4, p(f32(6)), p(f32(6)), 1e-5, None, 0, p(f32(8, 6)), 6, 8, 6, st()),  # ld < C
+        lib.b200_pc_patch_attention(p(f32(8, 96)), 96, p(b), p(i32(1, 4)), 1, 8, 32, 4, 0.25, p(f32(8, 32)), 32,
+                                    st()),                                                      # head_dim 8
+        lib.b200_pc_segment_max(p(x), 6, p(i32(3)), 2, 6, p(f32(6)), None, 0, p(f32(2, 6)), 6, st()),  # scale w/o shift
+        lib.b200_pc_cloud_mean(p(x), 6, p(i32(2)), 0, 6, p(i32(1)), p(f32(1, 6)), 6, st()),     # no clouds
+    ]
+    assert all(rc == -2 for rc in bad), bad
+    assert b"bad argument" in lib.b200_last_error() or b"b200_pc_" in lib.b200_last_error()
+
+
 def check_bad_inputs_raise(ops):
     model, _ = make_model(ops)
     c = P.synth_cloud(200, seed=8, box=(10, 10, 3))
@@ -254,4 +283,5 @@ def check_bad_inputs_raise(ops):
 ALL = [check_grid_coords_and_codes_bit_exact, check_argsort_neighbors_pool_plan, check_gather_gemm_epilogues,
        check_gather_gemm_tiled_shapes,
        check_layernorm_segment_max_cloud_mean, check_patch_attention_matches_flash_semantics,
-       check_encode_pc_matches_oracle_and_reference_fixture, check_edge_cases_match_oracle, check_bad_inputs_raise]
+       check_encode_pc_matches_oracle_and_reference_fixture, check_edge_cases_match_oracle, check_entry_points_reject_bad_arguments,
+       check_bad_inputs_raise]

@@ -71,6 +71,14 @@ def _worker(rank, world, port, q):
         avg = D.average_gradients(grads, ["a", "b"])
         assert torch.allclose(avg["a"], torch.full((4, 3), (1 + world) / 2.0))
         assert torch.allclose(avg["b"], torch.arange(6.0).view(2, 3).t() * (1 + world) / 2.0)
+        # modality-specific gradients: present on rank 0 only -> zeros appear on rank 1; present nowhere -> stay absent
+        g2 = {"w": torch.ones(2, 2)}
+        if rank == 0:
+            g2["audio"] = torch.full((3,), 4.0)
+        D.align_optional_gradients(g2, {"audio": (3,), "seg": (2, 5)})
+        assert sorted(g2) == ["audio", "w"] and g2["audio"].shape == (3,)
+        avg2 = D.average_gradients(g2, sorted(g2))
+        assert torch.allclose(avg2["audio"], torch.full((3,), 4.0 / world))
         q.put((rank, "ok"))
     except Exception as e:  # surfaced by the parent
         q.put((rank, repr(e)))
