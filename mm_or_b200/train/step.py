@@ -47,9 +47,11 @@ def no_decay(name):
 class FineTuner:
     def __init__(self, model, state_dict, lr=2e-5, mm_projector_lr=None, betas=(0.9, 0.999), eps=1e-8,
                  weight_decay=0.0, max_grad_norm=0.1, first_trainable_clip_layer=12, vocab_weight=None,
-                 trainable=None, lora=None, train_embed_tokens=False):
+                 trainable=None, lora=None, train_embed_tokens=False, group=None, shard_optimizer=False):
         """lora: a train.lora.LoraState -> the reference's LoRA recipe (train.py:1159-1175): the decoder's base
-        weights, norms and lm_head are frozen, the adapters train next to mm_projector / image_pooler / CLIP layers."""
+        weights, norms and lm_head are frozen, the adapters train next to mm_projector / image_pooler / CLIP layers.
+        group: data-parallel process group (same as set_process_group). shard_optimizer: keep fp32 master / m / v for
+        1 / world of every tensor on each rank (train/zero.py, ZeRO-1); needs `group`."""
         self.model = model
         self.dev = model.device
         self.first_clip = first_trainable_clip_layer
@@ -69,17 +71,32 @@ class FineTuner:
         self.sd = {k: v.detach().to(self.dev, BF).contiguous() for k, v in state_dict.items()}
         n_run = model.get_vision_tower().n_layers_run()     # CLIP layers past the selected hidden state are dead
         self.names = sorted(k for k in self.sd if pick(k) and self._has_backward(k, n_run))
-        self.master = {k: state_dict[k].detach().to(self.dev, torch.float32).contiguous().clone() for k in self.names}
-        if lora is not None:                       # adapters: masters from the LoraState, same optimizer
-            for k in lora.names():
-                self.sd[k] = lora.sd[k]
-                self.master[k] = lora.sd[k].float().clone()
-            self.names = sorted(self.names + lora.names())
-        self.m = {k: torch.zeros_like(v) for k, v in self.master.items()}
-        self.v = {k: torch.zeros_like(v) for k, v in self.master.items()}
+        self.zero = None
+        self.group = group
+        if shard_optimizer:
+            if group is None:
+                raise ValueError("shard_optimizer=True needs the data-parallel process group")
+            from .zero import ShardedAdamW
+            source = {k: state_dict[k] for k in self.names}
+            if lora is not None:
+                for k in lora.names():
+                    self.sd[k] = lora.sd[k]
+                    source[k] = lora.sd[k]
+                self.names = sorted(self.names + lora.names())
+            self.zero = ShardedAdamW(self.sd, source, self.names, group, betas=betas, eps=eps)
+            self.master, self.m, self.v = self.zero.master, self.zero.m, self.zero.v      # this rank's slices
+        else:
+            self.master = {k: state_dict[k].detach().to(self.dev, torch.float32).contiguous().clone()
+                           for k in self.names}
+            if lora is not None:                       # adapters: masters from the LoraState, same optimizer
+                for k in lora.names():
+                    self.sd[k] = lora.sd[k]
+                    self.master[k] = lora.sd[k].float().clone()
+                self.names = sorted(self.names + lora.names())
+            self.m = {k: torch.zeros_like(v) for k, v in self.master.items()}
+            self.v = {k: torch.zeros_like(v) for k, v in self.master.items()}
         self.step_count = 0
         self.last_grads = None
-        self.group = None
 
     def set_process_group(self, group):
         """Data-parallel fine-tuning: every rank runs forward_backward on its own samples; gradients
@@ -152,7 +169,7 @@ class FineTuner:
         """clip_grad_norm_(max_grad_norm) over the trainable set + AdamW; rebuilds the fused bf16 working weights."""
         if self.group is not None:
             from ..dist import align_optional_gradients, average_gradients
-            optional = {k: tuple(v.shape) for k, v in self.master.items()
+            optional = {k: tuple(self.sd[k].shape) for k in self.names
                         if k == "model.embed_tokens.weight" or k.startswith(("model.image_pooler.project_audio.",
                                                                              "model.image_pooler.segmasks_encoder."))}
             align_optional_gradients(grads, optional, self.group)  # ranks whose batch lacked a modality contribute zeros
@@ -168,11 +185,14 @@ class FineTuner:
         for i, k in enumerate(names):
             L.grad_sq_norm(g[k].contiguous(), out2=out2, accumulate=i > 0, max_norm=self.max_norm)
         clip = out2[1:]
-        for k in names:
-            lr = self.proj_lr if k.startswith("model.mm_projector.") else self.lr
-            wd = 0.0 if no_decay(k) else self.wd
-            L.adamw_step(self.master[k], self.sd[k], g[k].contiguous(), self.m[k], self.v[k], lr, self.betas[0],
-                         self.betas[1], self.eps, wd, self.step_count, clip_coef=clip)
+        lr_of = lambda k: self.proj_lr if k.startswith("model.mm_projector.") else self.lr
+        wd_of = lambda k: 0.0 if no_decay(k) else self.wd
+        if self.zero is not None:          # sharded states: update this rank's slices, all-gather the bf16 weights
+            self.zero.step({k: g[k] for k in names}, self.step_count, lr_of, wd_of, clip_coef=clip)
+        else:
+            for k in names:
+                L.adamw_step(self.master[k], self.sd[k], g[k].contiguous(), self.m[k], self.v[k], lr_of(k),
+                             self.betas[0], self.betas[1], self.eps, wd_of(k), self.step_count, clip_coef=clip)
         if self.lora is not None:
             self.lora.refuse()                     # adapters changed; the decoder's base weights did not
             self._reload_encoder()

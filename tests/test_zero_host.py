@@ -1,0 +1,95 @@
+"""world_size-2 gloo test (CPU) of the sharded optimizer's host logic (mm_or_b200/train/zero.py): slice ownership,
+the in-place and the staged all-gather of updated bf16 slices, skipped parameters. The update arithmetic itself is the
+CUDA kernel b200_adamw_step (parity vs torch.optim.AdamW: tests/test_gpu_train_ops.py); here a torch restatement of
+that kernel is injected so that the partition / gather logic can run without a GPU."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from mm_or_b200.train.zero import ShardedAdamW, slice_range
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def torch_adamw(master, param, grad, m, v, lr, beta1, beta2, eps, weight_decay, step, clip_coef=None):
+    """The arithmetic of adamw_kernel (csrc/train.cu): decoupled decay, bias-corrected step, bf16 working copy."""
+    g = grad.float() * (float(clip_coef) if clip_coef is not None else 1.0)
+    master.mul_(1.0 - lr * weight_decay)
+    m.mul_(beta1).add_(g, alpha=1 - beta1)
+    v.mul_(beta2).addcmul_(g, g, value=1 - beta2)
+    bc1, bc2 = 1 - beta1 ** step, 1 - beta2 ** step
+    master.sub_((lr / bc1) * m / (v.sqrt() / bc2 ** 0.5 + eps))
+    param.copy_(master.to(param.dtype))
+
+
+def test_slice_range_covers_every_element_once():
+    for n in (1, 7, 16, 37, 1024):
+        for world in (1, 2, 3, 8):
+            got = [slice_range(n, r, world) for r in range(world)]
+            assert got[0][0] == 0 and got[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(got, got[1:]))
+            assert all(hi - lo <= s for lo, hi, s in got)
+
+
+def _params():
+    g = torch.Generator().manual_seed(5)
+    shapes = {"even": (8, 16), "ragged": (37,), "tiny": (1,), "skipped": (6,)}
+    return {k: torch.randn(s, generator=g) for k, s in shapes.items()}
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        src = _params()
+        names = sorted(src)
+        params = {k: v.to(torch.bfloat16).contiguous() for k, v in src.items()}
+        opt = ShardedAdamW(params, src, names, dist.group.WORLD, adamw=torch_adamw)
+        assert opt.state_bytes() < 3 * 4 * sum(v.numel() for v in src.values())          # only a slice is held
+        # unsharded reference with the same arithmetic
+        ref_p = {k: v.to(torch.bfloat16) for k, v in src.items()}
+        ref = {k: dict(master=v.clone().reshape(-1), m=torch.zeros(v.numel()), v=torch.zeros(v.numel()))
+               for k, v in src.items()}
+        g = torch.Generator().manual_seed(77)                                              # same gradients on every rank
+        for step in (1, 2, 3):
+            grads = {k: torch.randn(src[k].shape, generator=g) for k in names if k != "skipped"}
+            clip = torch.tensor([0.5])
+            lr_of = lambda k: 1e-2 if k == "even" else 3e-3
+            wd_of = lambda k: 0.1 if k == "ragged" else 0.0
+            opt.step(grads, step, lr_of, wd_of, clip_coef=clip)
+            for k in grads:
+                r = ref[k]
+                torch_adamw(r["master"], ref_p[k].view(-1), grads[k].reshape(-1), r["m"], r["v"], lr_of(k), 0.9, 0.999,
+                            1e-8, wd_of(k), step, clip_coef=clip)
+            for k in names:
+                assert torch.equal(params[k], ref_p[k]), (k, step)                        # every slice arrived everywhere
+                lo, hi, _ = slice_range(src[k].numel(), rank, world)
+                if k != "skipped":
+                    assert torch.equal(opt.master[k], ref[k]["master"][lo:hi]), (k, step)
+        assert torch.equal(params["skipped"], src["skipped"].to(torch.bfloat16))
+        q.put((rank, "ok"))
+    except Exception as e:  # surfaced by the parent
+        q.put((rank, repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_adamw_world2_gloo():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(results) == [(0, "ok"), (1, "ok")], results
