@@ -410,10 +410,13 @@ int b200_pc_cloud_offsets(const int32_t* batch, int n, int n_clouds, int32_t* of
 /* Gather-GEMM: C[m, :] = epilogue(sum_t A[idx[m, t], 0:K] . W[t*K:(t+1)*K, 0:N]); idx NULL = plain Linear (taps 1).
  * W is [taps*K, N] row-major (the loader transposes nn.Linear / SubMConv3d weights once). Epilogue: + bias[N],
  * * scale[N] + shift[N] (BatchNorm1d in eval mode, folded), act 0 none / 2 GELU(erf), + residual[M, ldr]; C fp32, or
- * bf16 when out_bf16 (project_pc writes the pooler's token rows). */
+ * bf16 when out_bf16 (project_pc writes the pooler's token rows). When few rows meet many taps (the deep stages) the taps
+ * are split over CTAs and the partial sums pass through `workspace` (b200_pc_gemm_workspace_bytes; NULL / too small =
+ * single pass); the splits are added in order, so the result does not depend on scheduling. */
+size_t b200_pc_gemm_workspace_bytes(int M, int N, int K, int taps);
 int b200_pc_gemm_f32(const float* A, int lda, const int32_t* idx, int taps, const float* W, const float* bias,
                      const float* scale, const float* shift, int act, const float* residual, int ldr, void* C, int ldc,
-                     int out_bf16, int M, int N, int K, b200_stream_t stream);
+                     int out_bf16, int M, int N, int K, void* workspace, size_t workspace_bytes, b200_stream_t stream);
 
 /* out = residual + LayerNorm(x) * gamma + beta (nn.LayerNorm, biased variance; residual may be NULL). */
 int b200_pc_layernorm_f32(const float* x, int ld, const float* gamma, const float* beta, float eps,

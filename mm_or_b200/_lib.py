@@ -133,7 +133,8 @@ _SIGS = {
     "b200_pc_neighbors": (ci, [vp, vp, vp, ci, ci, ci, vp, vp, vp]),
     "b200_pc_pool_plan": (ci, [vp, vp, vp, ci, ci, vp, vp, vp, vp, vp]),
     "b200_pc_cloud_offsets": (ci, [vp, ci, ci, vp, vp]),
-    "b200_pc_gemm_f32": (ci, [vp, ci, vp, ci, vp, vp, vp, vp, ci, vp, ci, vp, ci, ci, ci, ci, ci, vp]),
+    "b200_pc_gemm_workspace_bytes": (sz, [ci, ci, ci, ci]),
+    "b200_pc_gemm_f32": (ci, [vp, ci, vp, ci, vp, vp, vp, vp, ci, vp, ci, vp, ci, ci, ci, ci, ci, vp, sz, vp]),
     "b200_pc_layernorm_f32": (ci, [vp, ci, vp, vp, cf, vp, ci, vp, ci, ci, ci, vp]),
     "b200_pc_patch_attention": (ci, [vp, ci, vp, vp, ci, ci, ci, ci, cf, vp, ci, vp]),
     "b200_pc_segment_max": (ci, [vp, ci, vp, ci, ci, vp, vp, ci, vp, ci, vp]),

@@ -357,52 +357,68 @@ __global__ void __launch_bounds__(256) gather_gemm_kernel(
 }
 
 // Fast path of the same contract for the shapes the network produces (K, lda, N multiples of 4, 16-byte aligned A / W):
-// 128 x BN tile (BN = 32 / 64 / 128 by output width), one (tap, 16-channel) slice per step so the gathered row index is
-// read once per slice and never divided, 128-bit global and shared loads, 8 x (BN / 16) outputs per thread laid out so
-// that the shared-memory reads of a quarter-warp are contiguous (no bank conflicts).
-constexpr int TM = 128, TK = 16;
+// TM x BN tile (TM = 128, or 64 when 128-row tiles would leave SMs idle; BN = 32 / 64 / 128 by output width), one
+// (tap, 16-channel) slice per step so the gathered row index is read once per slice and never divided, 128-bit global
+// and shared loads, (TM / 16) x (BN / 16) outputs per thread laid out so that the shared-memory reads of a quarter-warp
+// are contiguous (no bank conflicts). Deep stages have few rows and 27 taps: the taps are then split over blockIdx.z,
+// every split writes its raw partial sums to a workspace, and splitk_epilogue_kernel adds them in split order
+// (deterministic) and applies the epilogue.
+constexpr int TK = 16;
 
-template <int BN>
+__device__ __forceinline__ void gemm_epilogue_store(float v, int m, int nn, const float* bias, const float* scale,
+                                                    const float* shift, int act, const float* residual, int ldr,
+                                                    void* Cout, int ldc, int out_bf16) {
+  if (bias) v += bias[nn];
+  if (scale) v = v * scale[nn] + shift[nn];
+  if (act == 2) v = gelu_erf(v);
+  if (residual) v += residual[(size_t)m * ldr + nn];
+  if (out_bf16) reinterpret_cast<uint16_t*>(Cout)[(size_t)m * ldc + nn] = bf16_bits(v);
+  else reinterpret_cast<float*>(Cout)[(size_t)m * ldc + nn] = v;
+}
+
+template <int TMv, int BN>
 __global__ void __launch_bounds__(256) gather_gemm_tiled_kernel(
     const float* __restrict__ A, int lda, const int* __restrict__ idx, int taps, const float* __restrict__ W,
     const float* __restrict__ bias, const float* __restrict__ scale, const float* __restrict__ shift, int act,
-    const float* __restrict__ residual, int ldr, void* __restrict__ Cout, int ldc, int out_bf16, int M, int N, int K) {
+    const float* __restrict__ residual, int ldr, void* __restrict__ Cout, int ldc, int out_bf16, int M, int N, int K,
+    int taps_per_split, float* __restrict__ part) {
   constexpr int NH = BN == 128 ? 2 : 1;  // column halves per thread
   constexpr int CW = BN / 16 / NH;       // contiguous columns per half: 4, 4, 2
-  __shared__ __align__(16) float As[TK][TM + 4];
+  constexpr int RH = TMv / 64;           // row halves per thread: rows h*64 + ty*4 .. +3
+  constexpr int LPR = 256 / TMv;         // loader threads per tile row: 2 or 4
+  constexpr int KPT = TK / LPR;          // channels of a slice per loader thread: 8 or 4
+  __shared__ __align__(16) float As[TK][TMv + 4];
   __shared__ __align__(16) float Bs[TK][BN];
   const int tid = threadIdx.x;
-  const int m0 = blockIdx.y * TM, n0 = blockIdx.x * BN;
+  const int m0 = blockIdx.y * TMv, n0 = blockIdx.x * BN;
   const int tx = tid % 16, ty = tid / 16;
-  const int lr = tid / 2, lh = tid % 2;  // loader: row lr of the tile, channels lh*8 .. lh*8+7 of the slice
+  const int lr = tid / LPR, lk = (tid % LPR) * KPT;
   const int lm = m0 + lr;
-  float acc[8][NH * CW];
+  float acc[RH * 4][NH * CW];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < RH * 4; ++i) {
 #pragma unroll
     for (int j = 0; j < NH * CW; ++j) acc[i][j] = 0.f;
   }
+  const int t_begin = blockIdx.z * taps_per_split;
+  const int t_end = t_begin + taps_per_split < taps ? t_begin + taps_per_split : taps;
 
-  for (int t = 0; t < taps; ++t) {
+  for (int t = t_begin; t < t_end; ++t) {
     int row = -1;
     if (lm < M) row = idx ? idx[(size_t)lm * taps + t] : lm;
     const float* arow = row >= 0 ? A + (size_t)row * lda : nullptr;
     const float* wt = W + (size_t)t * K * N;
     for (int k0 = 0; k0 < K; k0 += TK) {
-      float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
-      int ka = k0 + lh * 8;
-      if (arow) {
-        if (ka < K) a0 = *reinterpret_cast<const float4*>(arow + ka);
-        if (ka + 4 < K) a1 = *reinterpret_cast<const float4*>(arow + ka + 4);
+#pragma unroll
+      for (int q = 0; q < KPT / 4; ++q) {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        int ka = k0 + lk + 4 * q;
+        if (arow && ka < K) a = *reinterpret_cast<const float4*>(arow + ka);
+        As[lk + 4 * q + 0][lr] = a.x;
+        As[lk + 4 * q + 1][lr] = a.y;
+        As[lk + 4 * q + 2][lr] = a.z;
+        As[lk + 4 * q + 3][lr] = a.w;
       }
-      As[lh * 8 + 0][lr] = a0.x;
-      As[lh * 8 + 1][lr] = a0.y;
-      As[lh * 8 + 2][lr] = a0.z;
-      As[lh * 8 + 3][lr] = a0.w;
-      As[lh * 8 + 4][lr] = a1.x;
-      As[lh * 8 + 5][lr] = a1.y;
-      As[lh * 8 + 6][lr] = a1.z;
-      As[lh * 8 + 7][lr] = a1.w;
       for (int v = tid; v < TK * BN / 4; v += 256) {
         int kk = v / (BN / 4), c4 = v % (BN / 4);
         int nn = n0 + c4 * 4;
@@ -413,11 +429,12 @@ __global__ void __launch_bounds__(256) gather_gemm_tiled_kernel(
       __syncthreads();
 #pragma unroll
       for (int kk = 0; kk < TK; ++kk) {
-        float a[8], b[NH * CW];
-        float4 x0 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
-        float4 x1 = *reinterpret_cast<const float4*>(&As[kk][64 + ty * 4]);
-        a[0] = x0.x; a[1] = x0.y; a[2] = x0.z; a[3] = x0.w;
-        a[4] = x1.x; a[5] = x1.y; a[6] = x1.z; a[7] = x1.w;
+        float a[RH * 4], b[NH * CW];
+#pragma unroll
+        for (int h = 0; h < RH; ++h) {
+          float4 x = *reinterpret_cast<const float4*>(&As[kk][h * 64 + ty * 4]);
+          a[h * 4 + 0] = x.x; a[h * 4 + 1] = x.y; a[h * 4 + 2] = x.z; a[h * 4 + 3] = x.w;
+        }
         if constexpr (CW == 4) {
 #pragma unroll
           for (int h = 0; h < NH; ++h) {
@@ -429,7 +446,7 @@ __global__ void __launch_bounds__(256) gather_gemm_tiled_kernel(
           b[0] = y.x; b[1] = y.y;
         }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < RH * 4; ++i) {
 #pragma unroll
           for (int j = 0; j < NH * CW; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
         }
@@ -438,7 +455,7 @@ __global__ void __launch_bounds__(256) gather_gemm_tiled_kernel(
     }
   }
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < RH * 4; ++i) {
     int m = m0 + (i / 4) * 64 + ty * 4 + (i % 4);
     if (m >= M) continue;
 #pragma unroll
@@ -448,14 +465,23 @@ __global__ void __launch_bounds__(256) gather_gemm_tiled_kernel(
         int nn = n0 + h * 64 + tx * CW + j;
         if (nn >= N) continue;
         float v = acc[i][h * CW + j];
-        if (bias) v += bias[nn];
-        if (scale) v = v * scale[nn] + shift[nn];
-        if (act == 2) v = gelu_erf(v);
-        if (residual) v += residual[(size_t)m * ldr + nn];
-        if (out_bf16) reinterpret_cast<uint16_t*>(Cout)[(size_t)m * ldc + nn] = bf16_bits(v);
-        else reinterpret_cast<float*>(Cout)[(size_t)m * ldc + nn] = v;
+        if (part) part[((size_t)blockIdx.z * M + m) * N + nn] = v;
+        else gemm_epilogue_store(v, m, nn, bias, scale, shift, act, residual, ldr, Cout, ldc, out_bf16);
       }
   }
+}
+
+// C[m, n] = epilogue(part[0][m][n] + part[1][m][n] + ...), splits added in order
+__global__ void splitk_epilogue_kernel(const float* __restrict__ part, int splits, const float* __restrict__ bias,
+                                       const float* __restrict__ scale, const float* __restrict__ shift, int act,
+                                       const float* __restrict__ residual, int ldr, void* __restrict__ Cout, int ldc,
+                                       int out_bf16, int M, int N) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)M * N) return;
+  int m = (int)(t / N), nn = (int)(t % N);
+  float v = 0.f;
+  for (int s = 0; s < splits; ++s) v += part[(size_t)s * M * N + t];
+  gemm_epilogue_store(v, m, nn, bias, scale, shift, act, residual, ldr, Cout, ldc, out_bf16);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -757,29 +783,75 @@ int b200_pc_cloud_offsets(const int32_t* batch, int n, int n_clouds, int32_t* of
   return 0;
 }
 
+// tile / split selection shared by the launcher and the workspace query
+struct GemmPlan {
+  bool fast;
+  int bn, tm, splits, taps_per_split;
+};
+static GemmPlan plan_gemm(int M, int N, int K, int taps, int lda, const void* A, const void* W) {
+  GemmPlan p{};
+  p.fast = K % 4 == 0 && lda % 4 == 0 && N % 4 == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0 &&
+           (reinterpret_cast<uintptr_t>(W) & 15) == 0;
+  p.bn = N <= 32 ? 32 : (N <= 64 ? 64 : 128);
+  p.tm = 128;
+  p.splits = 1;
+  p.taps_per_split = taps;
+  if (!p.fast) return p;
+  const long long sms = num_sms();
+  long long cols = (N + p.bn - 1) / p.bn;
+  if (cols * ((M + 127) / 128) < 2 * sms) p.tm = 64;  // 128-row tiles would leave SMs idle
+  long long ctas = cols * ((M + p.tm - 1) / p.tm);
+  if (taps > 1 && ctas < 2 * sms) {  // still starved: split the taps (deterministic two-pass reduction)
+    long long want = (2 * sms + ctas - 1) / ctas;
+    int s = (int)(want < taps ? want : taps);
+    if (s > 9) s = 9;
+    p.taps_per_split = (taps + s - 1) / s;
+    p.splits = (taps + p.taps_per_split - 1) / p.taps_per_split;
+  }
+  return p;
+}
+
+size_t b200_pc_gemm_workspace_bytes(int M, int N, int K, int taps) {
+  if (M <= 0 || N <= 0 || K <= 0 || taps <= 0) return 0;
+  GemmPlan p = plan_gemm(M, N, K, taps, K % 4 == 0 ? 4 : 1, nullptr, nullptr);  // aligned operands assumed
+  return p.splits > 1 ? (size_t)p.splits * M * N * sizeof(float) : 0;
+}
+
 int b200_pc_gemm_f32(const float* A, int lda, const int32_t* idx, int taps, const float* W, const float* bias,
                      const float* scale, const float* shift, int act, const float* residual, int ldr, void* C, int ldc,
-                     int out_bf16, int M, int N, int K, b200_stream_t stream_) {
+                     int out_bf16, int M, int N, int K, void* workspace, size_t workspace_bytes,
+                     b200_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (!A || !W || !C || M <= 0 || N <= 0 || K <= 0 || taps <= 0 || lda < K || ldc < N || (idx == nullptr && taps != 1) ||
       (act != 0 && act != 2) || ((scale == nullptr) != (shift == nullptr)) || (residual && ldr < N))
     return fail(-2, "b200_pc_gemm_f32: bad argument (M=%d N=%d K=%d taps=%d act=%d)", M, N, K, taps, act);
   double flops = 2.0 * M * N * (double)K * taps;
-  LaunchScope ls(kFamPointCloud, stream, 4.0 * ((double)M * K * taps + (double)K * taps * N + (double)M * N), flops);
-  bool fast = K % 4 == 0 && lda % 4 == 0 && N % 4 == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0 &&
-              (reinterpret_cast<uintptr_t>(W) & 15) == 0;
-  if (fast) {
-    int bn = N <= 32 ? 32 : (N <= 64 ? 64 : 128);
-    dim3 grid((N + bn - 1) / bn, (M + TM - 1) / TM);
-    if (bn == 32) {
-      B200_LAUNCH(gather_gemm_tiled_kernel<32>, grid, dim3(256), 0, stream, A, lda, idx, taps, W, bias, scale, shift,
-                  act, residual, ldr, C, ldc, out_bf16, M, N, K);
-    } else if (bn == 64) {
-      B200_LAUNCH(gather_gemm_tiled_kernel<64>, grid, dim3(256), 0, stream, A, lda, idx, taps, W, bias, scale, shift,
-                  act, residual, ldr, C, ldc, out_bf16, M, N, K);
+  GemmPlan p = plan_gemm(M, N, K, taps, lda, A, W);
+  if (p.splits > 1 && (!workspace || workspace_bytes < (size_t)p.splits * M * N * sizeof(float))) {
+    p.splits = 1;  // no room for the partial sums: one pass over all taps
+    p.taps_per_split = taps;
+  }
+  LaunchScope ls(kFamPointCloud, stream, 4.0 * ((double)M * K * taps + (double)K * taps * N + (double)M * N), flops,
+                 p.splits > 1 ? 2 : 1);
+  if (p.fast) {
+    dim3 grid((N + p.bn - 1) / p.bn, (M + p.tm - 1) / p.tm, p.splits);
+    float* part = p.splits > 1 ? reinterpret_cast<float*>(workspace) : nullptr;
+#define PC_GEMM_LAUNCH(TMV, BNV)                                                                                   \
+  B200_LAUNCH((gather_gemm_tiled_kernel<TMV, BNV>), grid, dim3(256), 0, stream, A, lda, idx, taps, W, bias, scale, \
+              shift, act, residual, ldr, C, ldc, out_bf16, M, N, K, p.taps_per_split, part)
+    if (p.tm == 128) {
+      if (p.bn == 32) PC_GEMM_LAUNCH(128, 32);
+      else if (p.bn == 64) PC_GEMM_LAUNCH(128, 64);
+      else PC_GEMM_LAUNCH(128, 128);
     } else {
-      B200_LAUNCH(gather_gemm_tiled_kernel<128>, grid, dim3(256), 0, stream, A, lda, idx, taps, W, bias, scale, shift,
-                  act, residual, ldr, C, ldc, out_bf16, M, N, K);
+      if (p.bn == 32) PC_GEMM_LAUNCH(64, 32);
+      else if (p.bn == 64) PC_GEMM_LAUNCH(64, 64);
+      else PC_GEMM_LAUNCH(64, 128);
+    }
+#undef PC_GEMM_LAUNCH
+    if (p.splits > 1) {
+      B200_LAUNCH(splitk_epilogue_kernel, dim3(blocks_for((long long)M * N, 256)), dim3(256), 0, stream, part, p.splits,
+                  bias, scale, shift, act, residual, ldr, C, ldc, out_bf16, M, N);
     }
   } else {  // odd shapes (the stem: K = 6) take the generic kernel
     dim3 grid((N + GN - 1) / GN, (M + GM - 1) / GM);

@@ -96,9 +96,12 @@ class PcOps:
             out = self.empty((M, N), torch.float32)
             ldc = N
         scale, shift = bn if bn is not None else (None, None)
+        nb = int(self.lib.b200_pc_gemm_workspace_bytes(M, N, K, taps))      # > 0 when the taps are split over CTAs
+        ws = self.empty(nb, torch.uint8) if nb else None
         self.call("b200_pc_gemm_f32", self.ptr(a), a.stride(0), self.ptr(idx), taps, self.ptr(w), self.ptr(bias),
                   self.ptr(scale), self.ptr(shift), act, self.ptr(residual),
-                  residual.stride(0) if residual is not None else 0, self.ptr(out), ldc, int(out_bf16), M, N, K)
+                  residual.stride(0) if residual is not None else 0, self.ptr(out), ldc, int(out_bf16), M, N, K,
+                  self.ptr(ws), nb)
         return out
 
     def layernorm(self, x, M, C, gamma, beta, eps, residual=None):

@@ -10,6 +10,7 @@
 
 namespace b200 {
 int fail(int code, const char* fmt, ...);
+inline int num_sms() { return 148; }  // B200
 enum { kFamTrain = 11, kFamPointCloud = 12 };
 struct LaunchScope {
   LaunchScope(int, cudaStream_t, double = 0.0, double = 0.0, int = 1) {}

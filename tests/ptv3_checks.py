@@ -121,8 +121,10 @@ def check_gather_gemm_tiled_shapes(ops):
     """The fast path (K, N multiples of 4): every tile width, partial tiles in M and N, absent taps, every epilogue."""
     d = lambda t: t.to(ops.device)
     g = torch.Generator().manual_seed(3)
+    # small M: 64-row tiles, taps split over CTAs (27 -> 9 x 3, 3 -> 3 x 1, 2 -> 2 x 1); M = 38000: 128-row tiles
     for M, K, N, taps in [(300, 32, 32, 27), (129, 64, 64, 27), (257, 32, 96, 1), (140, 128, 128, 1), (70, 256, 256, 3),
-                          (33, 512, 1024, 1), (200, 36, 44, 2), (5, 8, 4, 1)]:
+                          (33, 512, 1024, 1), (200, 36, 44, 2), (5, 8, 4, 1), (38000, 16, 32, 1), (19000, 8, 64, 2),
+                          (9600, 8, 128, 1), (38000, 8, 64, 1), (38000, 8, 128, 1), (5120, 8, 32, 27)]:   # last: 4 ragged splits (7, 7, 7, 6)
         a = torch.randn(M, K, generator=g)
         w = torch.randn(taps * K, N, generator=g) / (taps * K) ** 0.5
         idx = torch.randint(-1, M, (M, taps), generator=g).to(torch.int32) if taps > 1 else None
@@ -258,9 +260,9 @@ def check_entry_points_reject_bad_arguments(ops):
         lib.b200_pc_neighbors(p(c), p(g), p(b), 8, 4, 4, p(i32(8, 64)), p(i32(1)), st()),       # kernel size 4
         lib.b200_pc_pool_plan(p(c), p(g), p(b), 8, 5, p(i32(9)), p(i32(1)), p(g), p(b), st()),  # pooling depth 5
         lib.b200_pc_gemm_f32(p(x), 6, None, 2, p(f32(12, 4)), None, None, None, 0, None, 0, p(f32(8, 4)), 4, 0, 8, 4, 6,
-                             st()),                                                             # taps without indices
+                             None, 0, st()),                                                    # taps without indices
         lib.b200_pc_gemm_f32(p(x), 6, None, 1, p(f32(6, 4)), None, None, None, 1, None, 0, p(f32(8, 4)), 4, 0, 8, 4, 6,
-                             st()),                                                             # unsupported activation
+                             None, 0, st()),                                                    # unsupported activation
         lib.b200_pc_layernorm_f32(p(x), 4, p(f32(6)), p(f32(6)), 1e-5, None, 0, p(f32(8, 6)), 6, 8, 6, st()),  # ld < C
         lib.b200_pc_patch_attention(p(f32(8, 96)), 96, p(b), p(i32(1, 4)), 1, 8, 32, 4, 0.25, p(f32(8, 32)), 32,
                                     st()),                                                      # head_dim 8
