@@ -825,6 +825,7 @@ int b200_pc_gemm_f32(const float* A, int lda, const int32_t* idx, int taps, cons
   if (!A || !W || !C || M <= 0 || N <= 0 || K <= 0 || taps <= 0 || lda < K || ldc < N || (idx == nullptr && taps != 1) ||
       (act != 0 && act != 2) || ((scale == nullptr) != (shift == nullptr)) || (residual && ldr < N))
     return fail(-2, "b200_pc_gemm_f32: bad argument (M=%d N=%d K=%d taps=%d act=%d)", M, N, K, taps, act);
+  if ((M + 63) / 64 > 65535) return fail(-2, "b200_pc_gemm_f32: M=%d exceeds the grid (max %d rows)", M, 65535 * 64);
   double flops = 2.0 * M * N * (double)K * taps;
   GemmPlan p = plan_gemm(M, N, K, taps, lda, A, W);
   if (p.splits > 1 && (!workspace || workspace_bytes < (size_t)p.splits * M * N * sizeof(float))) {

@@ -14,8 +14,6 @@ network is invariant to it except for fp32 summation order in the final per-clou
 The order shuffles (`torch.randperm(4)`, pointtransformerv3.py:122-126 and :676-680, active in eval mode too) are
 drawn from torch's global CPU generator in the reference's sequence: one for the serialization, one per pooling.
 """
-import ctypes
-
 import torch
 
 from .. import _lib as L
@@ -299,10 +297,10 @@ class PointTransformerV3:
                         point_clouds[i].shape[0] == 0:
                     raise ValueError(f"point cloud {i}: expected (N > 0, {g['in_channels']}) xyz+rgb, got "
                                      f"{tuple(point_clouds[i].shape)}")
-            pts = torch.cat([point_clouds[i].detach().to("cpu", torch.float32) for i in valid]).contiguous()
+            # clouds may arrive on the host (the reference's loader) or already on the device: one copy either way
+            pts = torch.cat([point_clouds[i].detach().to(ops.device, torch.float32) for i in valid]).contiguous()
             batch = torch.cat([torch.full((point_clouds[i].shape[0],), j, dtype=torch.int32)
-                               for j, i in enumerate(valid)])
-            pts, batch = pts.to(ops.device), batch.to(ops.device)
+                               for j, i in enumerate(valid)]).to(ops.device)
             pts, nbr5, levels = self.plan(pts, batch, len(valid))
             feat = self.features(pts, nbr5, levels)
             row_map = torch.tensor(valid, dtype=torch.int32).to(ops.device)
