@@ -384,10 +384,13 @@ def cpu_reference_sample(args, layers=32):
     t_dec = (time.perf_counter() - t0) / n
     total = t_enc + t_pre + t_dec * (args.new_tokens - 1)
     return {"value": round(1.0 / total, 5), "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "1 inference (6 views, L=%d): encode %.1fs + prefill %.1fs measured in full; %d decode steps "
+            "sample": "1 inference (%d views, L=%d): encode %.1fs + prefill %.1fs measured in full; %d decode steps "
                       "measured (%.3fs/step), extrapolated to %d tokens; torch %s CPU bf16, %d threads"
-                      % (emb.shape[1], t_enc, t_pre, n, t_dec, args.new_tokens, torch.__version__, cores),
-            "seconds_per_inference": round(total, 1)}
+                      % (args.views, emb.shape[1], t_enc, t_pre, n, t_dec, args.new_tokens, torch.__version__, cores),
+            "seconds_per_inference": round(total, 1),
+            "stage_seconds": {"vision_tower_pooler_projector": round(t_enc, 2), "pack_prefill": round(t_pre, 2),
+                              "decode_per_step": round(t_dec, 4)},
+            "decode_tokens_per_s": round(1.0 / t_dec, 3), "threads": torch.get_num_threads()}
 
 
 def run_reference(args):
