@@ -1,0 +1,26 @@
+#!/bin/bash
+# First GPU pass of a round (1 GPU, ~6 min): everything that was written without hardware access gets run first, then
+# the numbers that DESIGN.md / profiles/README.md quote are re-measured. Output in gpurun_out/<tag>_*.
+#   gpurun --timeout 600 -- bash tools/gpu_first_pass.sh r2
+TAG=${1:-r2}
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.max.sm,clocks.max.mem,power.limit --format=csv > gpurun_out/${TAG}_gpu.txt
+# 1. tests that have never run on hardware: short leash, reported separately
+timeout 240 python -m pytest tests/test_gpu_zzz_baseline_configs.py tests/test_gpu_zz_pointcloud.py \
+  tests/test_gpu_zz_train_extras.py -m gpu -q --timeout 200 2>&1 | tail -25 > gpurun_out/${TAG}_pytest_new.log
+echo "new tests rc=${PIPESTATUS[0]}"; tail -6 gpurun_out/${TAG}_pytest_new.log
+# 2. the whole suite + smoke
+timeout 600 python -m pytest tests -m gpu -q --timeout 300 2>&1 | tail -25 > gpurun_out/${TAG}_pytest_gpu.log
+echo "pytest rc=${PIPESTATUS[0]}"; tail -5 gpurun_out/${TAG}_pytest_gpu.log
+timeout 200 python __graft_entry__.py smoke 2>&1 | tail -2
+# 3. point-cloud branch: timing (tile / tap-split selection of the gather-GEMM has not been timed yet) + launch list
+for N in 20000 60000 150000; do
+  timeout 90 python tools/pc_bench.py --points $N --clouds 2 >> gpurun_out/${TAG}_pc_bench.json 2>> gpurun_out/${TAG}_pc_bench.err
+done
+cat gpurun_out/${TAG}_pc_bench.json
+timeout 120 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/${TAG}_pc_launches.csv \
+  python tools/pc_bench.py --points 60000 --clouds 2 --iters 1 > /dev/null 2>&1
+echo "ncu pc list rc=$?"
+# 4. headline bench (config 2, default batch)
+timeout 900 python bench.py --steps 3 --warmup 3 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
+echo "bench rc=$?"; tail -c 3000 gpurun_out/${TAG}_bench.json; tail -3 gpurun_out/${TAG}_bench.err
