@@ -37,12 +37,13 @@ OUT = os.path.join(EMU, "_build", "libb200emu_fma.so" if FMA else "libb200emu.so
 
 def build():
     deps = SRCS + [os.path.join(EMU, "cuda_emu.h"), os.path.join(EMU, "emu_common.h"),
-                   os.path.join(EMU, "emu_support.cpp"), os.path.join(HERE, "..", "include", "b200_mmor.h")]
+                   os.path.join(EMU, "emu_support.cpp"), os.path.join(EMU, "selftest.cpp"),
+                   os.path.join(HERE, "..", "include", "b200_mmor.h")]
     if os.path.exists(OUT) and os.path.getmtime(OUT) >= max(os.path.getmtime(d) for d in deps):
         return OUT
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     cmd = ["g++", "-O2"] + (["-mfma"] if FMA else []) + ["-std=c++17", "-fPIC", "-shared", "-DB200_EMU", "-I" + EMU]
-    for src in SRCS + [os.path.join(EMU, "emu_support.cpp")]:
+    for src in SRCS + [os.path.join(EMU, "emu_support.cpp"), os.path.join(EMU, "selftest.cpp")]:
         cmd += ["-x", "c++", src]
     cmd += ["-o", OUT]
     r = subprocess.run(cmd, capture_output=True, text=True)
