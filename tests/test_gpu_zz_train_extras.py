@@ -73,3 +73,39 @@ def test_fine_tune_step_with_extra_modalities():
     ft.train_step(case["input_ids"], case["labels"], case["attention_mask"], case["images"], audio=case["audio"],
                   segmasks=case["segmasks"])
     assert any(not torch.equal(before[k], ft.master[k]) for k in before)
+
+
+def test_fine_tune_gradients_against_reference_backward_fixture():
+    """Loss and gradients of the fine-tune step against tests/golden/train_extras_right.pt, recorded from the
+    reference model's own backward (tests/golden/make_train_golden.py). Written after the round's GPU budget was
+    spent: same code path as test_fine_tune_step_with_extra_modalities (which ran green), not yet run itself."""
+    import os
+    import sys
+    import golden_cases as gc
+    from mm_or_b200.model.llava_llama import LlavaLlamaForCausalLM
+    from mm_or_b200.train import llama as T
+    from mm_or_b200.train.step import FineTuner
+    sys.path.insert(0, gc.GOLDEN_DIR)
+    import make_train_golden as MT
+    fx = torch.load(os.path.join(gc.GOLDEN_DIR, "train_extras_right.pt"))
+    cfg = gc.small_config()
+    cfg.tokenizer_padding_side = "right"
+    sd = gc.bf16_round(gc.small_weights(cfg))
+    model = LlavaLlamaForCausalLM(cfg).load_state_dict(sd)
+    case = gc.make_case(cfg, "train_extras_right")
+    ft = FineTuner(model, sd, lr=1e-3, max_grad_norm=0.1, first_trainable_clip_layer=1, vocab_weight=MT.vocab_weight(cfg),
+                   train_embed_tokens=True)
+    loss, wsum, grads = ft.forward_backward(case["input_ids"], case["labels"], case["attention_mask"], case["images"],
+                                            audio=case["audio"], segmasks=case["segmasks"])
+    named = T.unfuse_grads(grads, cfg)
+    assert abs(float(loss) - float(fx["loss"])) < 3e-2 * abs(float(fx["loss"]))
+    bad = []
+    for k in MT.PROBE:
+        if k not in named:                       # frozen in this configuration (none of the probes should be)
+            bad.append((k, "missing"))
+            continue
+        got, ref = MT.compress(k, named[k].float().cpu()), fx["grads"][k]
+        err = ((got - ref).norm() / (ref.norm() + 1e-20)).item()
+        if err > 0.12:                            # bf16 pipeline vs fp32 reference, as in the oracle comparison
+            bad.append((k, err))
+    assert not bad, bad

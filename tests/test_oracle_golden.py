@@ -55,3 +55,29 @@ def test_token_weights_formula():
     w = O.token_weights({5: 100.0, 7: 10.0}, 16)
     assert abs(w[5].item() - 1 / (math.log(100.0) + 1)) < 1e-7
     assert abs(w[0].item() - w[5].item() / 100) < 1e-9
+
+
+def test_training_gradients_match_reference_backward():
+    """Loss and parameter gradients of the oracle under torch autograd against tests/golden/train_extras_right.pt,
+    recorded from the reference model's own backward (tests/golden/make_train_golden.py): decoder, projector, pooler,
+    trainable CLIP layer, audio projection, seg-mask CNN and embed_tokens."""
+    import sys
+    sys.path.insert(0, os.path.join(gc.GOLDEN_DIR))
+    import make_train_golden as MT
+    fx = torch.load(os.path.join(gc.GOLDEN_DIR, "train_extras_right.pt"))
+    cfg = gc.small_config()
+    sd = gc.bf16_round(gc.small_weights(cfg))
+    case = gc.make_case(cfg, "train_extras_right")
+    w = MT.vocab_weight(cfg)
+    with torch.enable_grad():
+        params = {k: sd[k].clone().requires_grad_(True) for k in MT.PROBE}
+        out = O.multimodal_prefill({**sd, **params}, oracle_cfg(cfg), case["input_ids"], case["attention_mask"],
+                                   case["images"], labels=case["labels"], audio=case["audio"],
+                                   segmasks=case["segmasks"], padding_side="right")
+        loss = O.weighted_ce(out["logits"], out["modified_labels"], w)
+        loss.backward()
+    assert abs(loss.item() - fx["loss"].item()) < 1e-4
+    for k in MT.PROBE:
+        got, ref = MT.compress(k, params[k].grad.detach()), fx["grads"][k]
+        assert got.shape == ref.shape, k
+        assert ((got - ref).norm() / (ref.norm() + 1e-20)).item() < 5e-4, k
