@@ -77,3 +77,27 @@ def test_two_images_rejected():
     ids = torch.tensor([[IMAGE_TOKEN_INDEX, 4, IMAGE_TOKEN_INDEX]])
     with pytest.raises(NotImplementedError):
         plan_pack(ids.numpy(), None, None, 2)
+
+
+def test_plan_matches_reference_fixture():
+    """32 batches (left / right padding, labels or not, truncation, interior pads, a text-only row) through the
+    REFERENCE's own prepare_inputs_labels_for_multimodal (tests/golden/make_pack_golden.py -> pack_cases.pt): the
+    planner and the oracle reproduce source rows, labels, mask and position ids bit for bit."""
+    import os
+    recs = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pack_cases.pt"))
+    assert len(recs) == 32
+    for r in recs:
+        labels = r["labels"]
+        p = plan_pack(r["ids"].numpy(), r["mask"].numpy(), None if labels is None else labels.numpy(), r["t_vis"],
+                      r["side"], r["max_len"])
+        src, lab, m, pos = O.pack_plan(r["ids"], r["mask"], labels, r["t_vis"], r["side"], r["max_len"])
+        ref_mask = r["out_mask"].numpy()
+        assert p.src.shape == tuple(r["src"].shape), (r["side"], r["max_len"])
+        for got_src, got_lab, got_mask, got_pos in ((p.src, p.labels, p.mask, p.pos),
+                                                    (src.numpy(), lab.numpy(), m.numpy(), pos.numpy())):
+            assert np.array_equal(got_mask, ref_mask)
+            assert np.array_equal(got_src, r["src"].numpy())
+            if r["out_labels"] is not None:                  # the reference returns None when no labels were passed
+                assert np.array_equal(got_lab, r["out_labels"].numpy())
+            # pad rows: the reference leaves 0 there (llava_arch.py:313,331-338)
+            assert np.array_equal(got_pos * ref_mask, r["out_pos"].numpy() * ref_mask)
