@@ -98,6 +98,13 @@ class FineTuner:
         self.step_count = 0
         self.last_grads = None
 
+    def set_lr(self, factor):
+        """Scale both learning rates by `factor` of their initial values (train/schedule.py: the reference's cosine
+        schedule with warm-up multiplies every parameter group's initial lr, mm_projector_lr included)."""
+        if not hasattr(self, "_base_lr"):
+            self._base_lr = (self.lr, self.proj_lr)
+        self.lr, self.proj_lr = self._base_lr[0] * factor, self._base_lr[1] * factor
+
     def set_process_group(self, group):
         """Data-parallel fine-tuning: every rank runs forward_backward on its own samples; gradients
         are summed over ranks with ncclAllReduce and divided by the world size before clipping / AdamW, which keeps

@@ -105,3 +105,38 @@ def test_lora_fused_adapters_equal_per_projection_adapters():
     k = "model.layers.1.mlp.up_proj.weight"
     assert torch.allclose(merged[k], 2.0 * st.sd[param_name(1, "mlp", "up_proj", "B")].float()
                           @ st.sd[param_name(1, "mlp", "up_proj", "A")].float())
+
+
+def test_parameter_groups_match_reference_create_optimizer():
+    """decay / no-decay and projector-lr membership for every parameter the fine-tune step can train, against what the
+    reference's LLaVATrainer.create_optimizer computes on its own model (tests/golden/make_optimizer_golden.py)."""
+    import json
+    import os
+    ref = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "optimizer_groups.json")))
+    checked = 0
+    for name, r in ref.items():
+        trainable = (default_trainable(name, 0) or name == "model.embed_tokens.weight") and \
+            FineTuner._has_backward(name, 10 ** 6)
+        if not trainable:
+            continue
+        assert no_decay(name) == (not r["decay"]), name
+        assert name.startswith("model.mm_projector.") == r["projector"], name
+        checked += 1
+    assert checked > 100
+
+
+def test_cosine_schedule_matches_transformers():
+    """train/schedule.py against transformers.get_cosine_schedule_with_warmup driving a torch optimizer (the scheduler the
+    reference's HF Trainer builds for `--lr_scheduler_type cosine --warmup_ratio 0.03`)."""
+    import transformers
+    from mm_or_b200.train.schedule import cosine_with_warmup, warmup_steps
+    for total, ratio in ((100, 0.03), (37, 0.1), (5, 0.0), (1000, 0.03)):
+        w = warmup_steps(total, ratio)
+        p = torch.nn.Parameter(torch.zeros(1))
+        opt = torch.optim.AdamW([p], lr=2e-5)
+        sched = transformers.get_cosine_schedule_with_warmup(opt, num_warmup_steps=w, num_training_steps=total)
+        for step in range(total):
+            assert abs(opt.param_groups[0]["lr"] - 2e-5 * cosine_with_warmup(step, total, w)) < 1e-12, (total, step)
+            opt.step()
+            sched.step()
+    assert warmup_steps(100, 0.03) == 3 and warmup_steps(1000, 0.03) == 30
