@@ -140,3 +140,24 @@ def test_cosine_schedule_matches_transformers():
             opt.step()
             sched.step()
     assert warmup_steps(100, 0.03) == 3 and warmup_steps(1000, 0.03) == 30
+
+
+def test_vocab_weights_match_reference_fixture():
+    """train/loss_weights.py on the reference's own token-frequency file against the vector recorded with the
+    reference's arithmetic (tests/golden/make_token_weight_golden.py)."""
+    import os
+    from mm_or_b200.train.loss_weights import vocab_weight_from_frequencies
+    fx = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "token_weights.pt"))
+    vocab = dict(fx["piece_ids"])
+    used = set(vocab.values())
+    for i in range(32000):
+        if i not in used:
+            vocab[f"<filler{i}>"] = i
+    w = vocab_weight_from_frequencies(fx["frequencies"], vocab)
+    assert w.shape == (32000,) and w.dtype == torch.float32
+    for i, v in fx["vocab_weight_nonextra"].items():
+        assert float(w[i]) == v, i                                   # bit-identical fp32 values
+    assert float(w[0]) == fx["extra"] and abs(float(w.double().sum()) - fx["sum"]) < 1e-9
+    import pytest
+    with pytest.raises(KeyError):
+        vocab_weight_from_frequencies({"not a piece": 3}, vocab)
