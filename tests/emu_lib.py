@@ -45,10 +45,12 @@ def build():
     cmd = ["g++", "-O2"] + (["-mfma"] if FMA else []) + ["-std=c++17", "-fPIC", "-shared", "-DB200_EMU", "-I" + EMU]
     for src in SRCS + [os.path.join(EMU, "emu_support.cpp"), os.path.join(EMU, "selftest.cpp")]:
         cmd += ["-x", "c++", src]
-    cmd += ["-o", OUT]
+    tmp = f"{OUT}.{os.getpid()}.tmp"                     # atomic: parallel test workers may build at the same time
+    cmd += ["-o", tmp]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("emulator build failed:\n" + r.stderr)
+    os.replace(tmp, OUT)
     return OUT
 
 
