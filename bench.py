@@ -54,6 +54,8 @@ def parse_args():
     p.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer arm")
     p.add_argument("--no-graph", action="store_true", help="profiling runs only: eager decode loop (every launch "
                    "visible to ncu)")
+    p.add_argument("--pdl", action="store_true", help="programmatic dependent launch for the decode step's kernels "
+                   "(b200_set_pdl; off by default until timed on hardware)")
     return p.parse_args()
 
 
@@ -166,6 +168,8 @@ def run_b200(args):
     from mm_or_b200.model.llava_llama import LlavaLlamaForCausalLM
     from mm_or_b200.synth import make_state_dict
 
+    if args.pdl:
+        L.set_pdl(True)
     cfg = full_config(args.layers)
     t0 = time.time()
     sd = make_state_dict(cfg, seed=0, device=dev, dtype=torch.bfloat16)
@@ -303,7 +307,8 @@ def run_b200(args):
                        "KV cache streamed every decode step)", "parallelism": "dp%d" % world,
                        "exchange": {None: "none (1 GPU)", "peer": "visual tokens all-gathered by the projector GEMM "
                                     "epilogue (peer stores over NVLink)", "nccl": "ncclAllGather of visual tokens"}[exchange],
-                       "model_tflop_per_inference": round(flops / 1e12, 2)},
+                       "model_tflop_per_inference": round(flops / 1e12, 2),
+                       "programmatic_dependent_launch": bool(L.pdl_enabled())},
             "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": int(images_host.numel() * 2
                     + ids.numel() * 8), "d2h_bytes_per_step": int(B * (ids.shape[1] + args.new_tokens) * 8),
                     "ms_per_step": round(ms_e2e / args.steps, 2)},

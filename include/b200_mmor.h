@@ -46,6 +46,15 @@ int b200_prof_family_count(void);
 const char* b200_prof_family_name(int family);
 int b200_prof_collect(double* ms, double* alg_bytes, double* alg_flops, long long* launches);
 
+/* Programmatic dependent launch for the kernels of b200_llama_decode_step (no reference counterpart: the reference's
+ * decode step is ~1900 separate eager launches from Python). Off unless the environment has B200_PDL=1 or
+ * b200_set_pdl(1) was called before the step is launched / captured: the step's kernels are then launched with
+ * programmatic stream serialization, so each kernel's prologue -- and the first weight tiles of the GEMMs, which do
+ * not depend on the previous kernel -- overlaps the tail of the kernel before it. Results are bit-identical either
+ * way (same kernels, same arithmetic order). Process-wide switch; not yet timed on hardware. */
+int b200_set_pdl(int on);
+int b200_get_pdl(void);
+
 /* ============================================================================================================
  * Operator level (used by the stage entry points below and by the parity tests)
  * ========================================================================================================== */

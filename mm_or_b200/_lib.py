@@ -75,6 +75,8 @@ _SIGS = {
     "b200_prof_family_count": (ci, []),
     "b200_prof_family_name": (ctypes.c_char_p, [ci]),
     "b200_prof_collect": (ci, [vp, vp, vp, vp]),
+    "b200_set_pdl": (ci, [ci]),
+    "b200_get_pdl": (ci, []),
     "b200_gemm_bf16": (ci, [vp, ci, vp, ci, vp, ci, ci, ci, ci, vp, vp, ci, vp, ci, ci, ci, vp]),
     "b200_gemm_bf16_skinny": (ci, [vp, ci, vp, ci, vp, ci, ci, ci, ci, vp, vp, ci, ci, ci, ci, vp]),
     "b200_gemm_bf16_ex": (ci, [vp, ci, ci, vp, ci, ci, vp, ci, ci, ci, ci, vp, vp, ci, ci, ci, ci, cf, ci, vp]),
@@ -467,6 +469,16 @@ def note_graph_replay(kernels):
 def launch_count():
     """Kernels of this library executed so far in this process (direct launches + graph replays)."""
     return int(lib().b200_launch_count()) + _graph_launches
+
+
+def set_pdl(on=True):
+    """Programmatic dependent launch for the decode step's kernels (include/b200_mmor.h: b200_set_pdl). Call before
+    the first generate(): the decode CUDA graph is captured with whatever is set at that time."""
+    check(lib().b200_set_pdl(int(on)), "b200_set_pdl")
+
+
+def pdl_enabled():
+    return bool(lib().b200_get_pdl())
 
 
 def prof_enable(on=True):

@@ -37,6 +37,8 @@ __global__ void __launch_bounds__(kDecThreads) decode_attn_kernel(const DecodeAr
   __shared__ float red_o[kDecWarps][128];
   __shared__ float q_s[128];
 
+  griddep_wait();  // q / the new cache slot (rope_kv_kernel) and *ctx_dev (previous step) must be complete
+  griddep_launch();
   const int bh = blockIdx.x;
   const int b = bh / a.H, h = bh % a.H;
   const int split = blockIdx.y;
@@ -151,6 +153,8 @@ __global__ void __launch_bounds__(kDecThreads) decode_attn_kernel(const DecodeAr
 }
 
 __global__ void decode_combine_kernel(const DecodeArgs a) {
+  griddep_wait();
+  griddep_launch();
   const int bh = blockIdx.x;
   const int b = bh / a.H, h = bh % a.H;
   const int d = threadIdx.x;  // 128 threads
@@ -199,12 +203,9 @@ int decode_attn(DecodeArgs a, void* workspace, size_t workspace_bytes, cudaStrea
     cfg = true;
   }
   LaunchScope scope(kFamDecodeAttn, stream, 0.0, 0.0, a.splits > 1 ? 2 : 1);  // bytes depend on the device-side ctx
-  decode_attn_kernel<<<dim3(a.B * a.H, a.splits), kDecThreads, smem, stream>>>(a);
-  B200_CUDA_OK(cudaGetLastError());
-  if (a.splits > 1) {
-    decode_combine_kernel<<<a.B * a.H, 128, 0, stream>>>(a);
-    B200_CUDA_OK(cudaGetLastError());
-  }
+  B200_CUDA_OK(launch_ex(decode_attn_kernel, dim3(a.B * a.H, a.splits), dim3(kDecThreads), smem, stream, 0, true, a));
+  if (a.splits > 1)
+    B200_CUDA_OK(launch_ex(decode_combine_kernel, dim3(a.B * a.H), dim3(128), 0, stream, 0, true, a));
   return 0;
 }
 

@@ -33,6 +33,45 @@ int fail(int code, const char* fmt, ...);
 int num_sms();
 
 // ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch for the decode step (opt-in: environment B200_PDL=1 or b200_set_pdl(1); off by
+// default until it has been timed on hardware). With it on, the kernels of a decode step are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization: kernel n+1 is scheduled while kernel n drains, runs its
+// prologue (and the GEMMs their first weight tiles, which do not depend on kernel n) and blocks in griddep_wait()
+// (ptx.cuh) before it touches an activation. Every kernel launched through launch_ex(..., pdl_ok = true) MUST call
+// griddep_wait() before its first dependent global access: a grid that skipped it could finish before its
+// predecessor and release the grid after it too early.
+// ---------------------------------------------------------------------------------------------
+bool pdl_enabled();
+void set_pdl(bool on);
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_ex(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                             unsigned cluster_x, bool pdl_ok, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  unsigned n = 0;
+  if (cluster_x > 0) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster_x;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (pdl_ok && pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
+// ---------------------------------------------------------------------------------------------
 // launch accounting + optional per-family CUDA-event timing (errors.cu). Every host launcher opens a
 // LaunchScope around its <<<>>>; the counter feeds bench.py's "gpu_launches", the event timing its
 // "roofline" object (events are recorded on the launching stream; skipped while the stream is capturing).
@@ -85,6 +124,9 @@ struct GemmEpilogue {
   int out_fp32 = 0;  // 0: C is bf16, 1: C is fp32
   int accumulate = 0;  // fp32 output only: C += result
   float scale = 1.f;   // accumulator is multiplied by this before bias / activation / residual (LoRA alpha / r)
+  // programmatic dependent launch: operand B (the weights) is not written by the kernel launched before this one, so
+  // its first tiles may be fetched before the grid dependency resolves. Only the decode step sets it.
+  int b_const = 0;
   // fused GEMM -> all-gather: when n_peers > 0 every bf16 output vector is stored to the same offset of each
   // peer_c[p] (peer-mapped device pointers over NVLink, this rank's own buffer included) instead of C.
   int n_peers = 0;

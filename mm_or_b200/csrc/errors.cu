@@ -1,6 +1,7 @@
 // Error plumbing and launch accounting shared by every entry point of libb200mmor.so.
 #include <atomic>
 #include <cstdarg>
+#include <cstdlib>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -25,6 +26,19 @@ int fail(int code, const char* fmt, ...) {
 }
 
 const char* last_error_cstr() { return g_last_error.c_str(); }
+
+// programmatic dependent launch switch (common.h): -1 = not read yet, then 0 / 1
+static std::atomic<int> g_pdl{-1};
+bool pdl_enabled() {
+  int v = g_pdl.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* e = getenv("B200_PDL");
+    v = (e != nullptr && e[0] != '\0' && e[0] != '0') ? 1 : 0;
+    g_pdl.store(v, std::memory_order_relaxed);
+  }
+  return v != 0;
+}
+void set_pdl(bool on) { g_pdl.store(on ? 1 : 0, std::memory_order_relaxed); }
 
 // ---------------------------------------------------------------------------------------------
 // launch counter + per-family event timing
@@ -78,6 +92,12 @@ using namespace b200;
 extern "C" {
 
 long long b200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int b200_set_pdl(int on) {
+  set_pdl(on != 0);
+  return 0;
+}
+int b200_get_pdl(void) { return pdl_enabled() ? 1 : 0; }
 
 int b200_prof_enable(int on) {
   std::lock_guard<std::mutex> lk(g_prof_mu);

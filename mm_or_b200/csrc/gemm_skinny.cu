@@ -130,16 +130,27 @@ __global__ void __launch_bounds__(kSkThreads, (SkinnyCfg<MT, STAGES>::kSmemBytes
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
+  griddep_launch();  // (every thread; a no-op without programmatic dependent launch)
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
+      // Programmatic dependent launch: the weight tiles of the first stages are requested while the previous kernel
+      // is still draining (weights do not depend on it); the activation tiles follow after the wait.
+      const int pre = g.epi.b_const ? (nkb < kStages ? nkb : kStages) : 0;
+      for (int i = 0; i < pre; ++i) {
+        mbar_expect_tx(&full_bar[i], Cfg::kStageBytes);
+        tma_load_2d(smem_w + i * Cfg::kStageBytesW, &tmW, &full_bar[i], (kb0 + i) * kSkBK, nt * kSkBW);
+      }
+      griddep_wait();
       int stage = 0;
       uint32_t phase = 0;
       for (int i = 0; i < nkb; ++i) {
         const int kb = kb0 + i;
         mbar_wait(&empty_bar[stage], phase ^ 1u);
-        mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-        tma_load_2d(smem_w + stage * Cfg::kStageBytesW, &tmW, &full_bar[stage], kb * kSkBK, nt * kSkBW);
+        if (i >= pre) {
+          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          tma_load_2d(smem_w + stage * Cfg::kStageBytesW, &tmW, &full_bar[stage], kb * kSkBK, nt * kSkBW);
+        }
         tma_load_2d(smem_a + stage * Cfg::kStageBytesA, &tmA, &full_bar[stage], kb * kSkBK, 0);
         if (++stage == kStages) {
           stage = 0;
@@ -174,6 +185,7 @@ __global__ void __launch_bounds__(kSkThreads, (SkinnyCfg<MT, STAGES>::kSmemBytes
     const int q = warp & 3;
     const int r = q * 32 + lane;  // weight row inside the tile = TMEM lane
     const bool empty_split = kb1 <= kb0;  // only possible when S does not divide the k-blocks: partial = 0
+    griddep_wait();  // residual reads and C writes below must follow the previous kernel
     if (!empty_split) mbar_wait(tmem_full, 0);
     tc_fence_after_sync();
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
@@ -278,19 +290,9 @@ static int launch_skinny(const CUtensorMap& tmW, const CUtensorMap& tmA, const S
                        static_cast<double>(g.M) * n_out * (g.epi.out_fp32 ? 4 : 2) +
                        (g.epi.residual ? 2.0 * g.M * g.N : 0.0);
   LaunchScope scope(kFamGemmSkinny, stream, bytes, 2.0 * g.M * g.N * g.K);
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(static_cast<unsigned>(g.n_tiles * g.splits), 1, 1);
-  cfg.blockDim = dim3(kSkThreads, 1, 1);
-  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = static_cast<unsigned>(g.splits);
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  B200_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_skinny_kernel<MT, STAGES>, tmW, tmA, g));
+  B200_CUDA_OK(launch_ex(gemm_skinny_kernel<MT, STAGES>, dim3(static_cast<unsigned>(g.n_tiles * g.splits)),
+                         dim3(kSkThreads), Cfg::kSmemBytes, stream, static_cast<unsigned>(g.splits),
+                         g.epi.b_const != 0, tmW, tmA, g));
   return 0;
 }
 

@@ -106,17 +106,33 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
+  griddep_launch();  // (every thread; a no-op without programmatic dependent launch)
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
+      // Programmatic dependent launch: weight tiles of the first k-blocks are requested before the previous kernel
+      // has finished (they do not depend on it); the activation tiles of the same stages follow after the wait.
+      int pre = 0;
+      if (g.epi.b_const && !g.b_mn && static_cast<int>(blockIdx.x) < num_tiles) {
+        int mt, nt;
+        tile_coords(blockIdx.x, g.m_tiles, g.n_tiles, mt, nt);
+        pre = k_blocks < kStages ? k_blocks : kStages;
+        for (int kb = 0; kb < pre; ++kb) {
+          mbar_expect_tx(&full_bar[kb], Cfg::kStageBytes);
+          tma_load_2d(smem_b + kb * Cfg::kStageBytesB, &tmB, &full_bar[kb], kb * kBK, nt * BN);
+        }
+      }
+      griddep_wait();
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         int mt, nt;
         tile_coords(tile, g.m_tiles, g.n_tiles, mt, nt);
         for (int kb = 0; kb < k_blocks; ++kb) {
+          const bool b_done = pre > 0;  // this stage's weight tile (and its expect_tx) was issued above
+          if (b_done) --pre;
           mbar_wait(&empty_bar[stage], phase ^ 1u);
-          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          if (!b_done) mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
           if (!g.a_mn) {
             tma_load_2d(smem_a + stage * Cfg::kStageBytesA, &tmA, &full_bar[stage], kb * kBK, mt * kBM);
           } else {  // [64 k rows][64 m] boxes, one 8 KB panel per 64 rows of the tile
@@ -124,7 +140,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
               tma_load_2d(smem_a + stage * Cfg::kStageBytesA + p * 8192, &tmA, &full_bar[stage], mt * kBM + p * 64,
                           kb * kBK);
           }
-          if (!g.b_mn) {
+          if (b_done) {
+          } else if (!g.b_mn) {
             tma_load_2d(smem_b + stage * Cfg::kStageBytesB, &tmB, &full_bar[stage], kb * kBK, nt * BN);
           } else {
             for (int p = 0; p < BN / 64; ++p)
@@ -175,6 +192,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     // ===================== epilogue (warps 2..5) =====================
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
     const GemmEpilogue& e = g.epi;
+    griddep_wait();  // residual reads and C writes below must follow the previous kernel
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       int mt, nt;
@@ -384,8 +402,8 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
                        static_cast<double>(g.M) * n_out * (g.epi.out_fp32 ? 4 : 2) +
                        (g.epi.residual ? 2.0 * g.M * g.N : 0.0);
   LaunchScope scope(g.M <= 128 ? kFamGemmSkinny : kFamGemm, stream, bytes, 2.0 * mnk);
-  gemm_bf16_tn_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, g);
-  B200_CUDA_OK(cudaGetLastError());
+  B200_CUDA_OK(launch_ex(gemm_bf16_tn_kernel<BN>, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, stream, 0,
+                         g.epi.b_const != 0, tmA, tmB, g));
   return 0;
 }
 

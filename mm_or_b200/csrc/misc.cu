@@ -62,6 +62,8 @@ __global__ void __launch_bounds__(128) rope_kv_kernel(bf16* __restrict__ qkv, co
                                                       bf16* __restrict__ kc, bf16* __restrict__ vc, int T, int H, int Lq,
                                                       int slot0_imm, const int* __restrict__ slot0_dev, int cap,
                                                       int max_pos) {
+  griddep_wait();    // qkv (previous GEMM) and *slot0_dev (previous step) must be complete
+  griddep_launch();
   const long long w = blockIdx.x * 4ll + (threadIdx.x >> 5);  // one warp per (token, head)
   if (w >= static_cast<long long>(T) * H) return;
   const int lane = threadIdx.x & 31;
@@ -100,9 +102,8 @@ int rope_kv_write(bf16* qkv, const int* kv_start, const float* cos_t, const floa
   if (slot0_dev == nullptr && slot0 + Lq > cap)
     return fail(-2, "rope_kv_write: slot %d + %d exceeds cache capacity %d", slot0, Lq, cap);
   LaunchScope scope(kFamRope, stream, static_cast<double>(warps) * 128 * 2 * 5, 0.0);
-  rope_kv_kernel<<<static_cast<unsigned>((warps + 3) / 4), 128, 0, stream>>>(qkv, kv_start, cos_t, sin_t, kc, vc, B * Lq,
-                                                                             H, Lq, slot0, slot0_dev, cap, max_pos);
-  B200_CUDA_OK(cudaGetLastError());
+  B200_CUDA_OK(launch_ex(rope_kv_kernel, dim3(static_cast<unsigned>((warps + 3) / 4)), dim3(128), 0, stream, 0, true, qkv,
+                         kv_start, cos_t, sin_t, kc, vc, B * Lq, H, Lq, slot0, slot0_dev, cap, max_pos));
   return 0;
 }
 
@@ -112,6 +113,8 @@ int rope_kv_write(bf16* qkv, const int* kv_start, const float* cos_t, const floa
 __global__ void __launch_bounds__(128) embed_rows_kernel(const int* __restrict__ ids, const bf16* __restrict__ table,
                                                          bf16* __restrict__ out, long long ldo, int rows, int D,
                                                          int vocab) {
+  griddep_wait();    // ids are the previous step's argmax output
+  griddep_launch();
   const int r = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (r >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -132,8 +135,8 @@ int embed_rows(const int* ids, const bf16* table, bf16* out, long long ldo, int 
   if (rows <= 0) return 0;
   if (D % 8) return fail(-2, "embed_rows: D must be a multiple of 8");
   LaunchScope scope(kFamEmbed, stream, 4.0 * rows * D, 0.0);
-  embed_rows_kernel<<<(rows + 3) / 4, 128, 0, stream>>>(ids, table, out, ldo, rows, D, vocab);
-  B200_CUDA_OK(cudaGetLastError());
+  B200_CUDA_OK(launch_ex(embed_rows_kernel, dim3((rows + 3) / 4), dim3(128), 0, stream, 0, true, ids, table, out, ldo,
+                         rows, D, vocab));
   return 0;
 }
 
@@ -154,6 +157,8 @@ __global__ void __launch_bounds__(256) argmax_kernel(const T* __restrict__ logit
                                                      int* __restrict__ out_tok, int* __restrict__ finished, int eos_id,
                                                      int pad_id, int* __restrict__ history, int hist_ld, int step_imm,
                                                      const int* __restrict__ step_dev) {
+  griddep_wait();
+  griddep_launch();
   const int r = blockIdx.x;
   const T* row = logits + static_cast<long long>(r) * ld;
   float best = -INFINITY;
@@ -198,24 +203,25 @@ int argmax_rows(const void* logits, int is_fp32, long long ld, int rows, int V, 
   if (rows <= 0) return 0;
   LaunchScope scope(kFamArgmax, stream, static_cast<double>(rows) * V * (is_fp32 ? 4 : 2), 0.0);
   if (is_fp32)
-    argmax_kernel<float><<<rows, 256, 0, stream>>>(static_cast<const float*>(logits), ld, V, out_tok, finished, eos_id,
-                                                   pad_id, history, hist_ld, step, step_dev);
+    B200_CUDA_OK(launch_ex(argmax_kernel<float>, dim3(rows), dim3(256), 0, stream, 0, true,
+                           static_cast<const float*>(logits), ld, V, out_tok, finished, eos_id, pad_id, history, hist_ld,
+                           step, step_dev));
   else
-    argmax_kernel<bf16><<<rows, 256, 0, stream>>>(static_cast<const bf16*>(logits), ld, V, out_tok, finished, eos_id,
-                                                  pad_id, history, hist_ld, step, step_dev);
-  B200_CUDA_OK(cudaGetLastError());
+    B200_CUDA_OK(launch_ex(argmax_kernel<bf16>, dim3(rows), dim3(256), 0, stream, 0, true,
+                           static_cast<const bf16*>(logits), ld, V, out_tok, finished, eos_id, pad_id, history, hist_ld,
+                           step, step_dev));
   return 0;
 }
 
 // decode-loop device counters: state[0] = KV slots in use, state[1] = decode step index
 __global__ void bump_counters_kernel(int* state) {
+  griddep_wait();  // the step's kernels read state[]: all of them are complete once the argmax before this one is
   state[0] += 1;
   state[1] += 1;
 }
 int bump_counters(int* state, cudaStream_t stream) {
   LaunchScope scope(kFamMisc, stream);
-  bump_counters_kernel<<<1, 1, 0, stream>>>(state);
-  B200_CUDA_OK(cudaGetLastError());
+  B200_CUDA_OK(launch_ex(bump_counters_kernel, dim3(1), dim3(1), 0, stream, 0, true, state));
   return 0;
 }
 

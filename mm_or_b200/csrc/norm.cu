@@ -47,6 +47,8 @@ __device__ __forceinline__ float warp_sum(float v) {
 // kVec = number of 16-byte vectors each lane holds (D = kVec * 256); values stay in registers across passes.
 template <int kVec, bool kRms>
 __global__ void __launch_bounds__(128) norm_kernel(const LnArgs a) {
+  griddep_wait();
+  griddep_launch();
   const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (row >= a.M) return;
   const int lane = threadIdx.x & 31;
@@ -127,14 +129,13 @@ static int launch_norm(const LnArgs& a, cudaStream_t stream) {
   const int grid = (a.M + 3) / 4;
   LaunchScope scope(kFamNorm, stream, 4.0 * a.M * a.D, 0.0);
   switch (a.D / 256) {
-    case 1: norm_kernel<1, kRms><<<grid, 128, 0, stream>>>(a); break;
-    case 2: norm_kernel<2, kRms><<<grid, 128, 0, stream>>>(a); break;
-    case 4: norm_kernel<4, kRms><<<grid, 128, 0, stream>>>(a); break;
-    case 8: norm_kernel<8, kRms><<<grid, 128, 0, stream>>>(a); break;
-    case 16: norm_kernel<16, kRms><<<grid, 128, 0, stream>>>(a); break;
+    case 1: B200_CUDA_OK(launch_ex(norm_kernel<1, kRms>, dim3(grid), dim3(128), 0, stream, 0, true, a)); break;
+    case 2: B200_CUDA_OK(launch_ex(norm_kernel<2, kRms>, dim3(grid), dim3(128), 0, stream, 0, true, a)); break;
+    case 4: B200_CUDA_OK(launch_ex(norm_kernel<4, kRms>, dim3(grid), dim3(128), 0, stream, 0, true, a)); break;
+    case 8: B200_CUDA_OK(launch_ex(norm_kernel<8, kRms>, dim3(grid), dim3(128), 0, stream, 0, true, a)); break;
+    case 16: B200_CUDA_OK(launch_ex(norm_kernel<16, kRms>, dim3(grid), dim3(128), 0, stream, 0, true, a)); break;
     default: return fail(-2, "norm: hidden size %d not supported (256/512/1024/2048/4096)", a.D);
   }
-  B200_CUDA_OK(cudaGetLastError());
   return 0;
 }
 

@@ -14,6 +14,18 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
 
 // ----------------------------------------------------------------------------------------------
+// programmatic dependent launch (griddepcontrol). Both are no-ops in a grid launched without the
+// programmatic-stream-serialization attribute, so kernels carry them unconditionally (common.h: launch_ex).
+//   griddep_wait():   returns once every prerequisite grid has completed and its writes are visible; everything a
+//                     kernel does before it (barrier init, TMEM alloc, prefetch of CONSTANT data such as weights)
+//                     overlaps the previous kernel's tail. No global write and no read of activations before it.
+//   griddep_launch(): lets the next kernel of the stream be scheduled as soon as every CTA of this grid has issued it
+//                     (or exited).
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// ----------------------------------------------------------------------------------------------
 // mbarrier
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

@@ -226,7 +226,9 @@ static size_t llama_prefill_ws(const b200_llama_weights* w, int Bn, int L, int a
 // 1.3-1.9x faster on the split-K cluster kernel, which keeps two streaming CTAs on every SM; the wide ones (qkv,
 // gate_up, lm_head) already fill the chip with 128-column tiles of the tiled kernel.
 static int linear(const bf16* A, int lda, const bf16* W, int ldw, void* C, int ldc, int T, int N, int K,
-                  const GemmEpilogue& e, bool decode, cudaStream_t st) {
+                  const GemmEpilogue& e_in, bool decode, cudaStream_t st) {
+  GemmEpilogue e = e_in;
+  e.b_const = decode ? 1 : 0;  // decode step: W is a weight matrix no kernel writes (PDL prefetch, common.h)
   if (decode && T <= 256) {
     const int n_tiles = (N + 127) / 128;
     if (n_tiles * 2 <= num_sms()) return gemm_skinny(A, lda, W, ldw, C, ldc, T, N, K, e, 0, st);
