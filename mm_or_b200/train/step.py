@@ -47,11 +47,14 @@ def no_decay(name):
 class FineTuner:
     def __init__(self, model, state_dict, lr=2e-5, mm_projector_lr=None, betas=(0.9, 0.999), eps=1e-8,
                  weight_decay=0.0, max_grad_norm=0.1, first_trainable_clip_layer=12, vocab_weight=None,
-                 trainable=None, lora=None, train_embed_tokens=False, group=None, shard_optimizer=False):
+                 trainable=None, lora=None, train_embed_tokens=False, group=None, shard_optimizer=False,
+                 shard_gradients=False, grad_comm_dtype=torch.bfloat16):
         """lora: a train.lora.LoraState -> the reference's LoRA recipe (train.py:1159-1175): the decoder's base
         weights, norms and lm_head are frozen, the adapters train next to mm_projector / image_pooler / CLIP layers.
         group: data-parallel process group (same as set_process_group). shard_optimizer: keep fp32 master / m / v for
-        1 / world of every tensor on each rank (train/zero.py, ZeRO-1); needs `group`."""
+        1 / world of every tensor on each rank (train/zero.py, ZeRO-1); needs `group`. shard_gradients (with
+        shard_optimizer): gradients are reduce-scattered in grad_comm_dtype instead of all-reduced in fp32, so a rank
+        only receives the averaged gradient of the slices it updates (ZeRO-2, the reference's scripts/zero2.json)."""
         self.model = model
         self.dev = model.device
         self.first_clip = first_trainable_clip_layer
@@ -73,6 +76,9 @@ class FineTuner:
         self.names = sorted(k for k in self.sd if pick(k) and self._has_backward(k, n_run))
         self.zero = None
         self.group = group
+        if shard_gradients and not shard_optimizer:
+            raise ValueError("shard_gradients=True needs shard_optimizer=True")
+        self.shard_gradients, self.grad_comm_dtype = shard_gradients, grad_comm_dtype
         if shard_optimizer:
             if group is None:
                 raise ValueError("shard_optimizer=True needs the data-parallel process group")
@@ -180,11 +186,19 @@ class FineTuner:
                         if k == "model.embed_tokens.weight" or k.startswith(("model.image_pooler.project_audio.",
                                                                              "model.image_pooler.segmasks_encoder."))}
             align_optional_gradients(grads, optional, self.group)  # ranks whose batch lacked a modality contribute zeros
-            average_gradients(grads, sorted(grads), self.group)    # in place on the (contiguous) fused gradients
+            if not self.shard_gradients:
+                average_gradients(grads, sorted(grads), self.group)    # in place on the (contiguous) fused gradients
         g = T.unfuse_grads(grads, self.model.config)
         if self.lora is not None:
             g.update(self.lora.unfuse_grads(grads))
         self.step_count += 1
+        lr_of = lambda k: self.proj_lr if k.startswith("model.mm_projector.") else self.lr
+        wd_of = lambda k: 0.0 if no_decay(k) else self.wd
+        if self.zero is not None and self.shard_gradients:
+            # ZeRO-2: reduce-scatter -> norm from the slices -> update of the local slices -> all-gather of the weights
+            out2 = self.zero.step_from_local_grads({k: g[k] for k in self.names if k in g}, self.step_count, lr_of,
+                                                   wd_of, max_norm=self.max_norm, comm_dtype=self.grad_comm_dtype)
+            return self._after_update(out2)
         out2 = torch.zeros(2, device=self.dev, dtype=torch.float32)
         # parameters that received no gradient this step (a modality absent from the batch) are skipped by the norm and
         # by AdamW, like parameters whose .grad is None in torch
@@ -192,14 +206,16 @@ class FineTuner:
         for i, k in enumerate(names):
             L.grad_sq_norm(g[k].contiguous(), out2=out2, accumulate=i > 0, max_norm=self.max_norm)
         clip = out2[1:]
-        lr_of = lambda k: self.proj_lr if k.startswith("model.mm_projector.") else self.lr
-        wd_of = lambda k: 0.0 if no_decay(k) else self.wd
         if self.zero is not None:          # sharded states: update this rank's slices, all-gather the bf16 weights
             self.zero.step({k: g[k] for k in names}, self.step_count, lr_of, wd_of, clip_coef=clip)
         else:
             for k in names:
                 L.adamw_step(self.master[k], self.sd[k], g[k].contiguous(), self.m[k], self.v[k], lr_of(k),
                              self.betas[0], self.betas[1], self.eps, wd_of(k), self.step_count, clip_coef=clip)
+        return self._after_update(out2)
+
+    def _after_update(self, out2):
+        """Rebuild the fused bf16 working weights the kernels read from the updated per-parameter tensors."""
         if self.lora is not None:
             self.lora.refuse()                     # adapters changed; the decoder's base weights did not
             self._reload_encoder()

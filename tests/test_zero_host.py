@@ -93,3 +93,70 @@ def test_sharded_adamw_world2_gloo():
     for p in procs:
         p.join(timeout=60)
     assert sorted(results) == [(0, "ok"), (1, "ok")], results
+
+
+def torch_sq_norm(t, out2):
+    out2[0] += (t.float() ** 2).sum()
+
+
+def _zero2_worker(rank, world, port, q):
+    """ZeRO-2 step (reduce-scattered gradients): every rank contributes a DIFFERENT gradient; the result must equal the
+    unsharded step on the mean gradient (rounded as the wire format rounds it), clipped by the GLOBAL norm."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        for comm in (torch.float32, torch.bfloat16):
+            src = _params()
+            names = sorted(src)
+            params = {k: v.to(torch.bfloat16).contiguous() for k, v in src.items()}
+            opt = ShardedAdamW(params, src, names, dist.group.WORLD, adamw=torch_adamw, sq_norm=torch_sq_norm)
+            ref_p = {k: v.to(torch.bfloat16) for k, v in src.items()}
+            ref = {k: dict(master=v.clone().reshape(-1), m=torch.zeros(v.numel()), v=torch.zeros(v.numel()))
+                   for k, v in src.items()}
+            lr_of = lambda k: 1e-2 if k == "even" else 3e-3
+            wd_of = lambda k: 0.1 if k == "ragged" else 0.0
+            max_norm = 0.7
+            for step in (1, 2):
+                per_rank = []
+                for r in range(world):          # every rank can rebuild all contributions: the expectation is local
+                    g = torch.Generator().manual_seed(1000 * step + r)
+                    per_rank.append({k: torch.randn(src[k].shape, generator=g) for k in names if k != "skipped"})
+                mine = {k: v.clone() for k, v in per_rank[rank].items()}
+                out2 = opt.step_from_local_grads(mine, step, lr_of, wd_of, max_norm=max_norm, comm_dtype=comm)
+                assert not mine                                            # full-size gradients were released
+                mean = {}
+                for k in per_rank[0]:
+                    tot = sum(p[k].to(comm).float() for p in per_rank).to(comm).float()
+                    mean[k] = tot / world
+                sq = sum((v ** 2).sum() for v in mean.values())
+                coef = torch.clamp(max_norm / (sq.sqrt() + 1e-6), max=1.0)
+                assert torch.allclose(out2[0], sq, rtol=1e-5) and torch.allclose(out2[1], coef, rtol=1e-5)
+                for k in mean:
+                    r_ = ref[k]
+                    torch_adamw(r_["master"], ref_p[k].view(-1), mean[k].reshape(-1), r_["m"], r_["v"], lr_of(k), 0.9,
+                                0.999, 1e-8, wd_of(k), step, clip_coef=out2[1])
+                for k in names:
+                    assert torch.equal(params[k], ref_p[k]), (k, step, comm)
+                    lo, hi, _ = slice_range(src[k].numel(), rank, world)
+                    if k != "skipped":
+                        assert torch.equal(opt.master[k], ref[k]["master"][lo:hi]), (k, step, comm)
+        q.put((rank, "ok"))
+    except Exception as e:  # surfaced by the parent
+        import traceback
+        q.put((rank, repr(e) + traceback.format_exc()[-800:]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_gradients_zero2_world2_gloo():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_zero2_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(results) == [(0, "ok"), (1, "ok")], results
