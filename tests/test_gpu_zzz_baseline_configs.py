@@ -69,3 +69,29 @@ def test_config2_rgb_depth_seg_audio_pack(env):
     pooled = model.encode_images_pooled(torch.cat(b["images"], 0).cuda(), [V] * B, None, b["audio"], b["segmasks"])
     visual = model.get_model().mm_projector(pooled)
     assert visual.shape == ref["visual"].shape and rel_err(visual, ref["visual"]) < TOL_STAGE
+
+
+def test_full_width_decoder_layer():
+    """configs[1] dimensions where the parity configuration is reduced: ONE decoder layer at the 7B width (hidden 4096,
+    32 heads x 128, MLP 11008, vocabulary 32000 -- the tile shapes, split-K cluster sizes and the lm_head / argmax
+    extent the benchmark runs) behind the full-width ViT / pooler / projector, greedy 4 tokens, against the oracle.
+    (The CPU oracle in bf16 differs from its fp32 self by 1.0e-2 on this case -- the band the tolerance allows for.)"""
+    torch.set_grad_enabled(False)
+    from mm_or_b200.model.llava_llama import LlavaLlamaForCausalLM
+    cfg = gc.small_config(hidden_size=4096, intermediate_size=11008, num_hidden_layers=1, num_attention_heads=32,
+                          vocab_size=32000)
+    sd = gc.bf16_round(gc.small_weights(cfg))
+    model = LlavaLlamaForCausalLM(cfg).load_state_dict(sd)
+    model.config.tokenizer_padding_side = "left"
+    ocfg = oracle_cfg(cfg)
+    b = synth_batch(cfg, 2, 1, 48, seed=53, jitter=5, image_pos=7)
+    out, lg = model.generate(b["input_ids"], images=b["images"], max_new_tokens=4, stop_on_eos=False,
+                             return_logits=True)
+    ref = O.multimodal_prefill(sd, ocfg, b["input_ids"], b["attention_mask"], b["images"], padding_side="left")
+    toks, ref_lg = O.greedy_decode(sd, ocfg, ref["logits"][:, -1], ref["kv"], ref["mask"], 4, stop_on_eos=False)
+    assert lg.shape == ref_lg.shape == (2, 4, 32000)
+    assert rel_err(lg, ref_lg) < TOL_E2E
+    err = (lg.cpu().float() - ref_lg).abs().max().item()
+    top2 = ref_lg.topk(2, -1).values
+    safe = (top2[..., 0] - top2[..., 1]) > 2 * err
+    assert torch.equal(out[:, b["input_ids"].shape[1]:].cpu()[safe], toks[safe])
