@@ -46,14 +46,21 @@ int b200_prof_family_count(void);
 const char* b200_prof_family_name(int family);
 int b200_prof_collect(double* ms, double* alg_bytes, double* alg_flops, long long* launches);
 
-/* Programmatic dependent launch for the kernels of b200_llama_decode_step (no reference counterpart: the reference's
- * decode step is ~1900 separate eager launches from Python). Off unless the environment has B200_PDL=1 or
- * b200_set_pdl(1) was called before the step is launched / captured: the step's kernels are then launched with
- * programmatic stream serialization, so each kernel's prologue -- and the first weight tiles of the GEMMs, which do
- * not depend on the previous kernel -- overlaps the tail of the kernel before it. Results are bit-identical either
- * way (same kernels, same arithmetic order). Process-wide switch; not yet timed on hardware. */
-int b200_set_pdl(int on);
-int b200_get_pdl(void);
+/* Process-wide tuning switches of the decode step (no reference counterpart: the reference's decode step is ~1900
+ * separate eager launches from Python). Both are OFF unless set here or through the environment variable named below
+ * BEFORE the step is launched / captured into a CUDA graph; results are bit-identical either way (same
+ * arithmetic in the same order per output element: "pdl" only changes scheduling, "decode_tiles" only which CTA owns
+ * an output column). Neither has been timed on hardware yet
+ * (DESIGN.md section 8), which is why they are switches.
+ *   "pdl"          (B200_PDL=1): programmatic dependent launch -- the step's kernels are launched with programmatic
+ *                  stream serialization, so each kernel's prologue, and the first weight tiles of the GEMMs (which do
+ *                  not depend on the previous kernel), overlap the tail of the kernel before it.
+ *   "decode_tiles" (B200_DECODE_TILES=1): the wide projections (qkv, gate_up, lm_head) choose their weight-tile width
+ *                  from {96, 128, 160, 224, 256} so that the tiles cover the SMs in as few waves as possible
+ *                  (12288 / 96 = 128 tiles, 22016 / 160 = 138, 32000 / 224 = 143 on 148 SMs) instead of 128 columns.
+ * b200_set_option returns 0, or -2 for an unknown name; b200_get_option returns 0 / 1, or -2. */
+int b200_set_option(const char* name, int value);
+int b200_get_option(const char* name);
 
 /* ============================================================================================================
  * Operator level (used by the stage entry points below and by the parity tests)

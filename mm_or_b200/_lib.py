@@ -75,8 +75,8 @@ _SIGS = {
     "b200_prof_family_count": (ci, []),
     "b200_prof_family_name": (ctypes.c_char_p, [ci]),
     "b200_prof_collect": (ci, [vp, vp, vp, vp]),
-    "b200_set_pdl": (ci, [ci]),
-    "b200_get_pdl": (ci, []),
+    "b200_set_option": (ci, [ctypes.c_char_p, ci]),
+    "b200_get_option": (ci, [ctypes.c_char_p]),
     "b200_gemm_bf16": (ci, [vp, ci, vp, ci, vp, ci, ci, ci, ci, vp, vp, ci, vp, ci, ci, ci, vp]),
     "b200_gemm_bf16_skinny": (ci, [vp, ci, vp, ci, vp, ci, ci, ci, ci, vp, vp, ci, ci, ci, ci, vp]),
     "b200_gemm_bf16_ex": (ci, [vp, ci, ci, vp, ci, ci, vp, ci, ci, ci, ci, vp, vp, ci, ci, ci, ci, cf, ci, vp]),
@@ -471,14 +471,25 @@ def launch_count():
     return int(lib().b200_launch_count()) + _graph_launches
 
 
+def set_option(name, value=True):
+    """Tuning switches of the decode step (include/b200_mmor.h: b200_set_option): "pdl", "decode_tiles". Call before
+    generate(): the decode CUDA graph is captured with whatever is set at that time."""
+    check(lib().b200_set_option(name.encode(), int(value)), "b200_set_option")
+
+
+def get_option(name):
+    v = int(lib().b200_get_option(name.encode()))
+    if v < 0:
+        check(v, "b200_get_option")
+    return bool(v)
+
+
 def set_pdl(on=True):
-    """Programmatic dependent launch for the decode step's kernels (include/b200_mmor.h: b200_set_pdl). Call before
-    the first generate(): the decode CUDA graph is captured with whatever is set at that time."""
-    check(lib().b200_set_pdl(int(on)), "b200_set_pdl")
+    set_option("pdl", on)
 
 
 def pdl_enabled():
-    return bool(lib().b200_get_pdl())
+    return get_option("pdl")
 
 
 def prof_enable(on=True):

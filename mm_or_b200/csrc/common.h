@@ -43,6 +43,10 @@ int num_sms();
 // ---------------------------------------------------------------------------------------------
 bool pdl_enabled();
 void set_pdl(bool on);
+// Tile widths 96 / 160 / 224 for the decode step's wide projections (stages.cu::decode_bn). Opt-in like PDL
+// (B200_DECODE_TILES=1 or b200_set_option("decode_tiles", 1)) until timed on hardware.
+bool decode_tiles_enabled();
+void set_decode_tiles(bool on);
 
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_ex(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,

@@ -27,18 +27,21 @@ int fail(int code, const char* fmt, ...) {
 
 const char* last_error_cstr() { return g_last_error.c_str(); }
 
-// programmatic dependent launch switch (common.h): -1 = not read yet, then 0 / 1
-static std::atomic<int> g_pdl{-1};
-bool pdl_enabled() {
-  int v = g_pdl.load(std::memory_order_relaxed);
-  if (v < 0) {
-    const char* e = getenv("B200_PDL");
-    v = (e != nullptr && e[0] != '\0' && e[0] != '0') ? 1 : 0;
-    g_pdl.store(v, std::memory_order_relaxed);
+// process-wide tuning switches (common.h): -1 = not read from the environment yet, then 0 / 1
+static std::atomic<int> g_pdl{-1}, g_decode_tiles{-1};
+static bool env_switch(std::atomic<int>& v, const char* name) {
+  int x = v.load(std::memory_order_relaxed);
+  if (x < 0) {
+    const char* e = getenv(name);
+    x = (e != nullptr && e[0] != '\0' && e[0] != '0') ? 1 : 0;
+    v.store(x, std::memory_order_relaxed);
   }
-  return v != 0;
+  return x != 0;
 }
+bool pdl_enabled() { return env_switch(g_pdl, "B200_PDL"); }
 void set_pdl(bool on) { g_pdl.store(on ? 1 : 0, std::memory_order_relaxed); }
+bool decode_tiles_enabled() { return env_switch(g_decode_tiles, "B200_DECODE_TILES"); }
+void set_decode_tiles(bool on) { g_decode_tiles.store(on ? 1 : 0, std::memory_order_relaxed); }
 
 // ---------------------------------------------------------------------------------------------
 // launch counter + per-family event timing
@@ -93,11 +96,21 @@ extern "C" {
 
 long long b200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
-int b200_set_pdl(int on) {
-  set_pdl(on != 0);
+int b200_set_option(const char* name, int value) {
+  if (name == nullptr) return fail(-2, "b200_set_option: null name");
+  const std::string n(name);
+  if (n == "pdl") set_pdl(value != 0);
+  else if (n == "decode_tiles") set_decode_tiles(value != 0);
+  else return fail(-2, "b200_set_option: unknown option '%s' (pdl, decode_tiles)", name);
   return 0;
 }
-int b200_get_pdl(void) { return pdl_enabled() ? 1 : 0; }
+int b200_get_option(const char* name) {
+  if (name == nullptr) return fail(-2, "b200_get_option: null name");
+  const std::string n(name);
+  if (n == "pdl") return pdl_enabled() ? 1 : 0;
+  if (n == "decode_tiles") return decode_tiles_enabled() ? 1 : 0;
+  return fail(-2, "b200_get_option: unknown option '%s' (pdl, decode_tiles)", name);
+}
 
 int b200_prof_enable(int on) {
   std::lock_guard<std::mutex> lk(g_prof_mu);

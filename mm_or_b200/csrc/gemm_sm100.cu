@@ -43,9 +43,17 @@ struct GemmCfg {
   static constexpr int kStageBytesA = kBM * kBK * 2;
   static constexpr int kStageBytesB = BN * kBK * 2;
   static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
-  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128) ? 6 : 8;
-  static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;  // power of two for BN in {32,64,128,256}
+  // BN in {32, 64, 128, 256} are the general-purpose tiles; 96 / 160 / 224 exist for the decode step's wide
+  // projections, where the tile width decides whether the weight tiles fill the 148 SMs in one wave
+  // (stages.cu::decode_bn): 12288 / 96 = 128 tiles, 22016 / 160 = 138, 32000 / 224 = 143.
+  static constexpr int kStages = (BN == 256) ? 4 : (BN == 224) ? 5 : (BN >= 128) ? 6 : (BN == 96) ? 7 : 8;
+  // two accumulators of BN columns; tcgen05.alloc takes a power of two >= 32
+  static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 :
+                                   (2 * BN <= 256) ? 256 : 512;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static_assert(BN % 32 == 0 && BN <= 256, "the epilogue drains 32 accumulator columns at a time");
+  static_assert(kStageBytesB % 1024 == 0, "SWIZZLE_128B tiles start on 1024-byte boundaries");
+  static_assert(kSmemBytes <= 227 * 1024, "shared memory per CTA");
 };
 
 __device__ __forceinline__ void tile_coords(int tile, int m_tiles, int n_tiles, int& mt, int& nt) {
@@ -429,7 +437,9 @@ int gemm_bf16_ex(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, int b
     while (bn > 32 && m_tiles * ((N + bn - 1) / bn) < sms) bn >>= 1;
   }
   if (b_mn && bn < 64) bn = 64;  // a transposed B tile is made of 64-column panels
-  if (bn != 32 && bn != 64 && bn != 128 && bn != 256) return fail(-2, "gemm: unsupported BN %d", bn);
+  if (bn != 32 && bn != 64 && bn != 96 && bn != 128 && bn != 160 && bn != 224 && bn != 256)
+    return fail(-2, "gemm: unsupported BN %d", bn);
+  if (b_mn && bn % 64 != 0) return fail(-2, "gemm: a transposed B operand needs BN %% 64 == 0 (got %d)", bn);
   GemmArgs g;
   g.C = C;
   g.ldc = ldc;
@@ -452,7 +462,10 @@ int gemm_bf16_ex(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, int b
     B200_TRY(make_tmap_2d(&tmB, B, N, K, ldb, bn));
   switch (bn) {
     case 256: return launch_gemm<256>(tmA, tmB, g, stream);
+    case 224: return launch_gemm<224>(tmA, tmB, g, stream);
+    case 160: return launch_gemm<160>(tmA, tmB, g, stream);
     case 128: return launch_gemm<128>(tmA, tmB, g, stream);
+    case 96: return launch_gemm<96>(tmA, tmB, g, stream);
     case 64: return launch_gemm<64>(tmA, tmB, g, stream);
     default: return launch_gemm<32>(tmA, tmB, g, stream);
   }

@@ -225,6 +225,26 @@ static size_t llama_prefill_ws(const b200_llama_weights* w, int Bn, int L, int a
 // (profiles/r1_skinny_gemm_notes.md): projections with few 128-row weight tiles (N = 4096: o_proj, down_proj) are
 // 1.3-1.9x faster on the split-K cluster kernel, which keeps two streaming CTAs on every SM; the wide ones (qkv,
 // gate_up, lm_head) already fill the chip with 128-column tiles of the tiled kernel.
+// Weight-tile width of a wide decode-step projection (opt-in, common.h: decode_tiles_enabled): the kernel is
+// persistent with one CTA per SM and HBM bound, so its time is (waves of tiles over the SMs) x (bytes of one tile);
+// pick the width that minimises waves x width. 7B shapes on 148 SMs: qkv 12288 -> 96 (128 tiles, one wave),
+// gate_up 22016 -> 160 (138 tiles), lm_head 32000 -> 224 (143 tiles); with 128 columns they take 96 / 172 / 250 tiles.
+static int decode_bn(int T, int N) {
+  static const int widths[] = {256, 224, 160, 128, 96};
+  const int sms = num_sms(), m_tiles = (T + 127) / 128;
+  int best = 128;
+  long long best_cost = -1;
+  for (int bn : widths) {
+    const long long tiles = static_cast<long long>(m_tiles) * ((N + bn - 1) / bn);
+    const long long cost = ((tiles + sms - 1) / sms) * bn;
+    if (best_cost < 0 || cost < best_cost) {
+      best_cost = cost;
+      best = bn;
+    }
+  }
+  return best;
+}
+
 static int linear(const bf16* A, int lda, const bf16* W, int ldw, void* C, int ldc, int T, int N, int K,
                   const GemmEpilogue& e_in, bool decode, cudaStream_t st) {
   GemmEpilogue e = e_in;
@@ -232,6 +252,7 @@ static int linear(const bf16* A, int lda, const bf16* W, int ldw, void* C, int l
   if (decode && T <= 256) {
     const int n_tiles = (N + 127) / 128;
     if (n_tiles * 2 <= num_sms()) return gemm_skinny(A, lda, W, ldw, C, ldc, T, N, K, e, 0, st);
+    if (decode_tiles_enabled()) return gemm_bf16_tn(A, lda, W, ldw, C, ldc, T, N, K, e, decode_bn(T, N), st);
     if (T <= 128) return gemm_bf16_tn(A, lda, W, ldw, C, ldc, T, N, K, e, 128, st);
   }
   return gemm_bf16_tn(A, lda, W, ldw, C, ldc, T, N, K, e, 0, st);

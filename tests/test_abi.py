@@ -45,3 +45,20 @@ def test_no_cpu_fallback():
     import torch
     with pytest.raises(L.B200Error):
         L.ptr(torch.zeros(4))
+
+
+def test_decode_step_switches_default_off_and_reject_unknown_names():
+    """b200_set_option / b200_get_option (host-side state only; the switches themselves are exercised on the GPU by
+    tests/test_gpu_zzzz_switches.py)."""
+    import pytest
+    for name in ("pdl", "decode_tiles"):
+        if os.environ.get("B200_" + name.upper(), "0") in ("", "0"):
+            assert L.get_option(name) is False
+        L.set_option(name, True)
+        assert L.get_option(name) is True
+        L.set_option(name, False)
+        assert L.get_option(name) is False
+    with pytest.raises(L.B200Error):
+        L.set_option("no_such_switch", 1)
+    with pytest.raises(L.B200Error):
+        L.get_option("no_such_switch")

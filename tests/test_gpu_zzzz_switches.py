@@ -1,0 +1,109 @@
+"""The decode step's opt-in switches (include/b200_mmor.h: b200_set_option) and the tile widths behind them.
+
+  "pdl"           programmatic dependent launch: the same kernels in the same arithmetic order, only their scheduling
+                  overlaps -> tokens and logits must be BIT-identical with the switch on and off, through the eager
+                  decode loop (return_logits) and through the captured CUDA graph.
+  "decode_tiles"  weight-tile widths 96 / 160 / 224 for the wide projections: per output element the same k order
+                  -> bit-identical as well; the new widths are also checked as plain GEMMs against torch.
+
+Opt-in like the switches themselves (B200_TEST_SWITCHES=1): neither has run on hardware yet, and a scheduling bug in
+the first would show up as a hang rather than a wrong number. tools/gpu_first_pass.sh runs this file under its own
+timeout before anything relies on it. Last file of the GPU suite on purpose."""
+import math
+import os
+
+import pytest
+import torch
+
+import golden_cases as gc
+from helpers import rel_err
+from mm_or_b200 import _lib as L
+from mm_or_b200.synth import synth_batch
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("B200_TEST_SWITCHES", "0") != "1",
+                                 reason="decode-step switches are opt-in until validated on hardware "
+                                        "(set B200_TEST_SWITCHES=1)")]
+
+
+def _model(**cfg_kw):
+    torch.set_grad_enabled(False)
+    from mm_or_b200.model.llava_llama import LlavaLlamaForCausalLM
+    cfg = gc.small_config(**cfg_kw)
+    sd = gc.bf16_round(gc.small_weights(cfg))
+    model = LlavaLlamaForCausalLM(cfg).load_state_dict(sd)
+    model.config.tokenizer_padding_side = "left"
+    return cfg, model
+
+
+@pytest.fixture(scope="module")
+def env():
+    return _model()
+
+
+def _with(option, fn):
+    assert not L.get_option(option)
+    try:
+        L.set_option(option, True)
+        assert L.get_option(option)
+        out = fn()
+        torch.cuda.synchronize()
+    finally:
+        L.set_option(option, False)
+    return out
+
+
+def test_unknown_option_is_an_error():
+    with pytest.raises(L.B200Error):
+        L.set_option("no_such_switch", 1)
+
+
+@pytest.mark.parametrize("batch", [2, 40, 130])       # decode GEMM tiles MT = 32 / 64 / 256
+def test_decode_step_bit_identical_with_pdl(env, batch):
+    cfg, model = env
+    b = synth_batch(cfg, batch, 1, 20, seed=60 + batch, jitter=4, image_pos=3)
+    kw = dict(images=b["images"], max_new_tokens=12, stop_on_eos=False)
+    ref_ids, ref_lg = model.generate(b["input_ids"], return_logits=True, **kw)           # eager loop
+    ref_graph = model.generate(b["input_ids"], **kw)                                     # CUDA graph
+    ids, lg = _with("pdl", lambda: model.generate(b["input_ids"], return_logits=True, **kw))
+    ids_graph = _with("pdl", lambda: model.generate(b["input_ids"], **kw))
+    assert torch.equal(ids, ref_ids) and torch.equal(lg, ref_lg)
+    assert torch.equal(ids_graph, ref_graph) and torch.equal(ref_graph, ref_ids)
+
+
+@pytest.mark.parametrize("option", ["pdl", "decode_tiles"])
+def test_wide_projection_on_the_tiled_kernel(option):
+    """lm_head with 12288 rows: 96 weight tiles x 2 > 148 SMs, so stages.cu::linear sends it to the tiled kernel
+    (gemm_sm100.cu): with "pdl" that kernel prefetches weights before the grid dependency resolves, with
+    "decode_tiles" it runs 96-column tiles (128 tiles, one wave) instead of 128-column ones."""
+    cfg, model = _model(vocab_size=12288)
+    b = synth_batch(cfg, 3, 1, 16, seed=70, jitter=2, image_pos=2)
+    kw = dict(images=b["images"], max_new_tokens=8, stop_on_eos=False)
+    ref_ids, ref_lg = model.generate(b["input_ids"], return_logits=True, **kw)
+    ids, lg = _with(option, lambda: model.generate(b["input_ids"], return_logits=True, **kw))
+    ids_graph = _with(option, lambda: model.generate(b["input_ids"], **kw))
+    assert torch.equal(ids, ref_ids) and torch.equal(lg, ref_lg) and torch.equal(ids_graph, ref_ids)
+
+
+@pytest.mark.parametrize("bn", [96, 160, 224])
+@pytest.mark.parametrize("M,N,K", [(64, 22016, 4096), (128, 12288, 4096), (130, 32000, 512), (100, 264, 72),
+                                   (1000, 1120, 1024)])
+def test_new_tile_widths_as_plain_gemms(bn, M, N, K):
+    """C = A W^T with the tile widths added for the decode step, incl. ragged N / K edges and several tiles per CTA,
+    against torch fp32 on the same bf16 inputs; and bit-identical to the 128-column tiles."""
+    g = torch.Generator(device="cuda").manual_seed(7)
+    a = torch.randn(M, K, generator=g, device="cuda").to(torch.bfloat16)
+    w = (torch.randn(N, K, generator=g, device="cuda") / math.sqrt(K)).to(torch.bfloat16)
+    out = L.gemm(a, w, bn=bn)
+    assert rel_err(out, a.float() @ w.float().t()) < 5e-3
+    assert torch.equal(out, L.gemm(a, w, bn=128))
+
+
+@pytest.mark.parametrize("bn", [96, 160, 224])
+def test_new_tile_widths_swiglu_epilogue(bn):
+    M, N, K = 48, 22016, 512
+    g = torch.Generator(device="cuda").manual_seed(8)
+    a = torch.randn(M, K, generator=g, device="cuda").to(torch.bfloat16)
+    w = (torch.randn(N, K, generator=g, device="cuda") / math.sqrt(K)).to(torch.bfloat16)
+    out = L.gemm(a, w, act=L.ACT_SWIGLU, bn=bn)
+    assert out.shape == (M, N // 2) and torch.equal(out, L.gemm(a, w, act=L.ACT_SWIGLU, bn=128))

@@ -9,8 +9,8 @@ nvidia-smi --query-gpu=name,clocks.max.sm,clocks.max.mem,power.limit --format=cs
 timeout 240 python -m pytest tests/test_gpu_zzz_baseline_configs.py tests/test_gpu_zz_pointcloud.py \
   tests/test_gpu_zz_train_extras.py -m gpu -q --timeout 200 2>&1 | tail -25 > gpurun_out/${TAG}_pytest_new.log
 echo "new tests rc=${PIPESTATUS[0]}"; tail -6 gpurun_out/${TAG}_pytest_new.log
-# 1b. programmatic dependent launch of the decode step (opt-in, never run on hardware): bit-identity first, then timing
-B200_TEST_PDL=1 timeout 300 python -m pytest tests/test_gpu_zzzz_pdl.py -m gpu -q --timeout 250 2>&1 | tail -8 \
+# 1b. the decode step's opt-in switches (programmatic dependent launch, tile widths 96/160/224; never run on hardware)
+B200_TEST_SWITCHES=1 timeout 300 python -m pytest tests/test_gpu_zzzz_switches.py -m gpu -q --timeout 250 2>&1 | tail -8 \
   > gpurun_out/${TAG}_pytest_pdl.log
 echo "pdl tests rc=${PIPESTATUS[0]}"; tail -4 gpurun_out/${TAG}_pytest_pdl.log
 # 2. the whole suite + smoke
@@ -32,5 +32,7 @@ echo "bench rc=$?"; tail -c 3000 gpurun_out/${TAG}_bench.json; tail -3 gpurun_ou
 #    (weights amortised over more samples: KV cache 0.56 GB per sample, 192 samples = 108 GB + 14 GB of weights)
 timeout 900 python bench.py --steps 3 --warmup 3 --pdl --no-cpu-baseline > gpurun_out/${TAG}_bench_pdl.json 2> gpurun_out/${TAG}_bench_pdl.err
 echo "bench --pdl rc=$?"; tail -c 1500 gpurun_out/${TAG}_bench_pdl.json
+timeout 900 python bench.py --steps 3 --warmup 3 --decode-tiles --no-cpu-baseline > gpurun_out/${TAG}_bench_tiles.json 2> gpurun_out/${TAG}_bench_tiles.err
+echo "bench --decode-tiles rc=$?"; tail -c 1500 gpurun_out/${TAG}_bench_tiles.json
 timeout 900 python bench.py --steps 2 --warmup 3 --batch 192 --no-cpu-baseline > gpurun_out/${TAG}_bench_b192.json 2> gpurun_out/${TAG}_bench_b192.err
 echo "bench b192 rc=$?"; tail -c 1500 gpurun_out/${TAG}_bench_b192.json
