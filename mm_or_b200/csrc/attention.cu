@@ -46,7 +46,8 @@ __global__ void __launch_bounds__(kDecThreads) decode_attn_kernel(const DecodeAr
 
   const int start = a.kv_start ? a.kv_start[b] : 0;
   const int ctx = a.ctx_dev ? min(*a.ctx_dev + a.ctx_add, a.cap) : a.ctx;
-  const int total = max(0, ctx - start);
+  const bool skip = a.finished != nullptr && a.finished[b] != 0;  // block-uniform: the row stopped at EOS earlier
+  const int total = skip ? 0 : max(0, ctx - start);
   const int per = (total + a.splits - 1) / a.splits;
   const int k0 = start + split * per;
   const int k1 = min(ctx, k0 + per);

@@ -239,6 +239,8 @@ struct DecodeArgs {
   const int* ctx_dev;   // ... or, when non-null, *ctx_dev + ctx_add (decode under a CUDA graph); ctx is then the
   int ctx_add;          //     upper bound used for launch sizing
   const int* kv_start;  // [B] first valid slot (left padding), or null
+  const int* finished;  // [B] or null: rows with finished[b] != 0 (EOS already emitted, HF greedy pads them from then
+                        // on) read no cache at all and get o = 0 -- their logits are never used
   float scale_log2;
   int splits;  // 0 = choose
   float* part_o;

@@ -261,7 +261,7 @@ static int linear(const bf16* A, int lda, const bf16* W, int ldw, void* C, int l
 static int llama_layer(const b200_llama_weights* w, const b200_llama_layer& Ly, bf16* x, bf16* nbuf, bf16* qkv,
                        bf16* act, const int* kv_start, const int* kv_len, bf16* kc, bf16* vc, int cap, int Bn, int L,
                        int decode, const int* state, int ctx_bound, void* dec_ws, size_t dec_ws_bytes,
-                       cudaStream_t st) {
+                       const int* finished, cudaStream_t st) {
   const bool sk = decode != 0;
   const int D = w->hidden, H = w->heads, T = Bn * L;
   B200_TRY(rmsnorm(x, D, B(Ly.attn_norm), w->rms_eps, nbuf, D, T, D, st));
@@ -307,6 +307,7 @@ static int llama_layer(const b200_llama_weights* w, const b200_llama_layer& Ly, 
     da.ctx_dev = state;
     da.ctx_add = 1;  // the token written by rope_kv_write above is visible to itself
     da.kv_start = kv_start;
+    da.finished = finished;
     da.scale_log2 = kLog2e / sqrtf(128.f);
     da.splits = 0;
     B200_TRY(decode_attn(da, dec_ws, dec_ws_bytes, st));
@@ -344,7 +345,7 @@ static int llama_prefill(const b200_llama_weights* w, bf16* x, const int* kv_sta
     bf16* kc = static_cast<bf16*>(c->k) + l * c->layer_stride;
     bf16* vc = static_cast<bf16*>(c->v) + l * c->layer_stride;
     B200_TRY(llama_layer(w, w->layers[l], x, nbuf, qkv, act, kv_start, kv_len, kc, vc, c->cap, Bn, L, 0, nullptr, 0,
-                         nullptr, 0, st));
+                         nullptr, 0, nullptr, st));
   }
   if (logits != nullptr) {
     GemmEpilogue e;
@@ -394,7 +395,7 @@ static int llama_decode_step(const b200_llama_weights* w, int* tokens, int* stat
     bf16* kc = static_cast<bf16*>(c->k) + l * c->layer_stride;
     bf16* vc = static_cast<bf16*>(c->v) + l * c->layer_stride;
     B200_TRY(llama_layer(w, w->layers[l], x, nbuf, qkv, act, kv_start, nullptr, kc, vc, c->cap, Bn, 1, 1, state,
-                         ctx_bound, dws, dws_bytes, st));
+                         ctx_bound, dws, dws_bytes, logits_out == nullptr ? finished : nullptr, st));
   }
   B200_TRY(rmsnorm(x, D, B(w->final_norm), w->rms_eps, nbuf, D, Bn, D, st));
   GemmEpilogue e;

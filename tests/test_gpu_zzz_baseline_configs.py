@@ -95,3 +95,39 @@ def test_full_width_decoder_layer():
     top2 = ref_lg.topk(2, -1).values
     safe = (top2[..., 0] - top2[..., 1]) > 2 * err
     assert torch.equal(out[:, b["input_ids"].shape[1]:].cpu()[safe], toks[safe])
+
+
+def test_rows_finished_at_eos_skip_their_cache_reads():
+    """A row that has emitted EOS is padded from then on (HF greedy) and its decode attention reads no KV cache any more
+    (DecodeArgs::finished, attention.cu); the rows still running must not notice. EOS is set to the first token of the
+    last row, so that row stops after one step while the others run to max_new_tokens. Checked (i) bit for bit against
+    the same model decoding WITHOUT the skip (return_logits=True keeps every row's logits alive, stages.cu) and
+    (ii) against the oracle's HF-greedy tokens wherever the oracle's top-2 margin exceeds twice the logit error."""
+    torch.set_grad_enabled(False)
+    from mm_or_b200.model.llava_llama import LlavaLlamaForCausalLM
+    cfg = gc.small_config()
+    ocfg = oracle_cfg(cfg)
+    sd = gc.bf16_round(gc.small_weights(cfg, peaked=40.0))
+    b = synth_batch(cfg, 3, 2, 24, seed=72, jitter=3, image_pos=5)  # oracle top-2 margins >= 1.1 on the running rows
+    steps, Lin = 12, b["input_ids"].shape[1]
+    ref = O.multimodal_prefill(sd, ocfg, b["input_ids"], b["attention_mask"], b["images"], padding_side="left")
+    free, _ = O.greedy_decode(sd, ocfg, ref["logits"][:, -1], ref["kv"], ref["mask"], steps, stop_on_eos=False)
+    eos = int(free[2, 0])
+    assert not (free[:2] == eos).any()                             # rows 0 and 1 never stop
+    ref = O.multimodal_prefill(sd, ocfg, b["input_ids"], b["attention_mask"], b["images"], padding_side="left")
+    toks, ref_lg = O.greedy_decode(sd, ocfg, ref["logits"][:, -1], ref["kv"], ref["mask"], steps, eos_id=eos,
+                                   stop_on_eos=True)
+    assert toks.shape[1] == steps and (toks[2, 1:] == 0).all()      # row 2: EOS, then pad
+    cfg.eos_token_id = eos
+    model = LlavaLlamaForCausalLM(cfg).load_state_dict(sd)
+    model.config.tokenizer_padding_side = "left"
+    full, lg = model.generate(b["input_ids"], images=b["images"], max_new_tokens=steps, return_logits=True)
+    skip = model.generate(b["input_ids"], images=b["images"], max_new_tokens=steps)      # graph path, skip active
+    assert torch.equal(skip, full)
+    gen = skip[:, Lin:].cpu()
+    assert gen.shape == toks.shape and (gen[2, 1:] == 0).all() and int(gen[2, 0]) == eos
+    err = (lg[:2].cpu().float() - ref_lg[:2]).abs().max().item()
+    top2 = ref_lg.topk(2, -1).values
+    safe = (top2[..., 0] - top2[..., 1]) > 2 * err
+    safe[2] = True                                                   # EOS / pad positions are exact by construction
+    assert torch.equal(gen[safe], toks[safe])
