@@ -61,6 +61,9 @@ int b200_prof_collect(double* ms, double* alg_bytes, double* alg_flops, long lon
  * b200_set_option returns 0, or -2 for an unknown name; b200_get_option returns 0 / 1, or -2. */
 int b200_set_option(const char* name, int value);
 int b200_get_option(const char* name);
+/* The weight-tile width "decode_tiles" picks for a projection with `n` output features at `rows` sequences on a
+ * device with `sms` SMs (host-side arithmetic only; exposed so that the policy can be pinned without a GPU). */
+int b200_decode_tile_width(int rows, int n, int sms);
 
 /* ============================================================================================================
  * Operator level (used by the stage entry points below and by the parity tests)

@@ -77,6 +77,7 @@ _SIGS = {
     "b200_prof_collect": (ci, [vp, vp, vp, vp]),
     "b200_set_option": (ci, [ctypes.c_char_p, ci]),
     "b200_get_option": (ci, [ctypes.c_char_p]),
+    "b200_decode_tile_width": (ci, [ci, ci, ci]),
     "b200_gemm_bf16": (ci, [vp, ci, vp, ci, vp, ci, ci, ci, ci, vp, vp, ci, vp, ci, ci, ci, vp]),
     "b200_gemm_bf16_skinny": (ci, [vp, ci, vp, ci, vp, ci, ci, ci, ci, vp, vp, ci, ci, ci, ci, vp]),
     "b200_gemm_bf16_ex": (ci, [vp, ci, ci, vp, ci, ci, vp, ci, ci, ci, ci, vp, vp, ci, ci, ci, ci, cf, ci, vp]),

@@ -229,9 +229,10 @@ static size_t llama_prefill_ws(const b200_llama_weights* w, int Bn, int L, int a
 // persistent with one CTA per SM and HBM bound, so its time is (waves of tiles over the SMs) x (bytes of one tile);
 // pick the width that minimises waves x width. 7B shapes on 148 SMs: qkv 12288 -> 96 (128 tiles, one wave),
 // gate_up 22016 -> 160 (138 tiles), lm_head 32000 -> 224 (143 tiles); with 128 columns they take 96 / 172 / 250 tiles.
-static int decode_bn(int T, int N) {
+static int decode_bn(int T, int N, int sms) {
   static const int widths[] = {256, 224, 160, 128, 96};
-  const int sms = num_sms(), m_tiles = (T + 127) / 128;
+  const int m_tiles = (T + 127) / 128;
+  if (sms <= 0) return 128;
   int best = 128;
   long long best_cost = -1;
   for (int bn : widths) {
@@ -252,7 +253,7 @@ static int linear(const bf16* A, int lda, const bf16* W, int ldw, void* C, int l
   if (decode && T <= 256) {
     const int n_tiles = (N + 127) / 128;
     if (n_tiles * 2 <= num_sms()) return gemm_skinny(A, lda, W, ldw, C, ldc, T, N, K, e, 0, st);
-    if (decode_tiles_enabled()) return gemm_bf16_tn(A, lda, W, ldw, C, ldc, T, N, K, e, decode_bn(T, N), st);
+    if (decode_tiles_enabled()) return gemm_bf16_tn(A, lda, W, ldw, C, ldc, T, N, K, e, decode_bn(T, N, num_sms()), st);
     if (T <= 128) return gemm_bf16_tn(A, lda, W, ldw, C, ldc, T, N, K, e, 128, st);
   }
   return gemm_bf16_tn(A, lda, W, ldw, C, ldc, T, N, K, e, 0, st);
@@ -503,6 +504,8 @@ int b200_llama_prefill(const b200_llama_weights* w, void* x, const int32_t* kv_s
   return llama_prefill(w, static_cast<bf16*>(x), kv_start, kv_len, cache, Bn, L, logits, all_logits, logits_fp32,
                        workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
+
+int b200_decode_tile_width(int rows, int n, int sms) { return decode_bn(rows, n, sms); }
 
 size_t b200_llama_decode_workspace_bytes(const b200_llama_weights* w, int Bn, int cap) {
   return llama_decode_ws(w, Bn, cap);

@@ -62,3 +62,19 @@ def test_decode_step_switches_default_off_and_reject_unknown_names():
         L.set_option("no_such_switch", 1)
     with pytest.raises(L.B200Error):
         L.get_option("no_such_switch")
+
+
+def test_decode_tile_width_policy():
+    """stages.cu::decode_bn minimises (waves of weight tiles over the SMs) x (tile width). Llama-7B on 148 SMs:
+    qkv 12288 -> 96 (128 tiles), gate_up 22016 -> 160 (138 tiles), lm_head 32000 -> 224 (143 tiles): one wave each."""
+    w = L.lib().b200_decode_tile_width
+    assert [w(64, n, 148) for n in (12288, 22016, 32000)] == [96, 160, 224]
+    assert [w(128, n, 148) for n in (12288, 22016, 32000)] == [96, 160, 224]
+    for rows in (1, 64, 128, 192, 256):
+        for n in (4096, 12288, 22016, 32000, 512):
+            bn = w(rows, n, 148)
+            assert bn in (96, 128, 160, 224, 256)
+            m_tiles = (rows + 127) // 128
+            cost = lambda b: -(-(m_tiles * -(-n // b)) // 148) * b
+            assert cost(bn) == min(cost(b) for b in (96, 128, 160, 224, 256))
+    assert w(64, 12288, 0) == 128                      # no device: the default width
