@@ -249,7 +249,10 @@ static int decode_bn(int T, int N, int sms) {
 static int linear(const bf16* A, int lda, const bf16* W, int ldw, void* C, int ldc, int T, int N, int K,
                   const GemmEpilogue& e_in, bool decode, cudaStream_t st) {
   GemmEpilogue e = e_in;
-  e.b_const = decode ? 1 : 0;  // decode step: W is a weight matrix no kernel writes (PDL prefetch, common.h)
+  // decode step with programmatic dependent launch: W is a weight matrix no kernel writes, so its first tiles may be
+  // requested before the previous kernel has finished (common.h). Off => the launch and load order of every GEMM is
+  // exactly the one validated on hardware.
+  e.b_const = (decode && pdl_enabled()) ? 1 : 0;
   if (decode && T <= 256) {
     const int n_tiles = (N + 127) / 128;
     if (n_tiles * 2 <= num_sms()) return gemm_skinny(A, lda, W, ldw, C, ldc, T, N, K, e, 0, st);
