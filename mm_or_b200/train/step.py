@@ -128,9 +128,11 @@ class FineTuner:
 
     # ------------------------------------------------------------------------------------------------------------
     def forward_backward(self, input_ids, labels, attention_mask, images, grads=None, accumulate=False, pc=None,
-                         audio=None, segmasks=None):
+                         audio=None, segmasks=None, grad_scale=1.0):
         """Returns (loss, weight sum, grads under the reference's names). pc / audio / segmasks as in
-        LlavaLlamaForCausalLM.forward (llava_llama.py:54-70): lists with one entry (or None) per sample."""
+        LlavaLlamaForCausalLM.forward (llava_llama.py:54-70): lists with one entry (or None) per sample.
+        grads + accumulate=True add this batch's gradients into an existing store; grad_scale multiplies the loss
+        gradient (1 / gradient_accumulation_steps, as HF Trainer scales the loss of every micro-batch)."""
         model, dev = self.model, self.dev
         cfg = model.config
         tower, pooler, proj = model.get_vision_tower(), model.get_image_pooler(), model.get_model().mm_projector
@@ -160,8 +162,8 @@ class FineTuner:
         L.embed_rows(torch.as_tensor(vis_ids.reshape(-1)).to(dev), vis, out=embeds)
         loss, wsum, g, d_emb = T.forward_backward(model, embeds.view(B, Lq, D), torch.from_numpy(plan.labels).to(dev),
                                                   torch.from_numpy(plan.lengths).to(dev), self.vocab_weight,
-                                                  grads=grads, accumulate=accumulate, lora=self.lora,
-                                                  train_base=self.lora is None)
+                                                  grad_scale=grad_scale, grads=grads, accumulate=accumulate,
+                                                  lora=self.lora, train_base=self.lora is None)
         # pack backward: visual rows of d_embeds back to the projector output (truncated tokens get zeros)
         d_vis = L.embed_rows(torch.as_tensor(plan.row_map).to(dev), d_emb.reshape(B * Lq, D), rows=B * Tv)
         if self.train_embed:                                   # nn.Embedding backward over the text rows
@@ -238,3 +240,20 @@ class FineTuner:
         self.last_grads = grads
         norm_sq = self.optimizer_step(grads)
         return loss, norm_sq
+
+    def train_step_accumulated(self, micro_batches):
+        """One optimizer step over several micro-batches (the reference recipe runs gradient_accumulation_steps 4,
+        README.md:143): HF Trainer divides every micro-batch loss by the number of micro-batches, sums the gradients and
+        steps once. micro_batches: list of dicts with the keyword arguments of train_step. Returns (mean loss, out2)."""
+        n = len(micro_batches)
+        if n == 0:
+            raise ValueError("train_step_accumulated: no micro-batches")
+        grads, total = None, 0.0
+        for i, mb in enumerate(micro_batches):
+            loss, _, grads = self.forward_backward(mb["input_ids"], mb["labels"], mb.get("attention_mask"), mb["images"],
+                                                   grads=grads, accumulate=i > 0, pc=mb.get("pc"),
+                                                   audio=mb.get("audio"), segmasks=mb.get("segmasks"),
+                                                   grad_scale=1.0 / n)
+            total = total + loss / n
+        self.last_grads = grads
+        return total, self.optimizer_step(grads)

@@ -109,3 +109,4 @@ def test_fine_tune_gradients_against_reference_backward_fixture():
         if err > 0.12:                            # bf16 pipeline vs fp32 reference, as in the oracle comparison
             bad.append((k, err))
     assert not bad, bad
+
