@@ -14,3 +14,13 @@ timeout ${BENCH_TIMEOUT:-300} python -m torch.distributed.run --nnodes=1 --nproc
   bench.py --gpus $N --steps ${STEPS:-2} --warmup 3 --batch ${BATCH:-64} --new-tokens ${NEWTOK:-256} \
   > gpurun_out/${TAG}_bench_n$N.json 2> gpurun_out/${TAG}_bench_n$N.err
 echo "bench N=$N rc=$?"; tail -c 3500 gpurun_out/${TAG}_bench_n$N.json; tail -8 gpurun_out/${TAG}_bench_n$N.err
+# fine-tune step, data parallel (BASELINE configs[4]): replicated state vs ZeRO-2 (sharded state + bf16 reduce-scatter);
+# TRAIN=0 skips it. Full fine-tuning holds 185 GB on one GPU unsharded, so the replicated arm runs the LoRA recipe.
+if [[ ${TRAIN:-1} == 1 ]]; then
+  for Z in 0 2; do
+    EXTRA=""; [[ $Z == 0 ]] && EXTRA="--lora-r 128"
+    timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29542 \
+      tools/train_bench.py --zero $Z $EXTRA > gpurun_out/${TAG}_train_z${Z}_n$N.json 2> gpurun_out/${TAG}_train_z${Z}_n$N.err
+    echo "train_bench zero=$Z N=$N rc=$?"; tail -c 1200 gpurun_out/${TAG}_train_z${Z}_n$N.json; tail -3 gpurun_out/${TAG}_train_z${Z}_n$N.err
+  done
+fi
