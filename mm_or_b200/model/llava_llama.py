@@ -19,7 +19,7 @@ from .. import _lib as L
 from ..config import LlavaConfig
 from ..constants import IGNORE_INDEX, IMAGE_TOKEN_INDEX
 from ..synth import POOLER_GEOMETRY
-from .pack import plan_pack
+from .pack import descriptor_row_counts, plan_pack
 
 VIT = "model.vision_tower.vision_tower.vision_model."
 POOL = "model.image_pooler."
@@ -556,18 +556,24 @@ class LlavaLlamaForCausalLM:
                                              images, vis_descriptor_embs=None, pc=None, audio=None, segmasks=None):
         """Returns (None, position_ids, attention_mask, past_key_values, inputs_embeds, labels) like
         llava_arch.py:188-353, plus the PackPlan as a 7th element for the native prefill."""
-        if vis_descriptor_embs is not None:
-            raise NotImplementedError("vis_descriptor_embs are not used by the MM2SG scene-graph path")
         if getattr(self.config, "tune_mm_mlp_adapter", False) and getattr(self.config, "mm_use_im_start_end", False):
             raise NotImplementedError                                             # llava_arch.py:216
         concat, split = self._images_to_batch(images)
         pooled = self.encode_images_pooled(concat, split, pc, audio, segmasks)   # (B, T_vis, 1024)
         B, t_vis, _ = pooled.shape
+        D = self.config.hidden_size
+        desc_rows = desc_table = None
+        if vis_descriptor_embs is not None:
+            # llava_arch.py:278-294: descriptor j of a sample replaces its j-th VIS_DESCRIPTOR placeholder. All
+            # descriptors of the batch form one (rows, D) table on the device; the plan says which row goes where.
+            per_sample, desc_rows = descriptor_row_counts(vis_descriptor_embs, B)
+            flat = [e.detach().reshape(-1, D) for per in per_sample for e in per]
+            desc_table = (torch.cat(flat).to(self.device, BF) if flat
+                          else torch.zeros((1, D), device=self.device, dtype=BF)).contiguous()
         plan = plan_pack(input_ids.cpu().numpy(), None if attention_mask is None else attention_mask.cpu().numpy(),
                          None if labels is None else labels.cpu().numpy(), t_vis,
                          getattr(self.config, "tokenizer_padding_side", "right"),
-                         getattr(self.config, "tokenizer_model_max_length", None))
-        D = self.config.hidden_size
+                         getattr(self.config, "tokenizer_model_max_length", None), desc_rows=desc_rows)
         embeds = torch.empty((B, plan.L, D), device=self.device, dtype=BF)
         if self._pg is None:
             self.model.mm_projector.project_pack(pooled.view(B * t_vis, -1), _i32(plan.row_map, self.device),
@@ -585,6 +591,10 @@ class LlavaLlamaForCausalLM:
                                         self.config.vocab_size, L.stream_ptr()), "b200_embed_rows")
             L.check(lib.b200_embed_rows(L.ptr(vis_dev), L.ptr(vis), L.ptr(embeds), D, B * plan.L, D, B * t_vis,
                                         L.stream_ptr()), "b200_embed_rows")
+        if desc_table is not None and (plan.desc_ids >= 0).any():
+            desc_dev = _i32(plan.desc_ids, self.device)         # third row source: descriptor rows; -2 = untouched
+            L.check(L.lib().b200_embed_rows(L.ptr(desc_dev), L.ptr(desc_table), L.ptr(embeds), D, B * plan.L, D,
+                                            desc_table.shape[0], L.stream_ptr()), "b200_embed_rows")
         new_labels = None if labels is None else torch.from_numpy(plan.labels).to(self.device)
         am = None if attention_mask is None else torch.from_numpy(plan.mask).to(self.device).to(attention_mask.dtype)
         pos = None if position_ids is None else torch.from_numpy(plan.pos).to(self.device)
@@ -667,7 +677,8 @@ class LlavaLlamaForCausalLM:
     @torch.no_grad()
     def generate(self, input_ids, images=None, do_sample=False, use_cache=True, max_new_tokens=20,
                  stopping_criteria=None, pc=None, audio=None, segmasks=None, attention_mask=None,
-                 stop_on_eos=True, check_every=16, use_cuda_graph=True, return_logits=False, **unused):
+                 stop_on_eos=True, check_every=16, use_cuda_graph=True, return_logits=False,
+                 vis_descriptor_embs=None, **unused):
         """Greedy decoding with the call signature the reference uses (scene_graph_prediction_model.py:221-231).
         Returns LongTensor (B, L_in + n_new): the prompt ids (incl. the -200 placeholder) followed by the new tokens.
         HF greedy_search semantics: finished rows emit pad_token_id; stops when every row has produced EOS."""
@@ -684,7 +695,7 @@ class LlavaLlamaForCausalLM:
         B = ids_cpu.shape[0]
         if images is not None and self.get_vision_tower() is not None:
             (_, _, _, _, embeds, _, plan) = self.prepare_inputs_labels_for_multimodal(
-                ids_cpu, None, attention_mask, None, None, images, None, pc, audio, segmasks)
+                ids_cpu, None, attention_mask, None, None, images, vis_descriptor_embs, pc, audio, segmasks)
             Lq = plan.L
             left = getattr(c, "tokenizer_padding_side", "right") == "left"
             kv_start = _i32(plan.kv_start if left else np.zeros(B, np.int32), self.device)

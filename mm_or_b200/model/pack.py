@@ -14,16 +14,35 @@ from ..constants import IGNORE_INDEX, IMAGE_TOKEN_INDEX, VIS_DESCRIPTOR_TOKEN_IN
 
 PAD_ROW = -1        # zero embedding row
 VISUAL_BASE = -2    # src == VISUAL_BASE - j  <=>  j-th visual token of the sample
+DESC_BASE = -(1 << 20)   # src == DESC_BASE - r  <=>  r-th row of the sample's concatenated vis_descriptor_embs
 
 
 class PackPlan:
-    __slots__ = ("src", "labels", "mask", "pos", "lengths", "kv_start", "row_map", "L", "t_vis")
+    __slots__ = ("src", "labels", "mask", "pos", "lengths", "kv_start", "row_map", "L", "t_vis", "desc_ids")
 
 
-def plan_pack(input_ids, attention_mask, labels, t_vis, padding_side="right", max_len=None):
+def descriptor_row_counts(vis_descriptor_embs, batch):
+    """Row counts of the reference's vis_descriptor_embs argument (llava_arch.py:278-290): a list with one list of
+    tensors per sample -- or, for a batch of one, the bare list of tensors (:279-280); a 1-D tensor is one row (:288).
+    Returns (per-sample lists of tensors, per-sample lists of row counts)."""
+    embs = vis_descriptor_embs
+    if len(embs) > 0 and type(embs[0]) is not list:
+        embs = [embs]
+    if len(embs) < batch:
+        raise IndexError(f"vis_descriptor_embs has {len(embs)} entries for a batch of {batch}")   # as :283 would
+    return embs, [[1 if e.ndim == 1 else int(e.shape[0]) for e in per] for per in embs]
+
+
+def plan_pack(input_ids, attention_mask, labels, t_vis, padding_side="right", max_len=None, desc_rows=None):
     """input_ids (B, Lt) int array with IMAGE_TOKEN_INDEX placeholders; attention_mask / labels optional.
+    desc_rows: None, or per sample the row counts of its vis_descriptor_embs (descriptor_row_counts): every
+    VIS_DESCRIPTOR_TOKEN_INDEX position of a row with an image is then replaced by the rows of the next descriptor
+    (one zero row when the sample has fewer descriptors than placeholders, llava_arch.py:284-286) followed by the text
+    up to the next placeholder (:278-294). With desc_rows=None that text is dropped, as in the reference.
     Returns a PackPlan:
-      src      (B, L) int32   >= 0 token id | PAD_ROW | VISUAL_BASE - j
+      desc_ids (B * L,) int32 or None: row of the batch's concatenated descriptor table to copy to that packed
+               position, -2 elsewhere (the "leave untouched" id of b200_embed_rows)
+      src      (B, L) int32   >= 0 token id | PAD_ROW | VISUAL_BASE - j | DESC_BASE - r
       labels   (B, L) int64   IGNORE_INDEX on visual and pad rows
       mask     (B, L) bool
       pos      (B, L) int64   arange over real rows, 0 on pads
@@ -58,6 +77,18 @@ def plan_pack(input_ids, attention_mask, labels, t_vis, padding_side="right", ma
                     raise NotImplementedError("one <image> placeholder per sample (MM2SG prompts have exactly one)")
                 parts.append(vis)
                 lparts.append(vlab)
+        if desc_rows is not None:
+            n_desc = int((r_ids == VIS_DESCRIPTOR_TOKEN_INDEX).sum())
+            first = np.concatenate([[0], np.cumsum(desc_rows[b])]).astype(np.int64)
+            for j in range(n_desc):
+                if j < len(desc_rows[b]):
+                    drow = DESC_BASE - np.arange(first[j], first[j + 1], dtype=np.int64)
+                else:
+                    drow = np.full(1, PAD_ROW, dtype=np.int64)          # "Using dummy tensor": zeros(4096)
+                parts.append(drow)
+                lparts.append(np.full(len(drow), IGNORE_INDEX, dtype=r_lab.dtype))
+                parts.append(r_ids[bounds[n_img + j + 1] + 1:bounds[n_img + j + 2]].astype(np.int64))
+                lparts.append(r_lab[bounds[n_img + j + 1] + 1:bounds[n_img + j + 2]])
         rows.append(np.concatenate(parts))
         rlabels.append(np.concatenate(lparts))
     if max_len is not None:
@@ -84,6 +115,12 @@ def plan_pack(input_ids, attention_mask, labels, t_vis, padding_side="right", ma
         p.labels[b, off:off + n] = rl
         p.mask[b, off:off + n] = True
         p.pos[b, off:off + n] = np.arange(n)
-        vis_at = np.where(r <= VISUAL_BASE)[0]
+        vis_at = np.where((r <= VISUAL_BASE) & (r > DESC_BASE))[0]
         p.row_map[b * t_vis + (VISUAL_BASE - r[vis_at])] = b * L + off + vis_at
+    p.desc_ids = None
+    if desc_rows is not None:
+        table0 = np.concatenate([[0], np.cumsum([sum(d) for d in desc_rows])]).astype(np.int64)
+        flat = p.src.reshape(-1).astype(np.int64)
+        sample = np.repeat(np.arange(B), L)
+        p.desc_ids = np.where(flat <= DESC_BASE, table0[sample] + (DESC_BASE - flat), -2).astype(np.int32)
     return p

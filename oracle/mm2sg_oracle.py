@@ -232,14 +232,19 @@ def encode_images_pooled(sd, images: List[torch.Tensor], cfg: Mm2sgCfg, audio=No
 
 
 # ----------------------------------------------------------------------------------------------------------------
-# (3) multimodal pack -- prepare_inputs_labels_for_multimodal (llava_arch.py:188-353), vis_descriptor_embs=None
+# (3) multimodal pack -- prepare_inputs_labels_for_multimodal (llava_arch.py:188-353), with / without vis_descriptor_embs
 # ----------------------------------------------------------------------------------------------------------------
+DESC_BASE = -(1 << 20)
+
+
 def pack_plan(input_ids: torch.Tensor, attention_mask: Optional[torch.Tensor], labels: Optional[torch.Tensor],
-              t_vis: int, padding_side: str = "right", max_len: Optional[int] = None):
+              t_vis: int, padding_side: str = "right", max_len: Optional[int] = None, desc_rows=None):
     """Pure index arithmetic of the pack: returns (src, labels, mask, position_ids) with src (B, L) int64 where
-    src >= 0 is a token id to embed, -1 a zero pad row, -2 - j the j-th visual token. Mirrors :235-338 including
-    the quirk that text following a VIS_DESCRIPTOR token is dropped when no descriptor embeddings are given
-    (:253-294) and truncation to tokenizer_model_max_length (:302-306)."""
+    src >= 0 is a token id to embed, -1 a zero pad row, -2 - j the j-th visual token, DESC_BASE - r the r-th row of
+    the sample's concatenated vis_descriptor_embs. Mirrors :235-338 including the quirk that text following a
+    VIS_DESCRIPTOR token is dropped when no descriptor embeddings are given (:253-294) and truncation to
+    tokenizer_model_max_length (:302-306). desc_rows: per sample the row counts of its descriptor tensors (:278-294:
+    descriptor j replaces the j-th VIS_DESCRIPTOR placeholder, one zero row when the sample has too few)."""
     B = input_ids.shape[0]
     am = torch.ones_like(input_ids, dtype=torch.bool) if attention_mask is None else attention_mask.bool()
     lab = torch.full_like(input_ids, IGNORE_INDEX) if labels is None else labels
@@ -262,6 +267,20 @@ def pack_plan(input_ids: torch.Tensor, attention_mask: Optional[torch.Tensor], l
             if i < n_img:
                 r.append(-2 - torch.arange(t_vis))
                 rl.append(torch.full((t_vis,), IGNORE_INDEX, dtype=lb.dtype))
+        if desc_rows is not None:
+            n_desc = int((ids == VIS_DESCRIPTOR_TOKEN_INDEX).sum())
+            done = 0
+            for j in range(n_desc):
+                if j < len(desc_rows[b]):
+                    k = int(desc_rows[b][j])
+                    d = DESC_BASE - torch.arange(done, done + k)
+                    done += k
+                else:
+                    d = torch.full((1,), -1, dtype=torch.long)          # dummy zeros(4096) row (:284-286)
+                r.append(d)
+                rl.append(torch.full((len(d),), IGNORE_INDEX, dtype=lb.dtype))
+                r.append(chunks[n_img + j + 1])
+                rl.append(lchunks[n_img + j + 1])
         rows.append(torch.cat(r))
         rlabels.append(torch.cat(rl))
     if max_len is not None:
@@ -284,16 +303,20 @@ def pack_plan(input_ids: torch.Tensor, attention_mask: Optional[torch.Tensor], l
     return src, out_l, mask, pos
 
 
-def pack_embeds(sd, src: torch.Tensor, visual: torch.Tensor) -> torch.Tensor:
-    """Materialise inputs_embeds (B, L, D) from a pack plan and the projected visual tokens (B, T_vis, D)."""
+def pack_embeds(sd, src: torch.Tensor, visual: torch.Tensor, desc=None) -> torch.Tensor:
+    """Materialise inputs_embeds (B, L, D) from a pack plan and the projected visual tokens (B, T_vis, D); desc: per
+    sample the (R_b, D) concatenation of its descriptor tensors (rows addressed by DESC_BASE - r)."""
     table = sd["model.embed_tokens.weight"]
     B, L = src.shape
     out = torch.zeros(B, L, table.shape[1], dtype=visual.dtype)
     for b in range(B):
         txt = src[b] >= 0
         out[b, txt] = table[src[b, txt]].to(visual.dtype)
-        vis = src[b] <= -2
+        vis = (src[b] <= -2) & (src[b] > DESC_BASE)
         out[b, vis] = visual[b, (-2 - src[b, vis])]
+        dsc = src[b] <= DESC_BASE
+        if bool(dsc.any()):
+            out[b, dsc] = desc[b][DESC_BASE - src[b, dsc]].to(visual.dtype)
     return out
 
 
@@ -364,10 +387,19 @@ def llama_forward(sd, x: torch.Tensor, mask: torch.Tensor, pos: torch.Tensor, cf
 #     model.generate(do_sample=False) (scene_graph_prediction_model.py:221-231; decode-step inputs llava_arch.py:192-201)
 # ----------------------------------------------------------------------------------------------------------------
 def multimodal_prefill(sd, cfg: Mm2sgCfg, input_ids, attention_mask, images, labels=None, audio=None, segmasks=None,
-                       padding_side="right", max_len=None, last_only=False, pc=None):
+                       padding_side="right", max_len=None, last_only=False, pc=None, vis_descriptor_embs=None):
+    """vis_descriptor_embs: as the reference takes it (llava_arch.py:278-290) -- one list of (D,) / (k, D) tensors per
+    sample, or the bare list for a batch of one."""
     visual = encode_images_pooled(sd, images, cfg, audio, segmasks, pc)
-    src, mlabels, mask, pos = pack_plan(input_ids, attention_mask, labels, visual.shape[1], padding_side, max_len)
-    emb = pack_embeds(sd, src, visual)
+    desc_rows = desc = None
+    if vis_descriptor_embs is not None:
+        embs = vis_descriptor_embs if type(vis_descriptor_embs[0]) is list else [vis_descriptor_embs]
+        desc_rows = [[1 if e.ndim == 1 else e.shape[0] for e in per] for per in embs]
+        D = visual.shape[-1]
+        desc = [torch.cat([e.reshape(-1, D) for e in per]) if per else torch.zeros(0, D) for per in embs]
+    src, mlabels, mask, pos = pack_plan(input_ids, attention_mask, labels, visual.shape[1], padding_side, max_len,
+                                        desc_rows=desc_rows)
+    emb = pack_embeds(sd, src, visual, desc)
     logits, kv = llama_forward(sd, emb, mask, pos, cfg.llm, last_only=last_only)
     return {"logits": logits, "kv": kv, "mask": mask, "pos": pos, "modified_labels": mlabels, "inputs_embeds": emb,
             "visual": visual}

@@ -21,8 +21,8 @@ import torch
 import golden_cases as gc
 from oracle.ref_shim import build_reference_model
 
-IGNORE, IMAGE = -100, -200
-PAD_ROW, VISUAL_BASE = -1, -2            # mm_or_b200/model/pack.py encoding of a decoded row
+IGNORE, IMAGE, DESCRIPTOR = -100, -200, 18610
+PAD_ROW, VISUAL_BASE, DESC_BASE = -1, -2, -(1 << 20)   # mm_or_b200/model/pack.py encoding of a decoded row
 
 
 def random_batch(rng, B, Lt, with_labels, interior_pad, text_only_row, vocab):
@@ -55,6 +55,79 @@ def cases(vocab):
     return out
 
 
+def descriptor_cases(vocab, D):
+    """Batches whose prompts carry VIS_DESCRIPTOR placeholders (llava_arch.py:243,253,278-294) together with
+    vis_descriptor_embs: fewer descriptors than placeholders (dummy zero row), more than placeholders (ignored), 2-D
+    descriptors (several rows), a text-only row, truncation, both padding sides, the bare-list form for a batch of 1."""
+    rng = np.random.default_rng(23)
+    out = []
+    for side in ("left", "right"):
+        for with_labels in (False, True):
+            for max_len in (None, 30):
+                for trial in range(3):
+                    B = 1 if trial == 2 else 3
+                    Lt = 24
+                    ids = torch.zeros(B, Lt, dtype=torch.long)
+                    embs = []
+                    for b in range(B):
+                        n = int(rng.integers(8, Lt + 1))
+                        row = torch.from_numpy(rng.integers(3, vocab, n))
+                        text_only = trial == 1 and b == 0
+                        n_desc = int(rng.integers(0, 4))
+                        if not text_only:
+                            spots = rng.choice(n, size=1 + n_desc, replace=False)
+                            row[int(spots[0])] = IMAGE
+                            for sp in spots[1:]:
+                                row[int(sp)] = DESCRIPTOR
+                        ids[b, Lt - n:] = row
+                        n_emb = max(0, n_desc + int(rng.integers(-1, 2)))
+                        per, r0 = [], 0
+                        for j in range(n_emb):
+                            k = 1 if rng.integers(0, 2) == 0 else int(rng.integers(2, 4))
+                            e = torch.zeros(k, D)
+                            e[:, 0] = torch.arange(r0, r0 + k, dtype=torch.float32)
+                            e[:, 1] = 3.0                           # flag: descriptor row
+                            e[:, 2] = float(b)
+                            r0 += k
+                            per.append(e[0] if k == 1 and rng.integers(0, 2) == 0 else e)   # 1-D and (1, D) forms
+                        embs.append(per)
+                    labels = None
+                    if with_labels:
+                        labels = ids.clone()
+                        labels[(ids <= 0) | (ids == DESCRIPTOR)] = IGNORE
+                    out.append(dict(side=side, max_len=max_len, ids=ids, mask=ids.ne(0), labels=labels,
+                                    t_vis=int(rng.integers(1, 9)),
+                                    embs=embs[0] if B == 1 and len(embs[0]) > 0 else embs))   # bare list: :279-280
+    return out
+
+
+def record(model, c, D):
+    B, t_vis = c["ids"].shape[0], c["t_vis"]
+    feats = torch.zeros(B, t_vis, D)
+    feats[:, :, 0] = torch.arange(t_vis, dtype=torch.float32)[None, :]
+    feats[:, :, 1] = 2.0                                   # flag: visual row
+    feats[:, :, 2] = torch.arange(B, dtype=torch.float32)[:, None]
+    model.encode_images_pooled = lambda *a, _f=feats: _f   # instance attribute shadows the method
+    model.config.tokenizer_padding_side = c["side"]
+    model.config.tokenizer_model_max_length = c["max_len"]
+    pos_in = torch.arange(c["ids"].shape[1])[None].expand(B, -1).clone()
+    images = [torch.zeros(1, 3, 2, 2) for _ in range(B)]
+    _, pos, am, _, emb, lab = model.prepare_inputs_labels_for_multimodal(
+        c["ids"], pos_in, c["mask"], None, c["labels"], images, c.get("embs"), None, None, None)
+    flag, val, samp = emb[..., 1].round().long(), emb[..., 0].round().long(), emb[..., 2].round().long()
+    src = torch.where(flag == 1, val, torch.where(flag == 2, VISUAL_BASE - val,
+                      torch.where(flag == 3, DESC_BASE - val, torch.full_like(val, PAD_ROW))))
+    assert bool(((flag < 2) | (samp == torch.arange(B)[:, None])).all())       # a row only holds its own visuals
+    rec = dict(side=c["side"], max_len=c["max_len"], t_vis=t_vis, ids=c["ids"], mask=c["mask"],
+               labels=c["labels"], src=src.to(torch.int32), out_labels=lab, out_mask=am.bool(), out_pos=pos)
+    if "embs" in c:
+        bare = type(c["embs"][0]) is not list
+        embs = [c["embs"]] if bare else c["embs"]
+        rec["desc_rows"] = [[1 if e.ndim == 1 else int(e.shape[0]) for e in per] for per in embs]
+        rec["bare_list"] = bare
+    return rec
+
+
 def main():
     torch.set_grad_enabled(False)
     cfg = gc.small_config()
@@ -66,29 +139,25 @@ def main():
     table[:, 0] = torch.arange(V, dtype=torch.float32)
     table[:, 1] = 1.0                                          # flag: text row
     model.get_model().embed_tokens.weight.data.copy_(table)
-    records = []
-    for c in cases(V):
-        B, t_vis = c["ids"].shape[0], c["t_vis"]
-        feats = torch.zeros(B, t_vis, D)
-        feats[:, :, 0] = torch.arange(t_vis, dtype=torch.float32)[None, :]
-        feats[:, :, 1] = 2.0                                   # flag: visual row
-        feats[:, :, 2] = torch.arange(B, dtype=torch.float32)[:, None]
-        model.encode_images_pooled = lambda *a, _f=feats: _f   # instance attribute shadows the method
-        model.config.tokenizer_padding_side = c["side"]
-        model.config.tokenizer_model_max_length = c["max_len"]
-        pos_in = torch.arange(c["ids"].shape[1])[None].expand(B, -1).clone()
-        images = [torch.zeros(1, 3, 2, 2) for _ in range(B)]
-        _, pos, am, _, emb, lab = model.prepare_inputs_labels_for_multimodal(
-            c["ids"], pos_in, c["mask"], None, c["labels"], images, None, None, None, None)
-        flag, val, samp = emb[..., 1].round().long(), emb[..., 0].round().long(), emb[..., 2].round().long()
-        src = torch.where(flag == 1, val, torch.where(flag == 2, VISUAL_BASE - val, torch.full_like(val, PAD_ROW)))
-        assert bool(((flag != 2) | (samp == torch.arange(B)[:, None])).all())       # a row only holds its own visuals
-        records.append(dict(side=c["side"], max_len=c["max_len"], t_vis=t_vis, ids=c["ids"], mask=c["mask"],
-                            labels=c["labels"], src=src.to(torch.int32), out_labels=lab, out_mask=am.bool(),
-                            out_pos=pos))
+    records = [record(model, c, D) for c in cases(V)]
+    del model.encode_images_pooled
+    # descriptor cases need hidden 4096: the reference's dummy descriptor is a hard-coded zeros(4096) (llava_arch.py:286)
+    import contextlib
+    import io
+    cfg4 = gc.small_config(hidden_size=4096, intermediate_size=64, num_hidden_layers=1, num_attention_heads=32)
+    model = build_reference_model(cfg4, gc.bf16_round(gc.small_weights(cfg4)))
+    model.config.mv_type = "learned"
+    D4 = cfg4.hidden_size
+    table = torch.zeros(V, D4)
+    table[:, 0] = torch.arange(V, dtype=torch.float32)
+    table[:, 1] = 1.0
+    model.get_model().embed_tokens.weight.data.copy_(table)
+    with contextlib.redirect_stdout(io.StringIO()):            # the reference prints when it substitutes a dummy row
+        desc_records = [record(model, c, D4) for c in descriptor_cases(V, D4)]
     del model.encode_images_pooled
     torch.save(records, os.path.join(gc.GOLDEN_DIR, "pack_cases.pt"))
-    print(len(records), "cases recorded")
+    torch.save(desc_records, os.path.join(gc.GOLDEN_DIR, "pack_desc_cases.pt"))
+    print(len(records), "+", len(desc_records), "cases recorded")
 
 
 if __name__ == "__main__":

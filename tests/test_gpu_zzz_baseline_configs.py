@@ -131,3 +131,31 @@ def test_rows_finished_at_eos_skip_their_cache_reads():
     safe = (top2[..., 0] - top2[..., 1]) > 2 * err
     safe[2] = True                                                   # EOS / pad positions are exact by construction
     assert torch.equal(gen[safe], toks[safe])
+
+
+def test_vis_descriptor_embeddings_in_the_pack(env):
+    """forward / generate with vis_descriptor_embs (llava_llama.py:54-70, llava_arch.py:278-294): descriptor rows are
+    spliced in at the VIS_DESCRIPTOR placeholders (index plan pinned bit for bit to the reference on the CPU,
+    tests/test_pack_host.py); here the device side -- the third row source of the pack -- against the oracle."""
+    from mm_or_b200.constants import VIS_DESCRIPTOR_TOKEN_INDEX
+    cfg, ocfg, sd, model = env
+    b = synth_batch(cfg, 3, 2, 26, seed=55, jitter=4, image_pos=6)
+    ids = b["input_ids"].clone()
+    ids[0, -3] = ids[0, -9] = VIS_DESCRIPTOR_TOKEN_INDEX           # two placeholders, one descriptor (2 rows) + dummy
+    ids[1, -5] = VIS_DESCRIPTOR_TOKEN_INDEX                          # one placeholder, two descriptors (second unused)
+    g = torch.Generator().manual_seed(5)
+    D = cfg.hidden_size
+    mk = lambda *s: (torch.randn(*s, generator=g) * 0.02).to(torch.bfloat16).float()
+    embs = [[mk(2, D)], [mk(D), mk(1, D)], []]
+    out, lg = model.generate(ids, images=b["images"], vis_descriptor_embs=embs, max_new_tokens=3, stop_on_eos=False,
+                             return_logits=True)
+    ref = O.multimodal_prefill(sd, ocfg, ids, b["attention_mask"], b["images"], padding_side="left",
+                               vis_descriptor_embs=embs)
+    toks, ref_lg = O.greedy_decode(sd, ocfg, ref["logits"][:, -1], ref["kv"], ref["mask"], 3, stop_on_eos=False)
+    assert rel_err(lg, ref_lg) < TOL_E2E
+    fw = model(input_ids=ids, attention_mask=b["attention_mask"], images=b["images"], vis_descriptor_embs=embs)
+    m = ref["mask"]                                                  # pad rows carry no defined logits
+    assert fw.logits.shape == ref["logits"].shape and rel_err(fw.logits.cpu()[m], ref["logits"][m]) < TOL_E2E
+    # without the embeddings the text after a placeholder is dropped (the reference's behaviour): a shorter pack
+    short = model(input_ids=ids, attention_mask=b["attention_mask"], images=b["images"])
+    assert short.logits.shape[1] < fw.logits.shape[1]

@@ -101,3 +101,41 @@ def test_plan_matches_reference_fixture():
                 assert np.array_equal(got_lab, r["out_labels"].numpy())
             # pad rows: the reference leaves 0 there (llava_arch.py:313,331-338)
             assert np.array_equal(got_pos * ref_mask, r["out_pos"].numpy() * ref_mask)
+
+
+def test_plan_with_vis_descriptors_matches_reference_fixture():
+    """24 batches with VIS_DESCRIPTOR placeholders and vis_descriptor_embs through the REFERENCE's own
+    prepare_inputs_labels_for_multimodal (tests/golden/make_pack_golden.py -> pack_desc_cases.pt; llava_arch.py:243,
+    253-294): placeholders before and after <image> (the visual tokens always take the FIRST split point), fewer
+    descriptors than placeholders (one zero row each), surplus descriptors (ignored), multi-row descriptors, a text-only
+    row (placeholders stay ordinary tokens), truncation, both padding sides, the bare-list form of a batch of one.
+    Planner and oracle reproduce source rows, labels, mask and position ids bit for bit."""
+    import os
+    from mm_or_b200.model.pack import DESC_BASE
+    recs = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pack_desc_cases.pt"))
+    assert len(recs) == 24 and any(r["bare_list"] for r in recs)
+    n_desc_rows = n_dummy = 0
+    for r in recs:
+        labels = r["labels"]
+        p = plan_pack(r["ids"].numpy(), r["mask"].numpy(), None if labels is None else labels.numpy(), r["t_vis"],
+                      r["side"], r["max_len"], desc_rows=r["desc_rows"])
+        src, lab, m, pos = O.pack_plan(r["ids"], r["mask"], labels, r["t_vis"], r["side"], r["max_len"],
+                                       desc_rows=r["desc_rows"])
+        ref_mask, ref_src = r["out_mask"].numpy(), r["src"].numpy()
+        assert p.src.shape == ref_src.shape
+        for got_src, got_lab, got_mask, got_pos in ((p.src, p.labels, p.mask, p.pos),
+                                                    (src.numpy(), lab.numpy(), m.numpy(), pos.numpy())):
+            assert np.array_equal(got_mask, ref_mask)
+            assert np.array_equal(got_src, ref_src)
+            if r["out_labels"] is not None:
+                assert np.array_equal(got_lab, r["out_labels"].numpy())
+            assert np.array_equal(got_pos * ref_mask, r["out_pos"].numpy() * ref_mask)
+        # desc_ids: the batch-wide table row behind every descriptor position, "untouched" (-2) elsewhere
+        first = np.concatenate([[0], np.cumsum([sum(d) for d in r["desc_rows"]])])
+        flat = ref_src.reshape(-1).astype(np.int64)
+        sample = np.repeat(np.arange(ref_src.shape[0]), ref_src.shape[1])
+        want = np.where(flat <= DESC_BASE, first[sample] + (DESC_BASE - flat), -2)
+        assert np.array_equal(p.desc_ids, want)
+        n_desc_rows += int((flat <= DESC_BASE).sum())
+        n_dummy += int(((ref_src == -1) & ref_mask).sum())
+    assert n_desc_rows > 20 and n_dummy > 3                    # the fixture exercises real and dummy descriptors
