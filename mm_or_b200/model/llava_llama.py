@@ -19,7 +19,7 @@ from .. import _lib as L
 from ..config import LlavaConfig
 from ..constants import IGNORE_INDEX, IMAGE_TOKEN_INDEX
 from ..synth import POOLER_GEOMETRY
-from .pack import descriptor_row_counts, plan_pack
+from .pack import DESC_BASE, descriptor_row_counts, plan_pack
 
 VIT = "model.vision_tower.vision_tower.vision_model."
 POOL = "model.image_pooler."
@@ -584,7 +584,8 @@ class LlavaLlamaForCausalLM:
             src = plan.src.reshape(B, plan.L).astype(np.int64)
             # two row gathers into the packed buffer: text / pad rows from embed_tokens, visual rows from `vis`
             text_ids = np.where(src >= -1, src, -2).astype(np.int32)
-            vis_ids = np.where(src <= -2, np.arange(B)[:, None] * t_vis + (-2 - src), -2).astype(np.int32)
+            vis_ids = np.where((src <= -2) & (src > DESC_BASE), np.arange(B)[:, None] * t_vis + (-2 - src),
+                               -2).astype(np.int32)
             lib = L.lib()
             text_dev, vis_dev = _i32(text_ids.reshape(-1), self.device), _i32(vis_ids.reshape(-1), self.device)
             L.check(lib.b200_embed_rows(L.ptr(text_dev), L.ptr(self.model.embed_tokens), L.ptr(embeds), D, B * plan.L, D,
