@@ -16,7 +16,7 @@ import numpy as np
 import torch
 
 from .. import _lib as L
-from ..model.pack import plan_pack
+from ..model.pack import DESC_BASE, descriptor_row_counts, plan_pack
 from . import encoder as E
 from . import llama as T
 
@@ -128,7 +128,7 @@ class FineTuner:
 
     # ------------------------------------------------------------------------------------------------------------
     def forward_backward(self, input_ids, labels, attention_mask, images, grads=None, accumulate=False, pc=None,
-                         audio=None, segmasks=None, grad_scale=1.0):
+                         audio=None, segmasks=None, grad_scale=1.0, vis_descriptor_embs=None):
         """Returns (loss, weight sum, grads under the reference's names). pc / audio / segmasks as in
         LlavaLlamaForCausalLM.forward (llava_llama.py:54-70): lists with one entry (or None) per sample.
         grads + accumulate=True add this batch's gradients into an existing store; grad_scale multiplies the loss
@@ -150,16 +150,23 @@ class FineTuner:
             xcache = E.extras_forward(pooler, tok3, keep, pc, audio, segmasks)
             tokens = tok3.view(B * Tv, Dv)
         vis, prc = E.projector_forward(proj, tokens)
+        desc_rows = desc_table = None
+        if vis_descriptor_embs is not None:      # inputs only (llava_arch.py:278-294): rows spliced in, no gradient
+            per_sample, desc_rows = descriptor_row_counts(vis_descriptor_embs, B)
+            flat = [e.detach().reshape(-1, D) for per in per_sample for e in per]
+            desc_table = torch.cat(flat).to(dev, BF).contiguous() if flat else None
         plan = plan_pack(input_ids.cpu().numpy(), None if attention_mask is None else attention_mask.cpu().numpy(),
                          None if labels is None else labels.cpu().numpy(), Tv, "right",
-                         getattr(cfg, "tokenizer_model_max_length", None))
+                         getattr(cfg, "tokenizer_model_max_length", None), desc_rows=desc_rows)
         Lq = plan.L
         src = plan.src.reshape(B, Lq).astype(np.int64)
         text_ids = np.where(src >= -1, src, -2).astype(np.int32)
-        vis_ids = np.where(src <= -2, np.arange(B)[:, None] * Tv + (-2 - src), -2).astype(np.int32)
+        vis_ids = np.where((src <= -2) & (src > DESC_BASE), np.arange(B)[:, None] * Tv + (-2 - src), -2).astype(np.int32)
         embeds = torch.empty((B * Lq, D), device=dev, dtype=BF)
         L.embed_rows(torch.as_tensor(text_ids.reshape(-1)).to(dev), model.model.embed_tokens, out=embeds)
         L.embed_rows(torch.as_tensor(vis_ids.reshape(-1)).to(dev), vis, out=embeds)
+        if desc_table is not None and (plan.desc_ids >= 0).any():
+            L.embed_rows(torch.as_tensor(plan.desc_ids).to(dev), desc_table, out=embeds)
         loss, wsum, g, d_emb = T.forward_backward(model, embeds.view(B, Lq, D), torch.from_numpy(plan.labels).to(dev),
                                                   torch.from_numpy(plan.lengths).to(dev), self.vocab_weight,
                                                   grad_scale=grad_scale, grads=grads, accumulate=accumulate,
@@ -234,9 +241,10 @@ class FineTuner:
         m.image_pooler.load_weights(self.sd, self.dev)
         m.mm_projector.load_weights(self.sd, self.dev)
 
-    def train_step(self, input_ids, labels, attention_mask, images, pc=None, audio=None, segmasks=None):
+    def train_step(self, input_ids, labels, attention_mask, images, pc=None, audio=None, segmasks=None,
+                   vis_descriptor_embs=None):
         loss, wsum, grads = self.forward_backward(input_ids, labels, attention_mask, images, pc=pc, audio=audio,
-                                                  segmasks=segmasks)
+                                                  segmasks=segmasks, vis_descriptor_embs=vis_descriptor_embs)
         self.last_grads = grads
         norm_sq = self.optimizer_step(grads)
         return loss, norm_sq
@@ -253,7 +261,8 @@ class FineTuner:
             loss, _, grads = self.forward_backward(mb["input_ids"], mb["labels"], mb.get("attention_mask"), mb["images"],
                                                    grads=grads, accumulate=i > 0, pc=mb.get("pc"),
                                                    audio=mb.get("audio"), segmasks=mb.get("segmasks"),
-                                                   grad_scale=1.0 / n)
+                                                   grad_scale=1.0 / n,
+                                                   vis_descriptor_embs=mb.get("vis_descriptor_embs"))
             total = total + loss / n
         self.last_grads = grads
         return total, self.optimizer_step(grads)
