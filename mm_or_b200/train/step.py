@@ -12,6 +12,8 @@ Frozen here (documented in DESIGN.md): CLIP embeddings and the CLIP layers below
 PointTransformerV3 (its token is computed, its training path is not built), and embed_tokens unless
 `train_embed_tokens=True` (full fine-tuning; the reference's LoRA recipe keeps it frozen).
 """
+import os
+
 import numpy as np
 import torch
 
@@ -240,6 +242,49 @@ class FineTuner:
         m.vision_tower.load_weights(self.sd, self.dev)
         m.image_pooler.load_weights(self.sd, self.dev)
         m.mm_projector.load_weights(self.sd, self.dev)
+
+    # ------------------------------------------------------------------------------------------------------------
+    def save_checkpoint(self, out_dir, base_model_name_or_path=None, optimizer=True):
+        """What train.py:1346-1360 leaves in output_dir (train/checkpoint.py): the LoRA recipe writes config.json,
+        adapter_config.json, adapter_model.bin and non_lora_trainables.bin (loadable with
+        load_pretrained_model(out_dir, model_base, "…lora…")); full fine-tuning writes config.json and the whole
+        state_dict. optimizer=True adds b200_optimizer.pt (masters, m, v, step) for load_optimizer; with a sharded
+        optimizer every rank writes its own slices (b200_optimizer.rankN.pt) and rank 0 the weights."""
+        from . import checkpoint as C
+        rank = 0
+        if self.group is not None:
+            import torch.distributed as dist
+            rank = dist.get_rank(self.group)
+        if rank == 0:
+            if self.lora is not None:
+                r = self.lora.r
+                C.export_lora_checkpoint(out_dir, self.model.config, self.lora.sd, r, self.lora.scale * r,
+                                         {k: self.sd[k] for k in self.names if "lora_" not in k},
+                                         base_model_name_or_path)
+            else:
+                C.export_full_checkpoint(out_dir, self.model.config, self.sd)
+        if optimizer:
+            os.makedirs(out_dir, exist_ok=True)
+            name = "b200_optimizer.pt" if self.zero is None else "b200_optimizer.rank%d.pt" % rank
+            if self.zero is not None or rank == 0:
+                C.save_optimizer(os.path.join(out_dir, name), self.master, self.m, self.v, self.step_count,
+                                 *getattr(self, "_base_lr", (self.lr, self.proj_lr)))
+        return out_dir
+
+    def load_optimizer(self, out_dir):
+        """Resume: masters / m / v / step count from save_checkpoint(optimizer=True); the bf16 working weights are
+        rebuilt from the masters."""
+        from . import checkpoint as C
+        if self.zero is not None:
+            raise NotImplementedError("resume with a sharded optimizer is not built yet (the bf16 weights would have to "
+                                      "be re-gathered from every rank's slices)")
+        self.step_count, lr, proj_lr = C.load_optimizer(os.path.join(out_dir, "b200_optimizer.pt"), self.master,
+                                                        self.m, self.v)
+        self._base_lr = (lr, proj_lr)
+        self.lr, self.proj_lr = lr, proj_lr
+        for k, mst in self.master.items():
+            self.sd[k].copy_(mst.to(BF))
+        self._after_update(None)
 
     def train_step(self, input_ids, labels, attention_mask, images, pc=None, audio=None, segmasks=None,
                    vis_descriptor_embs=None):
