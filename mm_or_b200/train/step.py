@@ -275,15 +275,18 @@ class FineTuner:
         """Resume: masters / m / v / step count from save_checkpoint(optimizer=True); the bf16 working weights are
         rebuilt from the masters."""
         from . import checkpoint as C
-        if self.zero is not None:
-            raise NotImplementedError("resume with a sharded optimizer is not built yet (the bf16 weights would have to "
-                                      "be re-gathered from every rank's slices)")
-        self.step_count, lr, proj_lr = C.load_optimizer(os.path.join(out_dir, "b200_optimizer.pt"), self.master,
-                                                        self.m, self.v)
+        name = "b200_optimizer.pt"
+        if self.zero is not None:              # sharded state: every rank reads the slices it wrote (same world size)
+            import torch.distributed as dist
+            name = "b200_optimizer.rank%d.pt" % dist.get_rank(self.group)
+        self.step_count, lr, proj_lr = C.load_optimizer(os.path.join(out_dir, name), self.master, self.m, self.v)
         self._base_lr = (lr, proj_lr)
         self.lr, self.proj_lr = lr, proj_lr
-        for k, mst in self.master.items():
-            self.sd[k].copy_(mst.to(BF))
+        if self.zero is not None:
+            self.zero.refresh_from_masters()   # slices -> bf16 -> all-gather
+        else:
+            for k, mst in self.master.items():
+                self.sd[k].copy_(mst.to(BF))
         self._after_update(None)
 
     def train_step(self, input_ids, labels, attention_mask, images, pc=None, audio=None, segmasks=None,

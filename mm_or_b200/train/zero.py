@@ -102,6 +102,19 @@ class ShardedAdamW:
                 g = grads[k] if sliced else grads[k].contiguous().view(-1)[lo:hi]
                 self.adamw(self.master[k], self.params[k].view(-1)[lo:hi], g, self.m[k], self.v[k], lr_of(k),
                            self.betas[0], self.betas[1], self.eps, wd_of(k), step, clip_coef=clip_coef)
+        self.gather_params(todo)
+
+    def refresh_from_masters(self):
+        """bf16 working weights <- this rank's fp32 master slices, then the all-gather of a step (resume: after the
+        slices were loaded from a checkpoint, train/checkpoint.py)."""
+        for k in self.names:
+            lo, hi = self.range[k]
+            if hi > lo:
+                self.params[k].view(-1)[lo:hi].copy_(self.master[k].to(self.params[k].dtype))
+        self.gather_params(self.names)
+
+    def gather_params(self, todo):
+        """All-gather of the updated bf16 slices (in place when the tensor divides evenly, staged otherwise)."""
         stage_in = stage_out = None
         for k in todo:
             flat = self.params[k].view(-1)

@@ -74,6 +74,19 @@ def _worker(rank, world, port, q):
                 if k != "skipped":
                     assert torch.equal(opt.master[k], ref[k]["master"][lo:hi]), (k, step)
         assert torch.equal(params["skipped"], src["skipped"].to(torch.bfloat16))
+        # resume: slices saved per rank, loaded into a fresh optimizer whose working weights are stale
+        import tempfile
+        from mm_or_b200.train import checkpoint as C
+        tmp = os.path.join(tempfile.gettempdir(), f"b200_zero_resume_{port}_rank{rank}.pt")
+        C.save_optimizer(tmp, opt.master, opt.m, opt.v, 3, 1e-2, 3e-3)
+        stale = {k: torch.zeros_like(v) for k, v in params.items()}
+        opt2 = ShardedAdamW(stale, src, names, dist.group.WORLD, adamw=torch_adamw)
+        assert C.load_optimizer(tmp, opt2.master, opt2.m, opt2.v) == (3, 1e-2, 3e-3)
+        opt2.refresh_from_masters()
+        os.remove(tmp)
+        for k in names:
+            assert torch.equal(stale[k], params[k]) or k == "skipped", k     # "skipped" never moved: master == source
+        assert torch.equal(stale["skipped"], src["skipped"].to(torch.bfloat16))
         q.put((rank, "ok"))
     except Exception as e:  # surfaced by the parent
         q.put((rank, repr(e)))
