@@ -36,3 +36,7 @@ timeout 900 python bench.py --steps 3 --warmup 3 --decode-tiles --no-cpu-baselin
 echo "bench --decode-tiles rc=$?"; tail -c 1500 gpurun_out/${TAG}_bench_tiles.json
 timeout 900 python bench.py --steps 2 --warmup 3 --batch 192 --no-cpu-baseline > gpurun_out/${TAG}_bench_b192.json 2> gpurun_out/${TAG}_bench_b192.err
 echo "bench b192 rc=$?"; tail -c 1500 gpurun_out/${TAG}_bench_b192.json
+# 256 samples per GPU: KV cache 146 GB + 14 GB of weights + ~10 GB of workspaces -- fits only if the allocator has
+# little slack; a CUDA out-of-memory error here is a Python exception, not a dead box
+timeout 900 python bench.py --steps 2 --warmup 3 --batch 256 --no-cpu-baseline --no-roofline > gpurun_out/${TAG}_bench_b256.json 2> gpurun_out/${TAG}_bench_b256.err
+echo "bench b256 rc=$?"; tail -c 1200 gpurun_out/${TAG}_bench_b256.json; tail -2 gpurun_out/${TAG}_bench_b256.err
