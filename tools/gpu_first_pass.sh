@@ -13,6 +13,9 @@ echo "new tests rc=${PIPESTATUS[0]}"; tail -6 gpurun_out/${TAG}_pytest_new.log
 B200_TEST_SWITCHES=1 timeout 300 python -m pytest tests/test_gpu_zzzz_switches.py -m gpu -q --timeout 250 2>&1 | tail -8 \
   > gpurun_out/${TAG}_pytest_pdl.log
 echo "pdl tests rc=${PIPESTATUS[0]}"; tail -4 gpurun_out/${TAG}_pytest_pdl.log
+# 1c. decode-step A/B of the switches at the real 7B size (only meaningful if 1b passed)
+timeout 400 python tools/decode_bench.py --batch 128 > gpurun_out/${TAG}_decode_bench.json 2> gpurun_out/${TAG}_decode_bench.err
+echo "decode_bench rc=$?"; cat gpurun_out/${TAG}_decode_bench.json; tail -2 gpurun_out/${TAG}_decode_bench.err
 # 2. the whole suite + smoke
 timeout 600 python -m pytest tests -m gpu -q --timeout 300 2>&1 | tail -25 > gpurun_out/${TAG}_pytest_gpu.log
 echo "pytest rc=${PIPESTATUS[0]}"; tail -5 gpurun_out/${TAG}_pytest_gpu.log
