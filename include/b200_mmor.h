@@ -481,6 +481,17 @@ int b200_segmask_backward(const b200_segmask_weights* w, const uint8_t* cls, int
 int b200_embed_grad(const void* d_rows, int64_t ld, const int32_t* row_list, const int32_t* seg_start,
                     const int32_t* seg_token, int n_seg, int D, float* d_table, int accumulate, b200_stream_t stream);
 
+/* ============================================================================================================
+ * NF4 storage of the frozen base weights (QLoRA recipe). Replaces bitsandbytes' Linear4bit storage as configured by
+ * LLaVA/llava/train/train.py:1098-1114 (BitsAndBytesConfig(load_in_4bit, bnb_4bit_quant_type='nf4', compute dtype
+ * bf16)); bitsandbytes==0.41.0 is not vendored, its published algorithm is restated (mm_or_b200/csrc/nf4.cu).
+ * w_bf16 / out_bf16: n bf16 values (n a multiple of 64); packed: n / 2 bytes, two 4-bit codes per byte with the even
+ * element in the high nibble; absmax: n / 64 fp32 block maxima. quantize followed by dequantize yields the weights
+ * a Linear4bit layer multiplies with.
+ * ============================================================================================================ */
+int b200_nf4_quantize(const void* w_bf16, int64_t n, uint8_t* packed, float* absmax, b200_stream_t stream);
+int b200_nf4_dequantize(const uint8_t* packed, const float* absmax, int64_t n, void* out_bf16, b200_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

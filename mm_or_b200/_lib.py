@@ -78,6 +78,8 @@ _SIGS = {
     "b200_set_option": (ci, [ctypes.c_char_p, ci]),
     "b200_get_option": (ci, [ctypes.c_char_p]),
     "b200_decode_tile_width": (ci, [ci, ci, ci]),
+    "b200_nf4_quantize": (ci, [vp, i64, vp, vp, vp]),
+    "b200_nf4_dequantize": (ci, [vp, vp, i64, vp, vp]),
     "b200_gemm_bf16": (ci, [vp, ci, vp, ci, vp, ci, ci, ci, ci, vp, vp, ci, vp, ci, ci, ci, vp]),
     "b200_gemm_bf16_skinny": (ci, [vp, ci, vp, ci, vp, ci, ci, ci, ci, vp, vp, ci, ci, ci, ci, vp]),
     "b200_gemm_bf16_ex": (ci, [vp, ci, ci, vp, ci, ci, vp, ci, ci, ci, ci, vp, vp, ci, ci, ci, ci, cf, ci, vp]),
@@ -153,7 +155,8 @@ _SIGS = {
 PC_SYMBOLS = sorted(k for k in _SIGS if k.startswith("b200_pc_"))
 # entry points whose kernels also build for the host against the test-only kernel emulator (tests/emu/)
 EMULATABLE_SYMBOLS = PC_SYMBOLS + ["b200_segmask_train_acts_bytes", "b200_segmask_forward_train",
-                                   "b200_segmask_backward_workspace_bytes", "b200_segmask_backward", "b200_embed_grad"]
+                                   "b200_segmask_backward_workspace_bytes", "b200_segmask_backward", "b200_embed_grad",
+                                   "b200_nf4_quantize", "b200_nf4_dequantize"]
 
 EXPORTED_SYMBOLS = ["b200_last_error"] + sorted(_SIGS)
 

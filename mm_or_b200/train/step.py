@@ -50,13 +50,16 @@ class FineTuner:
     def __init__(self, model, state_dict, lr=2e-5, mm_projector_lr=None, betas=(0.9, 0.999), eps=1e-8,
                  weight_decay=0.0, max_grad_norm=0.1, first_trainable_clip_layer=12, vocab_weight=None,
                  trainable=None, lora=None, train_embed_tokens=False, group=None, shard_optimizer=False,
-                 shard_gradients=False, grad_comm_dtype=torch.bfloat16):
+                 shard_gradients=False, grad_comm_dtype=torch.bfloat16, base_nf4=False, nf4_double_quant=True):
         """lora: a train.lora.LoraState -> the reference's LoRA recipe (train.py:1159-1175): the decoder's base
         weights, norms and lm_head are frozen, the adapters train next to mm_projector / image_pooler / CLIP layers.
         group: data-parallel process group (same as set_process_group). shard_optimizer: keep fp32 master / m / v for
         1 / world of every tensor on each rank (train/zero.py, ZeRO-1); needs `group`. shard_gradients (with
         shard_optimizer): gradients are reduce-scattered in grad_comm_dtype instead of all-reduced in fp32, so a rank
-        only receives the averaged gradient of the slices it updates (ZeRO-2, the reference's scripts/zero2.json)."""
+        only receives the averaged gradient of the slices it updates (ZeRO-2, the reference's scripts/zero2.json).
+        base_nf4 (LoRA only; the reference's `--bits 4`, train.py:1098-1114): the frozen decoder projections and lm_head
+        are replaced by their NF4 round trip Q(W) (train/nf4.py, double quantisation of the block maxima as in the
+        reference's default), so the adapters train against the weights a bitsandbytes Linear4bit would multiply with."""
         self.model = model
         self.dev = model.device
         self.first_clip = first_trainable_clip_layer
@@ -74,6 +77,17 @@ class FineTuner:
                                                                                          "lm_head.weight"))
         # the full reference-named state dict in bf16 on the device: the source the fused layouts are rebuilt from
         self.sd = {k: v.detach().to(self.dev, BF).contiguous() for k, v in state_dict.items()}
+        self.nf4_bytes = None
+        if base_nf4:
+            if lora is None:
+                raise ValueError("base_nf4=True is the QLoRA recipe: it needs lora=LoraState(...) (a 4-bit base is frozen)")
+            from .nf4 import qlora_base_
+            stored = qlora_base_(self.sd, double_quant=nf4_double_quant)
+            self.nf4_bytes = sum(q.nbytes() for q in stored.values())       # what the packed base would occupy
+            del stored
+            # the kernels read fused copies of the decoder weights: rebuild them from Q(W)
+            model._keep = model._w = model.lm_head = None
+            model.load_state_dict(self.sd, device=self.dev)
         n_run = model.get_vision_tower().n_layers_run()     # CLIP layers past the selected hidden state are dead
         self.names = sorted(k for k in self.sd if pick(k) and self._has_backward(k, n_run))
         self.zero = None

@@ -1,4 +1,4 @@
-"""TEST INFRASTRUCTURE: builds and loads tests/emu/_build/libb200emu.so -- mm_or_b200/csrc/{ptv3,train_extras}.cu compiled with g++
+"""TEST INFRASTRUCTURE: builds and loads tests/emu/_build/libb200emu.so -- mm_or_b200/csrc/{ptv3,train_extras,nf4}.cu compiled with g++
 -DB200_EMU against the CUDA-kernel emulator of tests/emu/cuda_emu.h -- and binds it like mm_or_b200/_lib.py binds the real
 library, so that the CPU test-suite executes the SAME kernel source (and the same host orchestration,
 mm_or_b200/model/point_transformer.py) against the oracle. Never imported by the product."""
@@ -14,7 +14,7 @@ from mm_or_b200.model.point_transformer import PcOps
 HERE = os.path.dirname(os.path.abspath(__file__))
 EMU = os.path.join(HERE, "emu")
 CSRC = os.path.join(HERE, "..", "mm_or_b200", "csrc")
-SRCS = [os.path.join(CSRC, "ptv3.cu"), os.path.join(CSRC, "train_extras.cu")]
+SRCS = [os.path.join(CSRC, "ptv3.cu"), os.path.join(CSRC, "train_extras.cu"), os.path.join(CSRC, "nf4.cu")]
 _lib = None
 
 

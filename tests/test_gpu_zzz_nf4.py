@@ -1,0 +1,63 @@
+"""GPU: the NF4 storage kernels (csrc/nf4.cu) through the C ABI against the numpy restatement -- bit-exact (byte /
+integer work) -- at a real projection's width, and the QLoRA arm of the fine-tune step (frozen base replaced by its NF4
+round trip). Written without GPU access (the same kernel source runs bit-exactly on the CPU emulator, tests/test_nf4.py);
+its own late file."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import nf4_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def bits(t):
+    return t.contiguous().cpu().view(torch.int16).numpy().view(np.uint16)
+
+
+def test_nf4_kernels_bit_exact_on_a_projection_sized_weight():
+    from mm_or_b200.train import nf4 as N
+    g = torch.Generator(device="cuda").manual_seed(0)
+    w = (torch.randn(1024, 4096, generator=g, device="cuda") * 0.02).to(torch.bfloat16)
+    w[5] = 0                                                            # all-zero blocks
+    w[7, ::64] = 3.0                                                    # one outlier per block
+    packed, absmax = N.quantize(w)
+    ref_p, ref_a = O.quantize(bits(w))
+    assert np.array_equal(packed.cpu().numpy(), ref_p) and np.array_equal(absmax.cpu().numpy(), ref_a)
+    out = N.dequantize(packed, absmax, w.shape)
+    assert np.array_equal(bits(out), O.dequantize(ref_p, ref_a))
+    # idempotent storage, and the double-quantised block maxima stay within the 8-bit code's resolution
+    p2, a2 = N.quantize(out)
+    assert torch.equal(p2, packed) and torch.equal(a2, absmax)
+    q = N.Nf4Weight(w, double_quant=True)
+    bm = q.block_maxima()
+    assert float((bm - absmax).abs().max()) < 0.02 * float(absmax.max())
+    assert q.nbytes() < 0.26 * w.numel() * 2
+
+
+def test_qlora_step_trains_against_the_quantised_base():
+    import golden_cases as gc
+    from mm_or_b200.model.llava_llama import LlavaLlamaForCausalLM
+    from mm_or_b200.train.lora import LoraState
+    from mm_or_b200.train.step import FineTuner
+    torch.set_grad_enabled(False)
+    cfg = gc.small_config()
+    cfg.tokenizer_padding_side = "right"
+    sd = gc.bf16_round(gc.small_weights(cfg))
+    case = gc.make_case(cfg, "train_right")
+    args = (case["input_ids"], case["labels"], case["attention_mask"], case["images"])
+    losses = {}
+    for nf4 in (False, True):
+        model = LlavaLlamaForCausalLM(cfg).load_state_dict(sd)
+        lora = LoraState(cfg, r=8, alpha=16, device="cuda", seed=1)
+        ft = FineTuner(model, sd, lr=1e-3, max_grad_norm=0.1, first_trainable_clip_layer=1, lora=lora, base_nf4=nf4)
+        k = "model.layers.0.self_attn.q_proj.weight"
+        if nf4:
+            assert ft.nf4_bytes and not torch.equal(ft.sd[k].cpu().float(), sd[k])        # base replaced by Q(W) ...
+            assert torch.equal(ft.sd["model.mm_projector.0.weight"].cpu().float(), sd["model.mm_projector.0.weight"])
+        loss0, _ = ft.train_step(*args)
+        loss1, _ = ft.train_step(*args)
+        losses[nf4] = (float(loss0), float(loss1))
+        assert np.isfinite(losses[nf4]).all() and losses[nf4][1] != losses[nf4][0]        # ... and the step still updates
+    # 4-bit base: a different, slightly worse starting loss (quantisation error), same order of magnitude
+    assert losses[True][0] != losses[False][0] and abs(losses[True][0] - losses[False][0]) < 0.5 * losses[False][0]

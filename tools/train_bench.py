@@ -79,6 +79,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=1)
     ap.add_argument("--lora-r", type=int, default=0, help="> 0: the reference's LoRA recipe (r 128, alpha 2r) instead "
                     "of full fine-tuning of the decoder")
+    ap.add_argument("--nf4", action="store_true", help="with --lora-r: NF4 round trip of the frozen base (QLoRA, --bits 4)")
     ap.add_argument("--zero", type=int, default=0, choices=[0, 1, 2], help="under torchrun: 0 = replicated optimizer "
                     "state + fp32 all-reduce, 1 = sharded state, 2 = sharded state + bf16 reduce-scatter (zero.py)")
     ap.add_argument("--accum", type=int, default=1, help="gradient accumulation steps (reference recipe: 4)")
@@ -116,7 +117,7 @@ def main():
         lora = LoraState(cfg, r=a.lora_r, alpha=2 * a.lora_r, device=dev)
     ft = FineTuner(model, sd, lr=2e-5, weight_decay=0.0, max_grad_norm=0.1, first_trainable_clip_layer=12, vocab_weight=w,
                    lora=lora, group=group, shard_optimizer=world > 1 and a.zero >= 1,
-                   shard_gradients=world > 1 and a.zero >= 2)
+                   shard_gradients=world > 1 and a.zero >= 2, base_nf4=a.nf4)
     del sd
     n_train = sum(ft.sd[k].numel() for k in ft.names)
     tokens = a.batch * (256 + 150 - 1 + 576) * a.accum
@@ -152,7 +153,9 @@ def main():
                           "scaling": "weak", "ms_per_step": round(ms, 1), "tokens_per_step_per_gpu": tokens,
                           "trainable_params": n_train, "decoder_layers": a.layers, "batch_per_gpu": a.batch,
                           "views": a.views, "gradient_accumulation": a.accum,
-                          "mode": "lora r=%d" % a.lora_r if a.lora_r else "full fine-tune",
+                          "mode": ("qlora (nf4 base) r=%d" if a.nf4 else "lora r=%d") % a.lora_r if a.lora_r
+                          else "full fine-tune",
+                          "nf4_packed_base_gb": round(ft.nf4_bytes / 1e9, 2) if ft.nf4_bytes else None,
                           "data_parallel": {0: "replicated state, fp32 all-reduce", 1: "ZeRO-1 (sharded fp32 state)",
                                             2: "ZeRO-2 (sharded state, bf16 reduce-scatter)"}[a.zero]
                           if world > 1 else "none",
