@@ -481,6 +481,14 @@ int b200_segmask_backward(const b200_segmask_weights* w, const uint8_t* cls, int
 int b200_embed_grad(const void* d_rows, int64_t ld, const int32_t* row_list, const int32_t* seg_start,
                     const int32_t* seg_token, int n_seg, int D, float* d_table, int accumulate, b200_stream_t stream);
 
+/* Inverted dropout on bf16 (the reference's train-mode nn.Dropout, e.g. lora_dropout 0.05, train/train.py:111,1165):
+ * y = mask * x / (1 - p), or y += ... with accumulate = 1 (the backward: dx += mask * g / (1 - p) with the SAME seed).
+ * The mask is a pure function of (seed, element index) -- Philox4x32-10, element i dropped iff word i mod 4 of
+ * Philox(counter i / 4, key seed) < floor(p * 2^32) -- so nothing is stored between forward and backward. torch's own
+ * generator stream is not reproducible outside torch: the distribution is kept, not the individual masks. */
+int b200_dropout(const void* x_bf16, void* y_bf16, int64_t n, float p, uint64_t seed, int accumulate,
+                 b200_stream_t stream);
+
 /* ============================================================================================================
  * NF4 storage of the frozen base weights (QLoRA recipe). Replaces bitsandbytes' Linear4bit storage as configured by
  * LLaVA/llava/train/train.py:1098-1114 (BitsAndBytesConfig(load_in_4bit, bnb_4bit_quant_type='nf4', compute dtype

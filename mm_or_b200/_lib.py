@@ -78,6 +78,7 @@ _SIGS = {
     "b200_set_option": (ci, [ctypes.c_char_p, ci]),
     "b200_get_option": (ci, [ctypes.c_char_p]),
     "b200_decode_tile_width": (ci, [ci, ci, ci]),
+    "b200_dropout": (ci, [vp, vp, i64, cf, ctypes.c_uint64, ci, vp]),
     "b200_nf4_quantize": (ci, [vp, i64, vp, vp, vp]),
     "b200_nf4_dequantize": (ci, [vp, vp, i64, vp, vp]),
     "b200_gemm_bf16": (ci, [vp, ci, vp, ci, vp, ci, ci, ci, ci, vp, vp, ci, vp, ci, ci, ci, vp]),
@@ -156,7 +157,7 @@ PC_SYMBOLS = sorted(k for k in _SIGS if k.startswith("b200_pc_"))
 # entry points whose kernels also build for the host against the test-only kernel emulator (tests/emu/)
 EMULATABLE_SYMBOLS = PC_SYMBOLS + ["b200_segmask_train_acts_bytes", "b200_segmask_forward_train",
                                    "b200_segmask_backward_workspace_bytes", "b200_segmask_backward", "b200_embed_grad",
-                                   "b200_nf4_quantize", "b200_nf4_dequantize"]
+                                   "b200_nf4_quantize", "b200_nf4_dequantize", "b200_dropout"]
 
 EXPORTED_SYMBOLS = ["b200_last_error"] + sorted(_SIGS)
 
@@ -375,6 +376,16 @@ def grad_sq_norm(grad, out2=None, accumulate=False, max_norm=0.0):
     check(lib().b200_grad_sq_norm(ptr(grad), int(grad.dtype == torch.float32), grad.numel(), int(accumulate),
                                   float(max_norm), ptr(out2), ptr(ws), ws.numel(), stream_ptr()), "b200_grad_sq_norm")
     return out2
+
+
+def dropout(x, p, seed, out=None, accumulate=False):
+    """out (+)= mask(seed) * x / (1 - p) on bf16 (b200_dropout); out=None allocates, out=x works in place."""
+    if out is None:
+        out = torch.empty_like(x)
+    assert x.dtype == torch.bfloat16 and out.dtype == torch.bfloat16 and x.is_contiguous() and out.is_contiguous()
+    check(lib().b200_dropout(ptr(x), ptr(out), x.numel(), float(p), int(seed) & 0xFFFFFFFFFFFFFFFF, int(accumulate),
+                             stream_ptr()), "b200_dropout")
+    return out
 
 
 def adamw_step(master, param, grad, m, v, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, step=1,

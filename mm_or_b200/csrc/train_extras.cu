@@ -188,6 +188,51 @@ __global__ void embed_grad_kernel(const uint16_t* __restrict__ d_rows, long long
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Inverted dropout with a counter-based generator (Philox4x32-10): element i is dropped iff word (i mod 4) of
+// Philox(counter = i / 4, key = seed) is below floor(p * 2^32); kept elements are multiplied by 1 / (1 - p). The mask
+// is a pure function of (seed, i): the backward pass re-creates it from the seed instead of storing it, and the same
+// kernel applied to the output gradient is the backward (accumulate = 1 adds into y: dx += mask * g / (1 - p)).
+// (The reference's dropout masks come from torch's own Philox stream and are not reproducible outside torch; what is
+// kept is the distribution: Bernoulli(1 - p) per element, scaled by 1 / (1 - p). LoRA dropout 0.05, train.py:111.)
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t k0, uint32_t k1, uint32_t (&out)[4]) {
+  uint32_t c[4] = {c0, c1, 0u, 0u};
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c[0];
+    const uint64_t p1 = (uint64_t)0xCD9E8D57u * c[2];
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0;
+    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1;
+    c[0] = n0;
+    c[1] = (uint32_t)p1;
+    c[2] = n2;
+    c[3] = (uint32_t)p0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[0] = c[0];
+  out[1] = c[1];
+  out[2] = c[2];
+  out[3] = c[3];
+}
+
+// one thread per group of 4 consecutive elements (one Philox call, 8 bytes in, 8 bytes out)
+__global__ void dropout_kernel(const uint16_t* __restrict__ x, uint16_t* __restrict__ y, long long n, uint32_t threshold,
+                               float scale, uint32_t k0, uint32_t k1, int accumulate) {
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g * 4 >= n) return;
+  uint32_t r[4];
+  philox4x32_10((uint32_t)g, (uint32_t)((unsigned long long)g >> 32), k0, k1, r);
+  for (int j = 0; j < 4; ++j) {
+    const long long i = g * 4 + j;
+    if (i >= n) break;
+    float v = r[j] < threshold ? 0.f : bf16_to_f32(x[i]) * scale;
+    if (accumulate) v += bf16_to_f32(y[i]);
+    y[i] = f32_to_bf16(v);
+  }
+}
+
 }  // namespace tx
 }  // namespace b200
 
@@ -281,6 +326,21 @@ int b200_embed_grad(const void* d_rows, int64_t ld, const int32_t* row_list, con
   B200_LAUNCH(embed_grad_kernel, dim3(n_seg), dim3(256), 0, stream, reinterpret_cast<const uint16_t*>(d_rows),
               (long long)ld, row_list, seg_start, seg_token, D, d_table, accumulate);
   TX_CHECK_LAUNCH("b200_embed_grad");
+  return 0;
+}
+
+int b200_dropout(const void* x, void* y, int64_t n, float p, uint64_t seed, int accumulate, b200_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (n == 0) return 0;
+  if (!x || !y || n < 0 || !(p >= 0.f) || !(p < 1.f))
+    return fail(-2, "b200_dropout: bad argument (n=%lld, p=%g must be in [0, 1))", (long long)n, (double)p);
+  const uint32_t threshold = (uint32_t)((double)p * 4294967296.0);  // floor(p * 2^32)
+  const long long groups = (n + 3) / 4;
+  LaunchScope ls(kFamTrain, stream, (accumulate ? 6.0 : 4.0) * (double)n, 0.0, 1);
+  B200_LAUNCH(dropout_kernel, dim3(tx_blocks(groups, 256)), dim3(256), 0, stream, reinterpret_cast<const uint16_t*>(x),
+              reinterpret_cast<uint16_t*>(y), (long long)n, threshold, 1.0f / (1.0f - p), (uint32_t)seed,
+              (uint32_t)(seed >> 32), accumulate);
+  TX_CHECK_LAUNCH("b200_dropout");
   return 0;
 }
 

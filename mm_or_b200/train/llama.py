@@ -55,12 +55,24 @@ def forward_backward(model, embeds, labels, lengths, vocab_weight=None, grad_sca
         L.check(lib.b200_rope_kv_write(L.ptr(qkv), None, L.ptr(rope_cos), L.ptr(rope_sin), cfg.max_position_embeddings,
                                        L.ptr(kc), L.ptr(vc), B, H, Lq, 0, Lq, L.stream_ptr()), "b200_rope_kv_write")
 
+    # LoRA dropout (peft: the adapter branch sees dropout(x), the base branch x; lora_dropout 0.05 in the reference's
+    # recipe, train.py:111,1165). The mask is a function of (seed, element): the backward re-creates it. One mask per
+    # FUSED projection (q, k, v share it; peft draws one per adapted Linear -- same distribution per projection, but
+    # correlated across q / k / v; stated in DESIGN.md).
+    p_drop = float(getattr(lora, "dropout", 0.0)) if lora is not None else 0.0
+    if p_drop > 0.0:
+        lora.rng_step = getattr(lora, "rng_step", 0) + 1
+    _fidx = {"qkv_w": 0, "o_w": 1, "gate_up_w": 2, "down_w": 3}
+
+    def drop_seed(i, fname):
+        return (int(getattr(lora, "seed", 0)) * 1000003 + lora.rng_step) * 4096 + i * 4 + _fidx[fname]
+
     def lin_fwd(i, fname, x_in, w, residual=None, keep=None):
-        """y = x w^T (+ residual) (+ LoRA: (alpha / r) * (x A_cat^T) B_blk^T added in place)."""
+        """y = x w^T (+ residual) (+ LoRA: (alpha / r) * (dropout(x) A_cat^T) B_blk^T added in place)."""
         y = L.gemm(x_in, w, residual=residual)
         if lora is not None:
             a_cat, b_blk = lora.fused[i][fname]
-            t = L.gemm(x_in, a_cat)
+            t = L.gemm(L.dropout(x_in, p_drop, drop_seed(i, fname)) if p_drop > 0.0 else x_in, a_cat)
             L.gemm_ex(t, b_blk, out=y, residual=y, scale=lora.scale)
             keep[fname] = t
         return y
@@ -112,9 +124,15 @@ def forward_backward(model, embeds, labels, lengths, vocab_weight=None, grad_sca
             db, accb = slot(f"_lora.layers.{layer}.{fname}.B", tuple(b_blk.shape))
             L.gemm_ex(dy, t, a_t=True, w_t=True, out=db, accumulate=accb, scale=lora.scale)
             da, acca = slot(f"_lora.layers.{layer}.{fname}.A", tuple(a_cat.shape))
-            L.gemm_ex(dt, x_saved, a_t=True, w_t=True, out=da, accumulate=acca)
-            if need_dx:
-                L.gemm_ex(dt, a_cat, w_t=True, out=dx, residual=dx)
+            if p_drop > 0.0:
+                seed = drop_seed(layer, fname)
+                L.gemm_ex(dt, L.dropout(x_saved, p_drop, seed), a_t=True, w_t=True, out=da, accumulate=acca)
+                if need_dx:                         # dx += mask * (dt A) / (1 - p): the forward's mask, from its seed
+                    L.dropout(L.gemm_ex(dt, a_cat, w_t=True), p_drop, seed, out=dx, accumulate=True)
+            else:
+                L.gemm_ex(dt, x_saved, a_t=True, w_t=True, out=da, accumulate=acca)
+                if need_dx:
+                    L.gemm_ex(dt, a_cat, w_t=True, out=dx, residual=dx)
         return dx
 
     def norm_bwd(x_saved, dy, gamma, name, add=None):

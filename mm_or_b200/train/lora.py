@@ -29,8 +29,13 @@ def param_name(layer, module, proj, which):
 
 
 class LoraState:
-    def __init__(self, cfg, r=128, alpha=256, device="cuda", seed=0, init_b="zero"):
+    def __init__(self, cfg, r=128, alpha=256, device="cuda", seed=0, init_b="zero", dropout=0.0):
+        """dropout: lora_dropout of the adapter branch (0.05 in the reference's recipe, train.py:111; 0 keeps the step
+        deterministic, which is what the parity tests compare)."""
         self.cfg, self.r, self.scale = cfg, r, float(alpha) / r
+        if not 0.0 <= dropout < 1.0:
+            raise ValueError(f"lora dropout {dropout} not in [0, 1)")
+        self.dropout, self.seed, self.rng_step = float(dropout), int(seed), 0
         self.device = torch.device(device)
         D, F = cfg.hidden_size, cfg.intermediate_size
         self.shapes = {"q_proj": (D, D), "k_proj": (D, D), "v_proj": (D, D), "o_proj": (D, D), "gate_proj": (F, D),

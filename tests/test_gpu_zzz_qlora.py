@@ -61,3 +61,34 @@ def test_qlora_step_trains_against_the_quantised_base():
         assert np.isfinite(losses[nf4]).all() and losses[nf4][1] != losses[nf4][0]        # ... and the step still updates
     # 4-bit base: a different, slightly worse starting loss (quantisation error), same order of magnitude
     assert losses[True][0] != losses[False][0] and abs(losses[True][0] - losses[False][0]) < 0.5 * losses[False][0]
+
+
+def test_lora_dropout_masks_are_reproducible_from_the_seed():
+    """lora_dropout (0.05 in the recipe; 0.5 here so that it matters): the adapter branch sees dropout(x). The mask is a
+    function of (seed, step, layer, projection, element), so the backward re-creates the forward's mask: the same step
+    counter gives bit-identical loss and gradients, the next step another mask; p = 0 is the deterministic path."""
+    import golden_cases as gc
+    from mm_or_b200.model.llava_llama import LlavaLlamaForCausalLM
+    from mm_or_b200.train.lora import LoraState
+    from mm_or_b200.train.step import FineTuner
+    torch.set_grad_enabled(False)
+    cfg = gc.small_config()
+    cfg.tokenizer_padding_side = "right"
+    sd = gc.bf16_round(gc.small_weights(cfg))
+    case = gc.make_case(cfg, "train_right")
+    args = (case["input_ids"], case["labels"], case["attention_mask"], case["images"])
+    model = LlavaLlamaForCausalLM(cfg).load_state_dict(sd)
+    lora = LoraState(cfg, r=8, alpha=16, device="cuda", seed=1, init_b="randn", dropout=0.5)
+    ft = FineTuner(model, sd, lr=1e-3, max_grad_norm=0.1, first_trainable_clip_layer=1, lora=lora)
+    runs = []
+    for step in (0, 0, 1):
+        lora.rng_step = step                                            # forward_backward advances it by one
+        loss, _, g = ft.forward_backward(*args)
+        runs.append((float(loss), {k: v.clone() for k, v in g.items() if k.startswith("_lora.")}))
+    assert runs[0][0] == runs[1][0] and all(torch.equal(runs[0][1][k], runs[1][1][k]) for k in runs[0][1])
+    assert runs[2][0] != runs[0][0]
+    assert all(bool(torch.isfinite(v).all()) for v in runs[0][1].values())
+    assert any(float(v.abs().max()) > 0 for k, v in runs[0][1].items() if k.endswith(".A"))
+    lora.dropout = 0.0
+    base = [float(ft.forward_backward(*args)[0]) for _ in range(2)]
+    assert base[0] == base[1] and base[0] != runs[0][0]
