@@ -56,8 +56,9 @@ def parse_args():
                    "visible to ncu)")
     p.add_argument("--pdl", action="store_true", help="programmatic dependent launch for the decode step's kernels "
                    "(b200_set_pdl; off by default until timed on hardware)")
-    p.add_argument("--decode-tiles", action="store_true", help="tile widths 96 / 160 / 224 for the decode step's wide "
-                   "projections (b200_set_option decode_tiles; off by default until timed on hardware)")
+    p.add_argument("--decode-tiles", type=int, default=0, choices=[0, 1, 2], help="weight-tile widths of the decode "
+                   "step's wide projections (b200_set_option decode_tiles): 1 = 96 / 160 / 224 columns, one CTA per SM; "
+                   "2 = 64 / 96 / 128 columns, two CTAs per SM; 0 (default, the timed configuration) = 128 columns")
     return p.parse_args()
 
 
@@ -173,7 +174,7 @@ def run_b200(args):
     if args.pdl:
         L.set_option("pdl", True)
     if args.decode_tiles:
-        L.set_option("decode_tiles", True)
+        L.set_option("decode_tiles", args.decode_tiles)
     cfg = full_config(args.layers)
     t0 = time.time()
     sd = make_state_dict(cfg, seed=0, device=dev, dtype=torch.bfloat16)
@@ -313,7 +314,8 @@ def run_b200(args):
                                     "epilogue (peer stores over NVLink)", "nccl": "ncclAllGather of visual tokens"}[exchange],
                        "model_tflop_per_inference": round(flops / 1e12, 2),
                        "programmatic_dependent_launch": bool(L.get_option("pdl")),
-                       "decode_tile_widths": "96/160/224" if L.get_option("decode_tiles") else "128"},
+                       "decode_tile_widths": {0: "128", 1: "96/160/224, one CTA per SM",
+                                              2: "64/96/128, two CTAs per SM"}[int(L.get_option("decode_tiles"))]},
             "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": int(images_host.numel() * 2
                     + ids.numel() * 8), "d2h_bytes_per_step": int(B * (ids.shape[1] + args.new_tokens) * 8),
                     "ms_per_step": round(ms_e2e / args.steps, 2)},

@@ -55,15 +55,18 @@ int b200_prof_collect(double* ms, double* alg_bytes, double* alg_flops, long lon
  *   "pdl"          (B200_PDL=1): programmatic dependent launch -- the step's kernels are launched with programmatic
  *                  stream serialization, so each kernel's prologue, and the first weight tiles of the GEMMs (which do
  *                  not depend on the previous kernel), overlap the tail of the kernel before it.
- *   "decode_tiles" (B200_DECODE_TILES=1): the wide projections (qkv, gate_up, lm_head) choose their weight-tile width
- *                  from {96, 128, 160, 224, 256} so that the tiles cover the SMs in as few waves as possible
- *                  (12288 / 96 = 128 tiles, 22016 / 160 = 138, 32000 / 224 = 143 on 148 SMs) instead of 128 columns.
- * b200_set_option returns 0, or -2 for an unknown name; b200_get_option returns 0 / 1, or -2. */
+ *   "decode_tiles" (B200_DECODE_TILES=1|2): the wide projections (qkv, gate_up, lm_head) choose their weight-tile width
+ *                  so that the tiles cover the CTA slots in as few waves as possible instead of always 128 columns.
+ *                  1: one CTA per SM, widths {96, 128, 160, 224, 256} (12288 / 96 = 128 tiles, 22016 / 160 = 138,
+ *                  32000 / 224 = 143 on 148 SMs); 2: two CTAs per SM with half-depth rings, widths {64, 96, 128}
+ *                  (192 / 230 / 250 tiles on 296 slots).
+ * b200_set_option returns 0, or -2 for an unknown name / value; b200_get_option returns the value, or -2. */
 int b200_set_option(const char* name, int value);
 int b200_get_option(const char* name);
 /* The weight-tile width "decode_tiles" picks for a projection with `n` output features at `rows` sequences on a
- * device with `sms` SMs (host-side arithmetic only; exposed so that the policy can be pinned without a GPU). */
-int b200_decode_tile_width(int rows, int n, int sms);
+ * device with `sms` SMs and 1 or 2 CTAs per SM (host-side arithmetic only; exposed so that the policy can be pinned
+ * without a GPU). */
+int b200_decode_tile_width(int rows, int n, int sms, int ctas_per_sm);
 
 /* ============================================================================================================
  * Operator level (used by the stage entry points below and by the parity tests)
@@ -75,7 +78,8 @@ int b200_decode_tile_width(int rows, int n, int sms);
  * (model/llava_arch.py:182), Llama q/k/v/o/gate/up/down_proj and lm_head (model/language_model/llava_llama.py:93).
  *   act: 0 none, 1 quick_gelu, 2 gelu(erf), 3 SwiGLU over interleaved (gate, up) column pairs (C has N/2 columns)
  *   bias [N] / residual [M, ldr] / row_map [M] (output row per logical row, <0 drops the row) may be NULL
- *   out_fp32: C is float instead of bf16.  bn_hint: 0 = auto tile width, or 32/64/128/256. */
+ *   out_fp32: C is float instead of bf16.  bn_hint: 0 = auto tile width, or 32/64/96/128/160/224/256; -64/-96/-128 =
+ *   that width on half-depth rings with two CTAs per SM (the decode step's "decode_tiles" = 2 shape). */
 int b200_gemm_bf16(const void* A, int lda, const void* W, int ldw, void* C, int ldc, int M, int N, int K,
                    const void* bias, const void* residual, int ldr, const int32_t* row_map, int act, int out_fp32,
                    int bn_hint, b200_stream_t stream);

@@ -77,7 +77,7 @@ _SIGS = {
     "b200_prof_collect": (ci, [vp, vp, vp, vp]),
     "b200_set_option": (ci, [ctypes.c_char_p, ci]),
     "b200_get_option": (ci, [ctypes.c_char_p]),
-    "b200_decode_tile_width": (ci, [ci, ci, ci]),
+    "b200_decode_tile_width": (ci, [ci, ci, ci, ci]),
     "b200_dropout": (ci, [vp, vp, i64, cf, ctypes.c_uint64, ci, vp]),
     "b200_nf4_quantize": (ci, [vp, i64, vp, vp, vp]),
     "b200_nf4_dequantize": (ci, [vp, vp, i64, vp, vp]),
@@ -493,10 +493,11 @@ def set_option(name, value=True):
 
 
 def get_option(name):
+    """Value of a switch: False / True for "pdl"; 0 / 1 / 2 for "decode_tiles" (falsy when off either way)."""
     v = int(lib().b200_get_option(name.encode()))
     if v < 0:
         check(v, "b200_get_option")
-    return bool(v)
+    return v if name == "decode_tiles" else bool(v)
 
 
 def set_pdl(on=True):

@@ -40,6 +40,10 @@ int b200_gemm_bf16(const void* A, int lda, const void* W, int ldw, void* C, int 
   e.row_map = row_map;
   e.act = act;
   e.out_fp32 = out_fp32;
+  if (bn_hint < 0) {  // -64 / -96 / -128: the decode step's two-CTAs-per-SM shape of that width
+    e.ctas_per_sm = 2;
+    bn_hint = -bn_hint;
+  }
   return gemm_bf16_tn(static_cast<const bf16*>(A), lda, static_cast<const bf16*>(W), ldw, C, ldc, M, N, K, e,
                       bn_hint, static_cast<cudaStream_t>(stream));
 }

@@ -45,8 +45,8 @@ bool pdl_enabled();
 void set_pdl(bool on);
 // Tile widths 96 / 160 / 224 for the decode step's wide projections (stages.cu::decode_bn). Opt-in like PDL
 // (B200_DECODE_TILES=1 or b200_set_option("decode_tiles", 1)) until timed on hardware.
-bool decode_tiles_enabled();
-void set_decode_tiles(bool on);
+int decode_tiles_mode();       // 0 off, 1 widths for one CTA per SM, 2 two CTAs per SM (widths 64 / 96 / 128)
+void set_decode_tiles(int mode);
 
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_ex(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
@@ -131,6 +131,10 @@ struct GemmEpilogue {
   // programmatic dependent launch: operand B (the weights) is not written by the kernel launched before this one, so
   // its first tiles may be fetched before the grid dependency resolves. Only the decode step sets it.
   int b_const = 0;
+  // 2: the decode step's weight-streaming shape -- half the pipeline depth so that two CTAs are resident per SM (an SM
+  // streams cold weights at ~41 GB/s with two resident CTAs vs ~30 GB/s with one, profiles/r1_skinny_gemm_notes.md)
+  // and the grid has 2 x SMs slots; BN <= 128 only (two CTAs x two accumulators must fit the 512 TMEM columns).
+  int ctas_per_sm = 1;
   // fused GEMM -> all-gather: when n_peers > 0 every bf16 output vector is stored to the same offset of each
   // peer_c[p] (peer-mapped device pointers over NVLink, this rank's own buffer included) instead of C.
   int n_peers = 0;

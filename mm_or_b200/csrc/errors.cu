@@ -40,8 +40,16 @@ static bool env_switch(std::atomic<int>& v, const char* name) {
 }
 bool pdl_enabled() { return env_switch(g_pdl, "B200_PDL"); }
 void set_pdl(bool on) { g_pdl.store(on ? 1 : 0, std::memory_order_relaxed); }
-bool decode_tiles_enabled() { return env_switch(g_decode_tiles, "B200_DECODE_TILES"); }
-void set_decode_tiles(bool on) { g_decode_tiles.store(on ? 1 : 0, std::memory_order_relaxed); }
+int decode_tiles_mode() {
+  int x = g_decode_tiles.load(std::memory_order_relaxed);
+  if (x < 0) {
+    const char* e = getenv("B200_DECODE_TILES");
+    x = (e != nullptr && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 0;
+    g_decode_tiles.store(x, std::memory_order_relaxed);
+  }
+  return x;
+}
+void set_decode_tiles(int mode) { g_decode_tiles.store(mode < 0 ? 0 : (mode > 2 ? 2 : mode), std::memory_order_relaxed); }
 
 // ---------------------------------------------------------------------------------------------
 // launch counter + per-family event timing
@@ -100,7 +108,10 @@ int b200_set_option(const char* name, int value) {
   if (name == nullptr) return fail(-2, "b200_set_option: null name");
   const std::string n(name);
   if (n == "pdl") set_pdl(value != 0);
-  else if (n == "decode_tiles") set_decode_tiles(value != 0);
+  else if (n == "decode_tiles") {
+    if (value < 0 || value > 2) return fail(-2, "b200_set_option: decode_tiles takes 0, 1 or 2 (got %d)", value);
+    set_decode_tiles(value);
+  }
   else return fail(-2, "b200_set_option: unknown option '%s' (pdl, decode_tiles)", name);
   return 0;
 }
@@ -108,7 +119,7 @@ int b200_get_option(const char* name) {
   if (name == nullptr) return fail(-2, "b200_get_option: null name");
   const std::string n(name);
   if (n == "pdl") return pdl_enabled() ? 1 : 0;
-  if (n == "decode_tiles") return decode_tiles_enabled() ? 1 : 0;
+  if (n == "decode_tiles") return decode_tiles_mode();
   return fail(-2, "b200_get_option: unknown option '%s' (pdl, decode_tiles)", name);
 }
 

@@ -38,7 +38,7 @@ struct GemmArgs {
   GemmEpilogue epi;
 };
 
-template <int BN>
+template <int BN, int PER_SM = 1>
 struct GemmCfg {
   static constexpr int kStageBytesA = kBM * kBK * 2;
   static constexpr int kStageBytesB = BN * kBK * 2;
@@ -46,7 +46,10 @@ struct GemmCfg {
   // BN in {32, 64, 128, 256} are the general-purpose tiles; 96 / 160 / 224 exist for the decode step's wide
   // projections, where the tile width decides whether the weight tiles fill the 148 SMs in one wave
   // (stages.cu::decode_bn): 12288 / 96 = 128 tiles, 22016 / 160 = 138, 32000 / 224 = 143.
-  static constexpr int kStages = (BN == 256) ? 4 : (BN == 224) ? 5 : (BN >= 128) ? 6 : (BN == 96) ? 7 : 8;
+  // PER_SM = 2 (decode step only): half the ring so that two CTAs fit one SM -- 3 x 32 KB (BN 128), 3 x 28 KB (BN 96),
+  // 4 x 24 KB (BN 64) -- and their 2 x 2 accumulators the 512 TMEM columns.
+  static constexpr int kStages = PER_SM == 2 ? (BN == 64 ? 4 : 3)
+                                 : (BN == 256) ? 4 : (BN == 224) ? 5 : (BN >= 128) ? 6 : (BN == 96) ? 7 : 8;
   // two accumulators of BN columns; tcgen05.alloc takes a power of two >= 32
   static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 :
                                    (2 * BN <= 256) ? 256 : 512;
@@ -54,6 +57,8 @@ struct GemmCfg {
   static_assert(BN % 32 == 0 && BN <= 256, "the epilogue drains 32 accumulator columns at a time");
   static_assert(kStageBytesB % 1024 == 0, "SWIZZLE_128B tiles start on 1024-byte boundaries");
   static_assert(kSmemBytes <= 227 * 1024, "shared memory per CTA");
+  static_assert(PER_SM == 1 || (BN <= 128 && 2 * kTmemCols <= 512 && 2 * (kSmemBytes + 1024) <= 228 * 1024),
+                "two CTAs per SM: TMEM columns and shared memory of both must fit");
 };
 
 __device__ __forceinline__ void tile_coords(int tile, int m_tiles, int n_tiles, int& mt, int& nt) {
@@ -73,11 +78,11 @@ __device__ __forceinline__ float act_apply(float x, int act) {
   return x;
 }
 
-template <int BN>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+template <int BN, int PER_SM = 1>
+__global__ void __launch_bounds__(kGemmThreads, PER_SM)
     gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                         const GemmArgs g) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, PER_SM>;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -393,24 +398,25 @@ int num_sms() {
   return n;
 }
 
-template <int BN>
+template <int BN, int PER_SM = 1>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, PER_SM>;
   static bool configured = false;
   if (!configured) {
-    B200_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    B200_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, PER_SM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       Cfg::kSmemBytes));
     configured = true;
   }
   const int tiles = g.m_tiles * g.n_tiles;
-  const int grid = tiles < num_sms() ? tiles : num_sms();
+  const int slots = num_sms() * PER_SM;
+  const int grid = tiles < slots ? tiles : slots;
   const double mnk = static_cast<double>(g.M) * g.N * g.K;
   const int n_out = g.epi.act == kActSwiGLU ? g.N / 2 : g.N;
   const double bytes = 2.0 * (static_cast<double>(g.M) * g.K + static_cast<double>(g.N) * g.K) +
                        static_cast<double>(g.M) * n_out * (g.epi.out_fp32 ? 4 : 2) +
                        (g.epi.residual ? 2.0 * g.M * g.N : 0.0);
   LaunchScope scope(g.M <= 128 ? kFamGemmSkinny : kFamGemm, stream, bytes, 2.0 * mnk);
-  B200_CUDA_OK(launch_ex(gemm_bf16_tn_kernel<BN>, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, stream, 0,
+  B200_CUDA_OK(launch_ex(gemm_bf16_tn_kernel<BN, PER_SM>, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, stream, 0,
                          g.epi.b_const != 0, tmA, tmB, g));
   return 0;
 }
@@ -460,6 +466,15 @@ int gemm_bf16_ex(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, int b
     B200_TRY(make_tmap_2d(&tmB, B, K, N, ldb, 64));
   else
     B200_TRY(make_tmap_2d(&tmB, B, N, K, ldb, bn));
+  if (epi.ctas_per_sm == 2) {
+    if (a_mn || b_mn) return fail(-2, "gemm: two CTAs per SM is the decode step's K-major shape only");
+    switch (bn) {
+      case 128: return launch_gemm<128, 2>(tmA, tmB, g, stream);
+      case 96: return launch_gemm<96, 2>(tmA, tmB, g, stream);
+      case 64: return launch_gemm<64, 2>(tmA, tmB, g, stream);
+      default: return fail(-2, "gemm: two CTAs per SM needs BN 64 / 96 / 128 (got %d)", bn);
+    }
+  }
   switch (bn) {
     case 256: return launch_gemm<256>(tmA, tmB, g, stream);
     case 224: return launch_gemm<224>(tmA, tmB, g, stream);

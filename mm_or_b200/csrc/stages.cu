@@ -225,19 +225,26 @@ static size_t llama_prefill_ws(const b200_llama_weights* w, int Bn, int L, int a
 // (profiles/r1_skinny_gemm_notes.md): projections with few 128-row weight tiles (N = 4096: o_proj, down_proj) are
 // 1.3-1.9x faster on the split-K cluster kernel, which keeps two streaming CTAs on every SM; the wide ones (qkv,
 // gate_up, lm_head) already fill the chip with 128-column tiles of the tiled kernel.
-// Weight-tile width of a wide decode-step projection (opt-in, common.h: decode_tiles_enabled): the kernel is
-// persistent with one CTA per SM and HBM bound, so its time is (waves of tiles over the SMs) x (bytes of one tile);
-// pick the width that minimises waves x width. 7B shapes on 148 SMs: qkv 12288 -> 96 (128 tiles, one wave),
-// gate_up 22016 -> 160 (138 tiles), lm_head 32000 -> 224 (143 tiles); with 128 columns they take 96 / 172 / 250 tiles.
-static int decode_bn(int T, int N, int sms) {
-  static const int widths[] = {256, 224, 160, 128, 96};
+// Weight-tile width of a wide decode-step projection (opt-in, common.h: decode_tiles_mode): the kernel is persistent
+// and HBM bound, so its time is (waves of tiles over the CTA slots) x (bytes of one tile); pick the width that minimises
+// waves x width. Mode 1, one CTA per SM (148 slots): qkv 12288 -> 96 (128 tiles, one wave), gate_up 22016 -> 160 (138),
+// lm_head 32000 -> 224 (143); with 128 columns they take 96 / 172 / 250 tiles. Mode 2, two CTAs per SM (296 slots,
+// half-depth rings, widths 64 / 96 / 128): qkv -> 64 (192 tiles), gate_up -> 96 (230), lm_head -> 128 (250), one wave
+// each, and every SM that holds two CTAs streams faster (profiles/r1_skinny_gemm_notes.md).
+static int decode_bn(int T, int N, int sms, int per_sm) {
+  static const int wide[] = {256, 224, 160, 128, 96};
+  static const int half[] = {128, 96, 64};
+  const int* widths = per_sm == 2 ? half : wide;
+  const int n_widths = per_sm == 2 ? 3 : 5;
   const int m_tiles = (T + 127) / 128;
   if (sms <= 0) return 128;
+  const long long slots = static_cast<long long>(sms) * per_sm;
   int best = 128;
   long long best_cost = -1;
-  for (int bn : widths) {
+  for (int w = 0; w < n_widths; ++w) {
+    const int bn = widths[w];
     const long long tiles = static_cast<long long>(m_tiles) * ((N + bn - 1) / bn);
-    const long long cost = ((tiles + sms - 1) / sms) * bn;
+    const long long cost = ((tiles + slots - 1) / slots) * bn;
     if (best_cost < 0 || cost < best_cost) {
       best_cost = cost;
       best = bn;
@@ -256,7 +263,9 @@ static int linear(const bf16* A, int lda, const bf16* W, int ldw, void* C, int l
   if (decode && T <= 256) {
     const int n_tiles = (N + 127) / 128;
     if (n_tiles * 2 <= num_sms()) return gemm_skinny(A, lda, W, ldw, C, ldc, T, N, K, e, 0, st);
-    if (decode_tiles_enabled()) return gemm_bf16_tn(A, lda, W, ldw, C, ldc, T, N, K, e, decode_bn(T, N, num_sms()), st);
+    const int mode = decode_tiles_mode();
+    if (mode == 2) e.ctas_per_sm = 2;
+    if (mode != 0) return gemm_bf16_tn(A, lda, W, ldw, C, ldc, T, N, K, e, decode_bn(T, N, num_sms(), mode), st);
     if (T <= 128) return gemm_bf16_tn(A, lda, W, ldw, C, ldc, T, N, K, e, 128, st);
   }
   return gemm_bf16_tn(A, lda, W, ldw, C, ldc, T, N, K, e, 0, st);
@@ -508,7 +517,9 @@ int b200_llama_prefill(const b200_llama_weights* w, void* x, const int32_t* kv_s
                        workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
-int b200_decode_tile_width(int rows, int n, int sms) { return decode_bn(rows, n, sms); }
+int b200_decode_tile_width(int rows, int n, int sms, int ctas_per_sm) {
+  return decode_bn(rows, n, sms, ctas_per_sm == 2 ? 2 : 1);
+}
 
 size_t b200_llama_decode_workspace_bytes(const b200_llama_weights* w, int Bn, int cap) {
   return llama_decode_ws(w, Bn, cap);

@@ -53,11 +53,16 @@ def test_decode_step_switches_default_off_and_reject_unknown_names():
     import pytest
     for name in ("pdl", "decode_tiles"):
         if os.environ.get("B200_" + name.upper(), "0") in ("", "0"):
-            assert L.get_option(name) is False
+            assert not L.get_option(name)
         L.set_option(name, True)
-        assert L.get_option(name) is True
+        assert L.get_option(name) == 1
         L.set_option(name, False)
-        assert L.get_option(name) is False
+        assert not L.get_option(name)
+    L.set_option("decode_tiles", 2)                    # two CTAs per SM
+    assert L.get_option("decode_tiles") == 2
+    L.set_option("decode_tiles", 0)
+    with pytest.raises(L.B200Error):
+        L.set_option("decode_tiles", 3)
     with pytest.raises(L.B200Error):
         L.set_option("no_such_switch", 1)
     with pytest.raises(L.B200Error):
@@ -65,16 +70,19 @@ def test_decode_step_switches_default_off_and_reject_unknown_names():
 
 
 def test_decode_tile_width_policy():
-    """stages.cu::decode_bn minimises (waves of weight tiles over the SMs) x (tile width). Llama-7B on 148 SMs:
-    qkv 12288 -> 96 (128 tiles), gate_up 22016 -> 160 (138 tiles), lm_head 32000 -> 224 (143 tiles): one wave each."""
+    """stages.cu::decode_bn minimises (waves of weight tiles over the CTA slots) x (tile width). Llama-7B on 148 SMs, one
+    CTA per SM: qkv 12288 -> 96 (128 tiles), gate_up 22016 -> 160 (138), lm_head 32000 -> 224 (143); two CTAs per SM
+    (296 slots, widths 64 / 96 / 128): 64 (192 tiles), 96 (230), 128 (250): one wave each."""
     w = L.lib().b200_decode_tile_width
-    assert [w(64, n, 148) for n in (12288, 22016, 32000)] == [96, 160, 224]
-    assert [w(128, n, 148) for n in (12288, 22016, 32000)] == [96, 160, 224]
-    for rows in (1, 64, 128, 192, 256):
-        for n in (4096, 12288, 22016, 32000, 512):
-            bn = w(rows, n, 148)
-            assert bn in (96, 128, 160, 224, 256)
-            m_tiles = (rows + 127) // 128
-            cost = lambda b: -(-(m_tiles * -(-n // b)) // 148) * b
-            assert cost(bn) == min(cost(b) for b in (96, 128, 160, 224, 256))
-    assert w(64, 12288, 0) == 128                      # no device: the default width
+    assert [w(64, n, 148, 1) for n in (12288, 22016, 32000)] == [96, 160, 224]
+    assert [w(128, n, 148, 1) for n in (12288, 22016, 32000)] == [96, 160, 224]
+    assert [w(128, n, 148, 2) for n in (12288, 22016, 32000)] == [64, 96, 128]
+    for per_sm, widths in ((1, (96, 128, 160, 224, 256)), (2, (64, 96, 128))):
+        for rows in (1, 64, 128, 192, 256):
+            for n in (4096, 12288, 22016, 32000, 512):
+                bn = w(rows, n, 148, per_sm)
+                assert bn in widths
+                m_tiles = (rows + 127) // 128
+                cost = lambda b: -(-(m_tiles * -(-n // b)) // (148 * per_sm)) * b
+                assert cost(bn) == min(cost(b) for b in widths)
+    assert w(64, 12288, 0, 1) == 128                   # no device: the default width

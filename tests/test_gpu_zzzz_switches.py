@@ -41,11 +41,11 @@ def env():
     return _model()
 
 
-def _with(option, fn):
+def _with(option, fn, value=1):
     assert not L.get_option(option)
     try:
-        L.set_option(option, True)
-        assert L.get_option(option)
+        L.set_option(option, value)
+        assert L.get_option(option) == value
         out = fn()
         torch.cuda.synchronize()
     finally:
@@ -71,21 +71,22 @@ def test_decode_step_bit_identical_with_pdl(env, batch):
     assert torch.equal(ids_graph, ref_graph) and torch.equal(ref_graph, ref_ids)
 
 
-@pytest.mark.parametrize("option", ["pdl", "decode_tiles"])
-def test_wide_projection_on_the_tiled_kernel(option):
+@pytest.mark.parametrize("option,value", [("pdl", 1), ("decode_tiles", 1), ("decode_tiles", 2)])
+def test_wide_projection_on_the_tiled_kernel(option, value):
     """lm_head with 12288 rows: 96 weight tiles x 2 > 148 SMs, so stages.cu::linear sends it to the tiled kernel
     (gemm_sm100.cu): with "pdl" that kernel prefetches weights before the grid dependency resolves, with
-    "decode_tiles" it runs 96-column tiles (128 tiles, one wave) instead of 128-column ones."""
+    "decode_tiles" = 1 it runs 96-column tiles (128 tiles, one wave) instead of 128-column ones, with 2 it runs
+    64-column tiles on half-depth rings, two CTAs per SM."""
     cfg, model = _model(vocab_size=12288)
     b = synth_batch(cfg, 3, 1, 16, seed=70, jitter=2, image_pos=2)
     kw = dict(images=b["images"], max_new_tokens=8, stop_on_eos=False)
     ref_ids, ref_lg = model.generate(b["input_ids"], return_logits=True, **kw)
-    ids, lg = _with(option, lambda: model.generate(b["input_ids"], return_logits=True, **kw))
-    ids_graph = _with(option, lambda: model.generate(b["input_ids"], **kw))
+    ids, lg = _with(option, lambda: model.generate(b["input_ids"], return_logits=True, **kw), value)
+    ids_graph = _with(option, lambda: model.generate(b["input_ids"], **kw), value)
     assert torch.equal(ids, ref_ids) and torch.equal(lg, ref_lg) and torch.equal(ids_graph, ref_ids)
 
 
-@pytest.mark.parametrize("bn", [96, 160, 224])
+@pytest.mark.parametrize("bn", [96, 160, 224, -64, -96, -128])      # negative: two CTAs per SM, half-depth rings
 @pytest.mark.parametrize("M,N,K", [(64, 22016, 4096), (128, 12288, 4096), (130, 32000, 512), (100, 264, 72),
                                    (1000, 1120, 1024)])
 def test_new_tile_widths_as_plain_gemms(bn, M, N, K):
@@ -99,7 +100,7 @@ def test_new_tile_widths_as_plain_gemms(bn, M, N, K):
     assert torch.equal(out, L.gemm(a, w, bn=128))
 
 
-@pytest.mark.parametrize("bn", [96, 160, 224])
+@pytest.mark.parametrize("bn", [96, 160, 224, -64, -96, -128])
 def test_new_tile_widths_swiglu_epilogue(bn):
     M, N, K = 48, 22016, 512
     g = torch.Generator(device="cuda").manual_seed(8)
@@ -107,3 +108,21 @@ def test_new_tile_widths_swiglu_epilogue(bn):
     w = (torch.randn(N, K, generator=g, device="cuda") / math.sqrt(K)).to(torch.bfloat16)
     out = L.gemm(a, w, act=L.ACT_SWIGLU, bn=bn)
     assert out.shape == (M, N // 2) and torch.equal(out, L.gemm(a, w, act=L.ACT_SWIGLU, bn=128))
+
+
+@pytest.mark.parametrize("batch", [3, 100, 200])
+def test_all_switches_together_at_wide_shapes(batch):
+    """pdl + two CTAs per SM on the shapes that reach the tiled kernel (vocabulary 12288, one and two row tiles)."""
+    cfg, model = _model(vocab_size=12288)
+    b = synth_batch(cfg, batch, 1, 16, seed=80 + batch, jitter=2, image_pos=2)
+    kw = dict(images=b["images"], max_new_tokens=6, stop_on_eos=False)
+    ref = model.generate(b["input_ids"], **kw)
+    try:
+        L.set_option("pdl", 1)
+        L.set_option("decode_tiles", 2)
+        out = model.generate(b["input_ids"], **kw)
+        torch.cuda.synchronize()
+    finally:
+        L.set_option("pdl", 0)
+        L.set_option("decode_tiles", 0)
+    assert torch.equal(out, ref)

@@ -1,10 +1,10 @@
 """Decode-step timing on ONE B200 at the real 7B size, for A/B-ing the decode-step switches quickly (a full bench.py
 run costs a minute per arm): text-only prompts of the packed length (831), `--batch` rows, the captured CUDA-graph decode
 loop; ms per step = (time of a generate with N2 new tokens - time with N1) / (N2 - N1), CUDA events, 3 repetitions,
-minimum. Prints one JSON line per arm: none / pdl / decode_tiles / both (b200_set_option), with the implied HBM rate of
+minimum. Prints one JSON line per arm: none / pdl / tiles1 / tiles2 / pdl+tiles1 / pdl+tiles2 (b200_set_option), with the implied HBM rate of
 the weight stream + KV reads per step (13.21 GB of weights + 512 KiB per context token per row).
 
-  python tools/decode_bench.py [--batch 128] [--ctx 831] [--layers 32] [--arms none,pdl,decode_tiles,both]
+  python tools/decode_bench.py [--batch 128] [--ctx 831] [--layers 32] [--arms none,pdl,tiles1,tiles2,pdl+tiles2]
 """
 import argparse
 import json
@@ -41,7 +41,7 @@ def main():
     ap.add_argument("--layers", type=int, default=32)
     ap.add_argument("--n1", type=int, default=4)
     ap.add_argument("--n2", type=int, default=68)
-    ap.add_argument("--arms", default="none,pdl,decode_tiles,both")
+    ap.add_argument("--arms", default="none,pdl,tiles1,tiles2,pdl+tiles1,pdl+tiles2")
     a = ap.parse_args()
     torch.cuda.set_device(0)
     torch.set_grad_enabled(False)
@@ -54,9 +54,9 @@ def main():
     kw = dict(do_sample=False, use_cache=True, stop_on_eos=False)
     weights_gb = 13.21 * a.layers / 32 if a.layers != 32 else 13.21
     for arm in a.arms.split(","):
-        opts = {"none": (), "pdl": ("pdl",), "decode_tiles": ("decode_tiles",), "both": ("pdl", "decode_tiles")}[arm]
-        for o in ("pdl", "decode_tiles"):
-            L.set_option(o, o in opts)
+        pdl, tiles = "pdl" in arm, 2 if "tiles2" in arm else (1 if "tiles1" in arm else 0)
+        L.set_option("pdl", pdl)
+        L.set_option("decode_tiles", tiles)
         try:
             model.generate(ids, max_new_tokens=a.n1, **kw)                       # warm-up (lazy kernel attributes)
             t1 = timed(lambda: model.generate(ids, max_new_tokens=a.n1, **kw))
@@ -70,8 +70,8 @@ def main():
                               "prefill_plus_%d_steps_ms" % a.n1: round(t1, 1)}), flush=True)
         except Exception as e:  # noqa: BLE001 -- an arm that fails must not hide the others
             print(json.dumps({"arm": arm, "error": repr(e)[:300]}), flush=True)
-    for o in ("pdl", "decode_tiles"):
-        L.set_option(o, False)
+    L.set_option("pdl", 0)
+    L.set_option("decode_tiles", 0)
 
 
 if __name__ == "__main__":

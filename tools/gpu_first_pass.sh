@@ -35,7 +35,7 @@ echo "bench rc=$?"; tail -c 3000 gpurun_out/${TAG}_bench.json; tail -3 gpurun_ou
 #    (weights amortised over more samples: KV cache 0.56 GB per sample, 192 samples = 108 GB + 14 GB of weights)
 timeout 900 python bench.py --steps 3 --warmup 3 --pdl --no-cpu-baseline > gpurun_out/${TAG}_bench_pdl.json 2> gpurun_out/${TAG}_bench_pdl.err
 echo "bench --pdl rc=$?"; tail -c 1500 gpurun_out/${TAG}_bench_pdl.json
-timeout 900 python bench.py --steps 3 --warmup 3 --decode-tiles --no-cpu-baseline > gpurun_out/${TAG}_bench_tiles.json 2> gpurun_out/${TAG}_bench_tiles.err
+timeout 900 python bench.py --steps 3 --warmup 3 --decode-tiles 2 --pdl --no-cpu-baseline > gpurun_out/${TAG}_bench_tiles.json 2> gpurun_out/${TAG}_bench_tiles.err
 echo "bench --decode-tiles rc=$?"; tail -c 1500 gpurun_out/${TAG}_bench_tiles.json
 timeout 900 python bench.py --steps 2 --warmup 3 --batch 192 --no-cpu-baseline > gpurun_out/${TAG}_bench_b192.json 2> gpurun_out/${TAG}_bench_b192.err
 echo "bench b192 rc=$?"; tail -c 1500 gpurun_out/${TAG}_bench_b192.json
