@@ -9,7 +9,8 @@ torch owns the memory. The frozen CLIP layers run through the inference stage en
 
 The extra-modality tokens of the pooler (builder.py:176-189) are covered by extras_forward / extras_backward: the audio
 projection and the seg-mask CNN train (csrc/train_extras.cu); the point-cloud token is computed but PointTransformerV3
-stays frozen (its training path -- BatchNorm batch statistics, drop-path -- is not built). Dropout > 0 is not covered.
+stays frozen (its training path -- BatchNorm batch statistics, drop-path -- is not built). The pooler's train-mode
+hidden dropout is available (`pooler.dropout`, default 0); its attention-probability dropout is not.
 """
 import ctypes
 
@@ -176,18 +177,37 @@ def pooler_forward(pooler, hidden, split_sizes):
     gm = torch.as_tensor(gmap.reshape(-1)).to(dev)
     u = L.gather_add_rows(hidden.reshape(N * T, D), gm, t["pos_type"], B * S, period=S)
     cache["u"] = u
+    # train-mode hidden dropout of HF BertModel (hidden_dropout_prob 0.1 by default, builder.py:68-79): after the
+    # embedding LayerNorm and after the two output dense layers of every block, before the residual add. Off (p = 0)
+    # unless `pooler.dropout` is set; the masks are functions of (seed, step, site) and re-created in the backward
+    # (b200_dropout). NOT covered: attention_probs_dropout_prob (the probabilities never leave the flash kernel).
+    p_drop = float(getattr(pooler, "dropout", 0.0))
+    if p_drop > 0.0:
+        pooler.rng_step = getattr(pooler, "rng_step", 0) + 1
+    seed0 = (int(getattr(pooler, "seed", 0)) * 1000003 + getattr(pooler, "rng_step", 0)) * 64
+    cache["p_drop"], cache["seed0"] = p_drop, seed0
+
+    def dense_drop_add(x, w, b, residual, site):
+        """dropout(x w^T + b) + residual (BertSelfOutput / BertOutput); one fused GEMM when p = 0."""
+        if p_drop == 0.0:
+            return L.gemm(x, w, bias=b, residual=residual)
+        y = residual.clone()
+        return L.dropout(L.gemm(x, w, bias=b), p_drop, seed0 + site, out=y, accumulate=True)
+
     e = L.layernorm(u, t["emb_ln_w"], t["emb_ln_b"], eps)
-    for lt in layers_w:
+    if p_drop > 0.0:
+        e = L.dropout(e, p_drop, seed0, out=e)
+    for li, lt in enumerate(layers_w):
         c = {"e": e}
         c["qkv"] = L.gemm(e, lt["qkv_w"], bias=lt["qkv_b"])
         q, k, v = _heads(c["qkv"], B, S, H, hd)
         ctx, c["lse"] = L.flash_attention(q, k, v, kv_len=kv_len, return_lse=True)
         c["ctx"] = ctx.view(B * S, D)
-        c["y1"] = L.gemm(c["ctx"], lt["ao_w"], bias=lt["ao_b"], residual=e)
+        c["y1"] = dense_drop_add(c["ctx"], lt["ao_w"], lt["ao_b"], e, 1 + 2 * li)
         c["e1"] = L.layernorm(c["y1"], lt["ao_ln_w"], lt["ao_ln_b"], eps)
         c["z"] = L.gemm(c["e1"], lt["fc1_w"], bias=lt["fc1_b"])
         c["h"] = L.act_forward(c["z"], L.ACT_GELU)
-        c["y2"] = L.gemm(c["h"], lt["fc2_w"], bias=lt["fc2_b"], residual=c["e1"])
+        c["y2"] = dense_drop_add(c["h"], lt["fc2_w"], lt["fc2_b"], c["e1"], 2 + 2 * li)
         e = L.layernorm(c["y2"], lt["out_ln_w"], lt["out_ln_b"], eps)
         cache["layers"].append(c)
     pooled = e.view(B, S, D)[:, :keep]
@@ -206,18 +226,20 @@ def pooler_backward(pooler, cache, d_pooled, grads=None, accumulate=False):
     de = torch.zeros((B, S, D), device=pooler.device, dtype=BF)
     de[:, :keep] = d_pooled.to(BF)                    # rows >= keep of the last layer are not consumed (builder.py:175)
     de = de.view(B * S, D)
+    p_drop, seed0 = cache.get("p_drop", 0.0), cache.get("seed0", 0)
+    masked = (lambda gy, site: L.dropout(gy, p_drop, seed0 + site)) if p_drop > 0.0 else (lambda gy, site: gy)
     for i in range(len(layers_w) - 1, -1, -1):
         lt, c = layers_w[i], cache["layers"][i]
         p = POOL + f"encoder.layer.{i}."
         f = "_fused." + p
         dy2 = _ln_bwd(G, c["y2"], de, lt["out_ln_w"], eps, p + "output.LayerNorm.weight", p + "output.LayerNorm.bias")
-        dh = _lin_bwd(G, c["h"], lt["fc2_w"], dy2, p + "output.dense.weight", p + "output.dense.bias")
+        dh = _lin_bwd(G, c["h"], lt["fc2_w"], masked(dy2, 2 + 2 * i), p + "output.dense.weight", p + "output.dense.bias")
         dz = L.act_backward(c["z"], dh, L.ACT_GELU)
         de1 = _lin_bwd(G, c["e1"], lt["fc1_w"], dz, p + "intermediate.dense.weight", p + "intermediate.dense.bias",
                        residual=dy2)                                       # + the residual branch y2 = ... + e1
         dy1 = _ln_bwd(G, c["y1"], de1, lt["ao_ln_w"], eps, p + "attention.output.LayerNorm.weight",
                       p + "attention.output.LayerNorm.bias")
-        dctx = _lin_bwd(G, c["ctx"], lt["ao_w"], dy1, p + "attention.output.dense.weight",
+        dctx = _lin_bwd(G, c["ctx"], lt["ao_w"], masked(dy1, 1 + 2 * i), p + "attention.output.dense.weight",
                         p + "attention.output.dense.bias")
         dqkv = torch.empty_like(c["qkv"])
         q, k, v = _heads(c["qkv"], B, S, H, hd)
@@ -231,7 +253,7 @@ def pooler_backward(pooler, cache, d_pooled, grads=None, accumulate=False):
                 dst, acc = G.slot(p + f"attention.self.{n}" + suffix, tuple(part.shape))
                 dst.copy_(part if not acc else dst + part)
         del G.g[f + "qkv_w"], G.g[f + "qkv_b"]
-    du = _ln_bwd(G, cache["u"], de, t["emb_ln_w"], eps, POOL + "embeddings.LayerNorm.weight",
+    du = _ln_bwd(G, cache["u"], masked(de, 0), t["emb_ln_w"], eps, POOL + "embeddings.LayerNorm.weight",
                  POOL + "embeddings.LayerNorm.bias")
     # u = gather(hidden) + position[s] + token_type[0]: table gradients are sums over the batch (and over s)
     dpos, acc = G.slot(POOL + "embeddings.position_embeddings.weight", (t["pos_type"].shape[0], D))

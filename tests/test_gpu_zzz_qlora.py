@@ -92,3 +92,36 @@ def test_lora_dropout_masks_are_reproducible_from_the_seed():
     lora.dropout = 0.0
     base = [float(ft.forward_backward(*args)[0]) for _ in range(2)]
     assert base[0] == base[1] and base[0] != runs[0][0]
+
+
+def test_pooler_hidden_dropout_is_reproducible_and_off_by_default():
+    """HF BertModel's train-mode hidden dropout in the image pooler (hidden_dropout_prob 0.1; 0.3 here): same step
+    counter => bit-identical loss and pooler gradients (the backward re-creates the masks), next step => other masks,
+    p = 0 (the default) => the deterministic path the parity tests use."""
+    import golden_cases as gc
+    from mm_or_b200.model.llava_llama import LlavaLlamaForCausalLM
+    from mm_or_b200.train.step import FineTuner
+    torch.set_grad_enabled(False)
+    cfg = gc.small_config()
+    cfg.tokenizer_padding_side = "right"
+    sd = gc.bf16_round(gc.small_weights(cfg))
+    case = gc.make_case(cfg, "train_right")
+    args = (case["input_ids"], case["labels"], case["attention_mask"], case["images"])
+    model = LlavaLlamaForCausalLM(cfg).load_state_dict(sd)
+    ft = FineTuner(model, sd, lr=1e-3, max_grad_norm=0.1, first_trainable_clip_layer=1)
+    pooler = model.get_image_pooler()
+    assert float(getattr(pooler, "dropout", 0.0)) == 0.0
+    base = [float(ft.forward_backward(*args)[0]) for _ in range(2)]
+    assert base[0] == base[1]
+    pooler.dropout, pooler.seed = 0.3, 11
+    key = "model.image_pooler.bert.encoder.layer.0.output.dense.weight"
+    runs = []
+    for step in (0, 0, 1):
+        pooler.rng_step = step
+        loss, _, g = ft.forward_backward(*args)
+        runs.append((float(loss), g[key].clone()))
+    assert runs[0][0] == runs[1][0] and torch.equal(runs[0][1], runs[1][1])
+    assert runs[2][0] != runs[0][0] and runs[0][0] != base[0]
+    assert bool(torch.isfinite(runs[0][1]).all()) and float(runs[0][1].abs().max()) > 0
+    pooler.dropout = 0.0
+    assert float(ft.forward_backward(*args)[0]) == base[0]
