@@ -43,3 +43,9 @@ echo "bench b192 rc=$?"; tail -c 1500 gpurun_out/${TAG}_bench_b192.json
 # little slack; a CUDA out-of-memory error here is a Python exception, not a dead box
 timeout 900 python bench.py --steps 2 --warmup 3 --batch 256 --no-cpu-baseline --no-roofline > gpurun_out/${TAG}_bench_b256.json 2> gpurun_out/${TAG}_bench_b256.err
 echo "bench b256 rc=$?"; tail -c 1200 gpurun_out/${TAG}_bench_b256.json; tail -2 gpurun_out/${TAG}_bench_b256.err
+# 6. fine-tune step at 7B, LoRA vs QLoRA (NF4 round trip of the frozen base, LoRA dropout 0 in both: timing only)
+for EXTRA in "" "--nf4"; do
+  timeout 600 python tools/train_bench.py --lora-r 128 $EXTRA >> gpurun_out/${TAG}_train_lora.json 2>> gpurun_out/${TAG}_train_lora.err
+  echo "train_bench --lora-r 128 $EXTRA rc=$?"
+done
+cat gpurun_out/${TAG}_train_lora.json; tail -3 gpurun_out/${TAG}_train_lora.err
