@@ -1,7 +1,9 @@
 #!/bin/bash
-# First GPU pass of a round (1 GPU, ~6 min): everything that was written without hardware access gets run first, then
-# the numbers that DESIGN.md / profiles/README.md quote are re-measured. Output in gpurun_out/<tag>_*.
-#   gpurun --timeout 600 -- bash tools/gpu_first_pass.sh r2
+# First GPU pass of a round (1 GPU): everything that was written without hardware access gets run first -- each step
+# under its own timeout, reported separately --, then the numbers that DESIGN.md / profiles/README.md quote are
+# re-measured. About 30-40 minutes of box time in all (worst case, every timeout hit: 2 h); steps are independent, so
+# the script can be cut after any of them. Output in gpurun_out/<tag>_*.
+#   gpurun --timeout 3000 -- bash tools/gpu_first_pass.sh r2
 TAG=${1:-r2}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.max.sm,clocks.max.mem,power.limit --format=csv > gpurun_out/${TAG}_gpu.txt
