@@ -33,6 +33,10 @@ struct alignas(8) float2 {
   float x, y;
 };
 inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+struct alignas(8) uint2 {
+  unsigned x, y;
+};
+inline uint2 make_uint2(unsigned x, unsigned y) { return uint2{x, y}; }
 #define __align__(n) __attribute__((aligned(n)))
 typedef void* cudaStream_t;
 typedef int cudaError_t;
