@@ -103,15 +103,37 @@ def make_tensor(name, shape, kind, seed, device, dtype):
     return _normal(shape, 0.02, seed, name, device, dtype)
 
 
+def chain_successor(vocab):
+    """The fixed successor map of the `chain` weight set: t -> (t + stride) mod vocab, stride coprime with vocab (one
+    cycle through the whole vocabulary, so a greedy continuation never repeats a token before `vocab` steps)."""
+    import math
+    stride = vocab // 3 + 1
+    while math.gcd(stride, vocab) != 1:
+        stride += 1
+    return (torch.arange(vocab) + stride) % vocab
+
+
 def make_state_dict(config: LlavaConfig, seed=0, device="cpu", dtype=torch.float32, include_lm=True,
-                    include_vision=True, peaked_lm_head=0.0):
-    """peaked_lm_head > 0 scales lm_head so greedy margins are far above bf16 resolution (exact-token tests)."""
+                    include_vision=True, peaked_lm_head=0.0, chain=0.0, chain_embed_scale=16.0):
+    """peaked_lm_head > 0 scales lm_head (kept for the older tests; it scales the rounding error with the margin).
+    chain > 0 builds the exact-token weight set: `embed_tokens` is scaled by `chain_embed_scale` so that the current
+    token's embedding dominates the residual stream, and row succ(t) of lm_head gets `chain` x unit(embed[t]) added
+    (one one-hot-like component per context token). The greedy continuation is then t, succ(t), succ(succ(t)), ... --
+    all distinct -- with a top-2 margin of ~chain * sqrt(hidden) logits, far above the bf16 error of a logit, while
+    every decoder layer still contributes to the logits that the tests compare."""
     sd = {}
     for name, shape, kind in weight_specs(config, include_lm, include_vision):
         t = make_tensor(name, shape, kind, seed, device, dtype)
         if name == "lm_head.weight" and peaked_lm_head > 0:
             t = (t.float() * peaked_lm_head).to(dtype)
         sd[name] = t
+    if chain > 0 and include_lm:
+        e = sd["model.embed_tokens.weight"].float() * chain_embed_scale
+        succ = chain_successor(config.vocab_size).to(e.device)
+        w = sd["lm_head.weight"].float()
+        w[succ] += chain * e / e.norm(dim=1, keepdim=True)
+        sd["model.embed_tokens.weight"] = e.to(dtype)
+        sd["lm_head.weight"] = w.to(dtype)
     return sd
 
 

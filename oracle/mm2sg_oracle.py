@@ -406,9 +406,12 @@ def multimodal_prefill(sd, cfg: Mm2sgCfg, input_ids, attention_mask, images, lab
 
 
 def greedy_decode(sd, cfg: Mm2sgCfg, logits_last, kv, mask, max_new_tokens, eos_id=2, pad_id=0, stop_on_eos=True,
-                  logits_dtype=None):
+                  logits_dtype=None, forced_tokens=None):
     """HF greedy_search semantics: argmax of the last-position logits (optionally rounded to `logits_dtype` first, as
-    the bf16 reference does), finished rows emit pad, stop when every row has emitted EOS or at max_new_tokens."""
+    the bf16 reference does), finished rows emit pad, stop when every row has emitted EOS or at max_new_tokens.
+    forced_tokens (B, n): teacher forcing for the tests -- the token FED to step s + 1 is forced_tokens[:, s] instead
+    of the argmax (the argmax is still what is returned), so two implementations can be compared step by step on
+    identical inputs even where their argmax differs by a rounding-level tie."""
     B = logits_last.shape[0]
     unfinished = torch.ones(B, dtype=torch.long)
     out, all_logits = [], []
@@ -427,7 +430,8 @@ def greedy_decode(sd, cfg: Mm2sgCfg, logits_last, kv, mask, max_new_tokens, eos_
             break
         mask = torch.cat([mask, torch.ones(B, 1, dtype=torch.bool)], dim=1)          # llava_arch.py:195-199
         pos = mask.sum(1, keepdim=True) - 1                                             # llava_arch.py:200
-        emb = sd["model.embed_tokens.weight"][nxt][:, None].to(kv[0][0].dtype)
+        fed = nxt if forced_tokens is None else forced_tokens[:, step].to(nxt.device)
+        emb = sd["model.embed_tokens.weight"][fed][:, None].to(kv[0][0].dtype)
         cur, kv = llama_forward(sd, emb, mask, pos, cfg.llm, past=kv, last_only=True)
         cur = cur[:, -1]
     return torch.stack(out, dim=1), torch.stack(all_logits, dim=1)

@@ -139,6 +139,31 @@ def main():
             g["greedy_logits"] = lg.half()
         torch.save(g, os.path.join(gc.GOLDEN_DIR, name + ".pt"))
         print("wrote", name, {k: tuple(v.shape) for k, v in g.items()})
+    record_chain(cfg, ocfg)
+
+
+def record_chain(cfg, ocfg):
+    """The exact-token fixture: the reference's own greedy continuation under the `chain` weight set
+    (golden_cases.CHAIN), whose ids are all distinct and whose top-2 margins dwarf bf16 rounding."""
+    sd = gc.bf16_round(gc.small_weights(cfg, chain=True))
+    model = build_reference_model(cfg, sd)
+    model.config.tokenizer_padding_side = "left"
+    model.config.mv_type = "learned"
+    case = gc.make_case(cfg, "infer_left")
+    kw = dict(images=case["images"])
+    toks, lg = reference_greedy(model, case["input_ids"], case["attention_mask"], kw, gc.CHAIN_STEPS)
+    orc = O.multimodal_prefill(sd, ocfg, case["input_ids"], case["attention_mask"], case["images"],
+                               padding_side="left")
+    otoks, olg = O.greedy_decode(sd, ocfg, orc["logits"][:, -1], orc["kv"], orc["mask"], gc.CHAIN_STEPS,
+                                 stop_on_eos=False)
+    top2 = lg.topk(2, -1).values
+    margin = (top2[..., 0] - top2[..., 1]).min().item()
+    err = ((olg - lg).norm() / lg.norm()).item()
+    print("chain greedy ids reference:", toks.tolist(), "min top-2 margin", margin, "oracle logit rel err", err)
+    assert torch.equal(toks, otoks) and err < 2e-4
+    assert all(len(set(r)) == gc.CHAIN_STEPS for r in toks.tolist())
+    torch.save({"greedy_ids": toks, "greedy_logits": lg.half(), "min_margin": torch.tensor(margin)},
+               os.path.join(gc.GOLDEN_DIR, "infer_left_chain.pt"))
 
 
 if __name__ == "__main__":

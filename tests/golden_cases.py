@@ -21,8 +21,15 @@ def small_config(**kw):
     return LlavaConfig(**d)
 
 
-def small_weights(cfg, peaked=0.0, dtype=torch.float32):
-    return make_state_dict(cfg, seed=WEIGHT_SEED, device="cpu", dtype=dtype, peaked_lm_head=peaked)
+# the exact-token weight set (mm_or_b200.synth.make_state_dict: one-hot-per-context component in lm_head): the oracle's
+# top-2 margin is > 4 logits at every step on the small configuration, against a bf16 logit error of a few 1e-2
+CHAIN = dict(chain=0.5, chain_embed_scale=8.0)
+CHAIN_STEPS = 24
+
+
+def small_weights(cfg, peaked=0.0, dtype=torch.float32, chain=False):
+    kw = CHAIN if chain else {}
+    return make_state_dict(cfg, seed=WEIGHT_SEED, device="cpu", dtype=dtype, peaked_lm_head=peaked, **kw)
 
 
 def bf16_round(sd):

@@ -273,6 +273,9 @@ def check_entry_points_reject_bad_arguments(ops):
     assert b"bad argument" in lib.b200_last_error() or b"b200_pc_" in lib.b200_last_error()
 
 
+check_entry_points_reject_bad_arguments.no_launch = True      # its point is that nothing is launched
+
+
 def check_bad_inputs_raise(ops):
     model, _ = make_model(ops)
     c = P.synth_cloud(200, seed=8, box=(10, 10, 3))

@@ -107,8 +107,8 @@ def test_rows_finished_at_eos_skip_their_cache_reads():
     from mm_or_b200.model.llava_llama import LlavaLlamaForCausalLM
     cfg = gc.small_config()
     ocfg = oracle_cfg(cfg)
-    sd = gc.bf16_round(gc.small_weights(cfg, peaked=40.0))
-    b = synth_batch(cfg, 3, 2, 24, seed=72, jitter=3, image_pos=5)  # oracle top-2 margins >= 1.1 on the running rows
+    sd = gc.bf16_round(gc.small_weights(cfg, chain=True))
+    b = synth_batch(cfg, 3, 2, 24, seed=72, jitter=3, image_pos=5)  # chain weight set: oracle top-2 margins >= 3.5
     steps, Lin = 12, b["input_ids"].shape[1]
     ref = O.multimodal_prefill(sd, ocfg, b["input_ids"], b["attention_mask"], b["images"], padding_side="left")
     free, _ = O.greedy_decode(sd, ocfg, ref["logits"][:, -1], ref["kv"], ref["mask"], steps, stop_on_eos=False)

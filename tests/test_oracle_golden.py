@@ -49,6 +49,23 @@ def test_oracle_matches_reference_golden(setup, name):
         assert torch.equal(toks, g["greedy_ids"])
 
 
+def test_oracle_matches_reference_chain_fixture(setup):
+    """The exact-token fixture (reference greedy ids under the chain weight set): all ids distinct, margins large."""
+    cfg, ocfg, _ = setup
+    sd = gc.bf16_round(gc.small_weights(cfg, chain=True))
+    g = torch.load(os.path.join(gc.GOLDEN_DIR, "infer_left_chain.pt"))
+    case = gc.make_case(cfg, "infer_left")
+    out = O.multimodal_prefill(sd, ocfg, case["input_ids"], case["attention_mask"], case["images"], padding_side="left")
+    toks, lg = O.greedy_decode(sd, ocfg, out["logits"][:, -1], out["kv"], out["mask"], gc.CHAIN_STEPS, stop_on_eos=False)
+    assert torch.equal(toks, g["greedy_ids"]) and rel_err(lg, g["greedy_logits"]) < 2e-3
+    assert all(len(set(r)) >= 8 for r in g["greedy_ids"].tolist())
+    assert g["min_margin"].item() > 3.0
+    # teacher forcing with the same ids is the same computation
+    toks2, lg2 = O.greedy_decode(sd, ocfg, out["logits"][:, -1], out["kv"], out["mask"], gc.CHAIN_STEPS,
+                                 stop_on_eos=False, forced_tokens=g["greedy_ids"])
+    assert torch.equal(toks2, toks) and torch.equal(lg2, lg)
+
+
 def test_token_weights_formula():
     # train/train.py:1316-1322
     import math
