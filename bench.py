@@ -367,6 +367,17 @@ def cpu_weights(cfg):
     return sd
 
 
+def cpu_model():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown CPU"
+
+
 def cpu_reference_sample(args, layers=32):
     """Times ONE inference of the config-2 workload on the CPU oracle: encode (6 views) + pack + prefill measured in
     full, decode measured on `cpu_decode_steps` steps and extrapolated linearly to new_tokens (each step streams the
@@ -390,15 +401,20 @@ def cpu_reference_sample(args, layers=32):
     emb = O.pack_embeds(sd, src, visual)
     logits, kv = O.llama_forward(sd, emb, mask, pos, ocfg.llm, last_only=True)
     t_pre = time.perf_counter() - t0
-    n = max(1, args.cpu_decode_steps)
+    n = max(1, min(args.cpu_decode_steps, args.new_tokens - 1))
     t0 = time.perf_counter()
     O.greedy_decode(sd, ocfg, logits[:, -1], kv, mask, n + 1, stop_on_eos=False, logits_dtype=torch.bfloat16)
     t_dec = (time.perf_counter() - t0) / n
     total = t_enc + t_pre + t_dec * (args.new_tokens - 1)
+    full = n == args.new_tokens - 1
+    how = ("all %d decode steps measured (%.3fs/step): the whole inference is timed, nothing extrapolated"
+           % (n, t_dec)) if full else ("%d decode steps measured (%.3fs/step), extrapolated to %d tokens"
+                                       % (n, t_dec, args.new_tokens))
     return {"value": round(1.0 / total, 5), "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "1 inference (%d views, L=%d): encode %.1fs + prefill %.1fs measured in full; %d decode steps "
-                      "measured (%.3fs/step), extrapolated to %d tokens; torch %s CPU bf16, %d threads"
-                      % (args.views, emb.shape[1], t_enc, t_pre, n, t_dec, args.new_tokens, torch.__version__, cores),
+            "sample": "1 inference (%d views, L=%d): encode %.1fs + prefill %.1fs measured in full; %s; torch %s CPU "
+                      "bf16, %d threads on %s"
+                      % (args.views, emb.shape[1], t_enc, t_pre, how, torch.__version__, cores, cpu_model()),
+            "extrapolated": not full, "cpu_model": cpu_model(),
             "seconds_per_inference": round(total, 1),
             "stage_seconds": {"vision_tower_pooler_projector": round(t_enc, 2), "pack_prefill": round(t_pre, 2),
                               "decode_per_step": round(t_dec, 4)},
@@ -410,8 +426,11 @@ def run_reference(args):
     if rank != 0:
         return
     # one sample per step would take minutes of CPU time; weights are built once, each "step" is one bounded sample
+    # The reference arm measures the WHOLE inference (all new_tokens - 1 decode steps, ~40 s on 16 cores); at most two
+    # repetitions so that the arm ends within a few minutes whatever --steps says.
     vals, last = [], None
-    reps = max(1, min(args.steps, 3))
+    reps = max(1, min(args.steps, 2))
+    args.cpu_decode_steps = args.new_tokens - 1
     for i in range(reps):
         last = cpu_reference_sample(args, layers=args.layers)
         vals.append(last["value"])
