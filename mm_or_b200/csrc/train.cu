@@ -80,7 +80,8 @@ __device__ __forceinline__ void st_logit<bf16>(bf16* p, long long i, float v) {
 // one CTA per (b, l) row. row_loss[row] = w[y] * nll (0 for unsupervised rows).
 template <typename T>
 __global__ void __launch_bounds__(kCeThreads)
-    ce_row_kernel(const T* __restrict__ logits, long long ld, const long long* __restrict__ labels,
+    ce_row_kernel(const T* logits /* may alias dlogits: no __restrict__ */, long long ld,
+                  const long long* __restrict__ labels,
                   const float* __restrict__ vocab_w, int L, int V, const float* __restrict__ wsum, float grad_scale,
                   T* dlogits, long long ldd, float* __restrict__ row_loss) {
   __shared__ float red[kCeThreads / 32];
@@ -96,6 +97,9 @@ __global__ void __launch_bounds__(kCeThreads)
     return;
   }
   const T* xr = logits + row * ld;
+  // dlogits may alias logits (in-place gradient): every thread reads the label's logit BEFORE the barriers of the
+  // reductions below, i.e. before any thread of the block can reach the store loop that overwrites it
+  const float x_y = ld_logit<T>(xr, y);
   float mx = -INFINITY;
   for (int i = threadIdx.x; i < V; i += kCeThreads) mx = fmaxf(mx, ld_logit<T>(xr, i));
   mx = block_reduce(mx, red, true);
@@ -104,7 +108,7 @@ __global__ void __launch_bounds__(kCeThreads)
   se = block_reduce(se, red, false);
   const float lse = mx + __logf(se);
   const float w = vocab_w ? vocab_w[y] : 1.f;
-  if (threadIdx.x == 0) row_loss[row] = w * (lse - ld_logit<T>(xr, y));
+  if (threadIdx.x == 0) row_loss[row] = w * (lse - x_y);
   if (drow != nullptr) {
     const float W = *wsum;
     const float coef = W > 0.f ? grad_scale * w / W : 0.f;

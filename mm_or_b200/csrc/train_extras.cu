@@ -218,7 +218,9 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
 }
 
 // one thread per group of 4 consecutive elements (one Philox call, 8 bytes in, 8 bytes out)
-__global__ void dropout_kernel(const uint16_t* __restrict__ x, uint16_t* __restrict__ y, long long n, uint32_t threshold,
+// x and y may be the same buffer (in-place dropout, train/encoder.py): no __restrict__; every thread reads its own
+// elements before it writes them and touches no other thread's
+__global__ void dropout_kernel(const uint16_t* x, uint16_t* y, long long n, uint32_t threshold,
                                float scale, uint32_t k0, uint32_t k1, int accumulate) {
   const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (g * 4 >= n) return;

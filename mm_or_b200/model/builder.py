@@ -90,6 +90,43 @@ def merge_lora(sd, adapter_sd, adapter_cfg):
     return merged
 
 
+VIT_PREFIX = "model.vision_tower.vision_tower."
+
+
+def ensure_vision_weights(sd, config, overlay=None):
+    """The reference's LoRA flow starts from a LLaVA / Vicuna base WITHOUT CLIP weights: CLIPVisionTower.load_model()
+    fetches them from `config.mm_vision_tower` (multimodal_encoder/clip_encoder.py:20-24, model/builder.py:148-152) and
+    non_lora_trainables.bin then overlays only the unfrozen CLIP layers, the image pooler and the projector
+    (builder.py:153-176). Same order here: when `sd` has no vision tower, read it from the LOCAL directory
+    `config.mm_vision_tower` (there is no hub access; HF CLIPVisionModel keys `vision_model.*`), then apply `overlay`
+    (the remapped non-LoRA trainables). Whatever the route, a checkpoint that leaves the tower, the pooler or the
+    projector without weights is an error here -- not a generic 'weights not loaded' at the first encode."""
+    probe = VIT_PREFIX + "vision_model.pre_layrnorm.weight"
+    if probe not in sd and getattr(config, "mm_vision_tower", None):
+        src = str(config.mm_vision_tower)
+        if os.path.isdir(src):
+            clip = read_checkpoint_dir(src)
+            n = 0
+            for k, v in clip.items():
+                if k.startswith("vision_model."):
+                    sd[VIT_PREFIX + k] = v
+                    n += 1
+            if n == 0:
+                raise KeyError(f"{src}: no `vision_model.*` tensors (not a CLIP vision checkpoint)")
+    if overlay:
+        sd.update(overlay)
+    if getattr(config, "mm_vision_tower", None):
+        need = {"vision tower": probe, "image pooler": "model.image_pooler.bert.embeddings.LayerNorm.weight",
+                "mm_projector": "model.mm_projector.0.weight"}
+        missing = [f"{what} ({key.rsplit('.', 2)[0]}.*)" for what, key in need.items() if key not in sd]
+        if missing:
+            raise KeyError("checkpoint has no weights for: " + ", ".join(missing) + f". The base holds none, "
+                           f"`mm_vision_tower` = {config.mm_vision_tower!r} is not a local CLIP directory (the "
+                           "reference downloads it from the hub; this path has no network), and "
+                           "non_lora_trainables.bin / mm_projector.bin did not provide them.")
+    return sd
+
+
 def _tokenizer(path):
     from transformers import AutoTokenizer
     return AutoTokenizer.from_pretrained(path, use_fast=False)
@@ -116,7 +153,7 @@ def load_pretrained_model(model_path, model_base, model_name, load_8bit=False, l
         if not os.path.exists(nlt):
             raise FileNotFoundError(f"{nlt} not found (the hub download of builder.py:69-79 needs network access)")
         extra = remap_non_lora_trainables(torch.load(nlt, map_location="cpu", weights_only=True))
-        sd.update(extra)
+        ensure_vision_weights(sd, config, overlay=extra)       # CLIP from mm_vision_tower if the base has none
         with open(os.path.join(model_path, "adapter_config.json")) as f:
             acfg = json.load(f)
         adapters = [p for p in (os.path.join(model_path, "adapter_model.safetensors"),
@@ -129,11 +166,12 @@ def load_pretrained_model(model_path, model_base, model_name, load_8bit=False, l
         tokenizer = _tokenizer(model_base)
         sd = read_checkpoint_dir(model_base)
         proj = torch.load(os.path.join(model_path, "mm_projector.bin"), map_location="cpu", weights_only=True)
-        sd.update({k: v.to(torch.bfloat16) for k, v in proj.items()})
+        ensure_vision_weights(sd, config, overlay={k: v.to(torch.bfloat16) for k, v in proj.items()})
     else:
         config = LlavaConfig.from_pretrained(model_path)
         tokenizer = _tokenizer(model_path)
         sd = read_checkpoint_dir(model_path)
+        ensure_vision_weights(sd, config)
 
     model = LlavaLlamaForCausalLM(config)
     if getattr(config, "mm_use_im_patch_token", True):

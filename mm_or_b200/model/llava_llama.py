@@ -692,7 +692,9 @@ class LlavaLlamaForCausalLM:
         ids_cpu = input_ids.detach().to("cpu")
         if attention_mask is None:
             # HF infers the mask from the pad token when the caller passes none (scene_graph_prediction_model.py:221)
-            attention_mask = ids_cpu.ne(c.pad_token_id)
+            # (HF: an all-ones mask when the config has no pad token)
+            attention_mask = (ids_cpu.ne(c.pad_token_id) if c.pad_token_id is not None
+                              else torch.ones_like(ids_cpu, dtype=torch.bool))
         B = ids_cpu.shape[0]
         if images is not None and self.get_vision_tower() is not None:
             (_, _, _, _, embeds, _, plan) = self.prepare_inputs_labels_for_multimodal(
@@ -751,6 +753,10 @@ class LlavaLlamaForCausalLM:
                         return True
             return finished is not None and bool(finished.min().item() == 1)
 
+        if stopping_criteria:
+            # HF evaluates the criteria after EVERY step (mm_utils.py:74-105 KeywordsStoppingCriteria): a keyword stop
+            # that is not EOS must not let extra tokens through into the decoded text / the TakeMemory history
+            check_every = 1
         while n_done < max_new_tokens:
             if (n_done == 1 or n_done % check_every == 0) and stop_now():
                 break

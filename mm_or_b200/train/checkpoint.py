@@ -37,13 +37,32 @@ def adapter_config(r, alpha, base_model_name_or_path=None, dropout=0.05):
             "init_lora_weights": True, "modules_to_save": None, "layers_to_transform": None, "layers_pattern": None}
 
 
-def export_lora_checkpoint(out_dir, config, lora_sd, r, alpha, trainable_sd, base_model_name_or_path=None):
+POOLER_PREFIX = "model.image_pooler."
+
+
+def pooler_checkpoint_tensors(sd):
+    """Every `model.image_pooler.*` tensor of a state dict, trained or frozen, plus the BatchNorm step counters.
+    The reference marks all image_pooler parameters trainable (llava_arch.py:80-83), saves parameters that require grad
+    AND every buffer (train.py:168-178, the `_extended` variant), and its loader feeds the stripped entries to
+    `image_pooler.load_state_dict(..., strict=True)` (model/builder.py:160-176): a file that holds only the tensors this
+    FineTuner happened to update (no point_transformer.*, no bert.pooler.*, no word_embeddings) would make that load
+    raise. `num_batches_tracked` (a buffer of every BatchNorm of PointTransformerV3, absent from this repo's weights
+    because inference never reads it) is written as 0: the point-cloud encoder is frozen here, no batch was tracked."""
+    out = {k: v for k, v in sd.items() if k.startswith(POOLER_PREFIX)}
+    for k in list(out):
+        if k.endswith(".running_mean"):
+            out.setdefault(k[:-len("running_mean")] + "num_batches_tracked", torch.zeros((), dtype=torch.long))
+    return out
+
+
+def export_lora_checkpoint(out_dir, config, lora_sd, r, alpha, trainable_sd, base_model_name_or_path=None,
+                           dropout=0.05):
     """lora_sd: {`model.layers.N.<module>.<proj>.lora_{A,B}.weight`: tensor}; trainable_sd: {reference parameter name:
     tensor} of the non-LoRA trainables (projector, image pooler, unfrozen CLIP layers, ...)."""
     os.makedirs(out_dir, exist_ok=True)
     config.save_pretrained(out_dir)
     with open(os.path.join(out_dir, "adapter_config.json"), "w") as f:
-        json.dump(adapter_config(r, alpha, base_model_name_or_path), f, indent=1)
+        json.dump(adapter_config(r, alpha, base_model_name_or_path, dropout), f, indent=1)
     bad = [k for k in lora_sd if ".lora_A." not in k and ".lora_B." not in k]
     if bad:
         raise ValueError(f"not LoRA parameters: {bad[:3]}")

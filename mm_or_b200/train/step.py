@@ -272,9 +272,10 @@ class FineTuner:
         if rank == 0:
             if self.lora is not None:
                 r = self.lora.r
-                C.export_lora_checkpoint(out_dir, self.model.config, self.lora.sd, r, self.lora.scale * r,
-                                         {k: self.sd[k] for k in self.names if "lora_" not in k},
-                                         base_model_name_or_path)
+                trainable = {k: self.sd[k] for k in self.names if "lora_" not in k}
+                trainable.update(C.pooler_checkpoint_tensors(self.sd))      # the whole pooler state, frozen parts too
+                C.export_lora_checkpoint(out_dir, self.model.config, self.lora.sd, r, self.lora.scale * r, trainable,
+                                         base_model_name_or_path, dropout=self.lora.dropout)
             else:
                 C.export_full_checkpoint(out_dir, self.model.config, self.sd)
         if optimizer:

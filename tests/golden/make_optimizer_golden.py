@@ -1,7 +1,8 @@
 """Records which parameters the REFERENCE's LLaVATrainer.create_optimizer decays and which take mm_projector_lr
 (train/llava_trainer.py:203-233: decay_parameters = get_parameter_names(model, ALL_LAYERNORM_LAYERS) minus names
 containing "bias"; projector_parameters = names containing "mm_projector"), evaluated on the reference's own model
-instance (oracle/ref_shim.py) -> tests/golden/optimizer_groups.json.
+instance (oracle/ref_shim.py) -> tests/golden/optimizer_groups.json; and the state_dict key set of the reference's
+ImageEmbeddingPooler (what its loader's strict load_state_dict needs) -> tests/golden/pooler_state_keys.json.
 
 Run in the build container only:   python tests/golden/make_optimizer_golden.py
 """
@@ -36,6 +37,12 @@ def main():
         json.dump(rec, f, indent=0, sort_keys=True)
     print(len(rec), "parameters;", sum(v["decay"] for v in rec.values()), "decayed;",
           sum(v["projector"] for v in rec.values()), "projector")
+    # the key set the reference's loader demands of non_lora_trainables.bin for the image pooler: it loads the stripped
+    # `model.image_pooler.*` entries with strict=True (model/builder.py:160-176) -- every parameter AND buffer
+    keys = sorted(model.get_image_pooler().state_dict().keys())
+    with open(os.path.join(gc.GOLDEN_DIR, "pooler_state_keys.json"), "w") as f:
+        json.dump(keys, f, indent=0)
+    print(len(keys), "image_pooler state_dict keys")
 
 
 if __name__ == "__main__":

@@ -111,3 +111,36 @@ def test_load_pretrained_model_roundtrip(tmp_path, monkeypatch):
     a = model.generate(case["input_ids"], images=case["images"], max_new_tokens=4, stop_on_eos=False)
     b = ref.generate(case["input_ids"], images=case["images"], max_new_tokens=4, stop_on_eos=False)
     assert torch.equal(a, b)
+
+
+def test_lora_base_without_clip_takes_the_tower_from_mm_vision_tower(tmp_path):
+    """The reference's LoRA flow: the base holds no CLIP weights, load_model() fetches them from config.mm_vision_tower
+    and non_lora_trainables overlays the trained parts (model/builder.py:148-176). Here the tower comes from the LOCAL
+    directory config.mm_vision_tower; nothing is dropped silently."""
+    import golden_cases as gc
+    from safetensors.torch import save_file
+    cfg = gc.small_config()
+    full = {k: v.to(torch.bfloat16) for k, v in gc.small_weights(cfg).items()}
+    vit = B.VIT_PREFIX
+    clip_dir = tmp_path / "clip"
+    clip_dir.mkdir()
+    save_file({k[len(vit):]: v.contiguous() for k, v in full.items() if k.startswith(vit)},
+              str(clip_dir / "model.safetensors"))
+    base = {k: v for k, v in full.items() if k.startswith(("model.layers.", "model.embed", "model.norm", "lm_head"))}
+    trained_key = vit + "vision_model.encoder.layers.1.mlp.fc1.weight"          # an unfrozen CLIP layer
+    overlay = {k: v for k, v in full.items() if k.startswith(("model.image_pooler.", "model.mm_projector."))}
+    overlay[trained_key] = full[trained_key] + 1
+    cfg.mm_vision_tower = str(clip_dir)
+    sd = B.ensure_vision_weights(dict(base), cfg, overlay=overlay)
+    assert sorted(sd) == sorted(full)
+    assert torch.equal(sd[trained_key], full[trained_key] + 1)                      # overlay wins over the CLIP directory
+    assert torch.equal(sd[vit + "vision_model.pre_layrnorm.weight"], full[vit + "vision_model.pre_layrnorm.weight"])
+    # no local CLIP directory and an overlay without the tower: a loud error naming what is missing
+    cfg.mm_vision_tower = "openai/clip-vit-large-patch14-336"
+    with pytest.raises(KeyError, match="vision tower"):
+        B.ensure_vision_weights(dict(base), cfg, overlay=overlay)
+    with pytest.raises(KeyError, match="image pooler.*mm_projector"):
+        B.ensure_vision_weights({k: v for k, v in full.items() if not k.startswith(("model.image_pooler.",
+                                                                                    "model.mm_projector."))}, cfg)
+    # a full checkpoint passes untouched
+    assert sorted(B.ensure_vision_weights(dict(full), cfg)) == sorted(full)

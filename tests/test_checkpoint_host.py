@@ -97,3 +97,25 @@ def test_optimizer_state_round_trip_and_mismatch(tmp_path):
         C.load_optimizer(path, {"a.weight": torch.zeros(4, 3)}, mm2, v2)
     with pytest.raises(ValueError):
         C.load_optimizer(path, {"a.weight": torch.zeros(4, 3), "b.bias": torch.zeros(6)}, mm2, v2)
+
+
+def test_lora_checkpoint_holds_the_whole_image_pooler_state():
+    """The reference's loader feeds the stripped `model.image_pooler.*` entries of non_lora_trainables.bin to
+    image_pooler.load_state_dict(strict=True) (model/builder.py:160-176), so the file must hold EVERY parameter and
+    buffer of the pooler -- frozen ones (point_transformer.*, bert.pooler.*, word_embeddings) included. The required key
+    set is recorded from the reference's own ImageEmbeddingPooler (tests/golden/make_optimizer_golden.py)."""
+    from oracle import ptv3_oracle as P
+    cfg = gc.small_config()
+    sd = gc.small_weights(cfg)
+    sd.update(P.synth_weights())
+    want = set(json.load(open(os.path.join(gc.GOLDEN_DIR, "pooler_state_keys.json"))))
+    exported = C.pooler_checkpoint_tensors(sd)
+    got = {k[len(C.POOLER_PREFIX):] for k in exported}
+    # the two buffers the reference's loader pops before its strict load (model/builder.py:173-174) may be absent
+    optional = {"bert.embeddings.position_ids", "bert.embeddings.token_type_ids"}
+    assert got - optional == want - optional, (sorted(want - got)[:5], sorted(got - want)[:5])
+    assert {"point_transformer.embedding.stem.norm.num_batches_tracked", "bert.pooler.dense.weight",
+            "bert.embeddings.word_embeddings.weight"} <= got
+    assert exported[C.POOLER_PREFIX + "point_transformer.embedding.stem.norm.num_batches_tracked"].dtype == torch.long
+    # and the adapter config carries the dropout that was trained with
+    assert C.adapter_config(8, 16, dropout=0.0)["lora_dropout"] == 0.0

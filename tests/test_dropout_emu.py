@@ -63,6 +63,11 @@ def test_dropout_matches_the_restatement_and_its_own_backward():
         want = torch.where(keep, (x.float() * np.float32(1.0 / np.float32(1.0 - np.float32(p)))), torch.zeros(n))
         assert torch.equal(y, want.to(torch.bfloat16)), (n, p)
         assert torch.equal(run(x, p, seed), y)                                  # deterministic
+        xin = x.clone()
+        assert torch.equal(run(xin, p, seed, out=xin), y)                       # in place (out = x, train/encoder.py)
+        if n > 8:                                                               # ... and through an unaligned view
+            xo = x.clone()
+            assert torch.equal(run(xo[1:], p, seed, out=xo[1:]), run(x[1:].clone(), p, seed))
         if 0 < p < 1 and n > 100:
             assert not torch.equal(run(x, p, seed + 1), y)                      # another seed, another mask
         # backward = the same kernel on the gradient, accumulating into dx: the SAME elements survive

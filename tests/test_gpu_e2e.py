@@ -150,6 +150,16 @@ def test_generate_exact_tokens_with_peaked_head(env):
     toks, _ = O.greedy_decode(sd, ocfg, ref["logits"][:, -1], ref["kv"], ref["mask"], steps, stop_on_eos=True)
     out3 = model.generate(case["input_ids"], images=case["images"], max_new_tokens=steps)
     assert torch.equal(out3[:, Lt:].cpu(), toks)
+    # a stopping criterion that is not EOS is evaluated after EVERY step (HF StoppingCriteriaList; the reference's
+    # KeywordsStoppingCriteria, mm_utils.py:74-105): the output ends with the step at which it fired, no extra tokens
+    target = int(g["greedy_ids"][0, 4])
+
+    def keyword(ids, scores, **kw):
+        return bool(ids[0, -1] == target)
+
+    out4 = model.generate(case["input_ids"], images=case["images"], max_new_tokens=steps, stop_on_eos=False,
+                          stopping_criteria=[keyword])
+    assert out4.shape[1] == Lt + 5 and torch.equal(out4[:, Lt:].cpu(), g["greedy_ids"][:, :5])
 
 
 def test_text_only_generate(env):
