@@ -559,8 +559,9 @@ class LlavaLlamaForCausalLM:
         if getattr(self.config, "tune_mm_mlp_adapter", False) and getattr(self.config, "mm_use_im_start_end", False):
             raise NotImplementedError                                             # llava_arch.py:216
         concat, split = self._images_to_batch(images)
-        pooled = self.encode_images_pooled(concat, split, pc, audio, segmasks)   # (B, T_vis, 1024)
-        B, t_vis, _ = pooled.shape
+        pooled = self.encode_images_pooled(concat, split, pc, audio, segmasks)   # (blocks, T_vis, 1024)
+        NB, t_vis, _ = pooled.shape          # one block of visual tokens per entry of `images` ...
+        B = int(input_ids.shape[0])          # ... usually one per row; a row with k <image> placeholders takes k
         D = self.config.hidden_size
         desc_rows = desc_table = None
         if vis_descriptor_embs is not None:
@@ -573,10 +574,10 @@ class LlavaLlamaForCausalLM:
         plan = plan_pack(input_ids.cpu().numpy(), None if attention_mask is None else attention_mask.cpu().numpy(),
                          None if labels is None else labels.cpu().numpy(), t_vis,
                          getattr(self.config, "tokenizer_padding_side", "right"),
-                         getattr(self.config, "tokenizer_model_max_length", None), desc_rows=desc_rows)
+                         getattr(self.config, "tokenizer_model_max_length", None), desc_rows=desc_rows, n_blocks=NB)
         embeds = torch.empty((B, plan.L, D), device=self.device, dtype=BF)
         if self._pg is None:
-            self.model.mm_projector.project_pack(pooled.view(B * t_vis, -1), _i32(plan.row_map, self.device),
+            self.model.mm_projector.project_pack(pooled.view(NB * t_vis, -1), _i32(plan.row_map, self.device),
                                                  _i32(plan.src.reshape(-1), self.device), self.model.embed_tokens,
                                                  self.config.vocab_size, embeds, B * plan.L)
         else:
@@ -584,13 +585,11 @@ class LlavaLlamaForCausalLM:
             src = plan.src.reshape(B, plan.L).astype(np.int64)
             # two row gathers into the packed buffer: text / pad rows from embed_tokens, visual rows from `vis`
             text_ids = np.where(src >= -1, src, -2).astype(np.int32)
-            vis_ids = np.where((src <= -2) & (src > DESC_BASE), np.arange(B)[:, None] * t_vis + (-2 - src),
-                               -2).astype(np.int32)
             lib = L.lib()
-            text_dev, vis_dev = _i32(text_ids.reshape(-1), self.device), _i32(vis_ids.reshape(-1), self.device)
+            text_dev, vis_dev = _i32(text_ids.reshape(-1), self.device), _i32(plan.vis_ids, self.device)
             L.check(lib.b200_embed_rows(L.ptr(text_dev), L.ptr(self.model.embed_tokens), L.ptr(embeds), D, B * plan.L, D,
                                         self.config.vocab_size, L.stream_ptr()), "b200_embed_rows")
-            L.check(lib.b200_embed_rows(L.ptr(vis_dev), L.ptr(vis), L.ptr(embeds), D, B * plan.L, D, B * t_vis,
+            L.check(lib.b200_embed_rows(L.ptr(vis_dev), L.ptr(vis), L.ptr(embeds), D, B * plan.L, D, NB * t_vis,
                                         L.stream_ptr()), "b200_embed_rows")
         if desc_table is not None and (plan.desc_ids >= 0).any():
             desc_dev = _i32(plan.desc_ids, self.device)         # third row source: descriptor rows; -2 = untouched

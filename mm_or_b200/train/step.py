@@ -173,14 +173,15 @@ class FineTuner:
             desc_table = torch.cat(flat).to(dev, BF).contiguous() if flat else None
         plan = plan_pack(input_ids.cpu().numpy(), None if attention_mask is None else attention_mask.cpu().numpy(),
                          None if labels is None else labels.cpu().numpy(), Tv, "right",
-                         getattr(cfg, "tokenizer_model_max_length", None), desc_rows=desc_rows)
+                         getattr(cfg, "tokenizer_model_max_length", None), desc_rows=desc_rows, n_blocks=B)
+        if plan.src.shape[0] != B:
+            raise NotImplementedError("fine-tune step: one row of input_ids per entry of `images`")
         Lq = plan.L
         src = plan.src.reshape(B, Lq).astype(np.int64)
         text_ids = np.where(src >= -1, src, -2).astype(np.int32)
-        vis_ids = np.where((src <= -2) & (src > DESC_BASE), np.arange(B)[:, None] * Tv + (-2 - src), -2).astype(np.int32)
         embeds = torch.empty((B * Lq, D), device=dev, dtype=BF)
         L.embed_rows(torch.as_tensor(text_ids.reshape(-1)).to(dev), model.model.embed_tokens, out=embeds)
-        L.embed_rows(torch.as_tensor(vis_ids.reshape(-1)).to(dev), vis, out=embeds)
+        L.embed_rows(torch.as_tensor(plan.vis_ids).to(dev), vis, out=embeds)
         if desc_table is not None and (plan.desc_ids >= 0).any():
             L.embed_rows(torch.as_tensor(plan.desc_ids).to(dev), desc_table, out=embeds)
         loss, wsum, g, d_emb = T.forward_backward(model, embeds.view(B, Lq, D), torch.from_numpy(plan.labels).to(dev),

@@ -238,14 +238,22 @@ DESC_BASE = -(1 << 20)
 
 
 def pack_plan(input_ids: torch.Tensor, attention_mask: Optional[torch.Tensor], labels: Optional[torch.Tensor],
-              t_vis: int, padding_side: str = "right", max_len: Optional[int] = None, desc_rows=None):
+              t_vis: int, padding_side: str = "right", max_len: Optional[int] = None, desc_rows=None,
+              n_blocks: Optional[int] = None, return_blocks: bool = False):
     """Pure index arithmetic of the pack: returns (src, labels, mask, position_ids) with src (B, L) int64 where
     src >= 0 is a token id to embed, -1 a zero pad row, -2 - j the j-th visual token, DESC_BASE - r the r-th row of
     the sample's concatenated vis_descriptor_embs. Mirrors :235-338 including the quirk that text following a
     VIS_DESCRIPTOR token is dropped when no descriptor embeddings are given (:253-294) and truncation to
     tokenizer_model_max_length (:302-306). desc_rows: per sample the row counts of its descriptor tensors (:278-294:
-    descriptor j replaces the j-th VIS_DESCRIPTOR placeholder, one zero row when the sample has too few)."""
+    descriptor j replaces the j-th VIS_DESCRIPTOR placeholder, one zero row when the sample has too few).
+    n_blocks / return_blocks: the reference indexes image_features with ONE running counter over the batch
+    (cur_image_idx, :239,245,264-265): every <image> placeholder takes the next block, a text-only row skips one, an
+    index past the last block raises IndexError. return_blocks adds a fifth result, blk (B, L): the block a visual
+    position came from (-1 elsewhere)."""
     B = input_ids.shape[0]
+    n_blocks = B if n_blocks is None else n_blocks
+    cur_image_idx = 0
+    rblocks = []
     am = torch.ones_like(input_ids, dtype=torch.bool) if attention_mask is None else attention_mask.bool()
     lab = torch.full_like(input_ids, IGNORE_INDEX) if labels is None else labels
     rows, rlabels = [], []
@@ -254,19 +262,28 @@ def pack_plan(input_ids: torch.Tensor, attention_mask: Optional[torch.Tensor], l
         lb = lab[b][am[b]]
         n_img = int((ids == IMAGE_TOKEN_INDEX).sum())
         if n_img == 0:
+            if cur_image_idx >= n_blocks:
+                raise IndexError(f"index {cur_image_idx} is out of bounds for dimension 0 with size {n_blocks}")
+            cur_image_idx += 1                                                   # :250
             rows.append(ids.clone())
             rlabels.append(lb.clone())
+            rblocks.append(torch.full((len(ids),), -1, dtype=torch.long))
             continue
         cut = [-1] + torch.where((ids == IMAGE_TOKEN_INDEX) | (ids == VIS_DESCRIPTOR_TOKEN_INDEX))[0].tolist() + [len(ids)]
         chunks = [ids[cut[i] + 1:cut[i + 1]] for i in range(len(cut) - 1)]
         lchunks = [lb[cut[i] + 1:cut[i + 1]] for i in range(len(cut) - 1)]
-        r, rl = [], []
+        r, rl, rb = [], [], []
         for i in range(n_img + 1):
             r.append(chunks[i])
             rl.append(lchunks[i])
+            rb.append(torch.full((len(chunks[i]),), -1, dtype=torch.long))
             if i < n_img:
+                if cur_image_idx >= n_blocks:
+                    raise IndexError(f"index {cur_image_idx} is out of bounds for dimension 0 with size {n_blocks}")
                 r.append(-2 - torch.arange(t_vis))
                 rl.append(torch.full((t_vis,), IGNORE_INDEX, dtype=lb.dtype))
+                rb.append(torch.full((t_vis,), cur_image_idx, dtype=torch.long))
+                cur_image_idx += 1                                               # :265
         if desc_rows is not None:
             n_desc = int((ids == VIS_DESCRIPTOR_TOKEN_INDEX).sum())
             done = 0
@@ -279,19 +296,24 @@ def pack_plan(input_ids: torch.Tensor, attention_mask: Optional[torch.Tensor], l
                     d = torch.full((1,), -1, dtype=torch.long)          # dummy zeros(4096) row (:284-286)
                 r.append(d)
                 rl.append(torch.full((len(d),), IGNORE_INDEX, dtype=lb.dtype))
+                rb.append(torch.full((len(d),), -1, dtype=torch.long))
                 r.append(chunks[n_img + j + 1])
                 rl.append(lchunks[n_img + j + 1])
+                rb.append(torch.full((len(chunks[n_img + j + 1]),), -1, dtype=torch.long))
         rows.append(torch.cat(r))
         rlabels.append(torch.cat(rl))
+        rblocks.append(torch.cat(rb))
     if max_len is not None:
         rows = [r[:max_len] for r in rows]
         rlabels = [r[:max_len] for r in rlabels]
+        rblocks = [r[:max_len] for r in rblocks]
     L = max(len(r) for r in rows)
     src = torch.full((B, L), -1, dtype=torch.long)
     out_l = torch.full((B, L), IGNORE_INDEX, dtype=lab.dtype)
     mask = torch.zeros(B, L, dtype=torch.bool)
     pos = torch.zeros(B, L, dtype=torch.long)
-    for b, (r, rl) in enumerate(zip(rows, rlabels)):
+    blk = torch.full((B, L), -1, dtype=torch.long)
+    for b, (r, rl, rb) in enumerate(zip(rows, rlabels, rblocks)):
         n = len(r)
         if n == 0:
             continue
@@ -300,12 +322,16 @@ def pack_plan(input_ids: torch.Tensor, attention_mask: Optional[torch.Tensor], l
         out_l[b, sl] = rl
         mask[b, sl] = True
         pos[b, sl] = torch.arange(n)
+        blk[b, sl] = rb
+    if return_blocks:
+        return src, out_l, mask, pos, blk
     return src, out_l, mask, pos
 
 
-def pack_embeds(sd, src: torch.Tensor, visual: torch.Tensor, desc=None) -> torch.Tensor:
-    """Materialise inputs_embeds (B, L, D) from a pack plan and the projected visual tokens (B, T_vis, D); desc: per
-    sample the (R_b, D) concatenation of its descriptor tensors (rows addressed by DESC_BASE - r)."""
+def pack_embeds(sd, src: torch.Tensor, visual: torch.Tensor, desc=None, blk=None) -> torch.Tensor:
+    """Materialise inputs_embeds (B, L, D) from a pack plan and the projected visual tokens (blocks, T_vis, D); desc:
+    per sample the (R_b, D) concatenation of its descriptor tensors (rows addressed by DESC_BASE - r); blk: the block
+    of every visual position (pack_plan(return_blocks=True)), default block b for row b."""
     table = sd["model.embed_tokens.weight"]
     B, L = src.shape
     out = torch.zeros(B, L, table.shape[1], dtype=visual.dtype)
@@ -313,7 +339,7 @@ def pack_embeds(sd, src: torch.Tensor, visual: torch.Tensor, desc=None) -> torch
         txt = src[b] >= 0
         out[b, txt] = table[src[b, txt]].to(visual.dtype)
         vis = (src[b] <= -2) & (src[b] > DESC_BASE)
-        out[b, vis] = visual[b, (-2 - src[b, vis])]
+        out[b, vis] = visual[(blk[b, vis] if blk is not None else b), (-2 - src[b, vis])]
         dsc = src[b] <= DESC_BASE
         if bool(dsc.any()):
             out[b, dsc] = desc[b][DESC_BASE - src[b, dsc]].to(visual.dtype)
@@ -397,9 +423,9 @@ def multimodal_prefill(sd, cfg: Mm2sgCfg, input_ids, attention_mask, images, lab
         desc_rows = [[1 if e.ndim == 1 else e.shape[0] for e in per] for per in embs]
         D = visual.shape[-1]
         desc = [torch.cat([e.reshape(-1, D) for e in per]) if per else torch.zeros(0, D) for per in embs]
-    src, mlabels, mask, pos = pack_plan(input_ids, attention_mask, labels, visual.shape[1], padding_side, max_len,
-                                        desc_rows=desc_rows)
-    emb = pack_embeds(sd, src, visual, desc)
+    src, mlabels, mask, pos, blk = pack_plan(input_ids, attention_mask, labels, visual.shape[1], padding_side, max_len,
+                                             desc_rows=desc_rows, n_blocks=visual.shape[0], return_blocks=True)
+    emb = pack_embeds(sd, src, visual, desc, blk)
     logits, kv = llama_forward(sd, emb, mask, pos, cfg.llm, last_only=last_only)
     return {"logits": logits, "kv": kv, "mask": mask, "pos": pos, "modified_labels": mlabels, "inputs_embeds": emb,
             "visual": visual}

@@ -101,25 +101,64 @@ def descriptor_cases(vocab, D):
     return out
 
 
+def multi_image_cases(vocab):
+    """Rows with SEVERAL <image> placeholders: the reference walks `image_features` with one running index over the
+    batch (llava_arch.py:239,245,264-265), so `images` holds more view groups than there are rows. Also a text-only
+    row (it skips a block) and a batch that asks for more blocks than there are (the reference's IndexError)."""
+    rng = np.random.default_rng(37)
+    out = []
+    for side in ("left", "right"):
+        for with_labels in (False, True):
+            for max_len in (None, 36):
+                for trial in range(3):
+                    B, Lt = 3, 18
+                    ids = torch.zeros(B, Lt, dtype=torch.long)
+                    need = 0
+                    for b in range(B):
+                        n = int(rng.integers(6, Lt + 1))
+                        row = torch.from_numpy(rng.integers(3, vocab, n))
+                        n_img = 0 if (trial == 1 and b == 1) else int(rng.integers(1, 4))
+                        for sp in rng.choice(n, size=n_img, replace=False):
+                            row[int(sp)] = IMAGE
+                        need += max(n_img, 1)
+                        ids[b, Lt - n:] = row
+                    labels = None
+                    if with_labels:
+                        labels = ids.clone()
+                        labels[ids <= 0] = IGNORE
+                    out.append(dict(side=side, max_len=max_len, ids=ids, mask=ids.ne(0), labels=labels,
+                                    t_vis=int(rng.integers(1, 7)), n_blocks=need - (1 if trial == 2 else 0)))
+    return out
+
+
 def record(model, c, D):
     B, t_vis = c["ids"].shape[0], c["t_vis"]
-    feats = torch.zeros(B, t_vis, D)
+    NB = c.get("n_blocks", B)                              # entries of `images` = blocks of image features
+    feats = torch.zeros(NB, t_vis, D)
     feats[:, :, 0] = torch.arange(t_vis, dtype=torch.float32)[None, :]
     feats[:, :, 1] = 2.0                                   # flag: visual row
-    feats[:, :, 2] = torch.arange(B, dtype=torch.float32)[:, None]
+    feats[:, :, 2] = torch.arange(NB, dtype=torch.float32)[:, None]
     model.encode_images_pooled = lambda *a, _f=feats: _f   # instance attribute shadows the method
     model.config.tokenizer_padding_side = c["side"]
     model.config.tokenizer_model_max_length = c["max_len"]
     pos_in = torch.arange(c["ids"].shape[1])[None].expand(B, -1).clone()
-    images = [torch.zeros(1, 3, 2, 2) for _ in range(B)]
-    _, pos, am, _, emb, lab = model.prepare_inputs_labels_for_multimodal(
-        c["ids"], pos_in, c["mask"], None, c["labels"], images, c.get("embs"), None, None, None)
+    images = [torch.zeros(1, 3, 2, 2) for _ in range(NB)]
+    try:
+        _, pos, am, _, emb, lab = model.prepare_inputs_labels_for_multimodal(
+            c["ids"], pos_in, c["mask"], None, c["labels"], images, c.get("embs"), None, None, None)
+    except IndexError as e:                                 # more placeholders than feature blocks
+        return dict(side=c["side"], max_len=c["max_len"], t_vis=t_vis, ids=c["ids"], mask=c["mask"],
+                    labels=c["labels"], n_blocks=NB, raises="IndexError", message=str(e))
     flag, val, samp = emb[..., 1].round().long(), emb[..., 0].round().long(), emb[..., 2].round().long()
     src = torch.where(flag == 1, val, torch.where(flag == 2, VISUAL_BASE - val,
                       torch.where(flag == 3, DESC_BASE - val, torch.full_like(val, PAD_ROW))))
-    assert bool(((flag < 2) | (samp == torch.arange(B)[:, None])).all())       # a row only holds its own visuals
+    if "n_blocks" not in c:
+        assert bool(((flag < 2) | (samp == torch.arange(B)[:, None])).all())   # a row only holds its own visuals
     rec = dict(side=c["side"], max_len=c["max_len"], t_vis=t_vis, ids=c["ids"], mask=c["mask"],
                labels=c["labels"], src=src.to(torch.int32), out_labels=lab, out_mask=am.bool(), out_pos=pos)
+    if "n_blocks" in c:
+        rec["n_blocks"] = NB
+        rec["blocks"] = torch.where(flag == 2, samp, torch.full_like(samp, -1)).to(torch.int32)
     if "embs" in c:
         bare = type(c["embs"][0]) is not list
         embs = [c["embs"]] if bare else c["embs"]
@@ -140,6 +179,7 @@ def main():
     table[:, 1] = 1.0                                          # flag: text row
     model.get_model().embed_tokens.weight.data.copy_(table)
     records = [record(model, c, D) for c in cases(V)]
+    multi_records = [record(model, c, D) for c in multi_image_cases(V)]
     del model.encode_images_pooled
     # descriptor cases need hidden 4096: the reference's dummy descriptor is a hard-coded zeros(4096) (llava_arch.py:286)
     import contextlib
@@ -157,7 +197,9 @@ def main():
     del model.encode_images_pooled
     torch.save(records, os.path.join(gc.GOLDEN_DIR, "pack_cases.pt"))
     torch.save(desc_records, os.path.join(gc.GOLDEN_DIR, "pack_desc_cases.pt"))
-    print(len(records), "+", len(desc_records), "cases recorded")
+    torch.save(multi_records, os.path.join(gc.GOLDEN_DIR, "pack_multi_image_cases.pt"))
+    print(len(records), "+", len(desc_records), "+", len(multi_records), "cases recorded;",
+          sum("raises" in r for r in multi_records), "of the multi-image cases raise IndexError in the reference")
 
 
 if __name__ == "__main__":

@@ -159,3 +159,24 @@ def test_vis_descriptor_embeddings_in_the_pack(env):
     # without the embeddings the text after a placeholder is dropped (the reference's behaviour): a shorter pack
     short = model(input_ids=ids, attention_mask=b["attention_mask"], images=b["images"])
     assert short.logits.shape[1] < fw.logits.shape[1]
+
+
+def test_two_image_placeholders_in_one_prompt(env):
+    """A prompt with two <image> placeholders takes two consecutive entries of `images` (the reference's running
+    cur_image_idx, llava_arch.py:239,263-266; index plan pinned bit for bit to the reference on the CPU,
+    tests/test_pack_host.py): batch of 2 rows, 3 view groups -- row 0 holds two placeholders, row 1 one."""
+    cfg, ocfg, sd, model = env
+    b = synth_batch(cfg, 3, 2, 20, seed=77, jitter=0, image_pos=4)
+    ids = b["input_ids"][:2].clone()
+    ids[0, 11] = -200                                           # second placeholder in row 0
+    mask = ids.ne(0)
+    out, lg = model.generate(ids, images=b["images"], attention_mask=mask, max_new_tokens=3, stop_on_eos=False,
+                             return_logits=True)
+    ref = O.multimodal_prefill(sd, ocfg, ids, mask, b["images"], padding_side="left")
+    assert ref["mask"].shape[1] == 20 - 2 + 2 * 576 and ref["visual"].shape[0] == 3
+    toks, ref_lg = O.greedy_decode(sd, ocfg, ref["logits"][:, -1], ref["kv"], ref["mask"], 3, stop_on_eos=False)
+    assert out.shape == (2, 20 + 3) and rel_err(lg, ref_lg) < TOL_E2E
+    fw = model(input_ids=ids, attention_mask=mask, images=b["images"])
+    assert rel_err(fw.logits[ref["mask"]], ref["logits"][ref["mask"]]) < TOL_E2E
+    with pytest.raises(IndexError):                             # two blocks for three placeholders
+        model.generate(ids, images=b["images"][:2], attention_mask=mask, max_new_tokens=1)

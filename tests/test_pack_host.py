@@ -73,9 +73,54 @@ def test_empty_row_and_truncation():
     assert p.row_map.tolist()[5:] == [5, 6, 7, -1, -1]
 
 
-def test_two_images_rejected():
+def test_several_image_placeholders_match_reference_fixture():
+    """24 batches whose rows hold 0-3 <image> placeholders through the REFERENCE's own function
+    (tests/golden/make_pack_golden.py -> pack_multi_image_cases.pt; llava_arch.py:239,245,253-276): the k-th placeholder
+    of the batch takes the k-th entry of `images` (one running index; a text-only row skips one), and asking for more
+    blocks than there are raises IndexError like the reference. Planner and oracle reproduce source rows, the block of
+    every visual position, labels, mask and position ids bit for bit."""
+    import os
+    recs = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pack_multi_image_cases.pt"))
+    assert len(recs) == 24 and sum("raises" in r for r in recs) == 8
+    for r in recs:
+        labels = r["labels"]
+        args = (r["ids"].numpy(), r["mask"].numpy(), None if labels is None else labels.numpy(), r["t_vis"], r["side"],
+                r["max_len"])
+        if "raises" in r:
+            with pytest.raises(IndexError, match="out of bounds"):
+                plan_pack(*args, n_blocks=r["n_blocks"])
+            with pytest.raises(IndexError, match="out of bounds"):
+                O.pack_plan(r["ids"], r["mask"], labels, r["t_vis"], r["side"], r["max_len"], n_blocks=r["n_blocks"])
+            assert "out of bounds" in r["message"]
+            continue
+        p = plan_pack(*args, n_blocks=r["n_blocks"])
+        src, lab, m, pos, blk = O.pack_plan(r["ids"], r["mask"], labels, r["t_vis"], r["side"], r["max_len"],
+                                            n_blocks=r["n_blocks"], return_blocks=True)
+        ref_mask, ref_blk, t_vis = r["out_mask"].numpy(), r["blocks"].numpy(), r["t_vis"]
+        vis = p.vis_ids.reshape(p.src.shape)
+        planner_blk = np.where(vis >= 0, vis // t_vis, -1)
+        assert np.array_equal(planner_blk, ref_blk) and np.array_equal(blk.numpy(), ref_blk)
+        assert np.array_equal(np.where(vis >= 0, vis % t_vis, -1), np.where(ref_blk >= 0, VISUAL_BASE - p.src, -1))
+        for got_src, got_lab, got_mask, got_pos in ((p.src, p.labels, p.mask, p.pos),
+                                                    (src.numpy(), lab.numpy(), m.numpy(), pos.numpy())):
+            assert np.array_equal(got_mask, ref_mask)
+            assert np.array_equal(got_src, r["src"].numpy())
+            if r["out_labels"] is not None:
+                assert np.array_equal(got_lab, r["out_labels"].numpy())
+            assert np.array_equal(got_pos * ref_mask, r["out_pos"].numpy() * ref_mask)
+        # row_map is the inverse of vis_ids
+        flat = p.vis_ids
+        for dst in np.where(flat >= 0)[0]:
+            assert p.row_map[flat[dst]] == dst
+        assert int((p.row_map >= 0).sum()) == int((flat >= 0).sum())
+
+
+def test_two_images_one_row():
     ids = torch.tensor([[IMAGE_TOKEN_INDEX, 4, IMAGE_TOKEN_INDEX]])
-    with pytest.raises(NotImplementedError):
+    p = plan_pack(ids.numpy(), None, None, 2, n_blocks=2)
+    assert p.src.tolist() == [[-2, -3, 4, -2, -3]]
+    assert p.vis_ids.tolist() == [0, 1, -2, 2, 3] and p.row_map.tolist() == [0, 1, 3, 4]
+    with pytest.raises(IndexError):                          # one block for two placeholders, as the reference
         plan_pack(ids.numpy(), None, None, 2)
 
 
