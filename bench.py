@@ -51,14 +51,17 @@ def parse_args():
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-roofline", action="store_true")
     p.add_argument("--cpu-decode-steps", type=int, default=4)
+    p.add_argument("--no-train", action="store_true", help="skip the fine-tune-step sub-record (BASELINE configs[4])")
+    p.add_argument("--train-steps", type=int, default=3)
     p.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer arm")
     p.add_argument("--no-graph", action="store_true", help="profiling runs only: eager decode loop (every launch "
                    "visible to ncu)")
     p.add_argument("--pdl", action="store_true", help="programmatic dependent launch for the decode step's kernels "
                    "(b200_set_pdl; off by default until timed on hardware)")
-    p.add_argument("--decode-tiles", type=int, default=0, choices=[0, 1, 2], help="weight-tile widths of the decode "
-                   "step's wide projections (b200_set_option decode_tiles): 1 = 96 / 160 / 224 columns, one CTA per SM; "
-                   "2 = 64 / 96 / 128 columns, two CTAs per SM; 0 (default, the timed configuration) = 128 columns")
+    p.add_argument("--decode-tiles", type=int, default=None, choices=[0, 1, 2], help="weight-tile widths of the "
+                   "decode step's wide projections (b200_set_option decode_tiles): 1 (the library default since it was "
+                   "timed, profiles/r2_decode_bench.json) = 96 / 160 / 224 columns, one CTA per SM; 2 = 64 / 96 / 128 "
+                   "columns, two CTAs per SM; 0 = 128 columns")
     return p.parse_args()
 
 
@@ -173,7 +176,7 @@ def run_b200(args):
 
     if args.pdl:
         L.set_option("pdl", True)
-    if args.decode_tiles:
+    if args.decode_tiles is not None:
         L.set_option("decode_tiles", args.decode_tiles)
     cfg = full_config(args.layers)
     t0 = time.time()
@@ -235,14 +238,20 @@ def run_b200(args):
         launches = L.launch_count() - n0
         barrier()
         if world > 1:
+            every = [torch.zeros_like(ms) for _ in range(world)]
+            dist.all_gather(every, ms)
+            per_rank_ms.clear()
+            per_rank_ms.extend(round(float(x) / steps, 1) for x in every)
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()), launches
 
+    per_rank_ms = []                                     # device ms per step of every rank (the max is the headline)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     ms_total, launches = timed(step_resident, args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
+    rank_ms_resident = list(per_rank_ms)
     ms_e2e = float("nan") if args.no_e2e else timed(step_e2e, args.steps, 1)[0]
     n_inf = B * world * args.steps
     value = n_inf / (ms_total / 1e3)
@@ -298,6 +307,17 @@ def run_b200(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_reference_sample(args, layers=args.layers)
 
+    # ---- BASELINE configs[4]: the fine-tune step at the same N GPUs, AFTER the timed inference region (its own
+    #      device-timed region, max over ranks). The inference model and its buffers are released first.
+    train = None
+    if not args.no_train:
+        model.set_process_group(None)
+        del model, images_dev
+        import gc as _gc
+        _gc.collect()
+        torch.cuda.empty_cache()
+        train = finetune_record(args, cfg, dev, dist.group.WORLD if world > 1 else None)
+
     if rank == 0:
         flops = algorithmic_flops_per_inference(args.views, L_packed, args.new_tokens)
         line = {
@@ -323,13 +343,54 @@ def run_b200(args):
             "tensor_frac_whole_step": round(flops * n_inf / (ms_total / 1e3) / 1e12 / world / peaks()["tf_sustained"], 4),
             "init_s": round(t_init, 1),
         }
+        if rank_ms_resident:
+            line["per_rank_ms_per_step"] = rank_ms_resident      # weak scaling: the slowest rank sets `value`
         if roof is not None:
             line["roofline"] = roof
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if train is not None:
+            line["train"] = train
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def finetune_record(args, cfg, dev, group):
+    """The `train` sub-record: mm_or_b200/train/bench_step.py on this rank's GPU (ZeRO-2 over `group` when N > 1).
+    On one GPU the full fine-tune holds 12 B of fp32 state + 4 B of fp32 gradient per parameter (~150 GB of 180): if the
+    step with stored activations runs out of memory it is repeated with activation recomputation (the reference's own
+    gradient checkpointing). A failure is reported in the record, it never takes the inference line down."""
+    from mm_or_b200.train.bench_step import measure_finetune_step
+    import gc as _gc
+    import torch.distributed as dist
+    world = dist.get_world_size(group) if group is not None else 1
+    last = None
+    for recompute in (False, True):
+        ok = torch.ones(1, device=dev)
+        rec = None
+        try:
+            rec = measure_finetune_step(cfg, dev, group=group, batch=4, views=args.views, steps=args.train_steps,
+                                        warmup=1, zero=2, recompute=recompute)
+        except torch.cuda.OutOfMemoryError as e:
+            last = "out of memory with activation_recomputation=%s: %s" % (recompute, str(e)[:120])
+            ok.zero_()
+        except Exception as e:  # noqa: BLE001 -- reported, not raised: the inference numbers above stand on their own
+            return {"error": repr(e)[:300]}
+        if group is not None:
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)      # all ranks retry together
+        if ok.item() == 1:
+            pk = peaks()
+            if rec.get("tflops_per_gpu"):
+                rec["frac_of_sustained_bf16"] = round(rec["tflops_per_gpu"] / pk["tf_sustained"], 4)
+            if world > 1 and rec.get("collective_bytes_per_rank_per_step"):
+                rec["note"] = ("gradients reduce-scattered and updated slices all-gathered in bf16: %d MB per rank per "
+                               "step over NVLink" % (rec["collective_bytes_per_rank_per_step"] // (1 << 20)))
+            return rec
+        rec = None
+        _gc.collect()
+        torch.cuda.empty_cache()
+    return {"error": last}
 
 
 def measured_traffic(kernel):

@@ -43,8 +43,9 @@ int num_sms();
 // ---------------------------------------------------------------------------------------------
 bool pdl_enabled();
 void set_pdl(bool on);
-// Tile widths 96 / 160 / 224 for the decode step's wide projections (stages.cu::decode_bn). Opt-in like PDL
-// (B200_DECODE_TILES=1 or b200_set_option("decode_tiles", 1)) until timed on hardware.
+// Tile widths 96 / 160 / 224 for the decode step's wide projections (stages.cu::decode_bn). Default 1 since round 2
+// (timed on hardware: -4 % per decode step); B200_DECODE_TILES=0 / b200_set_option("decode_tiles", 0) restores the
+// 128-column tiles. PDL stays off: it measured 4 % SLOWER (profiles/r2_decode_bench.json).
 int decode_tiles_mode();       // 0 off, 1 widths for one CTA per SM, 2 two CTAs per SM (widths 64 / 96 / 128)
 void set_decode_tiles(int mode);
 

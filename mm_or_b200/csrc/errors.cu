@@ -44,7 +44,9 @@ int decode_tiles_mode() {
   int x = g_decode_tiles.load(std::memory_order_relaxed);
   if (x < 0) {
     const char* e = getenv("B200_DECODE_TILES");
-    x = (e != nullptr && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 0;
+    // default 1: timed on B200 at 128 rows x 7B (tools/decode_bench.py, profiles/r2_decode_bench.json): 14.21 ms per
+    // decode step against 14.85 with 128-column tiles (mode 0) and 14.36 with two CTAs per SM (mode 2)
+    x = (e != nullptr && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1;
     g_decode_tiles.store(x, std::memory_order_relaxed);
   }
   return x;

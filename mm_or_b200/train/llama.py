@@ -4,9 +4,10 @@ Reference: LlavaLlamaForCausalLM.forward (LLaVA/llava/model/language_model/llava
 with the FlashAttention-2 patch train/llama_flash_attn_monkey_patch.py:15-92) followed by LLaVATrainer.compute_loss
 (train/llava_trainer.py:136-174) and torch autograd. Here every tensor operation is a kernel of libb200mmor.so called
 through the C ABI (forward kernels of the inference path + the backward operators of train.cu / gemm_sm100.cu /
-attention_bwd_sm100.cu); torch only owns the memory. Activations are saved per layer (no recomputation):
-x_in, norm(x_in), qkv (q rotated), K / V in the head-major cache layout, attention context + log-sum-exp, x_mid,
-norm(x_mid), the SwiGLU pre-activation and its output.
+attention_bwd_sm100.cu); torch only owns the memory. Activations are saved per layer -- x_in, norm(x_in), qkv (q
+rotated), K / V in the head-major cache layout, attention context + log-sum-exp, x_mid, norm(x_mid), the SwiGLU
+pre-activation and its output -- or, with `recompute=True` (the reference's gradient checkpointing, train.py:1148), only
+x_in, the rest being recomputed layer by layer in the backward.
 
 Right-padded batches (train.py:1185-1191): `lengths[b]` real rows, keys beyond them are masked, labels are -100 there.
 Gradients are returned in fp32 under the reference's parameter names (q/k/v and gate/up are split back out of the fused
@@ -34,10 +35,15 @@ def _views(qkv, kc, vc, B, Lq, H):
 
 
 def forward_backward(model, embeds, labels, lengths, vocab_weight=None, grad_scale=1.0, grads=None, accumulate=False,
-                     need_input_grad=True, lora=None, train_base=True):
+                     need_input_grad=True, lora=None, train_base=True, recompute=False):
     """embeds (B, L, D) bf16 packed inputs_embeds, labels (B, L) int64 UNshifted modified_labels, lengths (B,) int32.
     lora: a train.lora.LoraState -- adapters on the seven linears of every layer (gradients under `_lora.*` keys);
     train_base = False freezes the base Linear weights (the QLoRA / LoRA recipe), norms and lm_head follow it too.
+    recompute: activation recomputation per decoder layer -- the reference trains with gradient checkpointing
+    (train.py:1148 `gradient_checkpointing_enable`, recipe README.md:119-165): the forward keeps only every layer's
+    input; the backward re-runs that layer's forward (same kernels, same dropout seeds => bit-identical activations and
+    gradients) right before differentiating it. What stays alive per layer drops from (a, qkv, K, V, ctx, lse, x_mid,
+    b, z, h) -- ~150 KB per token -- to x_in alone (8 KB per token), for one extra forward (+ 1/3 of the step's FLOPs).
     Returns (loss fp32 0-dim, weight sum, grads dict, d_embeds (B, L, D) bf16 or None)."""
     cfg = model.config
     lib = L.lib()
@@ -78,8 +84,10 @@ def forward_backward(model, embeds, labels, lengths, vocab_weight=None, grad_sca
         return y
 
     # ---------------------------------------------------------------- forward
-    caches = []
-    for i, lt in enumerate(layers):
+    def layer_forward(i, x, want_output=True):
+        """One decoder layer; returns (saved activations, output). want_output=False (recomputation in the backward)
+        stops after the SwiGLU: the down projection's result is not needed to differentiate the layer."""
+        lt = layers[i]
         c = LayerCache()
         c.t = {}
         c.x_in = x
@@ -95,8 +103,18 @@ def forward_backward(model, embeds, labels, lengths, vocab_weight=None, grad_sca
         c.b = L.rmsnorm(c.x_mid, lt["mlp_norm"], eps)
         c.z = lin_fwd(i, "gate_up_w", c.b, lt["gate_up_w"], keep=c.t)   # pre-activation kept for the backward
         c.h = L.swiglu_forward(c.z)
-        x = lin_fwd(i, "down_w", c.h, lt["down_w"], residual=c.x_mid, keep=c.t)
-        caches.append(c)
+        if lora is not None and not want_output:                        # the adapter's t = dropout(h) A^T is needed
+            a_cat, _ = lora.fused[i]["down_w"]
+            c.t["down_w"] = L.gemm(L.dropout(c.h, p_drop, drop_seed(i, "down_w")) if p_drop > 0.0 else c.h, a_cat)
+        y = lin_fwd(i, "down_w", c.h, lt["down_w"], residual=c.x_mid, keep=c.t) if want_output else None
+        return c, y
+
+    caches = []
+    for i in range(len(layers)):
+        c, y = layer_forward(i, x)
+        caches.append(x if recompute else c)           # recompute: keep the layer input only
+        x = y
+    del c
     x_last = x
     xf = L.rmsnorm(x_last, final_norm, eps)
     logits = L.gemm(xf, model.lm_head)                           # bf16 like the reference's bf16 lm_head
@@ -150,6 +168,8 @@ def forward_backward(model, embeds, labels, lengths, vocab_weight=None, grad_sca
     dx = norm_bwd(x_last, dxf, final_norm, "model.norm.weight")
     for i in range(len(layers) - 1, -1, -1):
         lt, c = layers[i], caches[i]
+        if recompute:
+            c, _ = layer_forward(i, c, want_output=False)
         p = f"_fused.layers.{i}."
         dh = lin_bwd(c.h, lt["down_w"], dx, p + "down_w", layer=i, fname="down_w", t=c.t.get("down_w"))
         dz = L.act_backward(c.z, dh, L.ACT_SWIGLU)

@@ -50,7 +50,8 @@ class FineTuner:
     def __init__(self, model, state_dict, lr=2e-5, mm_projector_lr=None, betas=(0.9, 0.999), eps=1e-8,
                  weight_decay=0.0, max_grad_norm=0.1, first_trainable_clip_layer=12, vocab_weight=None,
                  trainable=None, lora=None, train_embed_tokens=False, group=None, shard_optimizer=False,
-                 shard_gradients=False, grad_comm_dtype=torch.bfloat16, base_nf4=False, nf4_double_quant=True):
+                 shard_gradients=False, grad_comm_dtype=torch.bfloat16, base_nf4=False, nf4_double_quant=True,
+                 recompute_activations=False):
         """lora: a train.lora.LoraState -> the reference's LoRA recipe (train.py:1159-1175): the decoder's base
         weights, norms and lm_head are frozen, the adapters train next to mm_projector / image_pooler / CLIP layers.
         group: data-parallel process group (same as set_process_group). shard_optimizer: keep fp32 master / m / v for
@@ -59,9 +60,13 @@ class FineTuner:
         only receives the averaged gradient of the slices it updates (ZeRO-2, the reference's scripts/zero2.json).
         base_nf4 (LoRA only; the reference's `--bits 4`, train.py:1098-1114): the frozen decoder projections and lm_head
         are replaced by their NF4 round trip Q(W) (train/nf4.py, double quantisation of the block maxima as in the
-        reference's default), so the adapters train against the weights a bitsandbytes Linear4bit would multiply with."""
+        reference's default), so the adapters train against the weights a bitsandbytes Linear4bit would multiply with.
+        recompute_activations: the reference's gradient checkpointing (train.py:1148) for the decoder -- only every
+        layer's input is kept, the layer is re-run in the backward (train/llama.py); gradients are bit-identical."""
         self.model = model
         self.dev = model.device
+        # the reference's gradient checkpointing (train.py:1148): decoder activations recomputed layer by layer
+        self.recompute = bool(recompute_activations)
         self.first_clip = first_trainable_clip_layer
         self.lr, self.proj_lr = lr, (mm_projector_lr if mm_projector_lr is not None else lr)
         self.betas, self.eps, self.wd, self.max_norm = betas, eps, weight_decay, max_grad_norm
@@ -187,7 +192,8 @@ class FineTuner:
         loss, wsum, g, d_emb = T.forward_backward(model, embeds.view(B, Lq, D), torch.from_numpy(plan.labels).to(dev),
                                                   torch.from_numpy(plan.lengths).to(dev), self.vocab_weight,
                                                   grad_scale=grad_scale, grads=grads, accumulate=accumulate,
-                                                  lora=self.lora, train_base=self.lora is None)
+                                                  lora=self.lora, train_base=self.lora is None,
+                                                  recompute=self.recompute)
         # pack backward: visual rows of d_embeds back to the projector output (truncated tokens get zeros)
         d_vis = L.embed_rows(torch.as_tensor(plan.row_map).to(dev), d_emb.reshape(B * Lq, D), rows=B * Tv)
         if self.train_embed:                                   # nn.Embedding backward over the text rows

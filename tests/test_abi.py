@@ -47,22 +47,23 @@ def test_no_cpu_fallback():
         L.ptr(torch.zeros(4))
 
 
-def test_decode_step_switches_default_off_and_reject_unknown_names():
+def test_decode_step_switches_defaults_and_reject_unknown_names():
     """b200_set_option / b200_get_option (host-side state only; the switches themselves are exercised on the GPU by
-    tests/test_gpu_zzzz_switches.py)."""
+    tests/test_gpu_zzzz_switches.py). Defaults as timed on hardware: pdl off, decode_tiles 1."""
     import pytest
+    defaults = {"pdl": 0, "decode_tiles": 1}
     for name in ("pdl", "decode_tiles"):
-        if os.environ.get("B200_" + name.upper(), "0") in ("", "0"):
-            assert not L.get_option(name)
+        if os.environ.get("B200_" + name.upper()) is None:
+            assert int(L.get_option(name)) == defaults[name]
         L.set_option(name, True)
         assert L.get_option(name) == 1
         L.set_option(name, False)
         assert not L.get_option(name)
     L.set_option("decode_tiles", 2)                    # two CTAs per SM
     assert L.get_option("decode_tiles") == 2
-    L.set_option("decode_tiles", 0)
     with pytest.raises(L.B200Error):
         L.set_option("decode_tiles", 3)
+    L.set_option("decode_tiles", defaults["decode_tiles"])
     with pytest.raises(L.B200Error):
         L.set_option("no_such_switch", 1)
     with pytest.raises(L.B200Error):

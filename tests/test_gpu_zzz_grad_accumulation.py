@@ -42,3 +42,31 @@ def test_gradient_accumulation_matches_one_batch():
     loss, out2 = ft.train_step_accumulated([mb, mb])
     assert ft.step_count == 1 and abs(float(loss) - float(loss1)) < 1e-5 * abs(float(loss1))
     assert any(not torch.equal(before[k], ft.master[k]) for k in before)
+
+
+@pytest.mark.parametrize("with_lora", [False, True])
+def test_activation_recomputation_is_bit_identical(with_lora):
+    """recompute_activations (the reference's gradient checkpointing, train.py:1148): the backward re-runs every decoder
+    layer's forward from its saved input with the same kernels and the same dropout seeds, so loss and every gradient
+    equal the stored-activation step bit for bit -- full fine-tuning and the LoRA recipe with adapter dropout."""
+    import golden_cases as gc
+    from mm_or_b200.model.llava_llama import LlavaLlamaForCausalLM
+    from mm_or_b200.train.lora import LoraState
+    from mm_or_b200.train.step import FineTuner
+    cfg = gc.small_config()
+    cfg.tokenizer_padding_side = "right"
+    sd = gc.bf16_round(gc.small_weights(cfg))
+    case = gc.make_case(cfg, "train_right")
+    args = (case["input_ids"], case["labels"], case["attention_mask"], case["images"])
+    out = []
+    for recompute in (False, True):
+        model = LlavaLlamaForCausalLM(cfg).load_state_dict(sd)
+        lora = LoraState(cfg, r=8, alpha=16, device="cuda", seed=5, init_b="random", dropout=0.1) if with_lora else None
+        ft = FineTuner(model, sd, lr=1e-3, max_grad_norm=0.1, first_trainable_clip_layer=1, lora=lora,
+                       recompute_activations=recompute)
+        loss, _, g = ft.forward_backward(*args)
+        out.append((float(loss), {k: v.clone() for k, v in g.items()}))
+    (l0, g0), (l1, g1) = out
+    assert l0 == l1 and sorted(g0) == sorted(g1) and len(g0) > 10
+    for k in g0:
+        assert torch.equal(g0[k], g1[k]), k

@@ -83,6 +83,9 @@ def main():
     ap.add_argument("--zero", type=int, default=0, choices=[0, 1, 2], help="under torchrun: 0 = replicated optimizer "
                     "state + fp32 all-reduce, 1 = sharded state, 2 = sharded state + bf16 reduce-scatter (zero.py)")
     ap.add_argument("--accum", type=int, default=1, help="gradient accumulation steps (reference recipe: 4)")
+    ap.add_argument("--recompute", action="store_true", help="activation recomputation per decoder layer (the "
+                    "reference's gradient checkpointing, train.py:1148)")
+    ap.add_argument("--prof", action="store_true", help="one extra event-instrumented step: device time per kernel family")
     ap.add_argument("--cpu-reference", action="store_true", help="time the CPU oracle's forward + backward instead "
                     "(bounded sample, see cpu_reference)")
     a = ap.parse_args()
@@ -101,67 +104,14 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
         group = dist.group.WORLD
+    from mm_or_b200.train.bench_step import measure_finetune_step
     cfg = LlavaConfig(num_hidden_layers=a.layers, tokenizer_padding_side="right", mv_type="learned")
-    sd = make_state_dict(cfg, seed=0, device=dev, dtype=torch.bfloat16)
-    model = LlavaLlamaForCausalLM(cfg).load_state_dict(sd, device=dev)
-    b = synth_batch(cfg, a.batch, a.views, 256 + 150, seed=3 + rank, jitter=0, image_pos=40, dtype=torch.bfloat16)
-    ids = b["input_ids"]
-    labels = ids.clone()
-    labels[:, :256] = -100
-    labels[ids == -200] = -100
-    g = torch.Generator().manual_seed(1)
-    w = torch.rand(cfg.vocab_size, generator=g) + 0.01
-    lora = None
-    if a.lora_r > 0:
-        from mm_or_b200.train.lora import LoraState
-        lora = LoraState(cfg, r=a.lora_r, alpha=2 * a.lora_r, device=dev)
-    ft = FineTuner(model, sd, lr=2e-5, weight_decay=0.0, max_grad_norm=0.1, first_trainable_clip_layer=12, vocab_weight=w,
-                   lora=lora, group=group, shard_optimizer=world > 1 and a.zero >= 1,
-                   shard_gradients=world > 1 and a.zero >= 2, base_nf4=a.nf4)
-    del sd
-    n_train = sum(ft.sd[k].numel() for k in ft.names)
-    tokens = a.batch * (256 + 150 - 1 + 576) * a.accum
-    mb = dict(input_ids=ids, labels=labels, attention_mask=b["attention_mask"], images=b["images"])
-
-    def one_step():
-        if a.accum > 1:
-            return ft.train_step_accumulated([mb] * a.accum)
-        return ft.train_step(ids, labels, b["attention_mask"], b["images"])
-
-    losses = []
-    for _ in range(a.warmup):
-        loss, _ = one_step()
-        losses.append(float(loss))
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    n0 = L.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(a.steps):
-        loss, nsq = one_step()
-        losses.append(float(loss))
-    e1.record()
-    torch.cuda.synchronize()
-    ms = torch.tensor([e0.elapsed_time(e1) / a.steps], device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)          # device time, max over ranks
-    ms = float(ms)
+    rec = measure_finetune_step(cfg, dev, group=group, batch=a.batch, views=a.views, steps=a.steps, warmup=a.warmup,
+                                zero=a.zero if world > 1 else 0, lora_r=a.lora_r, nf4=a.nf4, accum=a.accum,
+                                recompute=a.recompute, prof=a.prof)
     if rank == 0:
-        print(json.dumps({"metric": "fine-tune step, trained tokens/s (%d GPU%s)" % (world, "s" if world > 1 else ""),
-                          "value": round(world * tokens / (ms / 1e3), 1), "unit": "tokens/s", "n_gpus": world,
-                          "scaling": "weak", "ms_per_step": round(ms, 1), "tokens_per_step_per_gpu": tokens,
-                          "trainable_params": n_train, "decoder_layers": a.layers, "batch_per_gpu": a.batch,
-                          "views": a.views, "gradient_accumulation": a.accum,
-                          "mode": ("qlora (nf4 base) r=%d" if a.nf4 else "lora r=%d") % a.lora_r if a.lora_r
-                          else "full fine-tune",
-                          "nf4_packed_base_gb": round(ft.nf4_bytes / 1e9, 2) if ft.nf4_bytes else None,
-                          "data_parallel": {0: "replicated state, fp32 all-reduce", 1: "ZeRO-1 (sharded fp32 state)",
-                                            2: "ZeRO-2 (sharded state, bf16 reduce-scatter)"}[a.zero]
-                          if world > 1 else "none",
-                          "losses": [round(x, 4) for x in losses], "grad_norm": round(float(nsq[0]) ** 0.5, 4),
-                          "gpu_launches_per_step": int((L.launch_count() - n0) / a.steps),
-                          "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 1e9, 1)}), flush=True)
+        rec["metric"] = "fine-tune step, trained tokens/s (%d GPU%s)" % (world, "s" if world > 1 else "")
+        print(json.dumps(rec), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
