@@ -272,7 +272,7 @@ class ImageEmbeddingPooler:
             for i, a in enumerate(audio):
                 if a is not None:
                     feats[i] = a.detach().to("cpu", BF)
-            feats = feats.to(self.device)
+            feats = feats.to(self.device, non_blocking=True)     # pageable source: staged at once, no stream sync
             L.gemm(feats, self.audio_w, out=out.view(B * T, D)[t::T], bias=self.audio_b)
             t += 1
         if segmasks is not None:                                      # _encode_segmasks (builder.py:161-167)
@@ -287,7 +287,7 @@ class ImageEmbeddingPooler:
                         maps.append(m.detach().to("cpu", torch.uint8))
                         rows.append(i * T + t + j)
             if maps:
-                cls = torch.stack(maps).contiguous().to(self.device)
+                cls = torch.stack(maps).contiguous().to(self.device, non_blocking=True)
                 rm = _i32(np.asarray(rows, dtype=np.int32), self.device)
                 nb = lib.b200_segmask_workspace_bytes(len(maps))
                 ws = self._ws_seg.get(nb, self.device)
@@ -361,6 +361,23 @@ class KVCache:
         off = b0 * self.heads * self.cap * 128 * 2
         return L.KvCache(k=self.k.data_ptr() + off, v=self.v.data_ptr() + off,
                          layer_stride=self.batch * self.heads * self.cap * 128, cap=self.cap)
+
+
+class DecodeSlot:
+    """The device buffers one greedy generation lives in -- KV cache, current tokens, step counters, history, finished
+    flags, first real slot per row -- and, once captured, the CUDA graph of one decode step over exactly these
+    buffers. generate() makes a fresh one per call; generate_stream() ping-pongs two, so the graph of a slot is
+    captured once and replayed for every batch that lands in it."""
+
+    def __init__(self, cfg, batch, cap, max_new_tokens, device):
+        self.key = (cfg.num_hidden_layers, batch, cfg.num_attention_heads, cap, max_new_tokens)
+        self.cache = KVCache(cfg.num_hidden_layers, batch, cfg.num_attention_heads, cap, device)
+        self.tokens = torch.empty(batch, device=device, dtype=torch.int32)
+        self.history = torch.empty((batch, max_new_tokens), device=device, dtype=torch.int32)
+        self.finished = torch.zeros(batch, device=device, dtype=torch.int32)
+        self.state = torch.empty(2, device=device, dtype=torch.int32)
+        self.kv_start = torch.empty(batch, device=device, dtype=torch.int32)
+        self.graph = None              # (CUDAGraph, kernels per replay, stop_on_eos it was captured with)
 
 
 class LlavaLlamaModel:
@@ -681,9 +698,21 @@ class LlavaLlamaForCausalLM:
                  vis_descriptor_embs=None, **unused):
         """Greedy decoding with the call signature the reference uses (scene_graph_prediction_model.py:221-231).
         Returns LongTensor (B, L_in + n_new): the prompt ids (incl. the -200 placeholder) followed by the new tokens.
-        HF greedy_search semantics: finished rows emit pad_token_id; stops when every row has produced EOS."""
+        HF greedy_search semantics: finished rows emit pad_token_id; stops when every row has produced EOS.
+        One call = the three phases below back to back on the current stream; generate_stream() overlaps them across
+        successive batches."""
         if do_sample:
             raise NotImplementedError("MM2SG decodes greedily (do_sample=False)")
+        job = self._gen_begin(input_ids, images, max_new_tokens, pc, audio, segmasks, attention_mask, stop_on_eos,
+                              return_logits, vis_descriptor_embs)
+        self._gen_decode(job, stopping_criteria, check_every, use_cuda_graph)
+        return self._gen_finish(job)
+
+    # ---- the three phases of a greedy generation ------------------------------------------------------------------
+    def _gen_begin(self, input_ids, images, max_new_tokens, pc=None, audio=None, segmasks=None, attention_mask=None,
+                   stop_on_eos=True, return_logits=False, vis_descriptor_embs=None, slot=None):
+        """Phase A (tensor-core bound): encode the views, pack, prefill the KV cache, first token from the prefill
+        logits -- everything enqueued on the current stream, no host synchronisation. Returns the job state."""
         if self._w is None:
             raise L.B200Error("weights not loaded")
         c = self.config
@@ -700,7 +729,7 @@ class LlavaLlamaForCausalLM:
                 ids_cpu, None, attention_mask, None, None, images, vis_descriptor_embs, pc, audio, segmasks)
             Lq = plan.L
             left = getattr(c, "tokenizer_padding_side", "right") == "left"
-            kv_start = _i32(plan.kv_start if left else np.zeros(B, np.int32), self.device)
+            kv_start_host = plan.kv_start if left else np.zeros(B, np.int32)
             kv_len = None if left else _i32(plan.lengths, self.device)
             if not left and (plan.lengths != Lq).any():
                 raise NotImplementedError("generate() with right-padded prompts of unequal length; the reference sets "
@@ -713,39 +742,58 @@ class LlavaLlamaForCausalLM:
             L.check(lib.b200_embed_rows(L.ptr(ids32.to(self.device).contiguous()), L.ptr(self.model.embed_tokens),
                                         L.ptr(embeds), c.hidden_size, B * Lq, c.hidden_size, c.vocab_size,
                                         L.stream_ptr()), "b200_embed_rows")
-            kv_start = _i32(am.argmax(1).astype(np.int32), self.device)
+            kv_start_host = am.argmax(1).astype(np.int32)
             kv_len = None
         cap = (Lq + max_new_tokens + 7) // 8 * 8
-        cache = KVCache(c.num_hidden_layers, B, c.num_attention_heads, cap, self.device)
+        if slot is None or slot.key != (c.num_hidden_layers, B, c.num_attention_heads, cap, max_new_tokens):
+            slot = DecodeSlot(c, B, cap, max_new_tokens, self.device)
+        # host -> device copies below never block the host on the stream (generate_stream relies on it)
+        slot.kv_start.copy_(torch.from_numpy(np.ascontiguousarray(kv_start_host, dtype=np.int32)), non_blocking=True)
+        kv_start, cache = slot.kv_start, slot.cache
         logits = self._prefill(embeds, kv_start, kv_len, cache, all_logits=False, logits_fp32=False)
         del embeds
         eos, pad = c.eos_token_id, c.pad_token_id if c.pad_token_id is not None else 0
-        tokens = torch.empty(B, device=self.device, dtype=torch.int32)
-        history = torch.full((B, max_new_tokens), pad, device=self.device, dtype=torch.int32)
-        finished = torch.zeros(B, device=self.device, dtype=torch.int32) if stop_on_eos else None
-        state = torch.tensor([Lq, 1], device=self.device, dtype=torch.int32)
+        job = ModelOutput(ids_cpu=ids_cpu, B=B, Lq=Lq, cap=cap, cache=cache, kv_start=kv_start, eos=eos, pad=pad,
+                          max_new_tokens=max_new_tokens, return_logits=return_logits, n_done=1, slot=slot)
+        job.tokens = slot.tokens
+        job.history = slot.history.fill_(pad)
+        job.finished = slot.finished.zero_() if stop_on_eos else None
+        job.state = slot.state
+        job.state.copy_(torch.tensor([Lq, 1], dtype=torch.int32), non_blocking=True)
         # first token from the prefill logits
-        L.check(lib.b200_argmax(L.ptr(logits), 0, c.vocab_size, B, c.vocab_size, L.ptr(tokens), L.ptr(finished), eos,
-                                pad, L.stream_ptr()), "b200_argmax")
-        history[:, 0] = tokens
-        step_logits = [logits.float().clone()] if return_logits else None
+        L.check(lib.b200_argmax(L.ptr(logits), 0, c.vocab_size, B, c.vocab_size, L.ptr(job.tokens), L.ptr(job.finished),
+                                eos, pad, L.stream_ptr()), "b200_argmax")
+        job.history[:, 0] = job.tokens
+        job.step_logits = [logits.float().clone()] if return_logits else None
+        return job
+
+    def _gen_decode(self, job, stopping_criteria=None, check_every=16, use_cuda_graph=True, capture_stream=None):
+        """Phase B (HBM bound): max_new_tokens - 1 decode steps on the current stream -- the identical launch sequence
+        captured once in a CUDA graph and replayed; the host synchronises only for stop checks."""
+        c, lib = self.config, L.lib()
+        B, cap, max_new_tokens = job.B, job.cap, job.max_new_tokens
+        tokens, state, history, finished = job.tokens, job.state, job.history, job.finished
+        return_logits = job.return_logits
         nb = lib.b200_llama_decode_workspace_bytes(ctypes.byref(self._w), B, cap)
         ws = self._ws_decode.get(nb, self.device)
-        cs = cache.struct(0)
+        cs = job.cache.struct(0)
         lg_out = torch.empty((B, c.vocab_size), device=self.device, dtype=BF) if return_logits else None
 
         def step():
-            L.check(lib.b200_llama_decode_step(ctypes.byref(self._w), L.ptr(tokens), L.ptr(state), L.ptr(kv_start),
-                                               ctypes.byref(cs), B, cap - 1, L.ptr(finished), eos, pad, L.ptr(history),
-                                               max_new_tokens, L.ptr(lg_out), L.ptr(ws), ws.numel(), L.stream_ptr()),
-                    "b200_llama_decode_step")
+            L.check(lib.b200_llama_decode_step(ctypes.byref(self._w), L.ptr(tokens), L.ptr(state), L.ptr(job.kv_start),
+                                               ctypes.byref(cs), B, cap - 1, L.ptr(finished), job.eos, job.pad,
+                                               L.ptr(history), max_new_tokens, L.ptr(lg_out), L.ptr(ws), ws.numel(),
+                                               L.stream_ptr()), "b200_llama_decode_step")
 
         n_done = 1
-        graph = None
+        graph = graph_kernels = None
+        slot = job.slot
+        if use_cuda_graph and not return_logits and slot.graph is not None and slot.graph[2] == (finished is not None):
+            graph, graph_kernels, _ = slot.graph          # this slot's decode step was captured by an earlier batch
 
         def stop_now():
             if stopping_criteria:
-                out_ids = torch.cat([ids_cpu, history[:, :n_done].to("cpu", torch.long)], dim=1)
+                out_ids = torch.cat([job.ids_cpu, history[:, :n_done].to("cpu", torch.long)], dim=1)
                 for sc in stopping_criteria:      # HF StoppingCriteriaList: stop if any criterion fires
                     r = sc(out_ids, None)
                     if bool(r.all()) if torch.is_tensor(r) else bool(r):
@@ -761,32 +809,109 @@ class LlavaLlamaForCausalLM:
                 break
             if graph is None and use_cuda_graph and n_done >= 2 and not return_logits:
                 # the first decode step ran eagerly (lazy kernel-attribute setup); capture the launch sequence once
+                # (capture_begin / capture_end directly: torch.cuda.graph() would synchronise the whole device first,
+                # i.e. wait for the other stream's encode + prefill in generate_stream; step() allocates nothing)
                 graph = torch.cuda.CUDAGraph()
-                side = torch.cuda.Stream()
+                side = capture_stream if capture_stream is not None else torch.cuda.Stream()
                 side.wait_stream(torch.cuda.current_stream())
                 n0 = lib.b200_launch_count()
                 with torch.cuda.stream(side):
-                    with torch.cuda.graph(graph, stream=side):
+                    graph.capture_begin(capture_error_mode="thread_local")
+                    try:
                         step()
+                    finally:
+                        graph.capture_end()
                 graph_kernels = lib.b200_launch_count() - n0
                 L.note_graph_replay(-graph_kernels)       # the capture itself executed nothing
                 torch.cuda.current_stream().wait_stream(side)
+                slot.graph = (graph, graph_kernels, finished is not None)
             if graph is not None:
                 graph.replay()
                 L.note_graph_replay(graph_kernels)
             else:
                 step()
             if return_logits:
-                step_logits.append(lg_out.float().clone())
+                job.step_logits.append(lg_out.float().clone())
             n_done += 1
-        gen = history[:, :n_done].to(torch.long)
+        job.n_done = n_done
+        return job
+
+    def _gen_finish(self, job):
+        """Phase C: the generated ids back to the caller's layout (synchronises on the job's stream work)."""
+        history, finished = job.history, job.finished
+        gen = history[:, :job.n_done].to(torch.long)
         if finished is not None:
             # HF stops right after the step in which the last unfinished row emitted EOS: trim later columns
-            is_eos = (gen == eos).to("cpu")
+            is_eos = (gen == job.eos).to("cpu")
             if bool(is_eos.any(1).all()):
                 last = int(is_eos.float().argmax(1).max().item()) + 1
                 gen = gen[:, :last]
-        out = torch.cat([ids_cpu.to(self.device), gen], dim=1)
-        if return_logits:
-            return out, torch.stack(step_logits[:gen.shape[1]], dim=1)
+        out = torch.cat([job.ids_cpu.to(self.device), gen], dim=1)
+        if job.return_logits:
+            return out, torch.stack(job.step_logits[:gen.shape[1]], dim=1)
         return out
+
+    @torch.no_grad()
+    def generate_stream(self, requests, max_new_tokens=20, stop_on_eos=True, stopping_criteria=None, check_every=16,
+                        prefill_chunk=None, vit_chunk=None, pooler_chunk=None):
+        """Pipelined greedy generation over a sequence of batches: while batch n decodes (HBM bound: 255 passes over the
+        weights and the KV cache), the views of batch n + 1 are encoded and its prompt prefilled (tensor-core bound) on a
+        second, lower-priority stream, so the tensor pipe and the memory system work at the same time instead of in turn
+        (DESIGN.md 8). `requests` yields dicts of generate() keyword arguments (input_ids, images, pc, audio, segmasks,
+        attention_mask, vis_descriptor_embs); outputs come back in order, one LongTensor per request, identical to what
+        generate() returns for it (same kernels, same arithmetic: only the scheduling differs).
+        Two decode slots (KV cache + step buffers + the captured graph of a decode step) are alive at a time and
+        ping-pong between the batches (0.56 GB per sample each at L = 831 + 256).
+        prefill_chunk / vit_chunk / pooler_chunk: samples / images per launch sequence of phase A while pipelined --
+        smaller chunks mean shorter tensor-core kernels, i.e. shorter waits for the decode stream's kernels when both
+        compete for the SMs' shared memory."""
+        cur_stream = torch.cuda.current_stream()
+        hi = torch.cuda.Stream(priority=-1)          # decode: the serial chain of ~260 small kernels per token
+        lo = torch.cuda.Stream(priority=0)           # encode + prefill: long tensor-core kernels, fill the gaps
+        cap_stream = torch.cuda.Stream(priority=-1)  # graph capture: the nodes inherit its priority
+        for s in (hi, lo):
+            s.wait_stream(cur_stream)
+        saved = (self.prefill_chunk, self.vit_chunk, self.pooler_chunk)
+        free_slots = []
+
+        def begin(req):
+            kw = dict(req)
+            ids = kw.pop("input_ids")
+            images = kw.pop("images", None)
+            with torch.cuda.stream(lo):
+                slot = free_slots.pop() if free_slots else None
+                job = self._gen_begin(ids, images, kw.pop("max_new_tokens", max_new_tokens), kw.get("pc"),
+                                      kw.get("audio"), kw.get("segmasks"), kw.get("attention_mask"), stop_on_eos,
+                                      False, kw.get("vis_descriptor_embs"), slot=slot)
+                job.ready = torch.cuda.Event()
+                job.ready.record(lo)
+            return job
+
+        try:
+            if prefill_chunk:
+                self.prefill_chunk = int(prefill_chunk)
+            if vit_chunk:
+                self.vit_chunk = int(vit_chunk)
+            if pooler_chunk:
+                self.pooler_chunk = int(pooler_chunk)
+            it = iter(requests)
+            first = next(it, None)
+            nxt = begin(first) if first is not None else None
+            while nxt is not None:
+                cur = nxt
+                req = next(it, None)
+                nxt = begin(req) if req is not None else None      # phase A of batch n + 1 goes first into its queue
+                with torch.cuda.stream(hi):
+                    hi.wait_event(cur.ready)
+                    self._gen_decode(cur, stopping_criteria, check_every, True, capture_stream=cap_stream)
+                    out = self._gen_finish(cur)                    # synchronises with the decode of batch n only
+                    done = torch.cuda.Event()
+                    done.record(hi)
+                done.synchronize()
+                free_slots.append(cur.slot)                        # ping-pong: batch n + 2 reuses cache and graph
+                cur = None
+                yield out
+        finally:
+            self.prefill_chunk, self.vit_chunk, self.pooler_chunk = saved
+            cur_stream.wait_stream(hi)
+            cur_stream.wait_stream(lo)

@@ -180,3 +180,31 @@ def test_error_behaviour(env):
         model(input_ids=torch.tensor([[1, -200, 3]]), images=torch.zeros(1, 3, 336, 336))
     with pytest.raises(NotImplementedError):
         model.generate(torch.tensor([[1, -200, 3]]), images=[torch.zeros(1, 3, 336, 336)], do_sample=True)
+
+
+def test_generate_stream_equals_generate(env):
+    """generate_stream (encode + prefill of batch n + 1 on a second stream while batch n decodes; two ping-ponged decode
+    slots whose captured decode-step graph is reused) returns, batch by batch, exactly the ids generate() returns: same
+    kernels and arithmetic, only the scheduling differs. Five batches: three of one shape (slot and graph reuse), one
+    with another batch size / prompt length (new slot), one with audio + seg-mask tokens."""
+    from mm_or_b200.synth import synth_batch
+    cfg, ocfg, sd, model = env
+    model.config.tokenizer_padding_side = "left"
+    reqs = []
+    for i, (B, tl, extras) in enumerate([(3, 24, False), (3, 24, False), (3, 24, False), (2, 17, False), (3, 24, True)]):
+        b = synth_batch(cfg, B, 2, tl, seed=200 + i, jitter=0 if i < 3 else 3, image_pos=4, audio=extras, segmasks=extras)
+        r = dict(input_ids=b["input_ids"], images=b["images"])
+        if extras:
+            r.update(audio=b["audio"], segmasks=b["segmasks"])
+        reqs.append(r)
+    for stop_on_eos in (False, True):
+        want = [model.generate(max_new_tokens=9, stop_on_eos=stop_on_eos, **r) for r in reqs]
+        got = list(model.generate_stream(reqs, max_new_tokens=9, stop_on_eos=stop_on_eos, prefill_chunk=2, vit_chunk=3,
+                                         pooler_chunk=2))
+        assert len(got) == len(want)
+        for g, w in zip(got, want):
+            assert torch.equal(g, w)
+    # an empty request sequence and a single request
+    assert list(model.generate_stream([], max_new_tokens=3)) == []
+    one = list(model.generate_stream(reqs[:1], max_new_tokens=3, stop_on_eos=False))
+    assert torch.equal(one[0], model.generate(max_new_tokens=3, stop_on_eos=False, **reqs[0]))
