@@ -51,6 +51,7 @@ def parse_args():
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-roofline", action="store_true")
     p.add_argument("--cpu-decode-steps", type=int, default=4)
+    p.add_argument("--no-pin", action="store_true", help="N > 1: do not pin every rank to its own slice of host cores")
     p.add_argument("--no-train", action="store_true", help="skip the fine-tune-step sub-record (BASELINE configs[4])")
     p.add_argument("--train-steps", type=int, default=3)
     p.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer arm")
@@ -173,6 +174,21 @@ def run_b200(args):
     from mm_or_b200 import _lib as L
     from mm_or_b200.model.llava_llama import LlavaLlamaForCausalLM
     from mm_or_b200.synth import make_state_dict
+
+    pinned_cores = None
+    if world > 1 and not args.no_pin:
+        # one node, N launcher processes: give every rank its own contiguous slice of the host cores so that the ranks'
+        # Python launch loops (encode + prefill are ~2300 launches per batch) do not migrate onto each other's cores
+        try:
+            cores = sorted(os.sched_getaffinity(0))
+            per = len(cores) // world
+            if per >= 2:
+                mine = cores[local * per:(local + 1) * per]
+                os.sched_setaffinity(0, mine)
+                torch.set_num_threads(max(1, min(per, 8)))
+                pinned_cores = per
+        except (AttributeError, OSError):
+            pass
 
     if args.pdl:
         L.set_option("pdl", True)
@@ -345,6 +361,7 @@ def run_b200(args):
         }
         if rank_ms_resident:
             line["per_rank_ms_per_step"] = rank_ms_resident      # weak scaling: the slowest rank sets `value`
+            line["host_cores_per_rank"] = pinned_cores
         if roof is not None:
             line["roofline"] = roof
         if cpu is not None:

@@ -201,6 +201,12 @@ int decode_attn(DecodeArgs a, void* workspace, size_t workspace_bytes, cudaStrea
   if (!cfg) {
     B200_CUDA_OK(cudaFuncSetAttribute(decode_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       kDecMaxCtx * (int)sizeof(float)));
+    // experiment knob (tools/corun_bench.py): ask for the same L1 / shared split as the tcgen05 GEMMs so that an SM
+    // needs no reconfiguration to hold both (the kernel streams K / V once: L1 capacity is irrelevant to it)
+    const char* e = getenv("B200_ATTN_CARVEOUT");
+    if (e != nullptr && e[0] == '1')
+      B200_CUDA_OK(cudaFuncSetAttribute(decode_attn_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                        cudaSharedmemCarveoutMaxShared));
     cfg = true;
   }
   LaunchScope scope(kFamDecodeAttn, stream, 0.0, 0.0, a.splits > 1 ? 2 : 1);  // bytes depend on the device-side ctx

@@ -15,6 +15,7 @@
 //               bias / activation / SwiGLU pairing / residual / row scatter, convert to bf16 and store 16 B
 //               vectors. TMEM holds two accumulators so the epilogue of tile i overlaps the main loop of i+1.
 #include <cstdarg>
+#include <cstdlib>
 #include <mutex>
 
 #include "common.h"
@@ -405,6 +406,12 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   if (!configured) {
     B200_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, PER_SM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       Cfg::kSmemBytes));
+    // experiment knob (tools/corun_bench.py): the full 228 KB shared carve-out instead of the smallest one that holds
+    // this kernel's ring, so that small-footprint kernels of another stream find room next to the persistent CTA
+    const char* e = getenv("B200_GEMM_CARVEOUT");
+    if (e != nullptr && e[0] == '1')
+      B200_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, PER_SM>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                        cudaSharedmemCarveoutMaxShared));
     configured = true;
   }
   const int tiles = g.m_tiles * g.n_tiles;
