@@ -51,6 +51,9 @@ def parse_args():
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-roofline", action="store_true")
     p.add_argument("--cpu-decode-steps", type=int, default=4)
+    p.add_argument("--no-configs", action="store_true", help="skip the configs[2] / configs[3] sub-records")
+    p.add_argument("--config-steps", type=int, default=2)
+    p.add_argument("--config-batch", type=int, default=64, help="samples per GPU per step of the configs[2] sub-record")
     p.add_argument("--no-pin", action="store_true", help="N > 1: do not pin every rank to its own slice of host cores")
     p.add_argument("--no-train", action="store_true", help="skip the fine-tune-step sub-record (BASELINE configs[4])")
     p.add_argument("--train-steps", type=int, default=3)
@@ -323,6 +326,14 @@ def run_b200(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_reference_sample(args, layers=args.layers)
 
+    # ---- BASELINE configs[2] and configs[3] at the same N GPUs: short device-timed regions of their own (1 warm-up +
+    #      `--config-steps` steps each, max over ranks), reported as sub-records next to the headline configs[1] line
+    other = None
+    if not args.no_configs:
+        if world > 1:
+            model.set_process_group(dist.group.WORLD, exchange=exchange)
+        other = other_config_records(args, cfg, model, dev, rank, world, exchange, timed)
+
     # ---- BASELINE configs[4]: the fine-tune step at the same N GPUs, AFTER the timed inference region (its own
     #      device-timed region, max over ranks). The inference model and its buffers are released first.
     train = None
@@ -366,11 +377,76 @@ def run_b200(args):
             line["roofline"] = roof
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if other is not None:
+            line["other_configs"] = other
         if train is not None:
             line["train"] = train
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def other_config_records(args, cfg, model, dev, rank, world, exchange, timed):
+    """configs[2]: per sample 6 RGB views + 6 depth + 6 seg-mask renderings = 18 encoder passes, an audio embedding and
+    three 32x32 class maps -> fused token pack with T_vis = 580, prefill, 256 greedy tokens. Mapping as in SURVEY.md 8d /
+    tests/test_gpu_zzz_baseline_configs.py: the reference has no depth / seg-mask IMAGE input, so the 12 extra frames go
+    through the tower and, as two more 6-view groups, through the pooler (pure throughput), while the RGB group, the
+    audio token and the class-map tokens feed the decoder.
+    configs[3]: 64 clips x 8 frames x 6 views over 8 GPUs = 64 samples + 384 images per GPU; the visual tokens are
+    all-gathered and every rank decodes the slice its NEIGHBOUR encoded (decode_shift = 1), so the exchange is
+    load-bearing. On fewer GPUs the per-GPU geometry is kept (weak scaling)."""
+    import torch.distributed as dist
+    from mm_or_b200.synth import synth_batch
+    out = {}
+    steps = max(1, args.config_steps)
+    gen_kw = dict(do_sample=False, use_cache=True, max_new_tokens=args.new_tokens, stop_on_eos=False)
+
+    def record(name, fn, samples, note):
+        try:
+            ms, _ = timed(fn, steps, 1)
+        except Exception as e:  # noqa: BLE001 -- a sub-record never takes the headline down
+            out[name] = {"error": repr(e)[:300]}
+            torch.cuda.empty_cache()
+            return
+        out[name] = {"value": round(samples * world * steps / (ms / 1e3), 3), "unit": UNIT, "n_gpus": world,
+                     "samples_per_gpu_per_step": samples, "steps": steps, "ms_per_step": round(ms / steps, 1),
+                     "workload": note}
+
+    # configs[2]
+    B3 = args.config_batch
+    b = synth_batch(cfg, B3, args.views, args.text_len, seed=300 + rank, jitter=args.jitter, image_pos=40, audio=True,
+                    segmasks=True, dtype=torch.bfloat16)
+    rgb = torch.stack(b["images"]).to(dev)
+    extra = synth_batch(cfg, B3, 2 * args.views, 8, seed=400 + rank, dtype=torch.bfloat16)["images"]
+    extra = torch.stack(extra).to(dev).flatten(0, 1)                       # (B * 12, 3, S, S): depth + seg renderings
+
+    def cfg3_step():
+        model.encode_images_pooled(extra, [args.views] * (2 * B3), None, None, None)
+        return model.generate(b["input_ids"], images=rgb, audio=b["audio"], segmasks=b["segmasks"], **gen_kw)
+
+    record("configs[2]", cfg3_step, B3,
+           "6-view RGB + depth + seg-mask renderings (18 ViT passes, 3 pooler passes per sample) + audio token + 3 "
+           "class-map tokens, T_vis = 580, prefill + %d greedy tokens" % args.new_tokens)
+    del rgb, extra, b
+    torch.cuda.empty_cache()
+
+    # configs[3]: 64 samples + 384 images per GPU, neighbour's slice decoded
+    B4 = 64
+    shift = 1 if world > 1 else 0
+    if world > 1:
+        model.set_process_group(dist.group.WORLD, exchange=exchange, decode_shift=shift)
+    mine = synth_batch(cfg, B4, args.views, args.text_len, seed=500 + rank, jitter=0, image_pos=40, dtype=torch.bfloat16)
+    owner = (rank + shift) % world
+    theirs = mine if owner == rank else synth_batch(cfg, B4, args.views, args.text_len, seed=500 + owner, jitter=0,
+                                                    image_pos=40, dtype=torch.bfloat16)
+    img4 = torch.stack(mine["images"]).to(dev)
+    record("configs[3]", lambda: model.generate(theirs["input_ids"], images=img4, **gen_kw), B4,
+           "temporal clips: 64 samples (8 clips x 8 frames) x 6 views = 384 images per GPU; visual tokens all-gathered "
+           "(%s), every rank decodes the slice rank + %d encoded; %d greedy tokens"
+           % (exchange or "single GPU: no exchange", shift, args.new_tokens))
+    if world > 1:
+        model.set_process_group(dist.group.WORLD, exchange=exchange, decode_shift=0)
+    return out
 
 
 def finetune_record(args, cfg, dev, group):

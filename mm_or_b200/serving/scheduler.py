@@ -82,3 +82,38 @@ class OnlineScheduler:
                 triplets = slot[2].add_prediction(int(f["frame_id"]), text)
                 results[slot[0]].append({"frame_id": int(f["frame_id"]), "text": text, "triplets": triplets})
         return results
+
+    def run_continuous(self, takes, batcher):
+        """The same online loop on a serving/continuous.py ContinuousBatcher: a take's next frame is submitted the
+        moment its previous answer is complete and joins the decode rows individually -- no round waits for its longest
+        answer. `batcher.max_new` bounds the answer length; stopping criteria are built per request. Returns the same
+        structure as run(); results are schedule-independent for the same reason (one memory + shuffle RNG per take)."""
+        results = {name: [] for name in takes}
+        state = {name: [iter(frames), TakeMemory(rng=self.rng_factory(name)), None] for name, frames in takes.items()}
+        in_flight = {}                                      # ticket -> (take name, frame, prompt length)
+
+        def feed():
+            for name, st in state.items():
+                if st[2] is not None or len(in_flight) >= self.max_batch:
+                    continue
+                frame = next(st[0], None)
+                if frame is None:
+                    continue
+                ids = self.tokenize(st[1].splice(frame["prompt"], int(frame["frame_id"]), self.image_token))[None]
+                kw = {k: [frame[k]] for k in ("pc", "audio", "segmasks") if frame.get(k) is not None}
+                criteria = self.criteria(ids) if self.criteria is not None else None
+                t = batcher.submit(ids, images=[frame["images"]], stopping_criteria=criteria, **kw)
+                st[2] = t
+                in_flight[t] = (name, frame, ids.shape[1])
+
+        feed()
+        while in_flight:
+            for ticket, out in batcher.run():
+                name, frame, n_prompt = in_flight.pop(ticket)
+                text = self.decode(out[n_prompt:].to("cpu")).strip()
+                triplets = state[name][1].add_prediction(int(frame["frame_id"]), text)
+                results[name].append({"frame_id": int(frame["frame_id"]), "text": text, "triplets": triplets})
+                state[name][2] = None
+            self.rounds += 1
+            feed()
+        return results
