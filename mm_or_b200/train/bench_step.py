@@ -36,7 +36,7 @@ def step_flops(cfg, batch, views, L_packed):
 
 
 def measure_finetune_step(cfg, dev, group=None, batch=4, views=6, steps=2, warmup=1, zero=2, lora_r=0, nf4=False,
-                          accum=1, recompute=False, prof=False, model=None, sd=None, seed=0):
+                          accum=1, recompute=False, prof=False, model=None, sd=None, seed=0, trace=False):
     """Builds the FineTuner, runs `warmup` + `steps` optimizer steps, returns the record (a dict; rank 0's is the one
     to print). model / sd: reuse an already loaded model and its reference-named bf16 state dict (bench.py)."""
     import torch.distributed as dist
@@ -83,11 +83,13 @@ def measure_finetune_step(cfg, dev, group=None, batch=4, views=6, steps=2, warmu
     n0 = L.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    timed_losses = []
     for _ in range(steps):
         loss, nsq = one_step()
-        losses.append(float(loss))
+        timed_losses.append(loss)            # read back after the timed region: no host synchronisation between steps
     e1.record()
     torch.cuda.synchronize(dev)
+    losses += [float(x) for x in timed_losses]
     mine = e0.elapsed_time(e1) / steps
     launches = int((L.launch_count() - n0) / steps)
     per_rank = [mine]
@@ -98,6 +100,13 @@ def measure_finetune_step(cfg, dev, group=None, batch=4, views=6, steps=2, warmu
         dist.all_gather(allms, t, group=group)
         per_rank = [round(float(x), 1) for x in allms]
         ms = max(per_rank)                                   # device time, max over ranks
+    phases = None
+    if trace:
+        from . import trace as TR
+        TR.enable(True)
+        one_step()
+        phases = TR.collect()
+        TR.enable(False)
     fam = None
     if prof:
         L.prof_enable(True)
@@ -126,6 +135,8 @@ def measure_finetune_step(cfg, dev, group=None, batch=4, views=6, steps=2, warmu
            "peak_mem_gb": round(torch.cuda.max_memory_allocated(dev) / 1e9, 1)}
     if fam is not None:
         rec["families"] = fam
+    if phases is not None:
+        rec["phase_ms_serialised"] = phases
     return rec
 
 

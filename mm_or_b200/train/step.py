@@ -214,15 +214,23 @@ class FineTuner:
         """clip_grad_norm_(max_grad_norm) over the trainable set + AdamW; rebuilds the fused bf16 working weights."""
         if self.group is not None:
             from ..dist import align_optional_gradients, average_gradients
+            from .trace import phase as _ph
             optional = {k: tuple(self.sd[k].shape) for k in self.names
                         if k == "model.embed_tokens.weight" or k.startswith(("model.image_pooler.project_audio.",
                                                                              "model.image_pooler.segmasks_encoder."))}
-            align_optional_gradients(grads, optional, self.group)  # ranks whose batch lacked a modality contribute zeros
+            with _ph("align_optional_gradients"):
+                if getattr(self, "_host_group", None) is None:
+                    from ..dist import host_side_group
+                    self._host_group = host_side_group(self.group)     # collective: every rank reaches it in step 1
+                # ranks whose batch lacked a modality contribute zeros
+                align_optional_gradients(grads, optional, self.group, host_group=self._host_group)
             if not self.shard_gradients:
                 average_gradients(grads, sorted(grads), self.group)    # in place on the (contiguous) fused gradients
-        g = T.unfuse_grads(grads, self.model.config)
-        if self.lora is not None:
-            g.update(self.lora.unfuse_grads(grads))
+        from .trace import phase
+        with phase("unfuse_grads"):
+            g = T.unfuse_grads(grads, self.model.config)
+            if self.lora is not None:
+                g.update(self.lora.unfuse_grads(grads))
         self.step_count += 1
         lr_of = lambda k: self.proj_lr if k.startswith("model.mm_projector.") else self.lr
         wd_of = lambda k: 0.0 if no_decay(k) else self.wd
@@ -248,6 +256,11 @@ class FineTuner:
 
     def _after_update(self, out2):
         """Rebuild the fused bf16 working weights the kernels read from the updated per-parameter tensors."""
+        from .trace import phase
+        with phase("refuse_working_weights"):
+            return self._after_update_impl(out2)
+
+    def _after_update_impl(self, out2):
         if self.lora is not None:
             self.lora.refuse()                     # adapters changed; the decoder's base weights did not
             self._reload_encoder()
@@ -313,10 +326,13 @@ class FineTuner:
 
     def train_step(self, input_ids, labels, attention_mask, images, pc=None, audio=None, segmasks=None,
                    vis_descriptor_embs=None):
-        loss, wsum, grads = self.forward_backward(input_ids, labels, attention_mask, images, pc=pc, audio=audio,
-                                                  segmasks=segmasks, vis_descriptor_embs=vis_descriptor_embs)
+        from .trace import phase
+        with phase("forward_backward"):
+            loss, wsum, grads = self.forward_backward(input_ids, labels, attention_mask, images, pc=pc, audio=audio,
+                                                      segmasks=segmasks, vis_descriptor_embs=vis_descriptor_embs)
         self.last_grads = grads
-        norm_sq = self.optimizer_step(grads)
+        with phase("optimizer_step (all)"):
+            norm_sq = self.optimizer_step(grads)
         return loss, norm_sq
 
     def train_step_accumulated(self, micro_batches):

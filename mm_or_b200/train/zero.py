@@ -16,6 +16,7 @@ import torch
 import torch.distributed as dist
 
 from .. import _lib as L
+from .trace import phase
 
 
 def slice_range(n, rank, world):
@@ -86,43 +87,52 @@ class ShardedAdamW:
         send = lay["send"].view(W, S)
         # pack: row r of the send buffer = rank r's slice of every tensor, side by side (one strided copy per tensor,
         # which is also the fp32 -> wire-dtype conversion); the zero padding of ragged tensors is never overwritten
-        for k in todo:
-            self._scatter_rows(send, grads.pop(k).reshape(-1), *lay["at"][k])
+        with phase("zero2.pack"):
+            for k in todo:
+                self._scatter_rows(send, grads.pop(k).reshape(-1), *lay["at"][k])
         # ONE reduce-scatter for the whole gradient set: this rank receives the sums of exactly the slices it updates
         recv = lay["recv"]
-        if dev.type == "cuda":
-            dist.reduce_scatter_tensor(recv, lay["send"], op=dist.ReduceOp.SUM, group=self.group)
-        else:   # gloo (CPU tests) has no reduce-scatter: all-reduce the buffer and cut -- the same sums
-            wire = lay["send"].float() if comm_dtype == torch.bfloat16 else lay["send"]      # gloo: no bf16 arithmetic
-            dist.all_reduce(wire, op=dist.ReduceOp.SUM, group=self.group)
-            recv.copy_(wire.view(W, S)[self.rank].to(comm_dtype))       # (exactly NCCL's bf16 sum for two ranks)
-        g32 = lay["g32"]
-        torch.div(recv.float(), W, out=g32)                              # mean over the ranks, fp32
-        out2 = torch.zeros(2, dtype=torch.float32, device=dev)
-        self.sq_norm(g32, out2)                                          # the padding is zero: it adds nothing
-        dist.all_reduce(out2[:1], op=dist.ReduceOp.SUM, group=self.group)       # slices partition every tensor
-        out2[1] = torch.clamp(max_norm / (out2[0].sqrt() + 1e-6), max=1.0) if max_norm > 0 else 1.0
+        with phase("zero2.reduce_scatter"):
+            if dev.type == "cuda":
+                dist.reduce_scatter_tensor(recv, lay["send"], op=dist.ReduceOp.SUM, group=self.group)
+            else:   # gloo (CPU tests) has no reduce-scatter: all-reduce the buffer and cut -- the same sums
+                wire = lay["send"].float() if comm_dtype == torch.bfloat16 else lay["send"]   # gloo: no bf16 arithmetic
+                dist.all_reduce(wire, op=dist.ReduceOp.SUM, group=self.group)
+                recv.copy_(wire.view(W, S)[self.rank].to(comm_dtype))   # (exactly NCCL's bf16 sum for two ranks)
+        # The mean over the ranks is never materialised: recv holds the SUMS in the wire dtype; the squared norm of the
+        # mean is sum(recv^2) / W^2 and AdamW multiplies every gradient by clip / W (one factor, applied in fp32 inside
+        # the kernel). For W a power of two this is bit-identical to dividing first.
+        with phase("zero2.mean_norm"):
+            out2 = torch.zeros(2, dtype=torch.float32, device=dev)
+            self.sq_norm(recv, out2)                                     # the padding is zero: it adds nothing
+            dist.all_reduce(out2[:1], op=dist.ReduceOp.SUM, group=self.group)   # slices partition every tensor
+            out2[0] /= float(W * W)
+            out2[1] = torch.clamp(max_norm / (out2[0].sqrt() + 1e-6), max=1.0) if max_norm > 0 else 1.0
+            scale = (out2[1:] / float(W)).contiguous()                   # clip coefficient x 1 / W
         # AdamW on this rank's slices; the updated bf16 slices are written straight into the all-gather send buffer
         ag_send = lay["ag_send"]
-        for k in todo:
-            off, s, n = lay["at"][k]
-            lo, hi = self.range[k]
-            if hi > lo:
-                self.adamw(self.master[k], ag_send[off:off + hi - lo], g32[off:off + hi - lo], self.m[k], self.v[k],
-                           lr_of(k), self.betas[0], self.betas[1], self.eps, wd_of(k), step, clip_coef=out2[1:])
+        with phase("zero2.adamw"):
+            for k in todo:
+                off, s, n = lay["at"][k]
+                lo, hi = self.range[k]
+                if hi > lo:
+                    self.adamw(self.master[k], ag_send[off:off + hi - lo], recv[off:off + hi - lo], self.m[k], self.v[k],
+                               lr_of(k), self.betas[0], self.betas[1], self.eps, wd_of(k), step, clip_coef=scale)
         # ONE all-gather of the updated slices (the reduce-scatter's send buffer is free again: it receives them)
         gathered = lay["send"] if lay["send"].dtype == ag_send.dtype else lay["ag_recv"]
-        if dev.type == "cuda":
-            dist.all_gather_into_tensor(gathered, ag_send, group=self.group)
-        else:
-            raw = ag_send.view(torch.uint8)
-            parts = [torch.empty_like(raw) for _ in range(W)]
-            dist.all_gather(parts, raw, group=self.group)
-            for r, part in enumerate(parts):
-                gathered.view(W, S)[r] = part.view(ag_send.dtype)
+        with phase("zero2.all_gather"):
+            if dev.type == "cuda":
+                dist.all_gather_into_tensor(gathered, ag_send, group=self.group)
+            else:
+                raw = ag_send.view(torch.uint8)
+                parts = [torch.empty_like(raw) for _ in range(W)]
+                dist.all_gather(parts, raw, group=self.group)
+                for r, part in enumerate(parts):
+                    gathered.view(W, S)[r] = part.view(ag_send.dtype)
         g2 = gathered.view(W, S)
-        for k in todo:
-            self._gather_rows(self.params[k].view(-1), g2, *lay["at"][k])
+        with phase("zero2.unpack"):
+            for k in todo:
+                self._gather_rows(self.params[k].view(-1), g2, *lay["at"][k])
         # (the gathered buffer doubles as the next step's send buffer: its padding is still zero, because every rank's
         # ag_send is zero wherever AdamW does not write)
         return out2
@@ -145,8 +155,7 @@ class ShardedAdamW:
             off += s
         S = (off + 7) // 8 * 8              # 16-byte aligned rows
         lay = dict(at=at, S=S, send=torch.zeros(self.world * S, dtype=comm_dtype, device=dev),
-                   recv=torch.empty(S, dtype=comm_dtype, device=dev), g32=torch.empty(S, dtype=torch.float32, device=dev),
-                   ag_send=torch.zeros(S, dtype=pdt, device=dev))
+                   recv=torch.empty(S, dtype=comm_dtype, device=dev), ag_send=torch.zeros(S, dtype=pdt, device=dev))
         if comm_dtype != pdt:
             lay["ag_recv"] = torch.empty(self.world * S, dtype=pdt, device=dev)
         cache[key] = lay

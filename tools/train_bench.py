@@ -85,6 +85,7 @@ def main():
     ap.add_argument("--accum", type=int, default=1, help="gradient accumulation steps (reference recipe: 4)")
     ap.add_argument("--recompute", action="store_true", help="activation recomputation per decoder layer (the "
                     "reference's gradient checkpointing, train.py:1148)")
+    ap.add_argument("--trace", action="store_true", help="one extra step with device-synchronised phase timing")
     ap.add_argument("--prof", action="store_true", help="one extra event-instrumented step: device time per kernel family")
     ap.add_argument("--cpu-reference", action="store_true", help="time the CPU oracle's forward + backward instead "
                     "(bounded sample, see cpu_reference)")
@@ -108,7 +109,7 @@ def main():
     cfg = LlavaConfig(num_hidden_layers=a.layers, tokenizer_padding_side="right", mv_type="learned")
     rec = measure_finetune_step(cfg, dev, group=group, batch=a.batch, views=a.views, steps=a.steps, warmup=a.warmup,
                                 zero=a.zero if world > 1 else 0, lora_r=a.lora_r, nf4=a.nf4, accum=a.accum,
-                                recompute=a.recompute, prof=a.prof)
+                                recompute=a.recompute, prof=a.prof, trace=a.trace)
     if rank == 0:
         rec["metric"] = "fine-tune step, trained tokens/s (%d GPU%s)" % (world, "s" if world > 1 else "")
         print(json.dumps(rec), flush=True)
