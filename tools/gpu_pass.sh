@@ -39,7 +39,7 @@ if [[ $STAGES == *bench* ]]; then
   done
 fi
 
-NCU_CMD="python bench.py --batch 16 --new-tokens 4 --steps 1 --warmup 0 --no-cpu-baseline --no-roofline --no-e2e"
+NCU_CMD="python bench.py --batch 16 --new-tokens 4 --steps 1 --warmup 0 --no-cpu-baseline --no-roofline --no-e2e --no-train --no-configs"
 if [[ $STAGES == *list* ]]; then
   # launch list of one whole step (all 32 layers, eager decode loop so that every launch is visible); only this
   # library's kernels (namespace b200) so that torch's weight-initialisation kernels do not eat the launch budget
