@@ -29,8 +29,13 @@ int flash_attn(const AttnArgs& a, int head_dim, cudaStream_t stream) {
 static constexpr int kDecThreads = 256;
 static constexpr int kDecWarps = kDecThreads / 32;
 static constexpr int kDecMaxCtx = 8192;  // per split chunk, scores staged in smem
+static constexpr int kDecDefaultOcc = 4;  // resident CTAs per SM the kernel is register-bounded for (see below)
 
-__global__ void __launch_bounds__(kDecThreads) decode_attn_kernel(const DecodeArgs a) {
+// MINB: resident CTAs per SM the register allocation is bounded for. 52 registers (no bound) allow 4 CTAs = 32 warps per
+// SM; 40 registers 6 CTAs, 32 registers 8 CTAs (a few bytes of spill outside the streaming loops). More resident warps
+// = more 16-byte loads in flight per SM for this pure-streaming kernel (timed: tools/decode_attn_bench.py).
+template <int MINB>
+__global__ void __launch_bounds__(kDecThreads, MINB) decode_attn_kernel(const DecodeArgs a) {
   extern __shared__ float dec_smem[];
   float* sc = dec_smem;                       // [chunk] scores / probabilities
   __shared__ float red[kDecWarps];
@@ -197,20 +202,28 @@ int decode_attn(DecodeArgs a, void* workspace, size_t workspace_bytes, cudaStrea
     a.part_ml = a.part_o + static_cast<size_t>(a.B) * a.H * a.splits * 128;
   }
   const int smem = chunk * sizeof(float);
+  // resident CTAs per SM (see the kernel): B200_ATTN_OCC = 4 | 6 | 8
+  static const int occ = [] {
+    const char* e = getenv("B200_ATTN_OCC");
+    const int v = e != nullptr ? atoi(e) : kDecDefaultOcc;
+    return (v == 6 || v == 8) ? v : 4;
+  }();
   static bool cfg = false;
   if (!cfg) {
-    B200_CUDA_OK(cudaFuncSetAttribute(decode_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      kDecMaxCtx * (int)sizeof(float)));
-    // experiment knob (tools/corun_bench.py): ask for the same L1 / shared split as the tcgen05 GEMMs so that an SM
-    // needs no reconfiguration to hold both (the kernel streams K / V once: L1 capacity is irrelevant to it)
-    const char* e = getenv("B200_ATTN_CARVEOUT");
-    if (e != nullptr && e[0] == '1')
-      B200_CUDA_OK(cudaFuncSetAttribute(decode_attn_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                        cudaSharedmemCarveoutMaxShared));
+    const int bytes = kDecMaxCtx * (int)sizeof(float);
+    B200_CUDA_OK(cudaFuncSetAttribute(decode_attn_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    B200_CUDA_OK(cudaFuncSetAttribute(decode_attn_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    B200_CUDA_OK(cudaFuncSetAttribute(decode_attn_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     cfg = true;
   }
   LaunchScope scope(kFamDecodeAttn, stream, 0.0, 0.0, a.splits > 1 ? 2 : 1);  // bytes depend on the device-side ctx
-  B200_CUDA_OK(launch_ex(decode_attn_kernel, dim3(a.B * a.H, a.splits), dim3(kDecThreads), smem, stream, 0, true, a));
+  const dim3 grid(a.B * a.H, a.splits), block(kDecThreads);
+  if (occ == 8)
+    B200_CUDA_OK(launch_ex(decode_attn_kernel<8>, grid, block, smem, stream, 0, true, a));
+  else if (occ == 6)
+    B200_CUDA_OK(launch_ex(decode_attn_kernel<6>, grid, block, smem, stream, 0, true, a));
+  else
+    B200_CUDA_OK(launch_ex(decode_attn_kernel<4>, grid, block, smem, stream, 0, true, a));
   if (a.splits > 1)
     B200_CUDA_OK(launch_ex(decode_combine_kernel, dim3(a.B * a.H), dim3(128), 0, stream, 0, true, a));
   return 0;

@@ -26,13 +26,16 @@ namespace b200 {
 static constexpr int kBM = 128;
 static constexpr int kBK = 64;  // 64 bf16 = 128 B = one swizzle row
 static constexpr int kGemmThreads = 192;
-static constexpr int kRasterGroupM = 16;
+static constexpr int kRasterGroupM = 16;  // legacy raster (B200_RASTER_MB=0): groups of 16 M tiles
 
 struct GemmArgs {
   void* C;
   int ldc;
   int M, N, K;
   int m_tiles, n_tiles;
+  // rasterisation (tile_coords): raster_n = 0 -> groups of raster_group consecutive M tiles walk over all N tiles (their
+  // A panel stays L2-resident, B streams once per group); raster_n = 1 -> groups of N tiles walk over all M tiles
+  int raster_n, raster_group;
   // operand majors: 0 = K-major ([rows, K], the nn.Linear forward layout), 1 = MN-major (the matrix is stored
   // [K, rows]: the transposed operands of the backward GEMMs dX = dY W and dW = dY^T X, read in place)
   int a_mn, b_mn;
@@ -62,15 +65,27 @@ struct GemmCfg {
                 "two CTAs per SM: TMEM columns and shared memory of both must fit");
 };
 
-__device__ __forceinline__ void tile_coords(int tile, int m_tiles, int n_tiles, int& mt, int& nt) {
-  // grouped rasterisation: kRasterGroupM consecutive M tiles share every B tile while it is L2-hot
-  const int per_group = kRasterGroupM * n_tiles;
-  const int group = tile / per_group;
-  const int first_m = group * kRasterGroupM;
-  const int gsize = min(kRasterGroupM, m_tiles - first_m);
-  const int r = tile - group * per_group;
-  mt = first_m + r % gsize;
-  nt = r / gsize;
+__device__ __forceinline__ void tile_coords(int tile, const GemmArgs& g, int& mt, int& nt) {
+  // grouped rasterisation: the tiles of a group share one operand panel while it is L2-hot (sizes chosen on the host,
+  // gemm_bf16_ex: the panel that is kept fits the L2 budget, the other operand is streamed once per group)
+  const int G = g.raster_group;
+  if (g.raster_n == 0) {
+    const int per_group = G * g.n_tiles;
+    const int group = tile / per_group;
+    const int first_m = group * G;
+    const int gsize = min(G, g.m_tiles - first_m);
+    const int r = tile - group * per_group;
+    mt = first_m + r % gsize;
+    nt = r / gsize;
+  } else {
+    const int per_group = G * g.m_tiles;
+    const int group = tile / per_group;
+    const int first_n = group * G;
+    const int gsize = min(G, g.n_tiles - first_n);
+    const int r = tile - group * per_group;
+    nt = first_n + r % gsize;
+    mt = r / gsize;
+  }
 }
 
 __device__ __forceinline__ float act_apply(float x, int act) {
@@ -129,7 +144,7 @@ __global__ void __launch_bounds__(kGemmThreads, PER_SM)
       int pre = 0;
       if (g.epi.b_const && !g.b_mn && static_cast<int>(blockIdx.x) < num_tiles) {
         int mt, nt;
-        tile_coords(blockIdx.x, g.m_tiles, g.n_tiles, mt, nt);
+        tile_coords(blockIdx.x, g, mt, nt);
         pre = k_blocks < kStages ? k_blocks : kStages;
         for (int kb = 0; kb < pre; ++kb) {
           mbar_expect_tx(&full_bar[kb], Cfg::kStageBytes);
@@ -141,7 +156,7 @@ __global__ void __launch_bounds__(kGemmThreads, PER_SM)
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         int mt, nt;
-        tile_coords(tile, g.m_tiles, g.n_tiles, mt, nt);
+        tile_coords(tile, g, mt, nt);
         for (int kb = 0; kb < k_blocks; ++kb) {
           const bool b_done = pre > 0;  // this stage's weight tile (and its expect_tx) was issued above
           if (b_done) --pre;
@@ -210,7 +225,7 @@ __global__ void __launch_bounds__(kGemmThreads, PER_SM)
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       int mt, nt;
-      tile_coords(tile, g.m_tiles, g.n_tiles, mt, nt);
+      tile_coords(tile, g, mt, nt);
       const int buf = it & 1;
       mbar_wait(&tmem_full[buf], (it >> 1) & 1u);
       tc_fence_after_sync();
@@ -464,6 +479,33 @@ int gemm_bf16_ex(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, int b
   g.a_mn = a_mn ? 1 : 0;
   g.b_mn = b_mn ? 1 : 0;
   g.epi = epi;
+  {
+    // Raster choice. DRAM traffic of a grouped raster = (kept operand, once) + (streamed operand) x (number of groups);
+    // the kept panel must stay in the 126 MB L2 next to the stream, so it gets a budget (default 40 MB; the round-1
+    // raster -- 16 M tiles per group whatever K -- re-read the 180 MB gate_up weights 6.5 times per prefill chunk:
+    // 1.37 GB of DRAM reads against 0.29 GB algorithmic, profiles/r2_ncu_gemm256llm.txt). B200_RASTER_MB=0 restores it.
+    static const int budget_mb = [] {
+      const char* e = getenv("B200_RASTER_MB");
+      return e != nullptr ? atoi(e) : 40;
+    }();
+    g.raster_n = 0;
+    g.raster_group = kRasterGroupM;
+    if (budget_mb > 0) {
+      const double budget = budget_mb * 1048576.0;
+      const double a_tile = 2.0 * kBM * K, b_tile = 2.0 * bn * K;
+      const double a_all = a_tile * g.m_tiles, b_all = b_tile * g.n_tiles;
+      auto clampi = [](double v, int hi) { return v < 1.0 ? 1 : (v > hi ? hi : static_cast<int>(v)); };
+      const int gm = clampi(budget / a_tile, g.m_tiles), gn = clampi(budget / b_tile, g.n_tiles);
+      const int groups_m = (g.m_tiles + gm - 1) / gm, groups_n = (g.n_tiles + gn - 1) / gn;
+      const double cost_m = a_all + b_all * groups_m, cost_n = b_all + a_all * groups_n;
+      if (cost_n < cost_m) {
+        g.raster_n = 1;
+        g.raster_group = (g.n_tiles + groups_n - 1) / groups_n;   // equal-sized groups
+      } else {
+        g.raster_group = (g.m_tiles + groups_m - 1) / groups_m;
+      }
+    }
+  }
   CUtensorMap tmA, tmB;
   if (a_mn)
     B200_TRY(make_tmap_2d(&tmA, A, K, M, lda, 64));
