@@ -52,6 +52,9 @@ def parse_args():
     p.add_argument("--no-roofline", action="store_true")
     p.add_argument("--cpu-decode-steps", type=int, default=4)
     p.add_argument("--no-configs", action="store_true", help="skip the configs[2] / configs[3] sub-records")
+    p.add_argument("--subrecord-timeout", type=float, default=300.0, help="seconds each sub-record phase "
+                   "(other configs, fine-tune step) may take before the headline line is printed without it")
+    p.add_argument("--cfg4-batch", type=int, default=64, help="samples per GPU of the configs[3] sub-record")
     p.add_argument("--config-steps", type=int, default=2)
     p.add_argument("--config-batch", type=int, default=64, help="samples per GPU per step of the configs[2] sub-record")
     p.add_argument("--no-pin", action="store_true", help="N > 1: do not pin every rank to its own slice of host cores")
@@ -326,25 +329,8 @@ def run_b200(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_reference_sample(args, layers=args.layers)
 
-    # ---- BASELINE configs[2] and configs[3] at the same N GPUs: short device-timed regions of their own (1 warm-up +
-    #      `--config-steps` steps each, max over ranks), reported as sub-records next to the headline configs[1] line
-    other = None
-    if not args.no_configs:
-        if world > 1:
-            model.set_process_group(dist.group.WORLD, exchange=exchange)
-        other = other_config_records(args, cfg, model, dev, rank, world, exchange, timed)
-
-    # ---- BASELINE configs[4]: the fine-tune step at the same N GPUs, AFTER the timed inference region (its own
-    #      device-timed region, max over ranks). The inference model and its buffers are released first.
-    train = None
-    if not args.no_train:
-        model.set_process_group(None)
-        del model, images_dev
-        import gc as _gc
-        _gc.collect()
-        torch.cuda.empty_cache()
-        train = finetune_record(args, cfg, dev, dist.group.WORLD if world > 1 else None)
-
+    # ---- the headline line is complete here; what follows can only ADD sub-records to it
+    line = None
     if rank == 0:
         flops = algorithmic_flops_per_inference(args.views, L_packed, args.new_tokens)
         line = {
@@ -377,16 +363,88 @@ def run_b200(args):
             line["roofline"] = roof
         if cpu is not None:
             line["cpu_baseline"] = cpu
-        if other is not None:
+
+    # Sub-records run under a watchdog: if one of them does not finish within its budget (a hung collective cannot be
+    # interrupted from Python), rank 0 prints the headline line as it stands -- with the phase that timed out named in
+    # it -- and every rank leaves with exit code 0. The sub-records can never cost the driver its headline number.
+    dog = SubRecordWatchdog(rank, line)
+    progress = lambda msg: print("[bench %.0fs] rank %d: %s" % (time.time() - t0, rank, msg), file=sys.stderr, flush=True)
+
+    # ---- BASELINE configs[2] and configs[3] at the same N GPUs: short device-timed regions of their own (1 warm-up +
+    #      `--config-steps` steps each, max over ranks), reported as sub-records next to the headline configs[1] line
+    if not args.no_configs:
+        dog.arm("other_configs", args.subrecord_timeout)
+        progress("configs[2] / configs[3] sub-records")
+        if world > 1:
+            model.set_process_group(dist.group.WORLD, exchange=exchange)
+        other = other_config_records(args, cfg, model, dev, rank, world, exchange, timed, progress)
+        dog.disarm()
+        if line is not None:
             line["other_configs"] = other
-        if train is not None:
+
+    # ---- BASELINE configs[4]: the fine-tune step at the same N GPUs, AFTER the timed inference region (its own
+    #      device-timed region, max over ranks). The inference model and its buffers are released first.
+    if not args.no_train:
+        dog.arm("train", args.subrecord_timeout)
+        progress("fine-tune sub-record")
+        model.set_process_group(None)
+        del model, images_dev
+        import gc as _gc
+        _gc.collect()
+        torch.cuda.empty_cache()
+        train = finetune_record(args, cfg, dev, dist.group.WORLD if world > 1 else None)
+        dog.disarm()
+        if line is not None:
             line["train"] = train
+    progress("done")
+
+    if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
+        dog.arm("destroy_process_group", 60, print_line=False)
         dist.destroy_process_group()
+        dog.disarm()
 
 
-def other_config_records(args, cfg, model, dev, rank, world, exchange, timed):
+class SubRecordWatchdog:
+    """Deadline for the optional sub-records of the bench line (see run_b200). arm(phase, seconds) starts the clock;
+    when it runs out rank 0 prints the line built so far with "sub_records_timed_out": phase and every rank calls
+    os._exit(0) -- the only way out of a hung collective."""
+
+    def __init__(self, rank, line):
+        import threading
+        self.rank, self.line = rank, line
+        self.lock = threading.Lock()
+        self.deadline = None
+        self.phase = None
+        self.print_line = True
+        t = threading.Thread(target=self._run, daemon=True)
+        t.start()
+
+    def arm(self, phase, seconds, print_line=True):
+        with self.lock:
+            self.phase, self.deadline, self.print_line = phase, time.time() + float(seconds), print_line
+
+    def disarm(self):
+        with self.lock:
+            self.deadline = None
+
+    def _run(self):
+        while True:
+            time.sleep(1.0)
+            with self.lock:
+                expired = self.deadline is not None and time.time() > self.deadline
+                phase, print_line = self.phase, self.print_line
+            if expired:
+                print("[bench] rank %d: sub-record phase %r exceeded its time budget; leaving" % (self.rank, phase),
+                      file=sys.stderr, flush=True)
+                if self.rank == 0 and self.line is not None and print_line:
+                    self.line["sub_records_timed_out"] = phase
+                    print(json.dumps(self.line), flush=True)
+                os._exit(0)
+
+
+def other_config_records(args, cfg, model, dev, rank, world, exchange, timed, progress=lambda m: None):
     """configs[2]: per sample 6 RGB views + 6 depth + 6 seg-mask renderings = 18 encoder passes, an audio embedding and
     three 32x32 class maps -> fused token pack with T_vis = 580, prefill, 256 greedy tokens. Mapping as in SURVEY.md 8d /
     tests/test_gpu_zzz_baseline_configs.py: the reference has no depth / seg-mask IMAGE input, so the 12 extra frames go
@@ -424,6 +482,7 @@ def other_config_records(args, cfg, model, dev, rank, world, exchange, timed):
         model.encode_images_pooled(extra, [args.views] * (2 * B3), None, None, None)
         return model.generate(b["input_ids"], images=rgb, audio=b["audio"], segmasks=b["segmasks"], **gen_kw)
 
+    progress("configs[2]: inputs ready, timing")
     record("configs[2]", cfg3_step, B3,
            "6-view RGB + depth + seg-mask renderings (18 ViT passes, 3 pooler passes per sample) + audio token + 3 "
            "class-map tokens, T_vis = 580, prefill + %d greedy tokens" % args.new_tokens)
@@ -431,7 +490,7 @@ def other_config_records(args, cfg, model, dev, rank, world, exchange, timed):
     torch.cuda.empty_cache()
 
     # configs[3]: 64 samples + 384 images per GPU, neighbour's slice decoded
-    B4 = 64
+    B4 = args.cfg4_batch
     shift = 1 if world > 1 else 0
     if world > 1:
         model.set_process_group(dist.group.WORLD, exchange=exchange, decode_shift=shift)
@@ -440,6 +499,7 @@ def other_config_records(args, cfg, model, dev, rank, world, exchange, timed):
     theirs = mine if owner == rank else synth_batch(cfg, B4, args.views, args.text_len, seed=500 + owner, jitter=0,
                                                     image_pos=40, dtype=torch.bfloat16)
     img4 = torch.stack(mine["images"]).to(dev)
+    progress("configs[3]: inputs ready, timing")
     record("configs[3]", lambda: model.generate(theirs["input_ids"], images=img4, **gen_kw), B4,
            "temporal clips: 64 samples (8 clips x 8 frames) x 6 views = 384 images per GPU; visual tokens all-gathered "
            "(%s), every rank decodes the slice rank + %d encoded; %d greedy tokens"

@@ -80,8 +80,12 @@ def host_side_group(group):
     """A gloo group over the ranks of `group` for tiny host-side agreements (a few flags per step). Exchanging them
     through NCCL would put the all-reduce behind the whole backward on the stream and make the host wait for it --
     i.e. serialise the Python launch loop of the optimizer step with the GPU (measured: ~100 ms per fine-tune step)."""
+    import os
     if dist.get_backend(group) == "gloo":
         return group
+    if os.environ.get("MASTER_ADDR", "") in ("127.0.0.1", "localhost", "::1"):
+        # one node: gloo must not try to resolve the container's hostname (it may not resolve): use the loopback device
+        os.environ.setdefault("GLOO_SOCKET_IFNAME", "lo")
     return dist.new_group(ranks=dist.get_process_group_ranks(group), backend="gloo")
 
 
@@ -109,21 +113,37 @@ def align_optional_gradients(grads, optional, group=None, host_group=None):
 
 
 class PeerGather:
-    """Symmetric (world, B_local, T, D) bf16 buffer on every rank with every peer's base pointer, for the fused
-    projector-GEMM + all-gather epilogue. Needs CUDA, NVLink peer access and torch symmetric memory."""
+    """Symmetric bf16 buffer on every rank, viewed as (world, B_local, T, D), with every peer's base pointer, for the
+    fused projector-GEMM + all-gather epilogue. Needs CUDA, NVLink peer access and torch symmetric memory.
+    The allocation (a collective rendezvous) happens once per capacity: a call with another batch geometry that fits
+    the capacity only re-views the same memory (`set_shape`), so successive workloads of different shapes -- the bench
+    runs configs[1], then configs[2] (580 tokens x 64 samples), then configs[3] -- never allocate a second symmetric
+    buffer next to a live one (which hung on 2 and 8 GPUs when it was tried, round 2)."""
 
-    def __init__(self, b_local, t_vis, hidden, group=None):
+    def __init__(self, b_local, t_vis, hidden, group=None, capacity=0):
         import torch.distributed._symmetric_memory as symm
         self.group = group if group is not None else dist.group.WORLD
         self.world = dist.get_world_size(self.group)
         self.rank = dist.get_rank(self.group)
-        self.shape = (self.world, b_local, t_vis, hidden)
-        self.buf = symm.empty(self.shape, dtype=torch.bfloat16, device=torch.device("cuda", torch.cuda.current_device()))
-        self.hdl = symm.rendezvous(self.buf, self.group)
+        self.capacity = max(int(capacity), self.world * b_local * t_vis * hidden)
+        self.flat = symm.empty((self.capacity,), dtype=torch.bfloat16,
+                               device=torch.device("cuda", torch.cuda.current_device()))
+        self.hdl = symm.rendezvous(self.flat, self.group)
         self.peer_ptrs = [int(p) for p in self.hdl.buffer_ptrs]
         if len(self.peer_ptrs) != self.world:
             raise RuntimeError("symmetric memory rendezvous returned %d peers for world %d"
                                % (len(self.peer_ptrs), self.world))
+        self.set_shape(b_local, t_vis, hidden)
+
+    def fits(self, b_local, t_vis, hidden):
+        return self.world * b_local * t_vis * hidden <= self.capacity
+
+    def set_shape(self, b_local, t_vis, hidden):
+        """Re-view the buffer for another batch geometry (same on every rank); no allocation, no collective."""
+        if not self.fits(b_local, t_vis, hidden):
+            raise ValueError("PeerGather: geometry exceeds the allocated capacity")
+        self.shape = (self.world, b_local, t_vis, hidden)
+        self.buf = self.flat[:self.world * b_local * t_vis * hidden].view(self.shape)
 
     def slot_offset_bytes(self):
         """Byte offset of this rank's (B_local, T, D) slot inside every peer's buffer."""

@@ -468,8 +468,12 @@ class LlavaLlamaForCausalLM:
         Dh = self.config.hidden_size
         proj = self.model.mm_projector
         if self._exchange == "peer":
-            if self._peer is None or self._peer.shape != (world, B, t_vis, Dh):
-                self._peer = D_.PeerGather(B, t_vis, Dh, self._pg)
+            if self._peer is None or not self._peer.fits(B, t_vis, Dh):
+                grow = 0 if self._peer is None else self._peer.capacity
+                self._peer = None                     # release the old buffer BEFORE the new rendezvous
+                self._peer = D_.PeerGather(B, t_vis, Dh, self._pg, capacity=grow)
+            elif self._peer.shape != (world, B, t_vis, Dh):
+                self._peer.set_shape(B, t_vis, Dh)    # same memory, other geometry: no allocation, no collective
             pg = self._peer
             pg.barrier()                              # every reader of the previous step's tokens is done
             lib = L.lib()

@@ -127,7 +127,9 @@ def forward_backward(model, embeds, labels, lengths, vocab_weight=None, grad_sca
 
     def slot(name, shape):
         if name not in g:
-            g[name] = torch.zeros(shape, device=dev, dtype=torch.float32)
+            # every slot of the decoder is written in full by its first producer (a GEMM or the norm backward with
+            # accumulate = False): no memset of the 27 GB gradient set
+            g[name] = torch.empty(shape, device=dev, dtype=torch.float32)
             return g[name], False
         return g[name], accumulate
 

@@ -51,6 +51,17 @@ def _worker(rank, world, port, exchange, q):
                                              stop_on_eos=False, return_logits=True)
         torch.cuda.synchronize()
         ok = torch.equal(out_ids, ref_ids) and torch.equal(out_lg, ref_lg)
+        # another batch geometry on the same model (one sample per rank): the symmetric buffer is re-viewed, not
+        # re-allocated (dist.PeerGather.set_shape) -- a second symmetric allocation next to a live one hung the bench's
+        # sub-records on 2 and 8 GPUs
+        model.set_process_group(None)
+        ref1, ref1_lg = model.generate(theirs["input_ids"][:1], images=theirs["images"][:1], max_new_tokens=4,
+                                       stop_on_eos=False, return_logits=True)
+        model.set_process_group(dist.group.WORLD, exchange=exchange, decode_shift=1)
+        out1, out1_lg = model.generate(theirs["input_ids"][:1], images=mine["images"][:1], max_new_tokens=4,
+                                       stop_on_eos=False, return_logits=True)
+        torch.cuda.synchronize()
+        ok = ok and torch.equal(out1, ref1) and torch.equal(out1_lg, ref1_lg)
         q.put((rank, "ok" if ok else "mismatch: max |dlogit| %g" % (out_lg - ref_lg).abs().max().item()))
         dist.barrier()
         dist.destroy_process_group()
