@@ -2,7 +2,8 @@
 `process_images(images, image_processor, model_cfg)` (LLaVA/llava/mm_utils.py:29-40) for image_aspect_ratio 'pad' (the
 MM2SG setting) and for the plain CLIPImageProcessor path: expand2square with the CLIP mean colour, PIL-exact bicubic
 resize to 336 on the shortest edge, centre crop, rescale, normalise, bf16 -- one call of b200_preprocess_images per
-batch of equally sized frames. The host only decodes the JPEGs and computes the (cached) resampling tables.
+batch of equally sized frames. The host computes the (cached) resampling tables and, by default, decodes the JPEGs
+with Pillow like the reference; frames passed as compressed `bytes` are decoded on the GPU by nvJPEG (jpeg.py).
 
 The tables follow Pillow's precompute_coeffs / normalize_coeffs_8bpc (src/libImaging/Resample.c, Pillow is a
 dependency of the reference through transformers' CLIPImageProcessor): bicubic a = -0.5, support 2 * max(scale, 1),
@@ -66,6 +67,7 @@ class GpuImageProcessor:
         self.device = torch.device(device)
         self._dev_tables = {}
         self._ws = L.Workspace()
+        self._jpeg = None
 
     def _table(self, in_size, out_size):
         key = (in_size, out_size)
@@ -75,9 +77,16 @@ class GpuImageProcessor:
         return self._dev_tables[key]
 
     def preprocess(self, images, pad=True):
-        """images: list of equally sized RGB frames (PIL images, uint8 HWC numpy arrays or uint8 HWC tensors), or one
-        (N, H, W, 3) uint8 array / tensor. Returns (N, 3, size, size) bf16 on the device."""
-        if isinstance(images, (list, tuple)):
+        """images: list of equally sized RGB frames (PIL images, uint8 HWC numpy arrays or uint8 HWC tensors), a list
+        of JPEG files as `bytes` (decoded on the GPU with nvJPEG, mm_or_b200/jpeg.py), or one (N, H, W, 3) uint8
+        array / tensor. Returns (N, 3, size, size) bf16 on the device."""
+        if isinstance(images, (list, tuple)) and len(images) and isinstance(images[0], (bytes, bytearray, memoryview)):
+            # compressed JPEG files: decoded on the GPU by nvJPEG (mm_or_b200/jpeg.py; opt-in by passing bytes)
+            if self._jpeg is None:
+                from .jpeg import GpuJpegDecoder
+                self._jpeg = GpuJpegDecoder(self.device)
+            batch = self._jpeg.decode_batch(images)
+        elif isinstance(images, (list, tuple)):
             frames = []
             for im in images:
                 if hasattr(im, "convert"):                              # PIL
