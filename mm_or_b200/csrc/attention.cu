@@ -43,7 +43,6 @@ __global__ void __launch_bounds__(kDecThreads, MINB) decode_attn_kernel(const De
   __shared__ float q_s[128];
 
   griddep_wait();  // q / the new cache slot (rope_kv_kernel) and *ctx_dev (previous step) must be complete
-  griddep_launch();
   const int bh = blockIdx.x;
   const int b = bh / a.H, h = bh % a.H;
   const int split = blockIdx.y;
@@ -133,6 +132,9 @@ __global__ void __launch_bounds__(kDecThreads, MINB) decode_attn_kernel(const De
     acc[6] += p * bf16lo(u.w);
     acc[7] += p * bf16hi(u.w);
   }
+  // late programmatic-launch trigger: this CTA has streamed its K and V (4096 CTAs run in ~7 waves; successors parked
+  // in griddepcontrol.wait must not take CTA slots from the later waves, see gemm_skinny.cu)
+  griddep_launch();
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 16);
   if (lane < 16) {

@@ -130,7 +130,6 @@ __global__ void __launch_bounds__(kSkThreads, (SkinnyCfg<MT, STAGES>::kSmemBytes
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
-  griddep_launch();  // (every thread; a no-op without programmatic dependent launch)
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
@@ -179,6 +178,11 @@ __global__ void __launch_bounds__(kSkThreads, (SkinnyCfg<MT, STAGES>::kSmemBytes
         }
       }
       if (kb1 > kb0) umma_commit(tmem_full);  // fires when every MMA above has completed (and has read its smem)
+      // Programmatic dependent launch, LATE trigger: the next kernel may be scheduled once every CTA of this grid has
+      // issued its last MMA -- its prologue then overlaps this kernel's drain + epilogue only. (Round 1 triggered at
+      // kernel entry: the successors' CTAs, parked in griddepcontrol.wait, held shared memory and CTA slots that the
+      // running kernel's later waves needed, and the step got 4 % slower.) A no-op without the launch attribute.
+      griddep_launch();
     }
   } else {
     // ===================== epilogue warps 2..5: drain TMEM =====================

@@ -135,7 +135,6 @@ __global__ void __launch_bounds__(kGemmThreads, PER_SM)
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
-  griddep_launch();  // (every thread; a no-op without programmatic dependent launch)
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
@@ -216,6 +215,8 @@ __global__ void __launch_bounds__(kGemmThreads, PER_SM)
         }
         umma_commit(&tmem_full[buf]);  // accumulator complete
       }
+      // late programmatic-launch trigger: after the last MMA of this CTA's last tile (see gemm_skinny.cu)
+      griddep_launch();
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
