@@ -652,10 +652,14 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": reps,
             "warmup": 0, "ms_per_step": round(1e3 / v, 1), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "configs[1] on host cores through the CPU oracle (port of the reference's PyTorch "
-                                   "path): bounded sample per step, see cpu_baseline.sample",
-                       "views": args.views, "text_tokens": args.text_len, "new_tokens": args.new_tokens,
-                       "decoder_layers": args.layers},
+            # the same workload as the B200 arm's config (one inference per step instead of 128 per GPU)
+            "config": {"workload": "configs[1]: 6-view 336x336 RGB -> CLIP ViT-L/14 (23 layers) + BERT pooler + "
+                                   "mlp2x_gelu projector + Llama-7B prefill + %d-token greedy decode" % args.new_tokens,
+                       "samples_per_step": 1, "views": args.views, "text_tokens": args.text_len,
+                       "packed_len": args.text_len - 1 + 576, "new_tokens": args.new_tokens,
+                       "decoder_layers": args.layers, "weights": "random-init, bf16",
+                       "arm": "host cores, CPU oracle (port of the reference's PyTorch path), whole inference timed, "
+                              "see cpu_baseline.sample"},
             "cpu_baseline": dict(last, value=v),
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
