@@ -59,6 +59,9 @@ int b200_prof_collect(double* ms, double* alg_bytes, double* alg_flops, long lon
  *                  1: one CTA per SM, widths {96, 128, 160, 224, 256} (12288 / 96 = 128 tiles, 22016 / 160 = 138,
  *                  32000 / 224 = 143 on 148 SMs); 2: two CTAs per SM with half-depth rings, widths {64, 96, 128}
  *                  (192 / 230 / 250 tiles on 296 slots).
+ *   "fused_rope"   (B200_FUSED_ROPE=0|1, default 1): RoPE of q / k and the KV-cache append of a decode step run inside
+ *                  the decode attention kernel (one launch less per layer) whenever the step has enough (row, head)
+ *                  pairs to fill the chip without splitting the context; 0 runs the separate RoPE kernel.
  * b200_set_option returns 0, or -2 for an unknown name / value; b200_get_option returns the value, or -2. */
 int b200_set_option(const char* name, int value);
 int b200_get_option(const char* name);

@@ -493,7 +493,7 @@ def set_option(name, value=True):
 
 
 def get_option(name):
-    """Value of a switch: False / True for "pdl"; 0 / 1 / 2 for "decode_tiles" (falsy when off either way)."""
+    """Value of a switch: False / True for "pdl" and "fused_rope"; 0 / 1 / 2 for "decode_tiles"."""
     v = int(lib().b200_get_option(name.encode()))
     if v < 0:
         check(v, "b200_get_option")

@@ -29,18 +29,19 @@ int flash_attn(const AttnArgs& a, int head_dim, cudaStream_t stream) {
 static constexpr int kDecThreads = 256;
 static constexpr int kDecWarps = kDecThreads / 32;
 static constexpr int kDecMaxCtx = 8192;  // per split chunk, scores staged in smem
-static constexpr int kDecDefaultOcc = 4;  // resident CTAs per SM the kernel is register-bounded for (see below)
 
-// MINB: resident CTAs per SM the register allocation is bounded for. 52 registers (no bound) allow 4 CTAs = 32 warps per
-// SM; 40 registers 6 CTAs, 32 registers 8 CTAs (a few bytes of spill outside the streaming loops). More resident warps
-// = more 16-byte loads in flight per SM for this pure-streaming kernel (timed: tools/decode_attn_bench.py).
-template <int MINB>
-__global__ void __launch_bounds__(kDecThreads, MINB) decode_attn_kernel(const DecodeArgs a) {
+// Register-bounded for 4 resident CTAs per SM (<= 64 registers): 6.25-6.5 TB/s at the benchmark's geometry; bounding it
+// for 6 / 8 CTAs (40 / 32 registers, small spills) measured 5.6-5.9 TB/s (profiles/r2_decode_attn_occupancy.json).
+// ROPE: fused RoPE + KV append of the decode step (DecodeArgs::rope_k, common.h), splits == 1.
+template <bool ROPE>
+__global__ void __launch_bounds__(kDecThreads, 4) decode_attn_kernel(const DecodeArgs a) {
   extern __shared__ float dec_smem[];
   float* sc = dec_smem;                       // [chunk] scores / probabilities
   __shared__ float red[kDecWarps];
   __shared__ float red_o[kDecWarps][128];
   __shared__ float q_s[128];
+  __shared__ float kn_s[ROPE ? 128 : 1];      // the step's new key (rotated, bf16-rounded) and value
+  __shared__ float vn_s[ROPE ? 128 : 1];
 
   griddep_wait();  // q / the new cache slot (rope_kv_kernel) and *ctx_dev (previous step) must be complete
   const int bh = blockIdx.x;
@@ -57,8 +58,44 @@ __global__ void __launch_bounds__(kDecThreads, MINB) decode_attn_kernel(const De
   const int k1 = min(ctx, k0 + per);
   const int n = max(0, k1 - k0);
 
-  if (threadIdx.x < 128) q_s[threadIdx.x] = __bfloat162float(a.q[b * a.q_rs + h * 128 + threadIdx.x]);
+  if (!ROPE) {
+    if (threadIdx.x < 128) q_s[threadIdx.x] = __bfloat162float(a.q[b * a.q_rs + h * 128 + threadIdx.x]);
+  } else {
+    // the token of this step lives at slot ctx - 1; rotary position = slot - kv_start (clamped like rope_kv_kernel)
+    const int slot = ctx - 1;
+    int p = slot - start;
+    p = p < 0 ? 0 : (p >= a.max_pos ? a.max_pos - 1 : p);
+    const long long cache_row = ((static_cast<long long>(b) * a.H + h) * a.cap + slot) * 128;
+    const int t = threadIdx.x;
+    if (t < 128) {
+      // threads 0..63 rotate q, 64..127 the new key: pair (i, i + 64), same arithmetic as rope_kv_kernel, results
+      // rounded to bf16 like the values that kernel stores
+      const int i = t & 63;
+      const bf16* src = (t < 64 ? a.q : a.rope_k) + b * a.q_rs + h * 128;
+      const float x = __bfloat162float(src[i]), y = __bfloat162float(src[i + 64]);
+      const float cs = a.cos_t[static_cast<long long>(p) * 64 + i], sn = a.sin_t[static_cast<long long>(p) * 64 + i];
+      const bf16 lo = __float2bfloat16(x * cs - y * sn), hi = __float2bfloat16(y * cs + x * sn);
+      if (t < 64) {
+        q_s[i] = __bfloat162float(lo);
+        q_s[i + 64] = __bfloat162float(hi);
+      } else {
+        kn_s[i] = __bfloat162float(lo);
+        kn_s[i + 64] = __bfloat162float(hi);
+        if (slot >= 0) {
+          a.kc_w[cache_row + i] = lo;
+          a.kc_w[cache_row + i + 64] = hi;
+        }
+      }
+    } else {
+      const int i = t - 128;
+      const bf16 v = a.rope_v[b * a.q_rs + h * 128 + i];
+      vn_s[i] = __bfloat162float(v);
+      if (slot >= 0) a.vc_w[cache_row + i] = v;
+    }
+  }
   __syncthreads();
+  // with the fusion the last key of the context (the one appended above) is scored from shared memory
+  const int ng = (ROPE && n > 0) ? n - 1 : n;
 
   const bf16* kbase = a.kc + (static_cast<long long>(b) * a.H + h) * a.cap * 128;
   const bf16* vbase = a.vc + (static_cast<long long>(b) * a.H + h) * a.cap * 128;
@@ -69,9 +106,9 @@ __global__ void __launch_bounds__(kDecThreads, MINB) decode_attn_kernel(const De
 #pragma unroll
   for (int j = 0; j < 16; ++j) qreg[j] = q_s[sub * 16 + j];
   float lmax = -INFINITY;
-  for (int base = warp * 4; base < n; base += kDecWarps * 4) {  // warp-uniform trip count (shuffles inside)
+  for (int base = warp * 4; base < ng; base += kDecWarps * 4) {  // warp-uniform trip count (shuffles inside)
     const int i = base + kq;
-    const bool ok = i < n;
+    const bool ok = i < ng;
     float acc = 0.f;
     if (ok) {
       const uint4* kp = reinterpret_cast<const uint4*>(kbase + static_cast<long long>(k0 + i) * 128 + sub * 16);
@@ -89,6 +126,15 @@ __global__ void __launch_bounds__(kDecThreads, MINB) decode_attn_kernel(const De
       if (sub == 0) sc[i] = acc;
       lmax = fmaxf(lmax, acc);
     }
+  }
+  if (ROPE && n > 0 && warp == 0) {  // the new key: q . k from shared memory (4 dims per lane)
+    float acc = q_s[lane * 4] * kn_s[lane * 4] + q_s[lane * 4 + 1] * kn_s[lane * 4 + 1] +
+                q_s[lane * 4 + 2] * kn_s[lane * 4 + 2] + q_s[lane * 4 + 3] * kn_s[lane * 4 + 3];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    acc *= a.scale_log2;
+    if (lane == 0) sc[n - 1] = acc;
+    lmax = fmaxf(lmax, acc);
   }
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, off));
@@ -120,7 +166,7 @@ __global__ void __launch_bounds__(kDecThreads, MINB) decode_attn_kernel(const De
   float acc[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-  for (int i = warp * 2 + vk; i < n; i += kDecWarps * 2) {
+  for (int i = warp * 2 + vk; i < ng; i += kDecWarps * 2) {
     const float p = sc[i];
     const uint4 u = __ldg(reinterpret_cast<const uint4*>(vbase + static_cast<long long>(k0 + i) * 128 + vsub * 8));
     acc[0] += p * bf16lo(u.x);
@@ -146,6 +192,7 @@ __global__ void __launch_bounds__(kDecThreads, MINB) decode_attn_kernel(const De
     float v = 0.f;
 #pragma unroll
     for (int w = 0; w < kDecWarps; ++w) v += red_o[w][threadIdx.x];
+    if (ROPE && n > 0) v += sc[n - 1] * vn_s[threadIdx.x];  // the appended token's own value
     if (a.splits == 1) {
       const float inv = gsum > 0.f ? 1.f / gsum : 0.f;
       a.o[b * a.o_rs + h * 128 + threadIdx.x] = __float2bfloat16(v * inv);
@@ -204,28 +251,23 @@ int decode_attn(DecodeArgs a, void* workspace, size_t workspace_bytes, cudaStrea
     a.part_ml = a.part_o + static_cast<size_t>(a.B) * a.H * a.splits * 128;
   }
   const int smem = chunk * sizeof(float);
-  // resident CTAs per SM (see the kernel): B200_ATTN_OCC = 4 | 6 | 8
-  static const int occ = [] {
-    const char* e = getenv("B200_ATTN_OCC");
-    const int v = e != nullptr ? atoi(e) : kDecDefaultOcc;
-    return (v == 6 || v == 8) ? v : 4;
-  }();
+  const bool rope = a.rope_k != nullptr;
+  if (rope && (a.splits != 1 || a.rope_v == nullptr || a.kc_w == nullptr || a.vc_w == nullptr || a.cos_t == nullptr ||
+               a.sin_t == nullptr || a.max_pos <= 0))
+    return fail(-2, "decode_attn: the fused RoPE + KV append needs splits == 1 and all of rope_v / kc_w / vc_w / tables");
   static bool cfg = false;
   if (!cfg) {
     const int bytes = kDecMaxCtx * (int)sizeof(float);
-    B200_CUDA_OK(cudaFuncSetAttribute(decode_attn_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    B200_CUDA_OK(cudaFuncSetAttribute(decode_attn_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    B200_CUDA_OK(cudaFuncSetAttribute(decode_attn_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    B200_CUDA_OK(cudaFuncSetAttribute(decode_attn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    B200_CUDA_OK(cudaFuncSetAttribute(decode_attn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     cfg = true;
   }
   LaunchScope scope(kFamDecodeAttn, stream, 0.0, 0.0, a.splits > 1 ? 2 : 1);  // bytes depend on the device-side ctx
   const dim3 grid(a.B * a.H, a.splits), block(kDecThreads);
-  if (occ == 8)
-    B200_CUDA_OK(launch_ex(decode_attn_kernel<8>, grid, block, smem, stream, 0, true, a));
-  else if (occ == 6)
-    B200_CUDA_OK(launch_ex(decode_attn_kernel<6>, grid, block, smem, stream, 0, true, a));
+  if (rope)
+    B200_CUDA_OK(launch_ex(decode_attn_kernel<true>, grid, block, smem, stream, 0, true, a));
   else
-    B200_CUDA_OK(launch_ex(decode_attn_kernel<4>, grid, block, smem, stream, 0, true, a));
+    B200_CUDA_OK(launch_ex(decode_attn_kernel<false>, grid, block, smem, stream, 0, true, a));
   if (a.splits > 1)
     B200_CUDA_OK(launch_ex(decode_combine_kernel, dim3(a.B * a.H), dim3(128), 0, stream, 0, true, a));
   return 0;

@@ -48,6 +48,10 @@ void set_pdl(bool on);
 // 128-column tiles. PDL stays off: it measured 4 % SLOWER (profiles/r2_decode_bench.json).
 int decode_tiles_mode();       // 0 off, 1 widths for one CTA per SM, 2 two CTAs per SM (widths 64 / 96 / 128)
 void set_decode_tiles(int mode);
+// RoPE + KV append fused into the decode attention kernel (DecodeArgs::rope_k) whenever the step does not split the
+// context; default on, B200_FUSED_ROPE=0 / b200_set_option("fused_rope", 0) runs rope_kv_kernel separately.
+bool fused_rope_enabled();
+void set_fused_rope(bool on);
 
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_ex(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
@@ -250,6 +254,17 @@ struct DecodeArgs {
   int splits;  // 0 = choose
   float* part_o;
   float* part_ml;
+  // Fused RoPE + KV append (the decode step, splits == 1 only; all null / 0 otherwise): the kernel of (row b, head h)
+  // rotates q and the step's new key itself (position = slot - kv_start[b], clamped like rope_kv_kernel), appends the
+  // rotated key and the value to the cache at slot ctx - 1, and scores / accumulates that one key from shared memory
+  // -- what rope_kv_kernel + a re-read would do, in one launch less per layer.
+  const bf16* rope_k;   // [B, q_rs]: the new key of head h at h * 128 (un-rotated), or null = no fusion
+  const bf16* rope_v;   // [B, q_rs]: the new value
+  bf16* kc_w;           // the cache again, writable
+  bf16* vc_w;
+  const float* cos_t;   // [max_pos, 64]
+  const float* sin_t;
+  int max_pos;
 };
 size_t decode_attn_workspace_bytes(int B, int H, int splits);
 int decode_attn_pick_splits(int B, int H, int ctx);

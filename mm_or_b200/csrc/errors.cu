@@ -51,6 +51,17 @@ int decode_tiles_mode() {
   }
   return x;
 }
+static std::atomic<int> g_fused_rope{-1};
+bool fused_rope_enabled() {
+  int x = g_fused_rope.load(std::memory_order_relaxed);
+  if (x < 0) {
+    const char* e = getenv("B200_FUSED_ROPE");
+    x = (e != nullptr && e[0] == '0') ? 0 : 1;      // default on
+    g_fused_rope.store(x, std::memory_order_relaxed);
+  }
+  return x != 0;
+}
+void set_fused_rope(bool on) { g_fused_rope.store(on ? 1 : 0, std::memory_order_relaxed); }
 void set_decode_tiles(int mode) { g_decode_tiles.store(mode < 0 ? 0 : (mode > 2 ? 2 : mode), std::memory_order_relaxed); }
 
 // ---------------------------------------------------------------------------------------------
@@ -114,7 +125,8 @@ int b200_set_option(const char* name, int value) {
     if (value < 0 || value > 2) return fail(-2, "b200_set_option: decode_tiles takes 0, 1 or 2 (got %d)", value);
     set_decode_tiles(value);
   }
-  else return fail(-2, "b200_set_option: unknown option '%s' (pdl, decode_tiles)", name);
+  else if (n == "fused_rope") set_fused_rope(value != 0);
+  else return fail(-2, "b200_set_option: unknown option '%s' (pdl, decode_tiles, fused_rope)", name);
   return 0;
 }
 int b200_get_option(const char* name) {
@@ -122,7 +134,8 @@ int b200_get_option(const char* name) {
   const std::string n(name);
   if (n == "pdl") return pdl_enabled() ? 1 : 0;
   if (n == "decode_tiles") return decode_tiles_mode();
-  return fail(-2, "b200_get_option: unknown option '%s' (pdl, decode_tiles)", name);
+  if (n == "fused_rope") return fused_rope_enabled() ? 1 : 0;
+  return fail(-2, "b200_get_option: unknown option '%s' (pdl, decode_tiles, fused_rope)", name);
 }
 
 int b200_prof_enable(int on) {

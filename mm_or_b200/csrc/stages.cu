@@ -280,8 +280,12 @@ static int llama_layer(const b200_llama_weights* w, const b200_llama_layer& Ly, 
   B200_TRY(rmsnorm(x, D, B(Ly.attn_norm), w->rms_eps, nbuf, D, T, D, st));
   GemmEpilogue e;
   B200_TRY(linear(nbuf, D, B(Ly.qkv_w), D, qkv, 3 * D, T, 3 * D, D, e, sk, st));
-  B200_TRY(rope_kv_write(qkv, kv_start, w->rope_cos, w->rope_sin, w->max_pos, kc, vc, Bn, H, L, 0,
-                         decode ? state : nullptr, cap, st));
+  // decode step with enough (row, head) pairs to fill the chip without splitting the context: the attention kernel
+  // rotates q / k and appends k / v itself (DecodeArgs::rope_k) -- one launch less per layer
+  const bool fuse_rope = decode && fused_rope_enabled() && decode_attn_pick_splits(Bn, H, ctx_bound + 1) == 1;
+  if (!fuse_rope)
+    B200_TRY(rope_kv_write(qkv, kv_start, w->rope_cos, w->rope_sin, w->max_pos, kc, vc, Bn, H, L, 0,
+                           decode ? state : nullptr, cap, st));
   if (!decode) {
     AttnArgs at{};
     at.q = qkv;
@@ -323,6 +327,16 @@ static int llama_layer(const b200_llama_weights* w, const b200_llama_layer& Ly, 
     da.finished = finished;
     da.scale_log2 = kLog2e / sqrtf(128.f);
     da.splits = 0;
+    if (fuse_rope) {
+      da.splits = 1;
+      da.rope_k = qkv + D;
+      da.rope_v = qkv + 2 * D;
+      da.kc_w = kc;
+      da.vc_w = vc;
+      da.cos_t = w->rope_cos;
+      da.sin_t = w->rope_sin;
+      da.max_pos = w->max_pos;
+    }
     B200_TRY(decode_attn(da, dec_ws, dec_ws_bytes, st));
   }
   GemmEpilogue eo;

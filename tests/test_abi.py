@@ -51,8 +51,8 @@ def test_decode_step_switches_defaults_and_reject_unknown_names():
     """b200_set_option / b200_get_option (host-side state only; the switches themselves are exercised on the GPU by
     tests/test_gpu_zzzz_switches.py). Defaults as timed on hardware: pdl off, decode_tiles 1."""
     import pytest
-    defaults = {"pdl": 0, "decode_tiles": 1}
-    for name in ("pdl", "decode_tiles"):
+    defaults = {"pdl": 0, "decode_tiles": 1, "fused_rope": 1}
+    for name in ("pdl", "decode_tiles", "fused_rope"):
         if os.environ.get("B200_" + name.upper()) is None:
             assert int(L.get_option(name)) == defaults[name]
         L.set_option(name, True)
@@ -64,6 +64,7 @@ def test_decode_step_switches_defaults_and_reject_unknown_names():
     with pytest.raises(L.B200Error):
         L.set_option("decode_tiles", 3)
     L.set_option("decode_tiles", defaults["decode_tiles"])
+    L.set_option("fused_rope", defaults["fused_rope"])
     with pytest.raises(L.B200Error):
         L.set_option("no_such_switch", 1)
     with pytest.raises(L.B200Error):

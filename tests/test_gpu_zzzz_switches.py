@@ -134,3 +134,43 @@ def test_all_switches_together_at_wide_shapes(batch):
         L.set_option("pdl", 0)
         L.set_option("decode_tiles", 0)
     assert torch.equal(out, ref)
+
+
+def test_fused_rope_kv_append_against_oracle_and_separate_kernel():
+    """The decode attention kernel rotates q / k and appends k / v itself whenever the step has >= 2 x SMs (row, head)
+    pairs (DecodeArgs::rope_k; default on). 96 rows x 4 heads = 384 CTAs take that path: logits against the CPU oracle,
+    against the same step with the separate RoPE kernel ("fused_rope" = 0; the only difference is the summation order of
+    the one new key's dot product), same greedy ids in the eager and the CUDA-graph loop, and a left-padded batch so
+    that the rotary position (slot - kv_start) differs per row."""
+    from helpers import TOL_E2E, oracle_cfg
+    from oracle import mm2sg_oracle as O
+    cfg, model = _model()
+    ocfg = oracle_cfg(cfg)
+    sd = gc.bf16_round(gc.small_weights(cfg))
+    g = torch.Generator().manual_seed(321)
+    B, Lt, steps = 96, 20, 6
+    ids = torch.zeros(B, Lt, dtype=torch.long)
+    for r in range(B):
+        n = int(torch.randint(9, Lt + 1, (1,), generator=g))
+        ids[r, Lt - n:] = torch.randint(3, cfg.vocab_size, (n,), generator=g)
+    assert L.get_option("fused_rope")
+    out, lg = model.generate(ids, max_new_tokens=steps, stop_on_eos=False, return_logits=True)
+    out_graph = model.generate(ids, max_new_tokens=steps, stop_on_eos=False)
+    assert torch.equal(out_graph, out)
+    try:
+        L.set_option("fused_rope", 0)
+        out0, lg0 = model.generate(ids, max_new_tokens=steps, stop_on_eos=False, return_logits=True)
+    finally:
+        L.set_option("fused_rope", 1)
+    assert rel_err(lg, lg0) < 2e-3
+    mask = ids.ne(0)
+    pos = (mask.long().cumsum(-1) - 1).clamp(min=0)
+    emb = sd["model.embed_tokens.weight"][ids] * mask[..., None]
+    l0, kv = O.llama_forward(sd, emb, mask, pos, ocfg.llm, last_only=True)
+    toks, ref_lg = O.greedy_decode(sd, ocfg, l0[:, -1], kv, mask, steps, stop_on_eos=False, forced_tokens=out[:, Lt:].cpu())
+    assert rel_err(lg, ref_lg) < TOL_E2E and rel_err(lg0, ref_lg) < TOL_E2E
+    err = (lg.cpu().float() - ref_lg).abs().max().item()
+    top2 = ref_lg.topk(2, -1).values
+    safe = (top2[..., 0] - top2[..., 1]) > 2 * err
+    assert safe.float().mean() > 0.5 and torch.equal(out[:, Lt:].cpu()[safe], toks[safe])
+    assert torch.equal(out0[:, Lt:].cpu()[safe], toks[safe])

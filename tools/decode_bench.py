@@ -57,6 +57,7 @@ def main():
         pdl, tiles = "pdl" in arm, 2 if "tiles2" in arm else (1 if "tiles1" in arm else 0)
         L.set_option("pdl", pdl)
         L.set_option("decode_tiles", tiles)
+        L.set_option("fused_rope", 0 if "nofuse" in arm else 1)      # RoPE + KV append inside the attention kernel
         try:
             model.generate(ids, max_new_tokens=a.n1, **kw)                       # warm-up (lazy kernel attributes)
             t1 = timed(lambda: model.generate(ids, max_new_tokens=a.n1, **kw))
@@ -71,7 +72,8 @@ def main():
         except Exception as e:  # noqa: BLE001 -- an arm that fails must not hide the others
             print(json.dumps({"arm": arm, "error": repr(e)[:300]}), flush=True)
     L.set_option("pdl", 0)
-    L.set_option("decode_tiles", 0)
+    L.set_option("decode_tiles", 1)
+    L.set_option("fused_rope", 1)
 
 
 if __name__ == "__main__":
