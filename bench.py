@@ -59,7 +59,7 @@ def parse_args():
     p.add_argument("--config-batch", type=int, default=64, help="samples per GPU per step of the configs[2] sub-record")
     p.add_argument("--no-pin", action="store_true", help="N > 1: do not pin every rank to its own slice of host cores")
     p.add_argument("--no-train", action="store_true", help="skip the fine-tune-step sub-record (BASELINE configs[4])")
-    p.add_argument("--train-steps", type=int, default=3)
+    p.add_argument("--train-steps", type=int, default=5)
     p.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer arm")
     p.add_argument("--no-graph", action="store_true", help="profiling runs only: eager decode loop (every launch "
                    "visible to ncu)")
@@ -524,7 +524,7 @@ def finetune_record(args, cfg, dev, group):
         rec = None
         try:
             rec = measure_finetune_step(cfg, dev, group=group, batch=4, views=args.views, steps=args.train_steps,
-                                        warmup=1, zero=2, recompute=recompute)
+                                        warmup=2, zero=2, recompute=recompute)
         except torch.cuda.OutOfMemoryError as e:
             last = "out of memory with activation_recomputation=%s: %s" % (recompute, str(e)[:120])
             ok.zero_()

@@ -81,16 +81,21 @@ def measure_finetune_step(cfg, dev, group=None, batch=4, views=6, steps=2, warmu
     if world > 1:
         dist.barrier(group)
     n0 = L.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    marks[0].record()
     timed_losses = []
-    for _ in range(steps):
+    for i in range(steps):
         loss, nsq = one_step()
+        marks[i + 1].record()
         timed_losses.append(loss)            # read back after the timed region: no host synchronisation between steps
-    e1.record()
     torch.cuda.synchronize(dev)
     losses += [float(x) for x in timed_losses]
-    mine = e0.elapsed_time(e1) / steps
+    # every step is timed on the device; the record quotes the MEDIAN step (a full fine-tune holds ~167 GB of a 180 GB
+    # device on one GPU, and a step in which the caching allocator has to return and re-request segments costs up to
+    # 100 ms more than its neighbours) and lists all of them
+    step_ms = [marks[i].elapsed_time(marks[i + 1]) for i in range(steps)]
+    mine = sorted(step_ms)[len(step_ms) // 2] if len(step_ms) % 2 else \
+        0.5 * (sorted(step_ms)[len(step_ms) // 2 - 1] + sorted(step_ms)[len(step_ms) // 2])
     launches = int((L.launch_count() - n0) / steps)
     per_rank = [mine]
     ms = mine
@@ -119,7 +124,8 @@ def measure_finetune_step(cfg, dev, group=None, batch=4, views=6, steps=2, warmu
     payload = n_train * 2                                    # bf16 bytes reduce-scattered, and again all-gathered
     rec = {"metric": "fine-tune step, trained tokens/s", "value": round(world * tokens / (ms / 1e3), 1),
            "unit": "tokens/s", "n_gpus": world, "scaling": "weak", "ms_per_step": round(ms, 1),
-           "per_rank_ms": per_rank, "tokens_per_step_per_gpu": tokens, "trainable_params": n_train,
+           "per_rank_ms": per_rank, "step_ms_this_rank": [round(x, 1) for x in step_ms], "timing": "median of %d "
+           "device-timed steps, max over ranks" % steps, "tokens_per_step_per_gpu": tokens, "trainable_params": n_train,
            "decoder_layers": cfg.num_hidden_layers, "batch_per_gpu": batch, "views": views,
            "gradient_accumulation": accum, "activation_recomputation": bool(recompute),
            "mode": (("qlora (nf4 base) r=%d" if nf4 else "lora r=%d") % lora_r) if lora_r else "full fine-tune",
