@@ -133,8 +133,9 @@ class ContinuousBatcher:
                                             L.ptr(model.model.embed_tokens), L.ptr(embeds), D, Lp, D, V, L.stream_ptr()),
                         "b200_embed_rows")
             if Lp + self.max_new > self.cap:
-                raise ValueError(f"request of {Lp} packed positions + {self.max_new} new tokens exceeds the cache "
-                                 f"capacity {self.cap}: raise max_prompt_len")
+                self.pending.popleft()          # it can never be served by this batcher: do not block the queue
+                raise ValueError(f"request {req['ticket']}: {Lp} packed positions + {self.max_new} new tokens exceed "
+                                 f"the cache capacity {self.cap}: raise max_prompt_len")
             if Lp > self.pos or self.pos + self.max_new > self.cap:
                 break                       # has to wait: P must grow to its length / the rows in flight must drain
             self.pending.popleft()

@@ -129,7 +129,6 @@ def test_online_scheduler_on_the_real_model(env):
     make = lambda mb: OnlineScheduler(model, tokenize, decode, pad_token_id=0, max_batch=mb, max_new_tokens=9)
     ref = make(1).run(_takes(cfg, 3))                           # the reference's schedule
     assert all(len(r["triplets"]) == 3 for frames in ref.values() for r in frames)
-    assert any("Short: e" in "".join(map(str, frames)) or True for frames in ref.values())
     batched = make(3)
     got = batched.run(_takes(cfg, 3))
     assert got == ref and batched.rounds < sum(len(v) for v in ref.values())
