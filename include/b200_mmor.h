@@ -284,6 +284,14 @@ int b200_llama_prefill(const b200_llama_weights* w, void* x, const int32_t* kv_s
                        const b200_kv_cache* cache, int B, int L, void* logits, int all_logits, int logits_fp32,
                        void* workspace, size_t workspace_bytes, b200_stream_t stream);
 
+/* Prefill that continues a cache (prefix-KV reuse of the online mode, scene_graph_prediction_model.py:140-199: every
+ * prompt starts with the same system text): slots [0, q0) of every row already hold keys / values -- the caller copied
+ * the shared prefix there, row b's copy starting at kv_start[b] --; x [B*Lq, hidden] are the tokens of slots
+ * [q0, q0 + Lq), which attend to all q0 + Lq keys. q0 = 0 is b200_llama_prefill. Workspace as for (B, Lq). */
+int b200_llama_prefill_from(const b200_llama_weights* w, void* x, const int32_t* kv_start, const int32_t* kv_len,
+                            const b200_kv_cache* cache, int B, int Lq, int q0, void* logits, int all_logits,
+                            int logits_fp32, void* workspace, size_t workspace_bytes, b200_stream_t stream);
+
 size_t b200_llama_decode_workspace_bytes(const b200_llama_weights* w, int B, int cap);
 /* One greedy decode step for B sequences (model/llava_arch.py:192-201 + HF greedy_search):
  * tokens [B] int32 (in: token to feed, out: argmax token), state[2] int32 device = {slots in use, step index} --

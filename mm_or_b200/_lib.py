@@ -127,6 +127,7 @@ _SIGS = {
     "b200_projector_gather": (ci, [_P(ProjectorWeights), vp, ci, vp, ci, sz, vp, sz, vp]),
     "b200_llama_prefill_workspace_bytes": (sz, [_P(LlamaWeights), ci, ci, ci]),
     "b200_llama_prefill": (ci, [_P(LlamaWeights), vp, vp, vp, _P(KvCache), ci, ci, vp, ci, ci, vp, sz, vp]),
+    "b200_llama_prefill_from": (ci, [_P(LlamaWeights), vp, vp, vp, _P(KvCache), ci, ci, ci, vp, ci, ci, vp, sz, vp]),
     "b200_llama_decode_workspace_bytes": (sz, [_P(LlamaWeights), ci, ci]),
     "b200_llama_decode_step": (ci, [_P(LlamaWeights), vp, vp, vp, _P(KvCache), ci, ci, vp, ci, ci, vp, ci, vp, vp,
                                     sz, vp]),

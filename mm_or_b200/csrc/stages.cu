@@ -274,7 +274,9 @@ static int linear(const bf16* A, int lda, const bf16* W, int ldw, void* C, int l
 static int llama_layer(const b200_llama_weights* w, const b200_llama_layer& Ly, bf16* x, bf16* nbuf, bf16* qkv,
                        bf16* act, const int* kv_start, const int* kv_len, bf16* kc, bf16* vc, int cap, int Bn, int L,
                        int decode, const int* state, int ctx_bound, void* dec_ws, size_t dec_ws_bytes,
-                       const int* finished, cudaStream_t st) {
+                       const int* finished, cudaStream_t st, int q0 = 0) {
+  // q0 (prefill only): cache slots [0, q0) of every row already hold keys / values (a shared prompt prefix copied in by
+  // the host); the L rows of x are the tokens of slots [q0, q0 + L) and attend to all q0 + L keys (bottom-right causal)
   const bool sk = decode != 0;
   const int D = w->hidden, H = w->heads, T = Bn * L;
   B200_TRY(rmsnorm(x, D, B(Ly.attn_norm), w->rms_eps, nbuf, D, T, D, st));
@@ -284,7 +286,7 @@ static int llama_layer(const b200_llama_weights* w, const b200_llama_layer& Ly, 
   // rotates q / k and appends k / v itself (DecodeArgs::rope_k) -- one launch less per layer
   const bool fuse_rope = decode && fused_rope_enabled() && decode_attn_pick_splits(Bn, H, ctx_bound + 1) == 1;
   if (!fuse_rope)
-    B200_TRY(rope_kv_write(qkv, kv_start, w->rope_cos, w->rope_sin, w->max_pos, kc, vc, Bn, H, L, 0,
+    B200_TRY(rope_kv_write(qkv, kv_start, w->rope_cos, w->rope_sin, w->max_pos, kc, vc, Bn, H, L, decode ? 0 : q0,
                            decode ? state : nullptr, cap, st));
   if (!decode) {
     AttnArgs at{};
@@ -303,7 +305,8 @@ static int llama_layer(const b200_llama_weights* w, const b200_llama_layer& Ly, 
     at.o_hs = 128;
     at.B = Bn;
     at.H = H;
-    at.Lq = at.Lk = L;
+    at.Lq = L;
+    at.Lk = q0 + L;
     at.kv_start = kv_start;
     at.kv_len = kv_len;
     at.causal = 1;
@@ -356,11 +359,12 @@ static int llama_layer(const b200_llama_weights* w, const b200_llama_layer& Ly, 
 
 static int llama_prefill(const b200_llama_weights* w, bf16* x, const int* kv_start, const int* kv_len,
                          const b200_kv_cache* c, int Bn, int L, void* logits, int all_logits, int logits_fp32, void* ws,
-                         size_t ws_bytes, cudaStream_t st) {
+                         size_t ws_bytes, cudaStream_t st, int q0 = 0) {
   if (Bn <= 0 || L <= 0) return 0;
   const int D = w->hidden;
   if (D / w->heads != 128 || D % w->heads) return fail(-2, "llama: head_dim must be 128");
-  if (L > c->cap) return fail(-2, "llama_prefill: L %d exceeds KV capacity %d", L, c->cap);
+  if (q0 < 0) return fail(-2, "llama_prefill: negative first slot %d", q0);
+  if (q0 + L > c->cap) return fail(-2, "llama_prefill: %d + %d slots exceed KV capacity %d", q0, L, c->cap);
   if (ws_bytes < llama_prefill_ws(w, Bn, L, all_logits)) return fail(-2, "llama_prefill: workspace too small");
   Arena a(ws, ws_bytes);
   const size_t T = static_cast<size_t>(Bn) * L;
@@ -372,7 +376,7 @@ static int llama_prefill(const b200_llama_weights* w, bf16* x, const int* kv_sta
     bf16* kc = static_cast<bf16*>(c->k) + l * c->layer_stride;
     bf16* vc = static_cast<bf16*>(c->v) + l * c->layer_stride;
     B200_TRY(llama_layer(w, w->layers[l], x, nbuf, qkv, act, kv_start, kv_len, kc, vc, c->cap, Bn, L, 0, nullptr, 0,
-                         nullptr, 0, nullptr, st));
+                         nullptr, 0, nullptr, st, q0));
   }
   if (logits != nullptr) {
     GemmEpilogue e;
@@ -529,6 +533,13 @@ int b200_llama_prefill(const b200_llama_weights* w, void* x, const int32_t* kv_s
                        void* workspace, size_t workspace_bytes, b200_stream_t stream) {
   return llama_prefill(w, static_cast<bf16*>(x), kv_start, kv_len, cache, Bn, L, logits, all_logits, logits_fp32,
                        workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int b200_llama_prefill_from(const b200_llama_weights* w, void* x, const int32_t* kv_start, const int32_t* kv_len,
+                            const b200_kv_cache* cache, int Bn, int Lq, int q0, void* logits, int all_logits,
+                            int logits_fp32, void* workspace, size_t workspace_bytes, b200_stream_t stream) {
+  return llama_prefill(w, static_cast<bf16*>(x), kv_start, kv_len, cache, Bn, Lq, logits, all_logits, logits_fp32,
+                       workspace, workspace_bytes, static_cast<cudaStream_t>(stream), q0);
 }
 
 int b200_decode_tile_width(int rows, int n, int sms, int ctas_per_sm) {

@@ -363,6 +363,33 @@ class KVCache:
                          layer_stride=self.batch * self.heads * self.cap * 128, cap=self.cap)
 
 
+class PrefixCache:
+    """Keys / values (layers, heads, p, 128) of a token prefix shared by the prompts of a batch (make_prefix_cache)."""
+
+    def __init__(self, ids, k, v, pad_token_id):
+        self.ids, self.k, self.v, self.p = ids.to(torch.long), k, v, int(ids.numel())
+        self.pad = pad_token_id
+
+    def plan(self, ids_cpu, attention_mask, kv_start_host, Lq):
+        """First cache slot the prefill has to compute (0 = no reuse): every row must start -- after its padding --
+        with the prefix ids, and at least one slot must remain to be computed."""
+        am = attention_mask.bool()
+        for r in range(ids_cpu.shape[0]):
+            real = ids_cpu[r][am[r]]
+            if real.numel() <= self.p or not torch.equal(real[:self.p], self.ids):
+                return 0
+        q0 = int(np.min(kv_start_host)) + self.p
+        return q0 if 0 < q0 < Lq else 0
+
+    def copy_into(self, cache, kv_start_host, q0):
+        """Row b receives the first q0 - kv_start[b] prefix tokens at slots [kv_start[b], q0)."""
+        for b, ks in enumerate(np.asarray(kv_start_host).tolist()):
+            n = min(self.p, q0 - int(ks))
+            if n > 0:
+                cache.k[:, b, :, ks:ks + n] = self.k[:, :, :n]
+                cache.v[:, b, :, ks:ks + n] = self.v[:, :, :n]
+
+
 class DecodeSlot:
     """The device buffers one greedy generation lives in -- KV cache, current tokens, step counters, history, finished
     flags, first real slot per row -- and, once captured, the CUDA graph of one decode step over exactly these
@@ -622,8 +649,9 @@ class LlavaLlamaForCausalLM:
         return None, pos, am, past_key_values, embeds, new_labels, plan
 
     # ---- decoder -----------------------------------------------------------------------------------------------
-    def _prefill(self, embeds, kv_start, kv_len, cache, all_logits, logits_fp32):
-        """embeds (B, L, D) (overwritten). Returns logits (B, V) or (B, L, V)."""
+    def _prefill(self, embeds, kv_start, kv_len, cache, all_logits, logits_fp32, q0=0):
+        """embeds (B, L, D) (overwritten). Returns logits (B, V) or (B, L, V). q0 > 0: the rows of `embeds` are the
+        tokens of cache slots [q0, q0 + L); slots below q0 already hold keys / values (prefix-KV reuse)."""
         B, Lq, D = embeds.shape
         V = self.config.vocab_size
         ldt = torch.float32 if logits_fp32 else BF
@@ -634,11 +662,11 @@ class LlavaLlamaForCausalLM:
             nb = lib.b200_llama_prefill_workspace_bytes(ctypes.byref(self._w), n, Lq, int(all_logits))
             ws = self._ws_prefill.get(nb, self.device)
             cs = cache.struct(s)
-            L.check(lib.b200_llama_prefill(ctypes.byref(self._w), L.ptr(embeds[s:]),
-                                           L.ptr(kv_start[s:]) if kv_start is not None else None,
-                                           L.ptr(kv_len[s:]) if kv_len is not None else None, ctypes.byref(cs), n, Lq,
-                                           L.ptr(logits[s:]), int(all_logits), int(logits_fp32), L.ptr(ws), ws.numel(),
-                                           L.stream_ptr()), "b200_llama_prefill")
+            L.check(lib.b200_llama_prefill_from(ctypes.byref(self._w), L.ptr(embeds[s:]),
+                                                L.ptr(kv_start[s:]) if kv_start is not None else None,
+                                                L.ptr(kv_len[s:]) if kv_len is not None else None, ctypes.byref(cs), n,
+                                                Lq, int(q0), L.ptr(logits[s:]), int(all_logits), int(logits_fp32),
+                                                L.ptr(ws), ws.numel(), L.stream_ptr()), "b200_llama_prefill")
         return logits
 
     def forward(self, input_ids=None, attention_mask=None, position_ids=None, past_key_values=None,
@@ -699,8 +727,10 @@ class LlavaLlamaForCausalLM:
     def generate(self, input_ids, images=None, do_sample=False, use_cache=True, max_new_tokens=20,
                  stopping_criteria=None, pc=None, audio=None, segmasks=None, attention_mask=None,
                  stop_on_eos=True, check_every=16, use_cuda_graph=True, return_logits=False,
-                 vis_descriptor_embs=None, **unused):
+                 vis_descriptor_embs=None, prefix_cache=None, **unused):
         """Greedy decoding with the call signature the reference uses (scene_graph_prediction_model.py:221-231).
+        prefix_cache (make_prefix_cache): keys / values of a token prefix every prompt of the batch starts with (the
+        fixed system text of the online mode) are copied into the KV cache instead of being recomputed.
         Returns LongTensor (B, L_in + n_new): the prompt ids (incl. the -200 placeholder) followed by the new tokens.
         HF greedy_search semantics: finished rows emit pad_token_id; stops when every row has produced EOS.
         One call = the three phases below back to back on the current stream; generate_stream() overlaps them across
@@ -708,13 +738,13 @@ class LlavaLlamaForCausalLM:
         if do_sample:
             raise NotImplementedError("MM2SG decodes greedily (do_sample=False)")
         job = self._gen_begin(input_ids, images, max_new_tokens, pc, audio, segmasks, attention_mask, stop_on_eos,
-                              return_logits, vis_descriptor_embs)
+                              return_logits, vis_descriptor_embs, prefix_cache=prefix_cache)
         self._gen_decode(job, stopping_criteria, check_every, use_cuda_graph)
         return self._gen_finish(job)
 
     # ---- the three phases of a greedy generation ------------------------------------------------------------------
     def _gen_begin(self, input_ids, images, max_new_tokens, pc=None, audio=None, segmasks=None, attention_mask=None,
-                   stop_on_eos=True, return_logits=False, vis_descriptor_embs=None, slot=None):
+                   stop_on_eos=True, return_logits=False, vis_descriptor_embs=None, slot=None, prefix_cache=None):
         """Phase A (tensor-core bound): encode the views, pack, prefill the KV cache, first token from the prefill
         logits -- everything enqueued on the current stream, no host synchronisation. Returns the job state."""
         if self._w is None:
@@ -754,7 +784,17 @@ class LlavaLlamaForCausalLM:
         # host -> device copies below never block the host on the stream (generate_stream relies on it)
         slot.kv_start.copy_(torch.from_numpy(np.ascontiguousarray(kv_start_host, dtype=np.int32)), non_blocking=True)
         kv_start, cache = slot.kv_start, slot.cache
-        logits = self._prefill(embeds, kv_start, kv_len, cache, all_logits=False, logits_fp32=False)
+        # prefix-KV reuse: rows that start with the cached prefix get its keys / values copied in; the prefill then
+        # starts at slot q0 = (smallest kv_start) + prefix length (rows with more left padding recompute the tail of
+        # their prefix inside the block -- same values)
+        q0 = 0
+        if prefix_cache is not None and kv_len is None:
+            q0 = prefix_cache.plan(ids_cpu, attention_mask, kv_start_host, Lq)
+            if q0 > 0:
+                prefix_cache.copy_into(cache, kv_start_host, q0)
+                embeds = embeds[:, q0:].contiguous()
+        self._last_prefill_q0 = q0
+        logits = self._prefill(embeds, kv_start, kv_len, cache, all_logits=False, logits_fp32=False, q0=q0)
         del embeds
         eos, pad = c.eos_token_id, c.pad_token_id if c.pad_token_id is not None else 0
         job = ModelOutput(ids_cpu=ids_cpu, B=B, Lq=Lq, cap=cap, cache=cache, kv_start=kv_start, eos=eos, pad=pad,
@@ -856,6 +896,28 @@ class LlavaLlamaForCausalLM:
         return out
 
     @torch.no_grad()
+    def make_prefix_cache(self, prefix_ids):
+        """Keys / values of a text prefix (1-D LongTensor of token ids, no placeholders, no padding) for every decoder
+        layer, computed once (B = 1 prefill) for generate(..., prefix_cache=...). In MM2SG's online mode every prompt
+        starts with the same system text before `<image>` (scene_graph_prediction_model.py:140-199, conversation.py:
+        253-263); a left-padded row's prefix sits at slots [kv_start, kv_start + p) and its rotary positions are
+        relative to kv_start, so the same keys / values are valid in every row."""
+        if self._w is None:
+            raise L.B200Error("weights not loaded")
+        c, lib = self.config, L.lib()
+        ids = prefix_ids.detach().to("cpu").reshape(-1)
+        p = int(ids.numel())
+        if p == 0 or int(ids.min()) < 0:
+            raise ValueError("make_prefix_cache: the prefix must be a non-empty run of real token ids")
+        emb = torch.empty((1, p, c.hidden_size), device=self.device, dtype=BF)
+        L.check(lib.b200_embed_rows(L.ptr(ids.to(torch.int32).to(self.device).contiguous()), L.ptr(self.model.embed_tokens),
+                                    L.ptr(emb), c.hidden_size, p, c.hidden_size, c.vocab_size, L.stream_ptr()),
+                "b200_embed_rows")
+        cache = KVCache(c.num_hidden_layers, 1, c.num_attention_heads, (p + 7) // 8 * 8, self.device)
+        self._prefill(emb, None, None, cache, all_logits=False, logits_fp32=False)
+        return PrefixCache(ids, cache.k[:, 0, :, :p].clone(), cache.v[:, 0, :, :p].clone(), c.pad_token_id)
+
+    @torch.no_grad()
     def generate_stream(self, requests, max_new_tokens=20, stop_on_eos=True, stopping_criteria=None, check_every=16,
                         prefill_chunk=None, vit_chunk=None, pooler_chunk=None):
         """Pipelined greedy generation over a sequence of batches: while batch n decodes (HBM bound: 255 passes over the
@@ -886,7 +948,8 @@ class LlavaLlamaForCausalLM:
                 slot = free_slots.pop() if free_slots else None
                 job = self._gen_begin(ids, images, kw.pop("max_new_tokens", max_new_tokens), kw.get("pc"),
                                       kw.get("audio"), kw.get("segmasks"), kw.get("attention_mask"), stop_on_eos,
-                                      False, kw.get("vis_descriptor_embs"), slot=slot)
+                                      False, kw.get("vis_descriptor_embs"), slot=slot,
+                                      prefix_cache=kw.get("prefix_cache"))
                 job.ready = torch.cuda.Event()
                 job.ready.record(lo)
             return job

@@ -33,7 +33,7 @@ def left_pad(id_rows, pad_id):
 
 class OnlineScheduler:
     def __init__(self, model, tokenize, decode, pad_token_id=0, max_batch=64, max_new_tokens=300,
-                 stopping_criteria_factory=None, rng_factory=None, image_token="<image>"):
+                 stopping_criteria_factory=None, rng_factory=None, image_token="<image>", prefix_cache=None):
         """tokenize(prompt) -> 1-D LongTensor with IMAGE_TOKEN_INDEX at the placeholder (the reference's
         tokenizer_image_token); decode(1-D LongTensor of new ids) -> text; stopping_criteria_factory(input_ids) -> list
         (the reference builds KeywordsStoppingCriteria from the batch's input_ids); rng_factory(take_name) -> the
@@ -43,6 +43,9 @@ class OnlineScheduler:
         self.criteria = stopping_criteria_factory
         self.rng_factory = rng_factory or (lambda name: random.Random(str(name)))
         self.image_token = image_token
+        # keys / values of the system text every prompt starts with (model.make_prefix_cache(tokenize(prompt)[:p])):
+        # copied into the KV cache of every round instead of being recomputed
+        self.prefix_cache = prefix_cache
         self.rounds = 0
 
     def run(self, takes):
@@ -73,6 +76,8 @@ class OnlineScheduler:
                 vals = [f.get(key) for _, f in batch]
                 kw[key] = vals if any(v is not None for v in vals) else None
             criteria = self.criteria(input_ids) if self.criteria is not None else None
+            if self.prefix_cache is not None:
+                kw["prefix_cache"] = self.prefix_cache
             out = self.model.generate(input_ids, images=[f["images"] for _, f in batch], do_sample=False,
                                       use_cache=True, max_new_tokens=self.max_new, stopping_criteria=criteria, **kw)
             self.rounds += 1

@@ -135,3 +135,38 @@ def test_online_scheduler_on_the_real_model(env):
     cb = ContinuousBatcher(model, rows=2, max_prompt_len=800, max_new_tokens=9, check_every=3)
     cont = make(2).run_continuous(_takes(cfg, 3), cb)
     assert cont == ref
+
+
+def test_prefix_kv_reuse_equals_full_prefill(env):
+    """Prefix-KV reuse (make_prefix_cache / generate(prefix_cache=...)): the keys / values of the system text every
+    prompt starts with are computed once and copied into each row's cache at its own left-padding offset; the prefill
+    then starts behind the prefix (b200_llama_prefill_from). Same greedy ids as the full prefill (chain weights:
+    margins of several logits), logits equal up to the bf16 rounding of a differently tiled online softmax; a batch
+    whose rows do not start with the prefix falls back to the full prefill."""
+    from helpers import rel_err
+    cfg, model = env
+    g = torch.Generator().manual_seed(5)
+    p = 13
+    prefix = torch.randint(8, cfg.vocab_size, (p,), generator=g)
+    tails = [5, 11, 2]
+    Lt = p + 1 + max(tails)
+    ids = torch.zeros(len(tails), Lt, dtype=torch.long)
+    for r, t in enumerate(tails):
+        row = torch.cat([prefix, torch.tensor([-200]), torch.randint(8, cfg.vocab_size, (t,), generator=g)])
+        ids[r, Lt - len(row):] = row
+    S = cfg.vision_config()["image_size"]
+    images = [torch.randn(1 + r % 2, 3, S, S, generator=g).to(torch.bfloat16).float() for r in range(len(tails))]
+    pc = model.make_prefix_cache(prefix)
+    kw = dict(images=images, max_new_tokens=7, stop_on_eos=False)
+    out_a, lg_a = model.generate(ids, return_logits=True, **kw)
+    assert model._last_prefill_q0 == 0
+    out_b, lg_b = model.generate(ids, return_logits=True, prefix_cache=pc, **kw)
+    assert model._last_prefill_q0 == int(ids.eq(0).sum(1).min()) + p                 # the prefix really was skipped
+    assert torch.equal(out_a, out_b) and rel_err(lg_b, lg_a) < 5e-3
+    assert torch.equal(model.generate(ids, prefix_cache=pc, **kw), out_a)              # CUDA-graph loop
+    other = ids.clone()
+    other[0, Lt - (p + 1 + tails[0])] += 1                                              # row 0 no longer starts with it
+    out_c = model.generate(other, prefix_cache=pc, **kw)
+    assert model._last_prefill_q0 == 0 and torch.equal(out_c, model.generate(other, **kw))
+    with pytest.raises(ValueError):
+        model.make_prefix_cache(torch.tensor([5, -200, 7]))
