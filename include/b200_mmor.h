@@ -339,6 +339,14 @@ int b200_preprocess_images(const uint8_t* images, int n, int H, int W, int pad_t
  * b200_norm_backward: LayerNorm (rms = 0) / RMSNorm (rms = 1) backward from the saved input x: dx bf16, dgamma / dbeta
  * fp32 [D] ((+)= with accumulate; dbeta ignored for RMSNorm). `add` (bf16 [M, D], may be NULL, may alias dx) is added
  * to dx: the gradient that reaches x through the residual connection around the norm. D in {512, 1024, 4096}. */
+/* C[M, N] (bf16) = scale * A[M, K] . dequant(W)^T (+ residual): W [N, K] given in 4-bit NormalFloat storage -- `codes`
+ * N * K / 2 bytes (row-major, two codes per byte, even element in the high nibble, b200_nf4_quantize's layout) and
+ * `absmax` one fp32 per block of 64 consecutive K values (N * K / 64 floats). The dequantisation bitsandbytes'
+ * Linear4bit performs in front of every matmul of the QLoRA recipe (reference: train/train.py:1098-1114) runs inside the
+ * GEMM's producer side: the packed weight is all that lives in HBM. Bit-identical to b200_gemm_bf16 on
+ * b200_nf4_dequantize(codes, absmax). K % 64 == 0, codes 16-byte aligned. */
+int b200_gemm_nf4(const void* A, int lda, const uint8_t* codes, const float* absmax, void* C, int ldc, int M, int N, int K,
+                  const void* residual, int ldr, float scale, b200_stream_t stream);
 int b200_gemm_bf16_ex(const void* A, int lda, int a_transposed, const void* W, int ldw, int w_transposed, void* C, int ldc,
                       int M, int N, int K, const void* bias, const void* residual, int ldr, int act, int out_fp32,
                       int accumulate, float scale, int bn_hint, b200_stream_t stream);

@@ -125,6 +125,7 @@ _SIGS = {
     "b200_projector_workspace_bytes": (sz, [_P(ProjectorWeights), ci]),
     "b200_projector_pack": (ci, [_P(ProjectorWeights), vp, ci, vp, vp, vp, ci, vp, ci, vp, sz, vp]),
     "b200_projector_gather": (ci, [_P(ProjectorWeights), vp, ci, vp, ci, sz, vp, sz, vp]),
+    "b200_gemm_nf4": (ci, [vp, ci, vp, vp, vp, ci, ci, ci, ci, vp, ci, cf, vp]),
     "b200_llama_prefill_workspace_bytes": (sz, [_P(LlamaWeights), ci, ci, ci]),
     "b200_llama_prefill": (ci, [_P(LlamaWeights), vp, vp, vp, _P(KvCache), ci, ci, vp, ci, ci, vp, sz, vp]),
     "b200_llama_prefill_from": (ci, [_P(LlamaWeights), vp, vp, vp, _P(KvCache), ci, ci, ci, vp, ci, ci, vp, sz, vp]),
@@ -231,6 +232,20 @@ def gemm(a, w, out=None, bias=None, residual=None, row_map=None, act=ACT_NONE, o
     rc = lib().b200_gemm_bf16(ptr(a), a.stride(0), ptr(w), w.stride(0), ptr(out), out.stride(0), M, N, K,
                               ptr(bias), ptr(residual), ldr, ptr(row_map), act, int(out_fp32), bn, stream_ptr())
     check(rc, "b200_gemm_bf16")
+    return out
+
+
+def gemm_nf4(a, codes, absmax, n, out=None, residual=None, scale=1.0):
+    """out = scale * a @ dequant(codes, absmax).T (+ residual). a (M, K) bf16; codes uint8 (n * K / 2,), absmax fp32
+    (n * K / 64,): the NF4 storage of an (n, K) weight (train/nf4.py); the weight is expanded to bf16 inside the GEMM."""
+    M, K = a.shape
+    assert a.stride(1) == 1 and codes.dtype == torch.uint8 and absmax.dtype == torch.float32
+    assert codes.numel() * 2 == n * K and absmax.numel() * 64 == n * K
+    if out is None:
+        out = torch.empty((M, n), device=a.device, dtype=torch.bfloat16)
+    check(lib().b200_gemm_nf4(ptr(a), a.stride(0), ptr(codes), ptr(absmax), ptr(out), out.stride(0), M, n, K,
+                              ptr(residual), residual.stride(0) if residual is not None else 0, float(scale),
+                              stream_ptr()), "b200_gemm_nf4")
     return out
 
 

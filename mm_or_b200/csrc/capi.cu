@@ -61,6 +61,16 @@ int b200_gemm_bf16_skinny(const void* A, int lda, const void* W, int ldw, void* 
                      static_cast<cudaStream_t>(stream));
 }
 
+int b200_gemm_nf4(const void* A, int lda, const uint8_t* codes, const float* absmax, void* C, int ldc, int M, int N, int K,
+                  const void* residual, int ldr, float scale, b200_stream_t stream) {
+  GemmEpilogue e;
+  e.scale = scale;
+  e.residual = static_cast<const bf16*>(residual);
+  e.ldr = ldr;
+  return gemm_nf4_tn(static_cast<const bf16*>(A), lda, codes, absmax, C, ldc, M, N, K, e,
+                     static_cast<cudaStream_t>(stream));
+}
+
 int b200_gemm_bf16_ex(const void* A, int lda, int a_transposed, const void* W, int ldw, int w_transposed, void* C, int ldc,
                       int M, int N, int K, const void* bias, const void* residual, int ldr, int act, int out_fp32,
                       int accumulate, float scale, int bn_hint, b200_stream_t stream) {

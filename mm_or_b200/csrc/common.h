@@ -152,6 +152,8 @@ int gemm_bf16_tn(const bf16* A, int lda, const bf16* B, int ldb, void* C, int ld
 
 // General form: a_mn / b_mn = 1 means the operand is stored transposed ([K, M] / [K, N]) and is read in place as an
 // MN-major tensor-core operand (backward GEMMs: dX = dY W uses b_mn, dW = dY^T X uses both).
+int gemm_nf4_tn(const bf16* A, int lda, const uint8_t* codes, const float* absmax, void* C, int ldc, int M, int N, int K,
+                const GemmEpilogue& epi, cudaStream_t stream);
 int gemm_bf16_ex(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, int b_mn, void* C, int ldc, int M, int N,
                  int K, const GemmEpilogue& epi, int bn_hint, cudaStream_t stream);
 

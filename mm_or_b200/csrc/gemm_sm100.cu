@@ -36,6 +36,12 @@ struct GemmArgs {
   // rasterisation (tile_coords): raster_n = 0 -> groups of raster_group consecutive M tiles walk over all N tiles (their
   // A panel stays L2-resident, B streams once per group); raster_n = 1 -> groups of N tiles walk over all M tiles
   int raster_n, raster_group;
+  // NF4 variant (template flag NF4): the B operand is the 4-bit NormalFloat storage of an [N, K] weight (nf4.cu: blocks
+  // of 64 consecutive K values, two codes per byte, one fp32 absmax per block); four extra warps expand it to bf16
+  // straight into the swizzled B stage -- the dequantisation of bitsandbytes' Linear4bit (reference call site
+  // train/train.py:1098-1114) fused into the GEMM's producer side, so only the packed base ever lives in HBM
+  const uint8_t* nf4_codes;
+  const float* nf4_absmax;
   // operand majors: 0 = K-major ([rows, K], the nn.Linear forward layout), 1 = MN-major (the matrix is stored
   // [K, rows]: the transposed operands of the backward GEMMs dX = dY W and dW = dY^T X, read in place)
   int a_mn, b_mn;
@@ -94,8 +100,15 @@ __device__ __forceinline__ float act_apply(float x, int act) {
   return x;
 }
 
-template <int BN, int PER_SM = 1>
-__global__ void __launch_bounds__(kGemmThreads, PER_SM)
+// the 16 NormalFloat levels (QLoRA, appendix E; the same literals as nf4.cu::level)
+static __device__ const float kNf4Levels[16] = {
+    -1.0f, -0.6961928009986877f, -0.5250730514526367f, -0.39491748809814453f, -0.28444138169288635f,
+    -0.18477343022823334f, -0.09105003625154495f, 0.0f, 0.07958029955625534f, 0.16093020141124725f,
+    0.24611230194568634f, 0.33791524171829224f, 0.44070982933044434f, 0.5626170039176941f, 0.7229568362236023f, 1.0f};
+static constexpr int kNf4Threads = 128;  // dequantisation warps 6..9 of the NF4 variant
+
+template <int BN, int PER_SM = 1, bool NF4 = false>
+__global__ void __launch_bounds__(NF4 ? kGemmThreads + kNf4Threads : kGemmThreads, PER_SM)
     gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                         const GemmArgs g) {
   using Cfg = GemmCfg<BN, PER_SM>;
@@ -110,6 +123,7 @@ __global__ void __launch_bounds__(kGemmThreads, PER_SM)
   uint64_t* tmem_full = empty_bar + kStages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* nf4_lut = reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes + 192);  // 16 floats, NF4 only
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -120,7 +134,7 @@ __global__ void __launch_bounds__(kGemmThreads, PER_SM)
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(&full_bar[s], 1);
+      mbar_init(&full_bar[s], NF4 ? 2 : 1);  // NF4: the TMA of the A tile + the dequantisation warps' arrival
       mbar_init(&empty_bar[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -130,6 +144,8 @@ __global__ void __launch_bounds__(kGemmThreads, PER_SM)
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  if (NF4 && threadIdx.x >= kGemmThreads && threadIdx.x < kGemmThreads + 16)
+    nf4_lut[threadIdx.x - kGemmThreads] = kNf4Levels[threadIdx.x - kGemmThreads];
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -141,7 +157,7 @@ __global__ void __launch_bounds__(kGemmThreads, PER_SM)
       // Programmatic dependent launch: weight tiles of the first k-blocks are requested before the previous kernel
       // has finished (they do not depend on it); the activation tiles of the same stages follow after the wait.
       int pre = 0;
-      if (g.epi.b_const && !g.b_mn && static_cast<int>(blockIdx.x) < num_tiles) {
+      if (!NF4 && g.epi.b_const && !g.b_mn && static_cast<int>(blockIdx.x) < num_tiles) {
         int mt, nt;
         tile_coords(blockIdx.x, g, mt, nt);
         pre = k_blocks < kStages ? k_blocks : kStages;
@@ -160,7 +176,7 @@ __global__ void __launch_bounds__(kGemmThreads, PER_SM)
           const bool b_done = pre > 0;  // this stage's weight tile (and its expect_tx) was issued above
           if (b_done) --pre;
           mbar_wait(&empty_bar[stage], phase ^ 1u);
-          if (!b_done) mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          if (!b_done) mbar_expect_tx(&full_bar[stage], NF4 ? Cfg::kStageBytesA : Cfg::kStageBytes);
           if (!g.a_mn) {
             tma_load_2d(smem_a + stage * Cfg::kStageBytesA, &tmA, &full_bar[stage], kb * kBK, mt * kBM);
           } else {  // [64 k rows][64 m] boxes, one 8 KB panel per 64 rows of the tile
@@ -168,7 +184,7 @@ __global__ void __launch_bounds__(kGemmThreads, PER_SM)
               tma_load_2d(smem_a + stage * Cfg::kStageBytesA + p * 8192, &tmA, &full_bar[stage], mt * kBM + p * 64,
                           kb * kBK);
           }
-          if (b_done) {
+          if (b_done || NF4) {
           } else if (!g.b_mn) {
             tma_load_2d(smem_b + stage * Cfg::kStageBytesB, &tmB, &full_bar[stage], kb * kBK, nt * BN);
           } else {
@@ -217,6 +233,81 @@ __global__ void __launch_bounds__(kGemmThreads, PER_SM)
       }
       // late programmatic-launch trigger: after the last MMA of this CTA's last tile (see gemm_skinny.cu)
       griddep_launch();
+    }
+  } else if (NF4 && warp >= 6) {
+    // ===================== NF4 dequantisation (warps 6..9): codes -> bf16 B stage =====================
+    // Thread t owns rows t, t + 128, ... of the BN x 64 tile: 32 bytes of codes + one absmax per row and k-block
+    // (the k-block IS the quantisation block: 64 consecutive K values of a weight row). Value = level[code] * absmax
+    // rounded to bf16 -- the arithmetic of nf4.cu::dequantize_kernel --, written in the K-major SWIZZLE_128B layout
+    // the TMA would have produced: row r at r * 128 B, 16-byte chunk c at position c ^ (r & 7).
+    constexpr int kRows = BN >= 128 ? BN / 128 : 1;  // tile rows per dequantisation thread (BN is 128 or 256 here)
+    constexpr int kAhead = 4;  // k-blocks whose codes are in flight in registers (HBM latency ~ 1 us >> one MMA stage)
+    const int t = threadIdx.x - kGemmThreads;
+    const long long kblocks_total = g.K / kBK;
+    const int my_tiles = (num_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
+                         static_cast<int>(gridDim.x);
+    const long long total = static_cast<long long>(my_tiles) * k_blocks;  // (tile, k-block) iterations of this CTA
+    uint4 c0[kAhead][kRows], c1[kAhead][kRows];
+    float am[kAhead][kRows];
+    // codes + absmax of iteration `it` -> register slot `slot` (compile-time index: the loops below are unrolled)
+    auto fetch = [&](long long it, int slot) {
+      const int tile = static_cast<int>(blockIdx.x) + static_cast<int>(it / k_blocks) * static_cast<int>(gridDim.x);
+      const int kb = static_cast<int>(it % k_blocks);
+      int mt, nt;
+      tile_coords(tile, g, mt, nt);
+#pragma unroll
+      for (int j = 0; j < kRows; ++j) {
+        const long long n = static_cast<long long>(nt) * BN + t + 128 * j;
+        c0[slot][j] = make_uint4(0u, 0u, 0u, 0u);
+        c1[slot][j] = c0[slot][j];
+        am[slot][j] = 0.f;
+        if (n < g.N) {
+          const uint4* src = reinterpret_cast<const uint4*>(g.nf4_codes + (n * g.K + static_cast<long long>(kb) * kBK) / 2);
+          c0[slot][j] = __ldg(src);
+          c1[slot][j] = __ldg(src + 1);
+          am[slot][j] = __ldg(g.nf4_absmax + n * kblocks_total + kb);
+        }
+      }
+    };
+#pragma unroll
+    for (int s0 = 0; s0 < kAhead; ++s0)
+      if (s0 < total) fetch(s0, s0);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (long long it0 = 0; it0 < total; it0 += kAhead) {
+#pragma unroll
+      for (int s0 = 0; s0 < kAhead; ++s0) {
+        const long long it = it0 + s0;
+        if (it < total) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          uint8_t* sb = smem_b + stage * Cfg::kStageBytesB;
+#pragma unroll
+          for (int j = 0; j < kRows; ++j) {
+            const int r = t + 128 * j;
+            const uint32_t words[8] = {c0[s0][j].x, c0[s0][j].y, c0[s0][j].z, c0[s0][j].w,
+                                       c1[s0][j].x, c1[s0][j].y, c1[s0][j].z, c1[s0][j].w};
+            const float m = am[s0][j];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {  // word c = bytes 4c..4c+3 = elements 8c..8c+7 (even element: high nibble)
+              const uint32_t wd = words[c];
+              uint4 o;
+              o.x = pack_bf16x2(nf4_lut[(wd >> 4) & 15u] * m, nf4_lut[wd & 15u] * m);
+              o.y = pack_bf16x2(nf4_lut[(wd >> 12) & 15u] * m, nf4_lut[(wd >> 8) & 15u] * m);
+              o.z = pack_bf16x2(nf4_lut[(wd >> 20) & 15u] * m, nf4_lut[(wd >> 16) & 15u] * m);
+              o.w = pack_bf16x2(nf4_lut[(wd >> 28) & 15u] * m, nf4_lut[(wd >> 24) & 15u] * m);
+              *reinterpret_cast<uint4*>(sb + r * 128 + ((c ^ (r & 7)) << 4)) = o;
+            }
+          }
+          if (it + kAhead < total) fetch(it + kAhead, s0);         // refill this register slot
+          fence_proxy_async_smem();                                  // generic-proxy writes -> visible to tcgen05.mma
+          asm volatile("bar.sync 1, %0;" ::"n"(kNf4Threads) : "memory");  // all rows of the stage are in place
+          if (t == 0) mbar_arrive(&full_bar[stage]);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
@@ -415,19 +506,19 @@ int num_sms() {
   return n;
 }
 
-template <int BN, int PER_SM = 1>
+template <int BN, int PER_SM = 1, bool NF4 = false>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g, cudaStream_t stream) {
   using Cfg = GemmCfg<BN, PER_SM>;
   static bool configured = false;
   if (!configured) {
-    B200_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, PER_SM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    B200_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, PER_SM, NF4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       Cfg::kSmemBytes));
     // experiment knob (tools/corun_bench.py): the full 228 KB shared carve-out instead of the smallest one that holds
     // this kernel's ring, so that small-footprint kernels of another stream find room next to the persistent CTA
     const char* e = getenv("B200_GEMM_CARVEOUT");
     if (e != nullptr && e[0] == '1')
-      B200_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, PER_SM>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                        cudaSharedmemCarveoutMaxShared));
+      B200_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, PER_SM, NF4>,
+                                        cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     configured = true;
   }
   const int tiles = g.m_tiles * g.n_tiles;
@@ -439,9 +530,42 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
                        static_cast<double>(g.M) * n_out * (g.epi.out_fp32 ? 4 : 2) +
                        (g.epi.residual ? 2.0 * g.M * g.N : 0.0);
   LaunchScope scope(g.M <= 128 ? kFamGemmSkinny : kFamGemm, stream, bytes, 2.0 * mnk);
-  B200_CUDA_OK(launch_ex(gemm_bf16_tn_kernel<BN, PER_SM>, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, stream, 0,
-                         g.epi.b_const != 0, tmA, tmB, g));
+  B200_CUDA_OK(launch_ex(gemm_bf16_tn_kernel<BN, PER_SM, NF4>, dim3(grid), dim3(NF4 ? kGemmThreads + kNf4Threads : kGemmThreads),
+                         Cfg::kSmemBytes, stream, 0, g.epi.b_const != 0, tmA, tmB, g));
   return 0;
+}
+
+// C[M, N] = epilogue(A[M, K] . dequant(W)[N, K]^T): W given as NF4 codes (N * K / 2 bytes, row-major [N, K]) and one fp32
+// absmax per block of 64 K values (N * K / 64 floats). Same tiles, MMA order and epilogue as gemm_bf16_tn on the
+// dequantised weight => bit-identical results.
+int gemm_nf4_tn(const bf16* A, int lda, const uint8_t* codes, const float* absmax, void* C, int ldc, int M, int N, int K,
+                const GemmEpilogue& epi, cudaStream_t stream) {
+  if (M <= 0 || N <= 0) return 0;
+  if (K <= 0 || K % kBK != 0) return fail(-2, "gemm_nf4: K (%d) must be a positive multiple of 64 (the NF4 block)", K);
+  if (A == nullptr || codes == nullptr || absmax == nullptr || C == nullptr) return fail(-2, "gemm_nf4: null operand");
+  if ((reinterpret_cast<uintptr_t>(codes) & 15) != 0) return fail(-2, "gemm_nf4: codes must be 16-byte aligned");
+  if (epi.act == kActSwiGLU || epi.n_peers != 0 || epi.ctas_per_sm == 2)
+    return fail(-2, "gemm_nf4: SwiGLU pairing / peer stores / two CTAs per SM are not built for the NF4 operand");
+  GemmArgs g;
+  g.C = C;
+  g.ldc = ldc;
+  g.M = M;
+  g.N = N;
+  g.K = K;
+  g.m_tiles = (M + kBM - 1) / kBM;
+  const int bn = (g.m_tiles * ((N + 255) / 256) >= num_sms()) ? 256 : 128;
+  g.n_tiles = (N + bn - 1) / bn;
+  g.a_mn = g.b_mn = 0;
+  g.epi = epi;
+  g.epi.b_const = 0;
+  g.raster_n = 0;
+  g.raster_group = g.m_tiles < 32 ? g.m_tiles : 32;
+  g.nf4_codes = codes;
+  g.nf4_absmax = absmax;
+  CUtensorMap tmA;
+  B200_TRY(make_tmap_2d(&tmA, A, M, K, lda, kBM));
+  if (bn == 256) return launch_gemm<256, 1, true>(tmA, tmA, g, stream);
+  return launch_gemm<128, 1, true>(tmA, tmA, g, stream);
 }
 
 // A: [M, K] (a_mn = 0) or stored transposed [K, M] (a_mn = 1); B: [N, K] (b_mn = 0) or [K, N] (b_mn = 1).
@@ -480,6 +604,8 @@ int gemm_bf16_ex(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, int b
   g.a_mn = a_mn ? 1 : 0;
   g.b_mn = b_mn ? 1 : 0;
   g.epi = epi;
+  g.nf4_codes = nullptr;
+  g.nf4_absmax = nullptr;
   {
     // Raster choice. DRAM traffic of a grouped raster = (kept operand, once) + (streamed operand) x (number of groups);
     // the kept panel must stay in the 126 MB L2 next to the stream, so it gets a budget (default 40 MB; the round-1

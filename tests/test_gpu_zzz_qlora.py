@@ -125,3 +125,44 @@ def test_pooler_hidden_dropout_is_reproducible_and_off_by_default():
     assert bool(torch.isfinite(runs[0][1]).all()) and float(runs[0][1].abs().max()) > 0
     pooler.dropout = 0.0
     assert float(ft.forward_backward(*args)[0]) == base[0]
+
+
+@pytest.mark.parametrize("M,N,K", [(300, 1000, 1024), (128, 256, 64), (3924, 12288, 4096), (777, 4096, 11008)])
+def test_fused_nf4_gemm_equals_dequantise_then_gemm(M, N, K):
+    """b200_gemm_nf4: the NF4 weight is expanded to bf16 inside the GEMM (four dequantisation warps write the swizzled B
+    stage that the TMA would have written) -- bit-identical to b200_gemm_bf16 on b200_nf4_dequantize(codes, absmax):
+    same tiles, same MMA order, same epilogue. Ragged N (rows beyond N are zero), both tile widths (128 / 256), a
+    residual + scale epilogue, K = 64 (one block)."""
+    from mm_or_b200 import _lib as L
+    from mm_or_b200.train import nf4 as N4
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    w = (torch.randn(N, K, generator=g, device="cuda") * 0.02).to(torch.bfloat16)
+    w[N // 2] = 0                                                          # an all-zero block row
+    x = torch.randn(M, K, generator=g, device="cuda").to(torch.bfloat16)
+    packed, absmax = N4.quantize(w)
+    wq = N4.dequantize(packed, absmax, w.shape)
+    ref = L.gemm(x, wq)
+    got = L.gemm_nf4(x, packed, absmax, N)
+    torch.cuda.synchronize()
+    assert got.shape == ref.shape and torch.isfinite(got.float()).all()
+    assert torch.equal(got, ref), (got.float() - ref.float()).abs().max().item()
+    res = torch.randn(M, N, generator=g, device="cuda").to(torch.bfloat16)
+    ref2 = L.gemm_ex(x, wq, residual=res, scale=0.5)
+    got2 = L.gemm_nf4(x, packed, absmax, N, residual=res, scale=0.5)
+    assert torch.equal(got2, ref2)
+    if M >= 3000:                                                           # timing note for the record (not asserted)
+        def t(fn):
+            for _ in range(3):
+                fn()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(10):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / 10
+        print("fused nf4 gemm %dx%dx%d: %.3f ms vs bf16 gemm %.3f ms (+ dequantise %.3f ms)"
+              % (M, N, K, t(lambda: L.gemm_nf4(x, packed, absmax, N)), t(lambda: L.gemm(x, wq)),
+                 t(lambda: N4.dequantize(packed, absmax, w.shape))))
+    with pytest.raises(L.B200Error):
+        L.gemm_nf4(x[:, :32].contiguous(), packed[:N * 16], absmax[:N // 2], N)      # K = 32: not a block multiple
