@@ -173,3 +173,70 @@ def test_sharded_gradients_zero2_world2_gloo():
     for p in procs:
         p.join(timeout=60)
     assert sorted(results) == [(0, "ok"), (1, "ok")], results
+
+
+def _zero2_world3_worker(rank, world, port, q):
+    """The flat (world, S) layout of the ZeRO-2 step with a world size that divides nothing: ragged last rows, a rank
+    whose slice of a tiny tensor is EMPTY, the alignment padding of a row. fp32 wire (the mean over 3 ranks is not a
+    power-of-two scaling, so sum * (clip / 3) and (sum / 3) * clip differ in the last bit: tolerance 1e-6 relative on the
+    masters, bf16 working weights equal up to one ulp)."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(9)
+        shapes = {"a": (7,), "b": (2,), "c": (5, 13), "d": (1,), "e": (64,)}
+        src = {k: torch.randn(s, generator=g) for k, s in shapes.items()}
+        names = sorted(src)
+        params = {k: v.to(torch.bfloat16).contiguous() for k, v in src.items()}
+        opt = ShardedAdamW(params, src, names, dist.group.WORLD, adamw=torch_adamw, sq_norm=torch_sq_norm)
+        ref = {k: dict(master=v.clone().reshape(-1), m=torch.zeros(v.numel()), v=torch.zeros(v.numel()))
+               for k, v in src.items()}
+        ref_p = {k: v.to(torch.bfloat16) for k, v in src.items()}
+        lr_of, wd_of = (lambda k: 5e-3), (lambda k: 0.05 if k == "c" else 0.0)
+        for step in (1, 2, 3):
+            per_rank = []
+            for r in range(world):
+                gr = torch.Generator().manual_seed(100 * step + r)
+                per_rank.append({k: torch.randn(src[k].shape, generator=gr) for k in names})
+            mine = {k: v.clone() for k, v in per_rank[rank].items()}
+            out2 = opt.step_from_local_grads(mine, step, lr_of, wd_of, max_norm=0.3, comm_dtype=torch.float32)
+            assert not mine
+            mean = {k: sum(p[k] for p in per_rank) / world for k in names}
+            sq = sum((v ** 2).sum() for v in mean.values())
+            coef = torch.clamp(0.3 / (sq.sqrt() + 1e-6), max=1.0)
+            assert torch.allclose(out2[0], sq, rtol=1e-5) and torch.allclose(out2[1], coef, rtol=1e-5)
+            for k in names:
+                r_ = ref[k]
+                torch_adamw(r_["master"], ref_p[k].view(-1), mean[k].reshape(-1), r_["m"], r_["v"], lr_of(k), 0.9, 0.999,
+                            1e-8, wd_of(k), step, clip_coef=coef)
+                lo, hi, _ = slice_range(src[k].numel(), rank, world)
+                assert opt.master[k].numel() == hi - lo
+                assert torch.allclose(opt.master[k], r_["master"][lo:hi], rtol=1e-5, atol=1e-7), (k, step)
+                assert torch.allclose(params[k].float(), ref_p[k].float(), rtol=1e-2, atol=1e-3), (k, step)
+            # every rank holds the same working weights bit for bit (each element was updated by exactly one rank)
+            flat = torch.cat([params[k].float().reshape(-1) for k in names])
+            gathered = [torch.zeros_like(flat) for _ in range(world)]
+            dist.all_gather(gathered, flat)
+            assert all(torch.equal(gathered[0], x) for x in gathered)
+        lo, hi, _ = slice_range(2, 2, 3)
+        assert (lo, hi) == (2, 2) or rank != 2                                # rank 2 owns nothing of tensor "b"
+        q.put((rank, "ok"))
+    except Exception as e:  # surfaced by the parent
+        import traceback
+        q.put((rank, repr(e) + traceback.format_exc()[-800:]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_gradients_zero2_world3_ragged_gloo():
+    world = 3
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_zero2_world3_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(results) == [(0, "ok"), (1, "ok"), (2, "ok")], results
