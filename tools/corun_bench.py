@@ -2,7 +2,10 @@
 decode attention of one layer (128 rows x 32 heads, ctx 900: 0.94 GB of K / V per launch) in a loop on a high-priority
 stream, the prefill gate_up GEMM (13296 x 22016 x 4096, SwiGLU epilogue) in a loop on a low-priority stream; each alone,
 then both at once. together ~ max(alone) => they co-run; together ~ sum(alone) => they time-slice.
-  python tools/corun_bench.py            (B200_ATTN_CARVEOUT=1 for the max-shared carve-out variant)
+  python tools/corun_bench.py            (B200_GEMM_CARVEOUT=1: the GEMM asks for the full 228 KB shared carve-out so that
+                                          attention CTAs fit beside it. The attention-side knob B200_ATTN_CARVEOUT that
+                                          profiles/r2_corun_attention_vs_gemm.json also shows was removed after the
+                                          experiment: it made the attention alone slower and changed nothing together.)
 """
 import json
 import os
@@ -55,7 +58,7 @@ def main():
         return [round(e0.elapsed_time(e), 2) for e in ends]
 
     attn_loop(); gemm_loop(); torch.cuda.synchronize()                     # warm-up (kernel attributes, tensor maps)
-    rec = {"carveout_env": os.environ.get("B200_ATTN_CARVEOUT", "0"),
+    rec = {"gemm_carveout_env": os.environ.get("B200_GEMM_CARVEOUT", "0"),
            "attn_alone_ms": timed([(attn_loop, hi)])[0], "gemm_alone_ms": timed([(gemm_loop, lo)])[0]}
     t = timed([(gemm_loop, lo), (attn_loop, hi)])
     rec["together_gemm_first"] = {"gemm_done_ms": t[0], "attn_done_ms": t[1]}

@@ -40,7 +40,7 @@ def main():
             torch.cuda.synchronize()
             us = e0.elapsed_time(e1) * 1e3 / n
             gb = B * H * ctx * 128 * 2 * 2 / 1e9
-            print(json.dumps({"occ": os.environ.get("B200_ATTN_OCC", "4"), "ctx": ctx, "splits": splits, "us_per_launch": round(us, 1),
+            print(json.dumps({"ctx": ctx, "splits": splits, "us_per_launch": round(us, 1),
                               "gb_per_s": round(gb / us * 1e6, 1)}), flush=True)
 
 

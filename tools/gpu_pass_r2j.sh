@@ -1,5 +1,7 @@
 #!/bin/bash
 # Round-2 pass j (1 GPU): decode-attention occupancy A/B, GEMM raster A/B (throughput + DRAM bytes of the prefill GEMMs).
+# (The B200_ATTN_OCC knob existed only for this pass: the 6 / 8-CTA builds were slower and were removed afterwards;
+#  profiles/r2_decode_attn_occupancy.json keeps the result.)
 mkdir -p gpurun_out
 for OCC in 4 6 8; do
   SPLITS1=1 B200_ATTN_OCC=$OCC timeout 100 python tools/decode_attn_bench.py >> gpurun_out/r2j_attn_occ.json 2>> gpurun_out/r2j_attn_occ.err
