@@ -46,3 +46,15 @@ def test_driver_facing_defaults():
              "print(a.gpus, a.batch, a.views, a.new_tokens, a.layers, a.impl, a.subrecord_timeout)\n")
     assert r.returncode == 0, r.stderr
     assert r.stdout.split() == ["1", "128", "6", "256", "32", "b200", "300.0"]
+
+
+def test_algorithmic_flop_counts_match_the_survey():
+    """configs[1] = 16.95 TFLOP per inference (6 views, L = 831, 256 new tokens); the fine-tune step of
+    configs[4] counts forward + 2 x forward of everything that is trained (179.3 TFLOP at 4 x 981 tokens per GPU)."""
+    r = _run("import bench\n"
+             "from mm_or_b200.config import LlavaConfig\n"
+             "from mm_or_b200.train.bench_step import step_flops\n"
+             "print(round(bench.algorithmic_flops_per_inference(6, 831, 256) / 1e12, 2))\n"
+             "print(round(step_flops(LlavaConfig(num_hidden_layers=32), 4, 6, 981) / 1e12, 1))\n")
+    assert r.returncode == 0, r.stderr
+    assert r.stdout.split() == ["16.95", "179.3"]
